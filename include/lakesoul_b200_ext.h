@@ -1,0 +1,71 @@
+/* SPDX-License-Identifier: Apache-2.0
+ *
+ * lakesoul_b200_ext.h -- extensions exported by liblakesoul_io_c.so next to the reference C-ABI
+ * (include/lakesoul_c_bindings.h). Nothing here exists in the reference; these entry points expose
+ *   (1) per-reader counters (bytes over PCIe, kernel launches) for bench.py's `e2e` leg, and
+ *   (2) the device-level scan plan: the same CUDA engine the reader uses, driven with columns that
+ *       are already resident in HBM (plain device pointers, no torch types) -- bench.py's `value`
+ *       leg and the `-m gpu` kernel parity tests call it through ctypes.
+ * All functions return 0 on success and -1 on error unless stated; lsb_last_error() gives the
+ * message for the calling thread.
+ */
+#ifndef LAKESOUL_B200_EXT_H
+#define LAKESOUL_B200_EXT_H
+
+#include <stdint.h>
+
+#include "lakesoul_c_bindings.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char *lsb_last_error(void);
+/* selects the CUDA device for this process (LAKESOUL_B200_DEVICE, else LOCAL_RANK, else 0);
+ * returns the device id or -1 when no GPU is usable (the engine has no CPU fallback) */
+int32_t lsb_init_device(void);
+const char *lsb_version(void);
+
+typedef struct LsbReaderStats {
+  int64_t rows_in, rows_out, h2d_bytes, d2h_bytes;
+  int32_t kernel_launches, pad;
+  double decode_ms, upload_ms, merge_ms, gather_ms, download_ms;
+} LsbReaderStats;
+int32_t lsb_reader_get_stats(CResult_Reader *reader, LsbReaderStats *out);
+
+/* ---- device-level plan --------------------------------------------------------------------- */
+typedef struct LsbPlan LsbPlan;
+
+/* nb hash buckets; bucket b owns files [bucket_file_begin[b], bucket_file_begin[b+1]) in commit
+ * order; file f has file_rows[f] rows sorted by primary key and starts at global row
+ * file_row_base[f] of every column buffer (NULL = files packed back to back). */
+LsbPlan *lsb_plan_create(int32_t nb, const int32_t *bucket_file_begin, const int64_t *file_rows,
+                         const int64_t *file_row_base, int64_t row_span, int32_t key_bits,
+                         int32_t batch_size, void *cuda_stream);
+void lsb_plan_destroy(LsbPlan *plan);
+
+/* pk_kind: 0 unsigned, 1 signed, 2 float (IEEE total order); pk_width in bytes (1,2,4,8);
+ * pk_validity[i] may be NULL. key_bits passed to lsb_plan_create must be
+ * sum(8*width + (validity ? 1 : 0)). */
+int32_t lsb_plan_merge(LsbPlan *plan, int32_t n_pk, const void *const *pk_values,
+                       const void *const *pk_validity, const int32_t *pk_width, const int32_t *pk_kind,
+                       void *cuda_stream);
+int32_t lsb_plan_identity(LsbPlan *plan, void *cuda_stream);
+/* blocks until the merge is done; fills out_base[nb+1] and batch_base[nb+1] (host arrays) */
+int32_t lsb_plan_sync_counts(LsbPlan *plan, int64_t *out_base, int64_t *batch_base, void *cuda_stream);
+const void *lsb_plan_winners(LsbPlan *plan); /* device uint32[total_out] of global row ids */
+int64_t lsb_plan_valid_stride(LsbPlan *plan);
+/* stats[8] = {rows_in, rows_out, tiles_level0, levels, log2(S), tile_capacity, launches, 0} */
+int32_t lsb_plan_stats(LsbPlan *plan, int64_t *stats);
+
+int32_t lsb_plan_gather_fixed(LsbPlan *plan, int32_t ncols, const void *const *src,
+                              const void *const *src_valid, void *const *dst, void *const *dst_valid,
+                              const int32_t *width, void *cuda_stream);
+int32_t lsb_plan_gather_var(LsbPlan *plan, const void *src_offsets, const void *src_data,
+                            const void *src_data_base, const void *src_valid, void *dst_offsets,
+                            void *dst_data, void *dst_valid, void *batch_data_start, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAKESOUL_B200_EXT_H */

@@ -1,0 +1,639 @@
+// SPDX-License-Identifier: Apache-2.0
+#include "device_scan.h"
+
+#include <arrow/util/bit_util.h>
+#include <arrow/util/bitmap_ops.h>
+
+#include <chrono>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+
+#include "general_merge.h"
+#include "filter_eval.h"
+
+namespace lsb {
+
+namespace {
+
+[[noreturn]] void fail(const std::string& m) { throw std::runtime_error(m); }
+
+#define SCAN_CUDA(x)                                                                      \
+  do {                                                                                    \
+    cudaError_t e_ = (x);                                                                 \
+    if (e_ != cudaSuccess) fail(std::string(#x) + " failed: " + cudaGetErrorString(e_));  \
+  } while (0)
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------------------------------
+// pinned host pool: cudaMallocHost is expensive (page pinning), readers come and go per
+// bucket, so blocks are recycled by power-of-two size class.
+// ---------------------------------------------------------------------------------------
+class PinnedPool {
+ public:
+  static PinnedPool& get() {
+    static PinnedPool* p = new PinnedPool();  // leaked on purpose: outlives late release callbacks
+    return *p;
+  }
+  std::shared_ptr<uint8_t> alloc(size_t n) {
+    size_t cls = 1 << 16;
+    while (cls < n) cls <<= 1;
+    uint8_t* p = nullptr;
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      auto& fl = free_[cls];
+      if (!fl.empty()) {
+        p = fl.back();
+        fl.pop_back();
+        cached_ -= cls;
+      }
+    }
+    if (!p) {
+      cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), cls);
+      if (e != cudaSuccess) fail(std::string("cudaMallocHost failed: ") + cudaGetErrorString(e));
+    }
+    return std::shared_ptr<uint8_t>(p, [this, cls](uint8_t* q) { release(q, cls); });
+  }
+
+ private:
+  void release(uint8_t* p, size_t cls) {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      if (cached_ + cls <= kMaxCached) {
+        free_[cls].push_back(p);
+        cached_ += cls;
+        return;
+      }
+    }
+    cudaFreeHost(p);
+  }
+  static constexpr size_t kMaxCached = 8ull << 30;
+  std::mutex mu_;
+  std::map<size_t, std::vector<uint8_t*>> free_;
+  size_t cached_ = 0;
+};
+
+class KeepAliveBuffer : public arrow::Buffer {
+ public:
+  KeepAliveBuffer(const uint8_t* p, int64_t n, std::shared_ptr<void> owner)
+      : arrow::Buffer(p, n), owner_(std::move(owner)) {}
+
+ private:
+  std::shared_ptr<void> owner_;
+};
+
+struct DevMem {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+ColumnKind classify_type(const arrow::DataType& t) {
+  ColumnKind k;
+  using T = arrow::Type;
+  auto fixed = [&](int w, bool pk, uint8_t kind) {
+    k.width = w; k.ok = true; k.pk_ok = pk; k.pk_kind = kind;
+  };
+  switch (t.id()) {
+    case T::BOOL: k.width = 0; k.ok = true; break;
+    case T::INT8: fixed(1, true, PK_SIGNED); break;
+    case T::UINT8: fixed(1, true, PK_UNSIGNED); break;
+    case T::INT16: fixed(2, true, PK_SIGNED); break;
+    case T::UINT16: fixed(2, true, PK_UNSIGNED); break;
+    case T::HALF_FLOAT: fixed(2, false, 0); break;
+    case T::INT32: case T::DATE32: case T::TIME32: fixed(4, true, PK_SIGNED); break;
+    case T::UINT32: fixed(4, true, PK_UNSIGNED); break;
+    case T::FLOAT: fixed(4, true, PK_FLOAT); break;
+    case T::INT64: case T::DATE64: case T::TIME64: case T::TIMESTAMP: case T::DURATION:
+      fixed(8, true, PK_SIGNED); break;
+    case T::UINT64: fixed(8, true, PK_UNSIGNED); break;
+    case T::DOUBLE: fixed(8, true, PK_FLOAT); break;
+    case T::INTERVAL_MONTHS: fixed(4, false, 0); break;
+    case T::INTERVAL_DAY_TIME: fixed(8, false, 0); break;
+    case T::INTERVAL_MONTH_DAY_NANO: fixed(16, false, 0); break;
+    case T::DECIMAL128: fixed(16, false, 0); break;
+    case T::DECIMAL256: fixed(32, false, 0); break;
+    case T::FIXED_SIZE_BINARY: {
+      const int w = static_cast<const arrow::FixedSizeBinaryType&>(t).byte_width();
+      if (w == 1 || w == 2 || w == 4 || w == 8 || w == 16 || w == 32) fixed(w, false, 0);
+      break;
+    }
+    case T::STRING: case T::BINARY: k.var = true; k.ok = true; break;
+    default: break;
+  }
+  return k;
+}
+
+static int num_class_of(const arrow::DataType& t) {
+  switch (t.id()) {
+    case arrow::Type::INT8: return NC_I8;
+    case arrow::Type::INT16: return NC_I16;
+    case arrow::Type::INT32: return NC_I32;
+    case arrow::Type::INT64: return NC_I64;
+    case arrow::Type::UINT8: return NC_U8;
+    case arrow::Type::UINT16: return NC_U16;
+    case arrow::Type::UINT32: return NC_U32;
+    case arrow::Type::UINT64: return NC_U64;
+    case arrow::Type::FLOAT: return NC_F32;
+    case arrow::Type::DOUBLE: return NC_F64;
+    default: return NC_NONE;
+  }
+}
+
+MergeOp merge_op_from_name(const std::string& name) {
+  if (name == "UseLast") return MergeOp::UseLast;
+  if (name == "UseLastNotNull") return MergeOp::UseLastNotNull;
+  if (name == "SumAll") return MergeOp::SumAll;
+  if (name == "SumLast") return MergeOp::SumLast;
+  if (name == "JoinedLastByComma") return MergeOp::JoinedLastByComma;
+  if (name == "JoinedLastBySemicolon") return MergeOp::JoinedLastBySemicolon;
+  if (name == "JoinedAllByComma") return MergeOp::JoinedAllByComma;
+  if (name == "JoinedAllBySemicolon") return MergeOp::JoinedAllBySemicolon;
+  fail("Invalid MergeOperator name");
+}
+
+// ---------------------------------------------------------------------------------------
+struct DeviceScan::Impl : std::enable_shared_from_this<DeviceScan::Impl> {
+  ScanSpec spec;
+  std::vector<BucketFiles> buckets;
+  cudaStream_t stream = nullptr;
+  ScanCounters ctr;
+
+  // input layout
+  int nb = 0, F = 0, C = 0;
+  std::vector<int32_t> bucket_file_begin;
+  std::vector<int64_t> file_rows, file_row_base;
+  std::vector<const arrow::Table*> file_table;
+  int64_t span = 0;
+
+  struct DevColumn {
+    ColumnKind kind;
+    DevMem values, validity, data;
+    std::vector<char> present;         // per file
+    std::vector<int64_t> bucket_data;  // var: data base of each bucket
+    DevMem d_bucket_data;
+    int64_t data_bytes = 0;
+    bool any_nulls = false;
+    bool all_present = true;
+  };
+  std::vector<DevColumn> cols;
+  std::vector<void*> dev_allocs;
+
+  MergePlan* plan = nullptr;
+  GeneralMerge* general = nullptr;
+
+  // outputs (pinned host)
+  struct OutColumn {
+    ColumnKind kind;
+    bool has_valid = false;
+    std::shared_ptr<uint8_t> h_values, h_valid, h_offsets, h_data;
+    std::vector<int64_t> batch_data_start;
+  };
+  std::vector<OutColumn> outs;
+  std::vector<int64_t> out_base, batch_base;
+  int64_t vstride = 0;
+  bool ran = false;
+
+  ~Impl() {
+    if (general) general_destroy(general);
+    if (plan) plan_destroy(plan);
+    free_device();
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  void* dalloc(size_t bytes) {
+    void* p = nullptr;
+    SCAN_CUDA(cudaMallocAsync(&p, std::max<size_t>(bytes, 16), stream));
+    dev_allocs.push_back(p);
+    return p;
+  }
+  void free_device() {
+    for (void* p : dev_allocs) cudaFreeAsync(p, stream);
+    dev_allocs.clear();
+    if (stream) cudaStreamSynchronize(stream);
+  }
+  void h2d(void* dst, const void* src, size_t n) {
+    if (n == 0) return;
+    SCAN_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, stream));
+    ctr.h2d_bytes += (int64_t)n;
+  }
+  void d2h(void* dst, const void* src, size_t n) {
+    if (n == 0) return;
+    SCAN_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, stream));
+    ctr.d2h_bytes += (int64_t)n;
+  }
+
+  void layout();
+  void upload();
+  void upload_column(int c);
+  void merge_and_gather();
+};
+
+void DeviceScan::Impl::layout() {
+  nb = (int)buckets.size();
+  C = spec.physical_schema->num_fields();
+  bucket_file_begin.assign(nb + 1, 0);
+  for (int b = 0; b < nb; ++b)
+    bucket_file_begin[b + 1] = bucket_file_begin[b] + (int)buckets[b].files.size();
+  F = bucket_file_begin[nb];
+  file_rows.resize(F);
+  file_row_base.resize(F);
+  file_table.resize(F);
+  int64_t pos = 0;
+  for (int b = 0, f = 0; b < nb; ++b) {
+    for (auto& t : buckets[b].files) {
+      file_table[f] = t.get();
+      file_rows[f] = t->num_rows();
+      // 64-row alignment keeps validity bitmaps byte-copyable and 16-byte alignment for
+      // every fixed width; the spare row after each file holds the closing string offset.
+      file_row_base[f] = pos;
+      pos = (pos + file_rows[f] + 1 + 63) & ~63ll;
+      ctr.rows_in += file_rows[f];
+      ++f;
+    }
+  }
+  span = pos;
+}
+
+void DeviceScan::Impl::upload_column(int c) {
+  const auto& field = spec.physical_schema->field(c);
+  DevColumn& dc = cols[c];
+  dc.kind = classify_type(*field->type());
+  if (!dc.kind.ok) fail("unsupported column type for the GPU reader: " + field->ToString());
+  dc.present.assign(F, 0);
+  // pass 1: presence, nulls, var sizes
+  std::vector<int64_t> file_data_pos(F, 0);
+  dc.bucket_data.assign(nb, 0);
+  int64_t data_pos = 0;
+  for (int b = 0; b < nb; ++b) {
+    dc.bucket_data[b] = data_pos;
+    for (int f = bucket_file_begin[b]; f < bucket_file_begin[b + 1]; ++f) {
+      auto col = file_table[f]->GetColumnByName(field->name());
+      if (!col) { dc.all_present = false; continue; }
+      if (!col->type()->Equals(*field->type()))
+        fail("column '" + field->name() + "' has type " + col->type()->ToString() + " in a file but " +
+             field->type()->ToString() + " is expected");
+      dc.present[f] = 1;
+      if (col->null_count() > 0) dc.any_nulls = true;
+      if (dc.kind.var) {
+        file_data_pos[f] = data_pos;
+        for (const auto& ch : col->chunks()) {
+          const auto& ba = static_cast<const arrow::BinaryArray&>(*ch);
+          data_pos += ba.value_offset(ba.length()) - ba.value_offset(0);
+        }
+        if (data_pos - dc.bucket_data[b] > 0x7fffff00ll)
+          fail("variable-width column '" + field->name() + "' exceeds 2 GiB in one hash bucket");
+      }
+    }
+  }
+  dc.data_bytes = data_pos;
+
+  const int w = dc.kind.width;
+  if (dc.kind.var) {
+    dc.values.bytes = (size_t)(span + 1) * 4;
+    dc.data.bytes = (size_t)data_pos;
+    dc.data.p = dalloc(dc.data.bytes);
+    dc.d_bucket_data.p = dalloc(sizeof(int64_t) * nb);
+    h2d(dc.d_bucket_data.p, dc.bucket_data.data(), sizeof(int64_t) * nb);
+  } else if (w == 0) {
+    dc.values.bytes = (size_t)(span / 8 + 8);
+  } else {
+    dc.values.bytes = (size_t)span * w;
+  }
+  dc.values.p = dalloc(dc.values.bytes);
+  if (dc.any_nulls) {
+    dc.validity.bytes = (size_t)(span / 8 + 8);
+    dc.validity.p = dalloc(dc.validity.bytes);
+    SCAN_CUDA(cudaMemsetAsync(dc.validity.p, 0xff, dc.validity.bytes, stream));
+  }
+
+  std::vector<uint8_t> bits;
+  std::vector<int32_t> offs;
+  for (int b = 0; b < nb; ++b) {
+    for (int f = bucket_file_begin[b]; f < bucket_file_begin[b + 1]; ++f) {
+      if (!dc.present[f]) continue;
+      auto col = file_table[f]->GetColumnByName(field->name());
+      const int64_t base = file_row_base[f];
+      const int64_t n = file_rows[f];
+      // validity of the whole file, assembled at bit offset 0
+      if (dc.any_nulls && col->null_count() > 0) {
+        bits.assign((size_t)((n + 7) / 8), 0xff);
+        int64_t r0 = 0;
+        for (const auto& ch : col->chunks()) {
+          if (ch->null_count() > 0 && ch->null_bitmap_data())
+            arrow::internal::CopyBitmap(ch->null_bitmap_data(), ch->offset(), ch->length(), bits.data(), r0);
+          r0 += ch->length();
+        }
+        h2d(static_cast<uint8_t*>(dc.validity.p) + base / 8, bits.data(), bits.size());
+      }
+      int64_t r0 = 0;
+      int64_t dpos = file_data_pos[f];
+      if (w == 0 && !dc.kind.var) {
+        bits.assign((size_t)((n + 7) / 8), 0);
+        for (const auto& ch : col->chunks()) {
+          const auto& ba = static_cast<const arrow::BooleanArray&>(*ch);
+          arrow::internal::CopyBitmap(ba.values()->data(), ba.offset(), ba.length(), bits.data(), r0);
+          r0 += ch->length();
+        }
+        h2d(static_cast<uint8_t*>(dc.values.p) + base / 8, bits.data(), bits.size());
+        continue;
+      }
+      for (const auto& ch : col->chunks()) {
+        const int64_t len = ch->length();
+        if (len == 0) continue;
+        if (dc.kind.var) {
+          const auto& ba = static_cast<const arrow::BinaryArray&>(*ch);
+          const int32_t* o = ba.raw_value_offsets();  // already offset-adjusted
+          const int64_t first = o[0];
+          const int64_t nbytes = (int64_t)o[len] - first;
+          const int64_t delta = dpos - dc.bucket_data[b] - first;
+          offs.resize((size_t)len + 1);
+          for (int64_t i = 0; i <= len; ++i) offs[(size_t)i] = (int32_t)(o[i] + delta);
+          h2d(static_cast<int32_t*>(dc.values.p) + base + r0, offs.data(), sizeof(int32_t) * (size_t)(len + 1));
+          if (nbytes > 0)
+            h2d(static_cast<uint8_t*>(dc.data.p) + dpos, ba.value_data()->data() + first, (size_t)nbytes);
+          dpos += nbytes;
+        } else {
+          const uint8_t* src = ch->data()->buffers[1]->data() + (int64_t)ch->offset() * w;
+          h2d(static_cast<uint8_t*>(dc.values.p) + (base + r0) * w, src, (size_t)len * w);
+        }
+        r0 += len;
+      }
+      if (dc.kind.var && n == 0) {
+        const int32_t z = (int32_t)(dpos - dc.bucket_data[b]);
+        h2d(static_cast<int32_t*>(dc.values.p) + base, &z, sizeof(int32_t));
+      }
+    }
+  }
+}
+
+void DeviceScan::Impl::upload() {
+  cols.resize(C);
+  for (int c = 0; c < C; ++c) upload_column(c);
+}
+
+void DeviceScan::Impl::merge_and_gather() {
+  const bool do_merge = spec.merge && !spec.primary_keys.empty();
+  // ---- which path -----------------------------------------------------------------------
+  bool all_use_last = true;
+  for (auto op : spec.ops) all_use_last &= (op == MergeOp::UseLast);
+  bool partial = false;
+  for (int c = 0; c < C; ++c) partial |= !cols[c].all_present;
+  const bool general_path = do_merge && (!all_use_last || partial);
+
+  // ---- primary key ------------------------------------------------------------------------
+  PkDesc pk{};
+  int key_bits = 64;
+  if (do_merge) {
+    if ((int)spec.primary_keys.size() > kMaxPkCols)
+      fail("more than 4 primary key columns are not supported by the GPU reader");
+    pk.ncols = (int)spec.primary_keys.size();
+    key_bits = 0;
+    for (int i = 0; i < pk.ncols; ++i) {
+      const int c = spec.physical_schema->GetFieldIndex(spec.primary_keys[i]);
+      if (c < 0) fail("primary key column '" + spec.primary_keys[i] + "' is not in the schema");
+      const DevColumn& dc = cols[c];
+      if (!dc.kind.pk_ok)
+        fail("primary key column '" + spec.primary_keys[i] + "' of type " +
+             spec.physical_schema->field(c)->type()->ToString() + " is not supported by the GPU reader yet");
+      if (!dc.all_present) fail("primary key column '" + spec.primary_keys[i] + "' is missing from a file");
+      pk.col[i].values = dc.values.p;
+      pk.col[i].validity = static_cast<const uint8_t*>(dc.validity.p);
+      pk.col[i].width = (uint8_t)dc.kind.width;
+      pk.col[i].kind = dc.kind.pk_kind;
+      key_bits += dc.kind.width * 8 + (dc.validity.p ? 1 : 0);
+    }
+    if (key_bits > 128) fail("primary key wider than 128 bits is not supported by the GPU reader");
+    pk.key_bits = key_bits;
+  }
+
+  const double t0 = now_ms();
+  plan = plan_create(nb, bucket_file_begin.data(), file_rows.data(), file_row_base.data(), span,
+                     do_merge ? key_bits : 64, spec.batch_size, stream);
+  if (do_merge) plan_merge(plan, pk, stream);
+  else plan_identity(plan, stream);
+  plan_sync_counts(plan, stream);
+  ctr.kernel_launches += plan_stats(plan).launches;
+
+  // per-column winner lists / operator results (partial merge, non-UseLast operators)
+  std::vector<GeneralColumnIn> gin;
+  if (general_path) {
+    ctr.path = "merge-general";
+    gin.resize(C);
+    for (int c = 0; c < C; ++c) {
+      gin[c].op = spec.ops.empty() ? MergeOp::UseLast : spec.ops[c];
+      gin[c].present = cols[c].present.data();
+      gin[c].kind = cols[c].kind;
+      gin[c].num_class = num_class_of(*spec.physical_schema->field(c)->type());
+      gin[c].values = cols[c].values.p;
+      gin[c].validity = static_cast<const uint8_t*>(cols[c].validity.p);
+      gin[c].data = static_cast<const uint8_t*>(cols[c].data.p);
+      gin[c].bucket_data = static_cast<const int64_t*>(cols[c].d_bucket_data.p);
+      gin[c].data_bytes = cols[c].data_bytes;
+    }
+    general = general_create(plan, pk, gin, stream);
+    ctr.kernel_launches += general_launches(general);
+  } else {
+    ctr.path = do_merge ? "merge-full" : "concat";
+  }
+
+  // ---- post-merge predicate ------------------------------------------------------------
+  if (spec.filter) {
+    std::vector<FilterColumnIn> fin(C);
+    for (int c = 0; c < C; ++c) {
+      fin[c].name = spec.physical_schema->field(c)->name();
+      fin[c].type = spec.physical_schema->field(c)->type();
+      fin[c].kind = cols[c].kind;
+      fin[c].values = general ? general_values(general, c, cols[c].values.p) : cols[c].values.p;
+      fin[c].validity = general ? general_validity(general, c, static_cast<const uint8_t*>(cols[c].validity.p))
+                                : static_cast<const uint8_t*>(cols[c].validity.p);
+      fin[c].data = general ? general_data(general, c, static_cast<const uint8_t*>(cols[c].data.p))
+                            : static_cast<const uint8_t*>(cols[c].data.p);
+      fin[c].bucket_data = general ? general_bucket_data(general, c, static_cast<const int64_t*>(cols[c].d_bucket_data.p))
+                                   : static_cast<const int64_t*>(cols[c].d_bucket_data.p);
+      fin[c].win = general ? general_winners(general, c) : nullptr;
+    }
+    std::vector<uint32_t*> extra;
+    if (general) extra = general_winner_lists(general);
+    ctr.kernel_launches += apply_filter(plan, *spec.filter, fin, extra, stream);
+  }
+  ctr.merge_ms += now_ms() - t0;
+
+  out_base = plan_out_base(plan);
+  batch_base = plan_batch_base(plan);
+  vstride = plan_valid_stride_bytes(plan);
+  const int64_t U = out_base[nb];
+  const int64_t TB = batch_base[nb];
+  ctr.rows_out = U;
+
+  // ---- gather ---------------------------------------------------------------------------
+  const double t1 = now_ms();
+  outs.resize(C);
+  struct DevOut { void *values = nullptr, *valid = nullptr, *offsets = nullptr, *data = nullptr, *bstart = nullptr; };
+  std::vector<DevOut> dout(C);
+  std::vector<FixedCol> fixed;
+  for (int c = 0; c < C; ++c) {
+    DevColumn& dc = cols[c];
+    OutColumn& oc = outs[c];
+    oc.kind = dc.kind;
+    const uint32_t* win = general ? general_winners(general, c) : nullptr;
+    const void* src_values = general ? general_values(general, c, dc.values.p) : dc.values.p;
+    const uint8_t* src_valid = general ? general_validity(general, c, static_cast<const uint8_t*>(dc.validity.p))
+                                       : static_cast<const uint8_t*>(dc.validity.p);
+    oc.has_valid = src_valid != nullptr || (general && general_may_be_null(general, c));
+    if (U == 0) continue;
+    if (oc.has_valid) dout[c].valid = dalloc((size_t)(TB * vstride));
+    if (dc.kind.var) {
+      const uint8_t* src_data = general ? general_data(general, c, static_cast<const uint8_t*>(dc.data.p))
+                                        : static_cast<const uint8_t*>(dc.data.p);
+      const int64_t* bdata = general ? general_bucket_data(general, c, static_cast<const int64_t*>(dc.d_bucket_data.p))
+                                     : static_cast<const int64_t*>(dc.d_bucket_data.p);
+      const int64_t cap = general ? general_data_bytes(general, c, dc.data_bytes) : dc.data_bytes;
+      dout[c].offsets = dalloc((size_t)(U + TB) * 4);
+      dout[c].data = dalloc((size_t)cap);
+      dout[c].bstart = dalloc((size_t)(TB + 1) * 8);
+      VarCol vc{};
+      vc.src_offsets = static_cast<const int32_t*>(src_values);
+      vc.src_data = src_data;
+      vc.src_data_base = bdata;
+      vc.src_valid = src_valid;
+      vc.win = win;
+      vc.dst_offsets = static_cast<int32_t*>(dout[c].offsets);
+      vc.dst_data = static_cast<uint8_t*>(dout[c].data);
+      vc.dst_valid = static_cast<uint8_t*>(dout[c].valid);
+      vc.batch_data_start = static_cast<int64_t*>(dout[c].bstart);
+      gather_var(plan, vc, stream);
+      ctr.kernel_launches += 6;
+    } else {
+      const int w = dc.kind.width;
+      dout[c].values = dalloc(w == 0 ? (size_t)(TB * vstride) : (size_t)U * w);
+      FixedCol fc{};
+      fc.src = src_values;
+      fc.src_valid = src_valid;
+      fc.dst = dout[c].values;
+      fc.dst_valid = static_cast<uint8_t*>(dout[c].valid);
+      fc.win = win;
+      fc.width = w;
+      fixed.push_back(fc);
+    }
+  }
+  if (!fixed.empty() && U > 0) {
+    gather_fixed(plan, fixed.data(), (int)fixed.size(), stream);
+    ctr.kernel_launches += 1;
+  }
+
+  // ---- download ---------------------------------------------------------------------------
+  auto& pool = PinnedPool::get();
+  for (int c = 0; c < C && U > 0; ++c) {
+    OutColumn& oc = outs[c];
+    if (oc.has_valid) {
+      oc.h_valid = pool.alloc((size_t)(TB * vstride));
+      d2h(oc.h_valid.get(), dout[c].valid, (size_t)(TB * vstride));
+    }
+    if (oc.kind.var) {
+      oc.h_offsets = pool.alloc((size_t)(U + TB) * 4);
+      d2h(oc.h_offsets.get(), dout[c].offsets, (size_t)(U + TB) * 4);
+      oc.batch_data_start.resize((size_t)TB + 1);
+      d2h(oc.batch_data_start.data(), dout[c].bstart, (size_t)(TB + 1) * 8);
+    } else {
+      const size_t n = oc.kind.width == 0 ? (size_t)(TB * vstride) : (size_t)U * oc.kind.width;
+      oc.h_values = pool.alloc(n);
+      d2h(oc.h_values.get(), dout[c].values, n);
+    }
+  }
+  SCAN_CUDA(cudaStreamSynchronize(stream));
+  ctr.gather_ms += now_ms() - t1;
+  const double t2 = now_ms();
+  for (int c = 0; c < C && U > 0; ++c) {
+    OutColumn& oc = outs[c];
+    if (!oc.kind.var) continue;
+    const int64_t total = oc.batch_data_start[(size_t)TB];
+    for (int64_t g = 0; g < TB; ++g)
+      if (oc.batch_data_start[(size_t)g + 1] - oc.batch_data_start[(size_t)g] > 0x7fffffffll)
+        fail("string data of one output batch exceeds 2 GiB");
+    oc.h_data = pool.alloc((size_t)std::max<int64_t>(total, 1));
+    d2h(oc.h_data.get(), dout[c].data, (size_t)total);
+  }
+  SCAN_CUDA(cudaStreamSynchronize(stream));
+  ctr.download_ms += now_ms() - t2;
+}
+
+DeviceScan::DeviceScan(ScanSpec spec, std::vector<BucketFiles> buckets) : impl_(std::make_shared<Impl>()) {
+  impl_->spec = std::move(spec);
+  impl_->buckets = std::move(buckets);
+  if (impl_->spec.ops.empty())
+    impl_->spec.ops.assign(impl_->spec.physical_schema->num_fields(), MergeOp::UseLast);
+}
+DeviceScan::~DeviceScan() = default;
+
+void DeviceScan::Run() {
+  Impl& I = *impl_;
+  if (I.ran) return;
+  SCAN_CUDA(cudaStreamCreateWithFlags(&I.stream, cudaStreamNonBlocking));
+  I.layout();
+  const double t0 = now_ms();
+  I.upload();
+  SCAN_CUDA(cudaStreamSynchronize(I.stream));
+  I.ctr.upload_ms += now_ms() - t0;
+  I.merge_and_gather();
+  // device memory is no longer needed: only the pinned host copy backs the exported batches
+  if (I.general) { general_destroy(I.general); I.general = nullptr; }
+  plan_destroy(I.plan);
+  I.plan = nullptr;
+  I.free_device();
+  I.buckets.clear();  // drop the decoded inputs
+  I.file_table.clear();
+  I.ran = true;
+}
+
+int DeviceScan::num_buckets() const { return impl_->nb; }
+int64_t DeviceScan::num_rows(int b) const { return impl_->out_base[b + 1] - impl_->out_base[b]; }
+int64_t DeviceScan::num_batches(int b) const { return impl_->batch_base[b + 1] - impl_->batch_base[b]; }
+const ScanCounters& DeviceScan::counters() const { return impl_->ctr; }
+
+std::shared_ptr<arrow::RecordBatch> DeviceScan::Batch(int b, int64_t i) const {
+  const Impl& I = *impl_;
+  const int64_t bs = I.spec.batch_size;
+  const int64_t U = I.out_base[b + 1] - I.out_base[b];
+  const int64_t rows = std::min<int64_t>(bs, U - i * bs);
+  if (rows <= 0) fail("batch index out of range");
+  const int64_t gb = I.batch_base[b] + i;
+  const int64_t u0 = I.out_base[b] + i * bs;
+  std::shared_ptr<void> owner = std::const_pointer_cast<Impl>(I.shared_from_this());
+  std::vector<std::shared_ptr<arrow::Array>> arrays;
+  for (int c = 0; c < I.C; ++c) {
+    const auto& oc = I.outs[c];
+    const auto& type = I.spec.physical_schema->field(c)->type();
+    std::shared_ptr<arrow::Buffer> valid;
+    int64_t null_count = 0;
+    if (oc.has_valid) {
+      const uint8_t* vp = oc.h_valid.get() + gb * I.vstride;
+      null_count = rows - arrow::internal::CountSetBits(vp, 0, rows);
+      if (null_count > 0) valid = std::make_shared<KeepAliveBuffer>(vp, (rows + 7) / 8, owner);
+    }
+    std::shared_ptr<arrow::ArrayData> data;
+    if (oc.kind.var) {
+      const uint8_t* op = oc.h_offsets.get() + (u0 + gb) * 4;
+      const int64_t d0 = oc.batch_data_start[(size_t)gb], d1 = oc.batch_data_start[(size_t)gb + 1];
+      auto offsets = std::make_shared<KeepAliveBuffer>(op, (rows + 1) * 4, owner);
+      auto bytes = std::make_shared<KeepAliveBuffer>(oc.h_data.get() + d0, d1 - d0, owner);
+      data = arrow::ArrayData::Make(type, rows, {valid, offsets, bytes}, null_count, 0);
+    } else if (oc.kind.width == 0) {
+      auto values = std::make_shared<KeepAliveBuffer>(oc.h_values.get() + gb * I.vstride, (rows + 7) / 8, owner);
+      data = arrow::ArrayData::Make(type, rows, {valid, values}, null_count, 0);
+    } else {
+      const int w = oc.kind.width;
+      auto values = std::make_shared<KeepAliveBuffer>(oc.h_values.get() + u0 * w, rows * w, owner);
+      data = arrow::ArrayData::Make(type, rows, {valid, values}, null_count, 0);
+    }
+    arrays.push_back(arrow::MakeArray(data));
+  }
+  return arrow::RecordBatch::Make(I.spec.physical_schema, rows, std::move(arrays));
+}
+
+}  // namespace lsb

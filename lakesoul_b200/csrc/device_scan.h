@@ -1,0 +1,68 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// device_scan.h -- one scan group (a set of hash buckets) on the GPU:
+// decoded file columns -> HBM column buffers -> PK merge -> winner gather -> pinned host
+// Arrow buffers, exported as zero-copy RecordBatches of <= batch_size rows.
+//
+// This is the B200 replacement for MergeParquetExec::execute + merge_stream
+// (reference rust/lakesoul-io/src/physical_plan/merge/mod.rs:233-374).
+#pragma once
+#include <arrow/api.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "filter.h"
+#include "mor_engine.h"
+#include "scan_types.h"
+
+namespace lsb {
+
+ColumnKind classify_type(const arrow::DataType& t);
+
+// merge_operator.rs:41-53 -- unknown names are an error (the reference panics)
+MergeOp merge_op_from_name(const std::string& name);
+
+struct ScanSpec {
+  std::shared_ptr<arrow::Schema> physical_schema;  // columns carried through the merge, target order
+  std::vector<std::string> primary_keys;
+  std::vector<MergeOp> ops;     // one per physical column (UseLast by default)
+  bool merge = true;            // false = plain concatenation in file order (merge/mod.rs:297-312)
+  int batch_size = 8192;
+  std::shared_ptr<FilterExpr> filter;  // evaluated on the merged rows (session.rs:839-877), may be null
+};
+
+struct BucketFiles {
+  // one table per delta file (commit order); a table may lack some physical columns
+  std::vector<std::shared_ptr<arrow::Table>> files;
+};
+
+struct ScanCounters {
+  int64_t rows_in = 0, rows_out = 0, h2d_bytes = 0, d2h_bytes = 0;
+  int32_t kernel_launches = 0;
+  double upload_ms = 0, merge_ms = 0, gather_ms = 0, download_ms = 0;
+  std::string path;
+};
+
+class DeviceScan {
+ public:
+  DeviceScan(ScanSpec spec, std::vector<BucketFiles> buckets);
+  ~DeviceScan();
+  // runs upload -> merge -> (filter) -> gather -> download; synchronous on return
+  void Run();
+  int num_buckets() const;
+  int64_t num_batches(int bucket) const;
+  int64_t num_rows(int bucket) const;
+  // zero-copy over pinned host memory; columns == spec.physical_schema
+  std::shared_ptr<arrow::RecordBatch> Batch(int bucket, int64_t i) const;
+  const ScanCounters& counters() const;
+
+ private:
+  struct Impl;
+  std::shared_ptr<Impl> impl_;
+};
+
+}  // namespace lsb

@@ -1,0 +1,33 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// filter.h -- the parquet-mr FilterPredicate string grammar the JVM readers hand to the
+// native reader (reference rust/lakesoul-io/src/filter/parser.rs:50-265), parsed into a
+// small expression tree that the device evaluates on the merged rows (post-merge FilterExec,
+// reference session.rs:839-877) with SQL three-valued logic: a row survives only when the
+// predicate is TRUE.
+#pragma once
+#include <arrow/api.h>
+
+#include <memory>
+#include <set>
+#include <string>
+
+namespace lsb {
+
+struct FilterExpr {
+  enum Kind : int { kAnd, kOr, kNot, kCmp, kIsNull, kIsNotNull, kTrue, kFalse };
+  enum Op : int { kEq, kNe, kGt, kGe, kLt, kLe };
+  Kind kind = kTrue;
+  Op op = kEq;
+  std::shared_ptr<FilterExpr> left, right;  // kNot uses `right` like the reference parser
+  std::string column;                       // kCmp / kIsNull / kIsNotNull
+  std::shared_ptr<arrow::Scalar> literal;   // kCmp
+};
+
+// Throws std::runtime_error on malformed strings ("wrong filter str") or unparsable literals.
+std::shared_ptr<FilterExpr> parse_filter(const std::string& filter, const arrow::Schema& schema);
+std::shared_ptr<FilterExpr> conjunction(const std::vector<std::shared_ptr<FilterExpr>>& exprs);
+void filter_columns(const FilterExpr& e, std::set<std::string>* out);
+std::string filter_to_string(const FilterExpr& e);
+
+}  // namespace lsb

@@ -1,0 +1,1612 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// mor_engine.cu -- sm_100a kernels + host planning for the per-hash-bucket k-way
+// primary-key merge with last-writer-wins selection, and the winner gather.
+//
+// Algorithm (see DESIGN.md "PK merge"):
+//   * Total order of input rows = (pk, file_idx, row_idx)  -- the order in which the
+//     reference's loser tree pops ranges (sort_key_range.rs:182-187) and rows inside a range.
+//   * The last element of every equal-pk group in that order is exactly the row the
+//     reference keeps (sort_key_range.rs:402-412: last row of the run of the highest stream).
+//   * Work is cut into tiles of <= C elements by *regular sampling*: level l+1 = every S-th
+//     element of every run of level l. Splitters = every m-th element of the merged level
+//     l+1 list. With S*m + k*(S-1) <= C no tile can overflow, whatever the key distribution
+//     or duplicate structure (bound is on positions in the total order, not on key values).
+//   * One CTA merges one tile in shared memory (pairwise rank-merge tree over the k
+//     sub-runs, stable: lower file first), then marks group ends and emits winners.
+//   Every input key is read from HBM once at level 0 (+1/S, 1/S^2.. for sample levels).
+#include "mor_engine.h"
+#include "general_merge.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+namespace lsb {
+
+static thread_local std::string g_last_error;
+std::string last_error() { return g_last_error; }
+
+#define LSB_CUDA(x)                                                                   \
+  do {                                                                                \
+    cudaError_t e_ = (x);                                                             \
+    if (e_ != cudaSuccess) {                                                          \
+      g_last_error = std::string(#x) + " failed: " + cudaGetErrorString(e_);          \
+      throw std::runtime_error(g_last_error);                                         \
+    }                                                                                 \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// keys
+// ---------------------------------------------------------------------------------------
+struct K128 {
+  uint64_t hi, lo;
+};
+__device__ __forceinline__ bool key_lt(uint64_t a, uint64_t b) { return a < b; }
+__device__ __forceinline__ bool key_le(uint64_t a, uint64_t b) { return a <= b; }
+__device__ __forceinline__ bool key_ne(uint64_t a, uint64_t b) { return a != b; }
+__device__ __forceinline__ bool key_lt(const K128& a, const K128& b) {
+  return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
+}
+__device__ __forceinline__ bool key_le(const K128& a, const K128& b) { return !key_lt(b, a); }
+__device__ __forceinline__ bool key_ne(const K128& a, const K128& b) {
+  return a.hi != b.hi || a.lo != b.lo;
+}
+
+// Order-preserving unsigned image of one PK cell (cursor.rs:265-276 compare()/is_eq()):
+// signed -> flip sign bit; float -> IEEE total order (arrow total_cmp); null -> sorts first
+// and equals null (cursor.rs:444-476) via an extra leading validity bit.
+__device__ __forceinline__ uint64_t load_cell(const PkCol& c, int64_t row, bool& valid) {
+  valid = true;
+  if (c.validity) valid = (c.validity[row >> 3] >> (row & 7)) & 1;
+  uint64_t v;
+  switch (c.width) {
+    case 1: v = reinterpret_cast<const uint8_t*>(c.values)[row]; break;
+    case 2: v = reinterpret_cast<const uint16_t*>(c.values)[row]; break;
+    case 4: v = reinterpret_cast<const uint32_t*>(c.values)[row]; break;
+    default: v = reinterpret_cast<const uint64_t*>(c.values)[row]; break;
+  }
+  const int bits = c.width * 8;
+  const uint64_t top = 1ull << (bits - 1);
+  if (c.kind == PK_SIGNED) {
+    v ^= top;
+  } else if (c.kind == PK_FLOAT) {
+    const uint64_t mask = bits == 64 ? ~0ull : ((1ull << bits) - 1);
+    v = (v & top) ? (~v & mask) : (v | top);
+  }
+  return valid ? v : 0ull;
+}
+
+template <typename KeyT>
+struct KeyLoader;
+
+template <>
+struct KeyLoader<uint64_t> {
+  static __device__ __forceinline__ uint64_t load(const PkDesc& pk, int64_t row) {
+    uint64_t acc = 0;
+#pragma unroll
+    for (int c = 0; c < kMaxPkCols; ++c) {
+      if (c < pk.ncols) {
+        bool valid;
+        uint64_t v = load_cell(pk.col[c], row, valid);
+        const int bits = pk.col[c].width * 8;
+        if (pk.col[c].validity) acc = (acc << 1) | (valid ? 1ull : 0ull);
+        acc = bits == 64 ? v : ((acc << bits) | v);
+      }
+    }
+    return acc;
+  }
+};
+
+template <>
+struct KeyLoader<K128> {
+  static __device__ __forceinline__ void push(K128& a, uint64_t v, int bits) {
+    if (bits == 64) {
+      a.hi = a.lo;
+      a.lo = v;
+    } else {
+      a.hi = (a.hi << bits) | (a.lo >> (64 - bits));
+      a.lo = (a.lo << bits) | v;
+    }
+  }
+  static __device__ __forceinline__ K128 load(const PkDesc& pk, int64_t row) {
+    K128 acc{0, 0};
+#pragma unroll
+    for (int c = 0; c < kMaxPkCols; ++c) {
+      if (c < pk.ncols) {
+        bool valid;
+        uint64_t v = load_cell(pk.col[c], row, valid);
+        if (pk.col[c].validity) push(acc, valid ? 1ull : 0ull, 1);
+        push(acc, v, pk.col[c].width * 8);
+      }
+    }
+    return acc;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// device plan view
+// ---------------------------------------------------------------------------------------
+struct PlanDev {
+  const BucketDesc* buckets;
+  const int32_t* file_rows;       // F
+  const int64_t* file_row_base;   // F+1
+  int32_t* splits;                // all levels
+  uint2* mlist;                   // merged sample lists (x = file-in-bucket, y = level position)
+  const int32_t* tile_bucket;     // all levels, concatenated
+  const int32_t* tile_idx;
+  int32_t* tile_cnt;              // level-0 tiles
+  int64_t* tile_gstart;           // level-0 tiles: global merged position of the tile start
+  int64_t* tile_out;              // level-0 tiles + 1
+  uint32_t* win_tmp;              // N
+  uint32_t* win;                  // N
+  int64_t* out_base;              // nb+1
+  int64_t* batch_base;            // nb+1
+  const int64_t* dense_base;      // F+1: prefix of file_rows (rows packed without padding)
+  uint32_t* R;                    // general path: presence matrix (last row per output key and file)
+  const int64_t* rofs;            // general path: offset of each bucket's matrix inside R
+  int32_t* err;
+  int32_t nb;
+  int32_t log_s;
+  int32_t tile_cap;
+  int32_t batch_size;
+};
+
+constexpr int kTileThreads = 256;
+constexpr int kErrTileOverflow = 1;
+
+// largest r in [0, n) with arr[r] <= q   (arr non-decreasing, arr[0] <= q)
+template <typename T, typename Q>
+__device__ __forceinline__ int upper_idx(const T* arr, int n, Q q) {
+  int lo = 0, hi = n;  // invariant arr[lo] <= q, answer in [lo, hi)
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (arr[mid] <= q) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------------------
+// K_part: tile boundaries of level l from the merged list of level l+1
+// One warp per tile computes the tile's LOWER boundary; the last tile of a bucket also
+// writes the bucket's final boundary.
+// ---------------------------------------------------------------------------------------
+template <typename KeyT>
+__global__ void __launch_bounds__(128) part_kernel(PlanDev P, PkDesc pk, int level, int tile_ofs,
+                                                   int ntiles) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= ntiles) return;
+  const int t = tile_ofs + warp;
+  const int b = P.tile_bucket[t];
+  const int i = P.tile_idx[t];
+  const BucketDesc& B = P.buckets[b];
+  const int k = B.k;
+  const int T = B.ntiles[level];
+  int32_t* sp = P.splits + B.split_ofs[level];
+  const int sh = level * P.log_s;
+
+  int js = -1;
+  int64_t pprime = 0;
+  KeyT keyS{};
+  if (i > 0) {
+    const uint2 s = P.mlist[B.mlist_ofs[level + 1] + (int64_t)i * B.m - 1];
+    js = (int)s.x;
+    const int64_t ps = s.y;
+    const int64_t rowS =
+        P.file_row_base[B.file_begin + js] + (((ps + 1) << (sh + P.log_s)) - 1);
+    keyS = KeyLoader<KeyT>::load(pk, rowS);
+    pprime = ((ps + 1) << P.log_s) - 1;
+  }
+  for (int j = lane; j < k; j += 32) {
+    const int f = B.file_begin + j;
+    const int32_t nl = (int32_t)((int64_t)P.file_rows[f] >> sh);
+    int32_t v = 0;
+    if (i > 0) {
+      if (j == js) {
+        v = (int32_t)(pprime + 1);
+      } else {
+        const int64_t fb = P.file_row_base[f];
+        int lo = 0, hi = nl;
+        if (j < js) {  // count of elements with key <= keyS
+          while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            KeyT km = KeyLoader<KeyT>::load(pk, fb + ((((int64_t)mid + 1) << sh) - 1));
+            if (key_le(km, keyS)) lo = mid + 1; else hi = mid;
+          }
+        } else {  // count of elements with key < keyS
+          while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            KeyT km = KeyLoader<KeyT>::load(pk, fb + ((((int64_t)mid + 1) << sh) - 1));
+            if (key_lt(km, keyS)) lo = mid + 1; else hi = mid;
+          }
+        }
+        v = lo;
+      }
+    }
+    sp[(int64_t)i * k + j] = v;
+    if (i == T - 1) sp[(int64_t)T * k + j] = nl;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// block scan helper (exclusive), blockDim.x == kTileThreads
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int& total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) warp_sums[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    int s = lane < (kTileThreads / 32) ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, s, d);
+      if (lane >= d) s += y;
+    }
+    if (lane < (kTileThreads / 32)) warp_sums[lane] = s;  // inclusive warp totals
+  }
+  __syncthreads();
+  const int base = w == 0 ? 0 : warp_sums[w - 1];
+  total = warp_sums[kTileThreads / 32 - 1];
+  return base + x - v;
+}
+
+// ---------------------------------------------------------------------------------------
+// K_tile: merge one tile in shared memory.
+//   level > 0 : write the merged (file, level-pos) list      -> mlist
+//   level == 0: mark group ends, write winners (global rows) -> win_tmp, count -> tile_cnt
+// ---------------------------------------------------------------------------------------
+template <typename KeyT, bool kGeneral>
+__global__ void __launch_bounds__(kTileThreads) tile_kernel(PlanDev P, PkDesc pk, int level,
+                                                            int tile_ofs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C = P.tile_cap;
+  KeyT* K = reinterpret_cast<KeyT*>(smem_raw);
+  uint16_t* idxA = reinterpret_cast<uint16_t*>(K + C);
+  uint16_t* idxB = idxA + C;
+  // C is a multiple of 8 (host-checked), so everything below stays 8-byte aligned
+  int64_t* frb = reinterpret_cast<int64_t*>(idxB + C);
+  int32_t* seg_start = reinterpret_cast<int32_t*>(frb + kMaxFilesPerBucket);
+  int32_t* seg_lo = seg_start + kMaxFilesPerBucket + 1;
+  int32_t* scan_tmp = seg_lo + kMaxFilesPerBucket;  // 8 + 2 ints
+  __shared__ int64_t s_tile_start;
+  __shared__ int s_has_next;
+  __shared__ KeyT s_next_key;
+
+  const int t = tile_ofs + blockIdx.x;
+  const int b = P.tile_bucket[t];
+  const int i = P.tile_idx[t];
+  const BucketDesc& B = P.buckets[b];
+  const int k = B.k;
+  const int32_t* sp_lo = P.splits + B.split_ofs[level] + (int64_t)i * k;
+  const int32_t* sp_hi = sp_lo + k;
+  const int sh = level * P.log_s;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+
+  // ---- segment table -----------------------------------------------------------------
+  for (int j = tid; j < k; j += kTileThreads) {
+    seg_lo[j] = sp_lo[j];
+    seg_start[j + 1] = sp_hi[j] - sp_lo[j];  // lengths, scanned below
+    frb[j] = P.file_row_base[B.file_begin + j];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // serial-in-lane scan of <= 8 entries per lane, then warp scan
+    const int per = (k + 31) >> 5;
+    int sum = 0;
+    int64_t lsum = 0;
+    for (int x = 0; x < per; ++x) {
+      int j = lane * per + x;
+      if (j < k) { sum += seg_start[j + 1]; lsum += seg_lo[j]; }
+    }
+    int incl = sum;
+    int64_t lincl = lsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, incl, d);
+      int64_t ly = __shfl_up_sync(0xffffffffu, lincl, d);
+      if (lane >= d) { incl += y; lincl += ly; }
+    }
+    int run = incl - sum;
+    for (int x = 0; x < per; ++x) {
+      int j = lane * per + x;
+      if (j < k) { int len = seg_start[j + 1]; seg_start[j + 1] = run + len; run += len; }
+    }
+    if (lane == 0) seg_start[0] = 0;
+    if (lane == 31) s_tile_start = lincl;
+  }
+  __syncthreads();
+  const int L = seg_start[k];
+  if (L > C) {
+    if (tid == 0) atomicExch(P.err, kErrTileOverflow);
+    return;
+  }
+
+  // ---- load keys: one warp per segment, coalesced at level 0 --------------------------
+  for (int j = warp; j < k; j += kTileThreads / 32) {
+    const int s0 = seg_start[j], len = seg_start[j + 1] - s0;
+    const int64_t fb = frb[j];
+    const int64_t p0 = seg_lo[j];
+    for (int x = lane; x < len; x += 32) {
+      const int64_t row = fb + (((p0 + x + 1) << sh) - 1);
+      K[s0 + x] = KeyLoader<KeyT>::load(pk, row);
+      idxA[s0 + x] = (uint16_t)(s0 + x);
+    }
+  }
+  if (level == 0 && warp == (kTileThreads / 32 - 1)) {
+    // peek the first key after this tile (min over the k run heads)
+    bool have = false;
+    KeyT best{};
+    for (int j = lane; j < k; j += 32) {
+      const int32_t h = sp_hi[j];
+      if (h < P.file_rows[B.file_begin + j]) {
+        KeyT kk = KeyLoader<KeyT>::load(pk, frb[j] + h);
+        if (!have || key_lt(kk, best)) { best = kk; have = true; }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      bool oh = __shfl_xor_sync(0xffffffffu, (int)have, d);
+      KeyT ob;
+      if constexpr (sizeof(KeyT) == 8) {
+        ob = __shfl_xor_sync(0xffffffffu, best, d);
+      } else {
+        ob.hi = __shfl_xor_sync(0xffffffffu, best.hi, d);
+        ob.lo = __shfl_xor_sync(0xffffffffu, best.lo, d);
+      }
+      if (oh && (!have || key_lt(ob, best))) { best = ob; have = true; }
+    }
+    if (lane == 0) { s_has_next = have; s_next_key = best; }
+  }
+  __syncthreads();
+
+  // ---- pairwise rank-merge tree ------------------------------------------------------
+  uint16_t* in = idxA;
+  uint16_t* out = idxB;
+  int nr = k;
+  for (int pass = 0; nr > 1; ++pass) {
+    // run r of this pass spans original segments [r<<pass, (r+1)<<pass)
+    auto rb = [&](int r) -> int {
+      int s = r << pass;
+      return seg_start[s < k ? s : k];
+    };
+    for (int q = tid; q < L; q += kTileThreads) {
+      // find run containing q: largest r with rb(r) <= q
+      int lo = 0, hi = nr;
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (rb(mid) <= q) lo = mid; else hi = mid;
+      }
+      const int r = lo;
+      const int base = r & ~1;
+      const uint16_t e = in[q];
+      if (base + 1 >= nr) {  // unpaired last run
+        out[q] = e;
+        continue;
+      }
+      const int a0 = rb(base), mid0 = rb(base + 1), end0 = rb(base + 2);
+      const KeyT key = K[e];
+      int dst;
+      if (r == base) {
+        // left run: count right elements strictly smaller
+        int l = mid0, h = end0;
+        while (l < h) {
+          int m2 = (l + h) >> 1;
+          if (key_lt(K[in[m2]], key)) l = m2 + 1; else h = m2;
+        }
+        dst = q + (l - mid0);
+      } else {
+        // right run: count left elements <= key
+        int l = a0, h = mid0;
+        while (l < h) {
+          int m2 = (l + h) >> 1;
+          if (key_le(K[in[m2]], key)) l = m2 + 1; else h = m2;
+        }
+        dst = a0 + (q - mid0) + (l - a0);
+      }
+      out[dst] = e;
+    }
+    __syncthreads();
+    uint16_t* tmp = in; in = out; out = tmp;
+    nr = (nr + 1) >> 1;
+  }
+  // `in` now holds the merged order
+
+  if (level > 0) {
+    uint2* ml = P.mlist + B.mlist_ofs[level] + s_tile_start;
+    for (int q = tid; q < L; q += kTileThreads) {
+      const int e = in[q];
+      const int j = upper_idx(seg_start, k, e);
+      ml[q] = make_uint2((unsigned)j, (unsigned)(seg_lo[j] + (e - seg_start[j])));
+    }
+    return;
+  }
+
+  // ---- level 0: group ends -> winners ---------------------------------------------------
+  const int E = (L + kTileThreads - 1) / kTileThreads;
+  const int q0 = min(tid * E, L), q1 = min(q0 + E, L);
+  const bool has_next = s_has_next != 0;
+  const KeyT next_key = s_next_key;
+  int cnt = 0;
+  for (int q = q0; q < q1; ++q) {
+    const KeyT kq = K[in[q]];
+    bool end;
+    if (q + 1 < L) end = key_ne(kq, K[in[q + 1]]);
+    else end = has_next ? key_ne(kq, next_key) : true;
+    cnt += end ? 1 : 0;
+  }
+  int total;
+  int off = block_exclusive_scan(cnt, scan_tmp, total);
+  const int t0 = blockIdx.x;  // level-0 tiles start at tile_ofs
+  if constexpr (kGeneral) {
+    // second pass: R[u][j] = last row of output key u inside file j
+    int64_t u_run = P.tile_out[t0] + off - P.out_base[b];
+    uint32_t* Rb = P.R + P.rofs[b];
+    for (int q = q0; q < q1; ++q) {
+      const int e = in[q];
+      const KeyT kq = K[e];
+      const int j = upper_idx(seg_start, k, e);
+      bool end, sub_last;
+      if (q + 1 < L) {
+        const int e2 = in[q + 1];
+        end = key_ne(kq, K[e2]);
+        sub_last = end || upper_idx(seg_start, k, e2) != j;
+      } else {
+        end = has_next ? key_ne(kq, next_key) : true;
+        const int32_t h = sp_hi[j];
+        sub_last = true;
+        if (h < P.file_rows[B.file_begin + j]) {
+          const KeyT kn = KeyLoader<KeyT>::load(pk, frb[j] + h);
+          sub_last = key_ne(kn, kq);
+        }
+      }
+      if (sub_last) Rb[u_run * k + j] = (uint32_t)(frb[j] + seg_lo[j] + (e - seg_start[j]));
+      if (end) ++u_run;
+    }
+    return;
+  }
+  const int64_t gstart = B.row_base + s_tile_start;
+  uint32_t* wt = P.win_tmp + gstart;
+  for (int q = q0; q < q1; ++q) {
+    const int e = in[q];
+    const KeyT kq = K[e];
+    bool end;
+    if (q + 1 < L) end = key_ne(kq, K[in[q + 1]]);
+    else end = has_next ? key_ne(kq, next_key) : true;
+    if (end) {
+      const int j = upper_idx(seg_start, k, e);
+      wt[off++] = (uint32_t)(frb[j] + seg_lo[j] + (e - seg_start[j]));
+    }
+  }
+  if (tid == 0) {
+    P.tile_cnt[t0] = total;
+    P.tile_gstart[t0] = gstart;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K_scan: exclusive scan of level-0 tile counts -> tile_out; bucket output bases; batch bases
+// single block of 1024 threads
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) scan_kernel(PlanDev P, int ntiles0) {
+  __shared__ int64_t wsum[32];
+  __shared__ int64_t carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  auto scan_chunk = [&](int64_t v) -> int64_t {  // returns exclusive prefix incl. carry
+    int64_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int64_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int64_t s = wsum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int64_t y = __shfl_up_sync(0xffffffffu, s, d);
+        if (lane >= d) s += y;
+      }
+      wsum[lane] = s;
+    }
+    __syncthreads();
+    const int64_t carry = carry_s;
+    const int64_t res = carry + (w == 0 ? 0 : wsum[w - 1]) + x - v;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + wsum[31];
+    __syncthreads();
+    return res;
+  };
+  for (int base = 0; base < ntiles0; base += 1024) {
+    const int t = base + tid;
+    const int64_t v = t < ntiles0 ? P.tile_cnt[t] : 0;
+    const int64_t ex = scan_chunk(v);
+    if (t < ntiles0) P.tile_out[t] = ex;
+  }
+  if (tid == 0) P.tile_out[ntiles0] = carry_s;
+  __syncthreads();
+  for (int b = tid; b <= P.nb; b += 1024) {
+    P.out_base[b] = b < P.nb ? P.tile_out[P.buckets[b].tile_base[0]] : P.tile_out[ntiles0];
+  }
+}
+
+// batch_base[b] = number of output batches before bucket b (batches never span buckets)
+__global__ void __launch_bounds__(1024) batch_base_kernel(PlanDev P) {
+  __shared__ int64_t wsum[32];
+  __shared__ int64_t carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < P.nb; base += 1024) {
+    const int b = base + tid;
+    int64_t v = 0;
+    if (b < P.nb) {
+      const int64_t u = P.out_base[b + 1] - P.out_base[b];
+      v = (u + P.batch_size - 1) / P.batch_size;
+    }
+    int64_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int64_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int64_t s2 = wsum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int64_t y = __shfl_up_sync(0xffffffffu, s2, d);
+        if (lane >= d) s2 += y;
+      }
+      wsum[lane] = s2;
+    }
+    __syncthreads();
+    const int64_t carry = carry_s;
+    if (b < P.nb) P.batch_base[b] = carry + (w == 0 ? 0 : wsum[w - 1]) + x - v;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + wsum[31];
+    __syncthreads();
+  }
+  if (tid == 0) P.batch_base[P.nb] = carry_s;
+}
+
+// winners of the "no merge" path: every input row, file order
+__global__ void __launch_bounds__(256) identity_kernel(PlanDev P, int F, int64_t n_in) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_in) return;
+  const int f = upper_idx(P.dense_base, F + 1, u);
+  P.win[u] = (uint32_t)(P.file_row_base[f] + (u - P.dense_base[f]));
+}
+__global__ void __launch_bounds__(256) identity_bases_kernel(PlanDev P, int F) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > P.nb) return;
+  P.out_base[b] = b < P.nb ? P.dense_base[P.buckets[b].file_begin] : P.dense_base[F];
+}
+
+__global__ void __launch_bounds__(256) compact_kernel(PlanDev P) {
+  const int t = blockIdx.x;
+  const int cnt = P.tile_cnt[t];
+  const uint32_t* src = P.win_tmp + P.tile_gstart[t];
+  uint32_t* dst = P.win + P.tile_out[t];
+  for (int x = threadIdx.x; x < cnt; x += blockDim.x) dst[x] = src[x];
+}
+
+// ---------------------------------------------------------------------------------------
+// gather: fixed width
+// ---------------------------------------------------------------------------------------
+constexpr int kGatherThreads = 256;
+constexpr int kRowsPerChunk = 2048;
+
+struct GatherGeom {
+  const uint32_t* win;
+  const int64_t* out_base;
+  const int64_t* batch_base;
+  int32_t nb;
+  int32_t batch_size;
+  int32_t chunks_per_batch;
+  int64_t valid_stride;  // bytes per batch
+};
+
+__device__ __forceinline__ bool chunk_geometry(const GatherGeom& G, int64_t chunk, int& b,
+                                               int64_t& gb, int64_t& u0, int& r_begin, int& r_end,
+                                               int& rows_in_batch) {
+  gb = chunk / G.chunks_per_batch;
+  const int c_in = (int)(chunk % G.chunks_per_batch);
+  b = upper_idx(G.batch_base, G.nb + 1, gb);
+  // skip buckets with zero batches that share the same base
+  const int64_t i = gb - G.batch_base[b];
+  const int64_t U = G.out_base[b + 1] - G.out_base[b];
+  const int64_t first = i * G.batch_size;
+  rows_in_batch = (int)min((int64_t)G.batch_size, U - first);
+  u0 = G.out_base[b] + first;
+  r_begin = c_in * kRowsPerChunk;
+  r_end = min(r_begin + kRowsPerChunk, (rows_in_batch + 31) & ~31);
+  return r_begin < r_end;
+}
+
+__global__ void __launch_bounds__(kGatherThreads) gather_fixed_kernel(GatherGeom G,
+                                                                      const FixedCol* cols) {
+  const FixedCol col = cols[blockIdx.y];
+  int b, r_begin, r_end, rows;
+  int64_t gb, u0;
+  if (!chunk_geometry(G, blockIdx.x, b, gb, u0, r_begin, r_end, rows)) return;
+  uint32_t* vwords =
+      col.dst_valid ? reinterpret_cast<uint32_t*>(col.dst_valid + gb * G.valid_stride) : nullptr;
+  const uint32_t* win = col.win ? col.win : G.win;
+  uint32_t* bwords =
+      col.width == 0 ? reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(col.dst) + gb * G.valid_stride)
+                     : nullptr;
+  for (int r = r_begin + threadIdx.x; r < r_end; r += kGatherThreads) {
+    const bool active = r < rows;
+    const int64_t u = u0 + r;
+    const uint32_t g = active ? win[u] : kNoRow;
+    const bool have = g != kNoRow;
+    if (col.width == 0) {
+      bool v = false;
+      if (have) v = (reinterpret_cast<const uint8_t*>(col.src)[g >> 3] >> (g & 7)) & 1;
+      const uint32_t word = __ballot_sync(0xffffffffu, v);
+      if ((threadIdx.x & 31) == 0) bwords[r >> 5] = word;
+    } else if (active) {
+      switch (col.width) {
+        case 1: reinterpret_cast<uint8_t*>(col.dst)[u] = have ? reinterpret_cast<const uint8_t*>(col.src)[g] : 0; break;
+        case 2: reinterpret_cast<uint16_t*>(col.dst)[u] = have ? reinterpret_cast<const uint16_t*>(col.src)[g] : 0; break;
+        case 4: reinterpret_cast<uint32_t*>(col.dst)[u] = have ? reinterpret_cast<const uint32_t*>(col.src)[g] : 0; break;
+        case 8: reinterpret_cast<uint64_t*>(col.dst)[u] = have ? reinterpret_cast<const uint64_t*>(col.src)[g] : 0; break;
+        case 16: reinterpret_cast<uint4*>(col.dst)[u] = have ? reinterpret_cast<const uint4*>(col.src)[g] : make_uint4(0, 0, 0, 0); break;
+        default: {
+          const uint4 z = make_uint4(0, 0, 0, 0);
+          reinterpret_cast<uint4*>(col.dst)[2 * u] = have ? reinterpret_cast<const uint4*>(col.src)[2 * (int64_t)g] : z;
+          reinterpret_cast<uint4*>(col.dst)[2 * u + 1] = have ? reinterpret_cast<const uint4*>(col.src)[2 * (int64_t)g + 1] : z;
+        } break;
+      }
+    }
+    if (vwords) {
+      bool bit = have;
+      if (have && col.src_valid) bit = (col.src_valid[g >> 3] >> (g & 7)) & 1;
+      const uint32_t word = __ballot_sync(0xffffffffu, bit);
+      if ((threadIdx.x & 31) == 0) vwords[r >> 5] = word;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// gather: variable width (Utf8 / Binary), two passes
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGatherThreads) var_len_kernel(GatherGeom G, VarCol col,
+                                                                 int32_t* len_out) {
+  int b, r_begin, r_end, rows;
+  int64_t gb, u0;
+  if (!chunk_geometry(G, blockIdx.x, b, gb, u0, r_begin, r_end, rows)) return;
+  uint32_t* vwords =
+      col.dst_valid ? reinterpret_cast<uint32_t*>(col.dst_valid + gb * G.valid_stride) : nullptr;
+  for (int r = r_begin + threadIdx.x; r < r_end; r += kGatherThreads) {
+    const bool active = r < rows;
+    const int64_t u = u0 + r;
+    bool bit = active;
+    if (active) {
+      const uint32_t g = (col.win ? col.win : G.win)[u];
+      if (g == kNoRow) bit = false;
+      else if (col.src_valid) bit = (col.src_valid[g >> 3] >> (g & 7)) & 1;
+      len_out[u] = bit ? (col.src_offsets[(int64_t)g + 1] - col.src_offsets[g]) : 0;
+    }
+    if (vwords) {
+      const uint32_t word = __ballot_sync(0xffffffffu, bit);
+      if ((threadIdx.x & 31) == 0) vwords[r >> 5] = word;
+    }
+  }
+}
+
+// device-wide exclusive scan int32 -> int64 (3 phases), chunk of 4096 per block
+constexpr int kScanChunk = 4096;
+__global__ void __launch_bounds__(256) scan_block_sums(const int32_t* in, int64_t n, int64_t* sums) {
+  const int64_t base = (int64_t)blockIdx.x * kScanChunk;
+  int64_t s = 0;
+  for (int x = threadIdx.x; x < kScanChunk; x += 256) {
+    const int64_t i = base + x;
+    if (i < n) s += in[i];
+  }
+  __shared__ int64_t ws[8];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int64_t t = 0;
+    for (int i = 0; i < 8; ++i) t += ws[i];
+    sums[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(1024) scan_sums_inplace(int64_t* sums, int nblocks) {
+  __shared__ int64_t wsum[32];
+  __shared__ int64_t carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + tid;
+    const int64_t v = i < nblocks ? sums[i] : 0;
+    int64_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int64_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int64_t s = wsum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int64_t y = __shfl_up_sync(0xffffffffu, s, d);
+        if (lane >= d) s += y;
+      }
+      wsum[lane] = s;
+    }
+    __syncthreads();
+    const int64_t carry = carry_s;
+    if (i < nblocks) sums[i] = carry + (w == 0 ? 0 : wsum[w - 1]) + x - v;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + wsum[31];
+    __syncthreads();
+  }
+  if (tid == 0) sums[nblocks] = carry_s;
+}
+__global__ void __launch_bounds__(256) scan_apply(const int32_t* in, int64_t n, const int64_t* sums,
+                                                  int64_t* out) {
+  // each block rescans its chunk serially per thread (16 items/thread), then block scan
+  __shared__ int64_t ws[8];
+  const int64_t base = (int64_t)blockIdx.x * kScanChunk;
+  constexpr int per = kScanChunk / 256;
+  int32_t v[per];
+  int64_t s = 0;
+#pragma unroll
+  for (int x = 0; x < per; ++x) {
+    const int64_t i = base + (int64_t)threadIdx.x * per + x;
+    v[x] = i < n ? in[i] : 0;
+    s += v[x];
+  }
+  int64_t incl = s;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int64_t y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += y;
+  }
+  if (lane == 31) ws[w] = incl;
+  __syncthreads();
+  int64_t wbase = 0;
+  for (int i = 0; i < w; ++i) wbase += ws[i];
+  int64_t run = sums[blockIdx.x] + wbase + incl - s;
+#pragma unroll
+  for (int x = 0; x < per; ++x) {
+    const int64_t i = base + (int64_t)threadIdx.x * per + x;
+    if (i < n) out[i] = run;
+    run += v[x];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) out[n] = sums[gridDim.x];
+}
+
+__global__ void __launch_bounds__(kGatherThreads) var_offsets_kernel(GatherGeom G, VarCol col,
+                                                                     const int64_t* doff,
+                                                                     int64_t total_batches,
+                                                                     int64_t total_out) {
+  int b, r_begin, r_end, rows;
+  int64_t gb, u0;
+  if (!chunk_geometry(G, blockIdx.x, b, gb, u0, r_begin, r_end, rows)) return;
+  const int64_t first = doff[u0];
+  int32_t* dst = col.dst_offsets + u0 + gb;  // every earlier batch contributed one extra entry
+  for (int r = r_begin + threadIdx.x; r < r_end; r += kGatherThreads) {
+    if (r < rows) {
+      dst[r] = (int32_t)(doff[u0 + r] - first);
+      if (r == rows - 1) dst[rows] = (int32_t)(doff[u0 + rows] - first);
+    }
+  }
+  if (r_begin == 0 && threadIdx.x == 0) {
+    col.batch_data_start[gb] = first;
+    if (gb == total_batches - 1) col.batch_data_start[total_batches] = doff[total_out];
+  }
+}
+
+// copy string bytes: one block per 256 output rows; each thread produces 4 output bytes at a time
+constexpr int kCopyRows = 256;
+__global__ void __launch_bounds__(256) var_copy_kernel(GatherGeom G, VarCol col, const int64_t* doff,
+                                                       int64_t total_out) {
+  __shared__ int64_t s_doff[kCopyRows + 1];
+  __shared__ int64_t s_src[kCopyRows];
+  const int64_t u_begin = (int64_t)blockIdx.x * kCopyRows;
+  const int nrows = (int)min((int64_t)kCopyRows, total_out - u_begin);
+  if (nrows <= 0) return;
+  for (int r = threadIdx.x; r <= nrows; r += 256) s_doff[r] = doff[u_begin + r];
+  for (int r = threadIdx.x; r < nrows; r += 256) {
+    const int64_t u = u_begin + r;
+    const int b = upper_idx(G.out_base, G.nb + 1, u);
+    // out_base may repeat for empty buckets: upper_idx returns the last bucket starting at <= u,
+    // which is the one that owns row u.
+    const uint32_t g = (col.win ? col.win : G.win)[u];
+    s_src[r] = g == kNoRow ? 0 : col.src_data_base[b] + col.src_offsets[g];
+  }
+  __syncthreads();
+  const int64_t byte0 = s_doff[0], byte1 = s_doff[nrows];
+  // word-aligned sweep over [byte0, byte1)
+  const int64_t w0 = byte0 & ~3ll;
+  for (int64_t wpos = w0 + (int64_t)threadIdx.x * 4; wpos < byte1; wpos += 256 * 4) {
+    int64_t x = max(wpos, byte0);
+    const int64_t xe = min(wpos + 4, byte1);
+    if (x >= xe) continue;
+    // row containing byte x: largest r with s_doff[r] <= x, skipping empty rows
+    int r = upper_idx(s_doff, nrows + 1, x);
+    if (x == wpos && xe == wpos + 4 && s_doff[r + 1] >= xe) {
+      // fast path: whole word inside one row
+      const uint8_t* sp = col.src_data + s_src[r] + (x - s_doff[r]);
+      uint32_t v = (uint32_t)sp[0] | ((uint32_t)sp[1] << 8) | ((uint32_t)sp[2] << 16) |
+                   ((uint32_t)sp[3] << 24);
+      *reinterpret_cast<uint32_t*>(col.dst_data + wpos) = v;
+    } else {
+      for (; x < xe; ++x) {
+        while (s_doff[r + 1] <= x) ++r;
+        col.dst_data[x] = col.src_data[s_src[r] + (x - s_doff[r])];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct MergePlan {
+  int nb = 0, F = 0;
+  int batch_size = 8192;
+  bool key128 = false;
+  int log_s = 6, tile_cap = 0, max_level = 0;
+  int64_t n_total = 0;  // global row span (>= input rows when files are padded apart)
+  int64_t n_in = 0;     // input rows
+  std::vector<BucketDesc> buckets;
+  std::vector<int32_t> level_tile_ofs, level_tile_cnt;  // per level
+  int32_t total_tiles = 0;
+  // device
+  BucketDesc* d_buckets = nullptr;
+  int32_t* d_file_rows = nullptr;
+  int64_t* d_file_row_base = nullptr;
+  int32_t* d_splits = nullptr;
+  uint2* d_mlist = nullptr;
+  int32_t *d_tile_bucket = nullptr, *d_tile_idx = nullptr, *d_tile_cnt = nullptr;
+  int64_t *d_tile_gstart = nullptr, *d_tile_out = nullptr;
+  uint32_t *d_win_tmp = nullptr, *d_win = nullptr;
+  int64_t *d_out_base = nullptr, *d_batch_base = nullptr;
+  int64_t* d_dense_base = nullptr;
+  uint32_t* d_R = nullptr;     // general path (owned by GeneralMerge, borrowed here while it runs)
+  int64_t* d_rofs = nullptr;
+  uint32_t* d_ctmp = nullptr;  // compaction scratch
+  PkDesc last_pk{};
+  int32_t* d_err = nullptr;
+  // pinned host mirrors
+  int64_t* h_counts = nullptr;  // out_base (nb+1) + batch_base (nb+1) + err
+  std::vector<int64_t> out_counts, out_base, batch_base;
+  bool merged = false, synced = false;
+  MergeStats stats;
+  // gather scratch
+  int32_t* d_len = nullptr;
+  int64_t* d_doff = nullptr;
+  int64_t* d_sums = nullptr;
+  FixedCol* d_cols = nullptr;
+  int d_cols_cap = 0;
+  size_t smem_bytes = 0;
+};
+
+static size_t tile_smem_bytes(int C, bool key128) {
+  size_t key = key128 ? 16 : 8;
+  return (size_t)C * key + (size_t)C * 2 * 2 + kMaxFilesPerBucket * 8 +
+         (kMaxFilesPerBucket + 1) * 4 + kMaxFilesPerBucket * 4 + 16 * 4;
+}
+
+template <typename T>
+static T* dev_alloc(size_t n) {
+  T* p = nullptr;
+  LSB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  return p;
+}
+
+MergePlan* plan_create(int nb, const int32_t* bucket_file_begin, const int64_t* file_rows,
+                       const int64_t* file_row_base, int64_t row_span, int key_bits, int batch_size,
+                       cudaStream_t stream) {
+  if (key_bits <= 0 || key_bits > 128) {
+    g_last_error = "primary key wider than 128 bits is not supported";
+    throw std::runtime_error(g_last_error);
+  }
+  if (batch_size <= 0) {
+    g_last_error = "batch_size must be positive";
+    throw std::runtime_error(g_last_error);
+  }
+  auto* P = new MergePlan();
+  try {
+    P->nb = nb;
+    P->F = bucket_file_begin[nb];
+    P->batch_size = batch_size;
+    P->key128 = key_bits > 64;
+    // 3 CTAs per SM: 3 * smem <= 227 KiB
+    P->tile_cap = P->key128 ? 3328 : 5632;
+    const int C = P->tile_cap;
+    int kmax = 1;
+    for (int b = 0; b < nb; ++b) kmax = std::max(kmax, bucket_file_begin[b + 1] - bucket_file_begin[b]);
+    if (kmax > kMaxFilesPerBucket) {
+      g_last_error = "more than 256 delta files in one hash bucket: compact the table first";
+      throw std::runtime_error(g_last_error);
+    }
+    // S = largest power of two <= 64 that keeps the per-tile slack k*(S-1) under C/5
+    int log_s = 6;
+    while (log_s > 3 && (int64_t)kmax * ((1 << log_s) - 1) > C / 5) --log_s;
+    P->log_s = log_s;
+    const int S = 1 << log_s;
+    if ((int64_t)kmax * (S - 1) + S > C) {
+      g_last_error = "too many delta files per bucket for the tile capacity";
+      throw std::runtime_error(g_last_error);
+    }
+
+    std::vector<int64_t> frb(P->F + 1, 0);
+    std::vector<int32_t> fr32(P->F);
+    for (int f = 0; f < P->F; ++f) {
+      if (file_rows[f] < 0 || file_rows[f] > 0x7fffffff) {
+        g_last_error = "file with more than 2^31-1 rows";
+        throw std::runtime_error(g_last_error);
+      }
+      fr32[f] = (int32_t)file_rows[f];
+      if (file_row_base) {
+        frb[f] = file_row_base[f];
+        if (f > 0 && frb[f] < frb[f - 1] + file_rows[f - 1]) {
+          g_last_error = "file_row_base overlaps the previous file";
+          throw std::runtime_error(g_last_error);
+        }
+      } else {
+        frb[f + 1] = frb[f] + file_rows[f];
+      }
+      P->n_in += file_rows[f];
+    }
+    if (file_row_base) frb[P->F] = row_span;
+    P->n_total = frb[P->F];
+    if (P->F > 0 && P->n_total < frb[P->F - 1] + file_rows[P->F - 1]) {
+      g_last_error = "row_span smaller than the last file";
+      throw std::runtime_error(g_last_error);
+    }
+    if (P->n_total >= 0xfffffff0ll) {
+      g_last_error = "scan batch exceeds 2^32 rows: split the bucket list";
+      throw std::runtime_error(g_last_error);
+    }
+
+    P->buckets.resize(nb);
+    int64_t split_total = 0, mlist_total = 0;
+    int max_level = 0;
+    for (int b = 0; b < nb; ++b) {
+      BucketDesc& B = P->buckets[b];
+      std::memset(&B, 0, sizeof(B));
+      B.file_begin = bucket_file_begin[b];
+      B.k = bucket_file_begin[b + 1] - bucket_file_begin[b];
+      B.row_base = B.k > 0 ? frb[B.file_begin] : (B.file_begin < P->F ? frb[B.file_begin] : P->n_total);
+      B.n_rows = 0;
+      for (int j = 0; j < B.k; ++j) B.n_rows += file_rows[B.file_begin + j];
+      B.m = (C - B.k * (S - 1)) / S;
+      // level sizes
+      int64_t M[kMaxLevels + 2];
+      int L = 0;
+      for (int l = 0; l <= kMaxLevels + 1; ++l) {
+        int64_t s = 0;
+        for (int j = 0; j < B.k; ++j) s += file_rows[B.file_begin + j] >> (l * log_s);
+        M[l] = s;
+      }
+      while (M[L] > C) {
+        ++L;
+        if (L > kMaxLevels) {
+          g_last_error = "bucket too large for the sampling depth";
+          throw std::runtime_error(g_last_error);
+        }
+      }
+      B.levels = L;
+      max_level = std::max(max_level, L);
+      for (int l = 0; l <= L; ++l) {
+        B.ntiles[l] = l == L ? 1 : (int32_t)(M[l + 1] / B.m + 1);
+        B.split_ofs[l] = split_total;
+        split_total += (int64_t)(B.ntiles[l] + 1) * std::max(B.k, 1);
+        if (l >= 1) {
+          B.mlist_ofs[l] = mlist_total;
+          mlist_total += M[l];
+        }
+      }
+    }
+    P->max_level = max_level;
+    // tiles per level, ordered by bucket then tile index
+    P->level_tile_ofs.assign(max_level + 1, 0);
+    P->level_tile_cnt.assign(max_level + 1, 0);
+    std::vector<int32_t> tb, ti;
+    for (int l = 0; l <= max_level; ++l) {
+      P->level_tile_ofs[l] = (int32_t)tb.size();
+      for (int b = 0; b < nb; ++b) {
+        BucketDesc& B = P->buckets[b];
+        if (B.levels < l) continue;
+        B.tile_base[l] = (int32_t)tb.size() - P->level_tile_ofs[l];
+        for (int i = 0; i < B.ntiles[l]; ++i) {
+          tb.push_back(b);
+          ti.push_back(i);
+        }
+      }
+      P->level_tile_cnt[l] = (int32_t)tb.size() - P->level_tile_ofs[l];
+    }
+    P->total_tiles = (int32_t)tb.size();
+    const int T0 = P->level_tile_cnt[0];
+
+    P->d_buckets = dev_alloc<BucketDesc>(nb);
+    P->d_file_rows = dev_alloc<int32_t>(P->F);
+    P->d_file_row_base = dev_alloc<int64_t>(P->F + 1);
+    P->d_splits = dev_alloc<int32_t>(split_total);
+    P->d_mlist = dev_alloc<uint2>(mlist_total);
+    P->d_tile_bucket = dev_alloc<int32_t>(tb.size());
+    P->d_tile_idx = dev_alloc<int32_t>(ti.size());
+    P->d_tile_cnt = dev_alloc<int32_t>(T0);
+    P->d_tile_gstart = dev_alloc<int64_t>(T0);
+    P->d_tile_out = dev_alloc<int64_t>(T0 + 1);
+    P->d_win_tmp = dev_alloc<uint32_t>(P->n_total);
+    P->d_win = dev_alloc<uint32_t>(P->n_total);
+    P->d_out_base = dev_alloc<int64_t>(nb + 1);
+    P->d_batch_base = dev_alloc<int64_t>(nb + 1);
+    P->d_err = dev_alloc<int32_t>(1);
+    P->d_dense_base = dev_alloc<int64_t>(P->F + 1);
+    std::vector<int64_t> dense(P->F + 1, 0);
+    for (int f = 0; f < P->F; ++f) dense[f + 1] = dense[f] + file_rows[f];
+    LSB_CUDA(cudaMemcpyAsync(P->d_dense_base, dense.data(), sizeof(int64_t) * (P->F + 1),
+                             cudaMemcpyHostToDevice, stream));
+    LSB_CUDA(cudaMallocHost(&P->h_counts, sizeof(int64_t) * (2 * (nb + 1) + 1)));
+    LSB_CUDA(cudaMemcpyAsync(P->d_buckets, P->buckets.data(), sizeof(BucketDesc) * nb,
+                             cudaMemcpyHostToDevice, stream));
+    LSB_CUDA(cudaMemcpyAsync(P->d_file_rows, fr32.data(), sizeof(int32_t) * P->F,
+                             cudaMemcpyHostToDevice, stream));
+    LSB_CUDA(cudaMemcpyAsync(P->d_file_row_base, frb.data(), sizeof(int64_t) * (P->F + 1),
+                             cudaMemcpyHostToDevice, stream));
+    LSB_CUDA(cudaMemcpyAsync(P->d_tile_bucket, tb.data(), sizeof(int32_t) * tb.size(),
+                             cudaMemcpyHostToDevice, stream));
+    LSB_CUDA(cudaMemcpyAsync(P->d_tile_idx, ti.data(), sizeof(int32_t) * ti.size(),
+                             cudaMemcpyHostToDevice, stream));
+    LSB_CUDA(cudaMemsetAsync(P->d_err, 0, sizeof(int32_t), stream));
+    // host vectors above die at scope exit: make the copies complete first
+    LSB_CUDA(cudaStreamSynchronize(stream));
+
+    P->smem_bytes = tile_smem_bytes(C, P->key128);
+    LSB_CUDA(cudaFuncSetAttribute(tile_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tile_smem_bytes(5632, false)));
+    LSB_CUDA(cudaFuncSetAttribute(tile_kernel<K128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tile_smem_bytes(3328, true)));
+    LSB_CUDA(cudaFuncSetAttribute(tile_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tile_smem_bytes(5632, false)));
+    LSB_CUDA(cudaFuncSetAttribute(tile_kernel<K128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tile_smem_bytes(3328, true)));
+    P->stats.n_rows = P->n_in;
+    P->stats.tiles_l0 = T0;
+    P->stats.levels = max_level;
+    P->stats.log_s = log_s;
+    P->stats.tile_cap = C;
+  } catch (...) {
+    plan_destroy(P);
+    throw;
+  }
+  return P;
+}
+
+void plan_destroy(MergePlan* P) {
+  if (!P) return;
+  cudaFree(P->d_buckets); cudaFree(P->d_file_rows); cudaFree(P->d_file_row_base);
+  cudaFree(P->d_splits); cudaFree(P->d_mlist); cudaFree(P->d_tile_bucket); cudaFree(P->d_tile_idx);
+  cudaFree(P->d_tile_cnt); cudaFree(P->d_tile_gstart); cudaFree(P->d_tile_out);
+  cudaFree(P->d_win_tmp); cudaFree(P->d_win); cudaFree(P->d_out_base); cudaFree(P->d_batch_base);
+  cudaFree(P->d_dense_base); cudaFree(P->d_ctmp);
+  cudaFree(P->d_err); cudaFree(P->d_len); cudaFree(P->d_doff); cudaFree(P->d_sums);
+  cudaFree(P->d_cols);
+  if (P->h_counts) cudaFreeHost(P->h_counts);
+  delete P;
+}
+
+static PlanDev plan_dev(const MergePlan* P) {
+  PlanDev D{};
+  D.buckets = P->d_buckets;
+  D.file_rows = P->d_file_rows;
+  D.file_row_base = P->d_file_row_base;
+  D.splits = P->d_splits;
+  D.mlist = P->d_mlist;
+  D.tile_bucket = P->d_tile_bucket;
+  D.tile_idx = P->d_tile_idx;
+  D.tile_cnt = P->d_tile_cnt;
+  D.tile_gstart = P->d_tile_gstart;
+  D.tile_out = P->d_tile_out;
+  D.win_tmp = P->d_win_tmp;
+  D.win = P->d_win;
+  D.out_base = P->d_out_base;
+  D.batch_base = P->d_batch_base;
+  D.dense_base = P->d_dense_base;
+  D.R = P->d_R;
+  D.rofs = P->d_rofs;
+  D.err = P->d_err;
+  D.nb = P->nb;
+  D.log_s = P->log_s;
+  D.tile_cap = P->tile_cap;
+  D.batch_size = P->batch_size;
+  return D;
+}
+
+template <typename KeyT>
+static int run_levels(MergePlan* P, const PkDesc& pk, cudaStream_t stream) {
+  PlanDev D = plan_dev(P);
+  int launches = 0;
+  for (int l = P->max_level; l >= 0; --l) {
+    const int nt = P->level_tile_cnt[l];
+    if (nt == 0) continue;
+    const int ofs = P->level_tile_ofs[l];
+    const int warps_per_block = 4;
+    part_kernel<KeyT><<<(nt + warps_per_block - 1) / warps_per_block, 128, 0, stream>>>(D, pk, l, ofs, nt);
+    tile_kernel<KeyT, false><<<nt, kTileThreads, P->smem_bytes, stream>>>(D, pk, l, ofs);
+    launches += 2;
+  }
+  return launches;
+}
+
+void plan_merge(MergePlan* P, const PkDesc& pk, cudaStream_t stream) {
+  const bool want128 = pk.key_bits > 64;
+  if (want128 != P->key128) {
+    g_last_error = "plan was created for a different key width";
+    throw std::runtime_error(g_last_error);
+  }
+  int launches = 0;
+  if (P->n_total > 0) {
+    launches += P->key128 ? run_levels<K128>(P, pk, stream) : run_levels<uint64_t>(P, pk, stream);
+  }
+  PlanDev D = plan_dev(P);
+  const int T0 = P->level_tile_cnt[0];
+  scan_kernel<<<1, 1024, 0, stream>>>(D, T0);
+  batch_base_kernel<<<1, 1024, 0, stream>>>(D);
+  launches += 2;
+  if (T0 > 0) {
+    compact_kernel<<<T0, 256, 0, stream>>>(D);
+    ++launches;
+  }
+  LSB_CUDA(cudaGetLastError());
+  P->stats.launches = launches;
+  P->last_pk = pk;
+  P->merged = true;
+  P->synced = false;
+}
+
+void plan_identity(MergePlan* P, cudaStream_t stream) {
+  PlanDev D = plan_dev(P);
+  int launches = 0;
+  if (P->n_in > 0) {
+    identity_kernel<<<(unsigned)((P->n_in + 255) / 256), 256, 0, stream>>>(D, P->F, P->n_in);
+    ++launches;
+  }
+  identity_bases_kernel<<<(P->nb + 1 + 255) / 256, 256, 0, stream>>>(D, P->F);
+  batch_base_kernel<<<1, 1024, 0, stream>>>(D);
+  launches += 2;
+  LSB_CUDA(cudaGetLastError());
+  P->stats.launches = launches;
+  P->merged = true;
+  P->synced = false;
+}
+
+const std::vector<int64_t>& plan_sync_counts(MergePlan* P, cudaStream_t stream) {
+  if (!P->merged) {
+    g_last_error = "plan_sync_counts before plan_merge";
+    throw std::runtime_error(g_last_error);
+  }
+  if (!P->synced) {
+    const int nb = P->nb;
+    LSB_CUDA(cudaMemcpyAsync(P->h_counts, P->d_out_base, sizeof(int64_t) * (nb + 1),
+                             cudaMemcpyDeviceToHost, stream));
+    LSB_CUDA(cudaMemcpyAsync(P->h_counts + nb + 1, P->d_batch_base, sizeof(int64_t) * (nb + 1),
+                             cudaMemcpyDeviceToHost, stream));
+    LSB_CUDA(cudaMemcpyAsync(P->h_counts + 2 * (nb + 1), P->d_err, sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, stream));
+    LSB_CUDA(cudaStreamSynchronize(stream));
+    const int32_t err = *reinterpret_cast<int32_t*>(P->h_counts + 2 * (nb + 1));
+    if (err != 0) {
+      g_last_error = "merge kernel reported error code " + std::to_string(err);
+      throw std::runtime_error(g_last_error);
+    }
+    P->out_base.assign(P->h_counts, P->h_counts + nb + 1);
+    P->batch_base.assign(P->h_counts + nb + 1, P->h_counts + 2 * (nb + 1));
+    P->out_counts.resize(nb);
+    for (int b = 0; b < nb; ++b) P->out_counts[b] = P->out_base[b + 1] - P->out_base[b];
+    P->stats.n_out = P->out_base[nb];
+    P->synced = true;
+  }
+  return P->out_counts;
+}
+
+const MergeStats& plan_stats(const MergePlan* P) { return P->stats; }
+int64_t plan_total_rows(const MergePlan* P) { return P->n_in; }
+int plan_num_buckets(const MergePlan* P) { return P->nb; }
+int plan_batch_size(const MergePlan* P) { return P->batch_size; }
+const uint32_t* plan_winners(const MergePlan* P) { return P->d_win; }
+const int64_t* plan_out_base_dev(const MergePlan* P) { return P->d_out_base; }
+int64_t plan_valid_stride_bytes(const MergePlan* P) {
+  return (((int64_t)P->batch_size + 7) / 8 + 63) / 64 * 64;
+}
+const std::vector<int64_t>& plan_out_base(const MergePlan* P) { return P->out_base; }
+const std::vector<int64_t>& plan_batch_base(const MergePlan* P) { return P->batch_base; }
+
+static GatherGeom make_geom(const MergePlan* P) {
+  GatherGeom G{};
+  G.win = P->d_win;
+  G.out_base = P->d_out_base;
+  G.batch_base = P->d_batch_base;
+  G.nb = P->nb;
+  G.batch_size = P->batch_size;
+  G.chunks_per_batch = (P->batch_size + kRowsPerChunk - 1) / kRowsPerChunk;
+  G.valid_stride = plan_valid_stride_bytes(P);
+  return G;
+}
+
+static void require_synced(const MergePlan* P) {
+  if (!P->synced) {
+    g_last_error = "gather before plan_sync_counts";
+    throw std::runtime_error(g_last_error);
+  }
+}
+
+void gather_fixed(MergePlan* P, const FixedCol* cols, int ncols, cudaStream_t stream) {
+  require_synced(P);
+  if (ncols <= 0) return;
+  const int64_t total_batches = P->batch_base[P->nb];
+  if (total_batches == 0) return;
+  if (P->d_cols_cap < ncols) {
+    cudaFree(P->d_cols);
+    P->d_cols = dev_alloc<FixedCol>(ncols);
+    P->d_cols_cap = ncols;
+  }
+  LSB_CUDA(cudaMemcpyAsync(P->d_cols, cols, sizeof(FixedCol) * ncols, cudaMemcpyHostToDevice, stream));
+  GatherGeom G = make_geom(P);
+  const int64_t chunks = total_batches * G.chunks_per_batch;
+  // grid.y <= 65535 columns; chunks in x (2^31-1)
+  for (int c0 = 0; c0 < ncols; c0 += 65535) {
+    dim3 grid((unsigned)chunks, (unsigned)std::min(65535, ncols - c0));
+    gather_fixed_kernel<<<grid, kGatherThreads, 0, stream>>>(G, P->d_cols + c0);
+  }
+  LSB_CUDA(cudaGetLastError());
+  // the descriptor table is reused by the next call: order the copy behind this launch
+}
+
+void plan_reserve_scratch(MergePlan* P, cudaStream_t) {
+  require_synced(P);
+  const int64_t U = P->out_base[P->nb];
+  if (!P->d_len) {
+    P->d_len = dev_alloc<int32_t>(U + 1);
+    P->d_doff = dev_alloc<int64_t>(U + 2);
+    P->d_sums = dev_alloc<int64_t>((U + kScanChunk - 1) / kScanChunk + 2);
+  }
+}
+
+void gather_var(MergePlan* P, const VarCol& col, cudaStream_t stream) {
+  require_synced(P);
+  plan_reserve_scratch(P, stream);
+  const int64_t U = P->out_base[P->nb];
+  const int64_t total_batches = P->batch_base[P->nb];
+  if (total_batches == 0) return;
+  GatherGeom G = make_geom(P);
+  const int64_t chunks = total_batches * G.chunks_per_batch;
+  var_len_kernel<<<(unsigned)chunks, kGatherThreads, 0, stream>>>(G, col, P->d_len);
+  const int nblocks = (int)((U + kScanChunk - 1) / kScanChunk);
+  scan_block_sums<<<nblocks, 256, 0, stream>>>(P->d_len, U, P->d_sums);
+  scan_sums_inplace<<<1, 1024, 0, stream>>>(P->d_sums, nblocks);
+  scan_apply<<<nblocks, 256, 0, stream>>>(P->d_len, U, P->d_sums, P->d_doff);
+  var_offsets_kernel<<<(unsigned)chunks, kGatherThreads, 0, stream>>>(G, col, P->d_doff, total_batches, U);
+  var_copy_kernel<<<(unsigned)((U + kCopyRows - 1) / kCopyRows), 256, 0, stream>>>(G, col, P->d_doff, U);
+  LSB_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------
+// winner compaction after the post-merge predicate
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) keep_to_i32(const uint8_t* keep, int64_t n, int32_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = keep[i] ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) scatter_kept(const uint8_t* keep, const int64_t* pos, int64_t n,
+                                                   const uint32_t* src, uint32_t* dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && keep[i]) dst[pos[i]] = src[i];
+}
+__global__ void __launch_bounds__(256) rebase_out(PlanDev P, const int64_t* pos, int64_t* new_base) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b <= P.nb) new_base[b] = pos[P.out_base[b]];
+}
+__global__ void __launch_bounds__(256) copy_i64(const int64_t* src, int64_t* dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+void plan_compact(MergePlan* P, const uint8_t* keep, const std::vector<uint32_t*>& extra_lists,
+                  cudaStream_t stream) {
+  require_synced(P);
+  const int64_t U = P->out_base[P->nb];
+  if (U == 0) return;
+  plan_reserve_scratch(P, stream);
+  if (!P->d_ctmp) P->d_ctmp = dev_alloc<uint32_t>(P->n_total);
+  const unsigned g = (unsigned)((U + 255) / 256);
+  keep_to_i32<<<g, 256, 0, stream>>>(keep, U, P->d_len);
+  const int nblocks = (int)((U + kScanChunk - 1) / kScanChunk);
+  scan_block_sums<<<nblocks, 256, 0, stream>>>(P->d_len, U, P->d_sums);
+  scan_sums_inplace<<<1, 1024, 0, stream>>>(P->d_sums, nblocks);
+  scan_apply<<<nblocks, 256, 0, stream>>>(P->d_len, U, P->d_sums, P->d_doff);
+  // plan winners: scatter into win_tmp, then swap roles
+  scatter_kept<<<g, 256, 0, stream>>>(keep, P->d_doff, U, P->d_win, P->d_win_tmp);
+  std::swap(P->d_win, P->d_win_tmp);
+  for (uint32_t* list : extra_lists) {
+    scatter_kept<<<g, 256, 0, stream>>>(keep, P->d_doff, U, list, P->d_ctmp);
+    LSB_CUDA(cudaMemcpyAsync(list, P->d_ctmp, sizeof(uint32_t) * U, cudaMemcpyDeviceToDevice, stream));
+  }
+  PlanDev D = plan_dev(P);
+  // new bases: out_base'[b] = pos[out_base[b]]  (pos has U+1 entries); staged through d_sums' tail
+  int64_t* nb_tmp = reinterpret_cast<int64_t*>(P->d_len);  // d_len no longer needed (>= (U+1)*4 bytes)
+  if ((int64_t)(P->nb + 1) * 8 > (U + 1) * 4) {
+    // tiny outputs with many buckets: use a dedicated buffer
+    cudaFree(P->d_sums);
+    P->d_sums = dev_alloc<int64_t>((U + kScanChunk - 1) / kScanChunk + 2 + P->nb + 1);
+    nb_tmp = P->d_sums + (U + kScanChunk - 1) / kScanChunk + 2;
+  }
+  rebase_out<<<(P->nb + 1 + 255) / 256, 256, 0, stream>>>(D, P->d_doff, nb_tmp);
+  copy_i64<<<(P->nb + 1 + 255) / 256, 256, 0, stream>>>(nb_tmp, P->d_out_base, P->nb + 1);
+  batch_base_kernel<<<1, 1024, 0, stream>>>(D);
+  LSB_CUDA(cudaGetLastError());
+  P->synced = false;
+}
+
+// ---------------------------------------------------------------------------------------
+// general path: partial merge + merge operators, resolved from the presence matrix R
+// ---------------------------------------------------------------------------------------
+struct GenColDev {
+  const void* values;
+  const uint8_t* validity;
+  const char* present;  // F entries (device)
+  uint32_t* win_out;    // U entries
+  void* opval;          // U * width (operators that compute values)
+  uint32_t* opvalid;    // bitmap words over output rows
+  int32_t op;
+  int32_t width;
+  int32_t num_class;
+};
+
+template <typename T>
+__device__ __forceinline__ T ld(const void* p, int64_t i) { return reinterpret_cast<const T*>(p)[i]; }
+__device__ __forceinline__ bool bit_at(const uint8_t* bm, int64_t i) { return !bm || ((bm[i >> 3] >> (i & 7)) & 1); }
+
+template <typename KeyT>
+__device__ __forceinline__ int64_t run_first(const PkDesc& pk, int64_t file_first, int64_t last) {
+  // in-file run of equal keys ending at `last` (sort_key_range.rs:99-113)
+  const KeyT kl = KeyLoader<KeyT>::load(pk, last);
+  int64_t r = last;
+  while (r > file_first && !key_ne(KeyLoader<KeyT>::load(pk, r - 1), kl)) --r;
+  return r;
+}
+
+template <typename T>
+__device__ __forceinline__ void store_val(void* p, int64_t i, T v) { reinterpret_cast<T*>(p)[i] = v; }
+
+template <typename KeyT, typename T>
+__device__ void sum_op(const PlanDev& P, const PkDesc& pk, const GenColDev& c, const BucketDesc& B,
+                       const uint32_t* Rrow, int64_t u, bool sum_all, bool& valid) {
+  T res = T(0);
+  valid = true;
+  for (int j = 0; j < B.k && valid; ++j) {
+    if (!c.present[B.file_begin + j]) continue;
+    const uint32_t last = Rrow[j];
+    if (last == kNoRow) continue;
+    if (sum_all) {
+      const int64_t first = run_first<KeyT>(pk, P.file_row_base[B.file_begin + j], last);
+      T part = T(0);
+      for (int64_t r = first; r <= (int64_t)last; ++r) {
+        if (!bit_at(c.validity, r)) { valid = false; break; }
+        part += ld<T>(c.values, r);
+      }
+      res += part;
+    } else {
+      if (!bit_at(c.validity, last)) { valid = false; break; }
+      res += ld<T>(c.values, last);
+    }
+  }
+  store_val<T>(c.opval, u, valid ? res : T(0));
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(256) resolve_kernel(PlanDev P, PkDesc pk, GenColDev c, int64_t U) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = u < U;
+  bool valid = false;
+  if (active) {
+    const int b = upper_idx(P.out_base, P.nb + 1, u);
+    const BucketDesc& B = P.buckets[b];
+    const uint32_t* Rrow = P.R + P.rofs[b] + (u - P.out_base[b]) * B.k;
+    const char* present = c.present + B.file_begin;
+    if (c.op == (int)MergeOp::UseLast) {
+      uint32_t w = kNoRow;
+      for (int j = B.k - 1; j >= 0; --j) {
+        if (present[j] && Rrow[j] != kNoRow) { w = Rrow[j]; break; }
+      }
+      c.win_out[u] = w;
+    } else if (c.op == (int)MergeOp::UseLastNotNull) {
+      uint32_t w = kNoRow;
+      for (int j = B.k - 1; j >= 0 && w == kNoRow; --j) {
+        if (!present[j] || Rrow[j] == kNoRow) continue;
+        const int64_t last = Rrow[j];
+        const int64_t first = run_first<KeyT>(pk, P.file_row_base[B.file_begin + j], last);
+        for (int64_t r = last; r >= first; --r) {
+          if (bit_at(c.validity, r)) { w = (uint32_t)r; break; }
+        }
+      }
+      c.win_out[u] = w;
+    } else {
+      const bool all = c.op == (int)MergeOp::SumAll;
+      switch (c.num_class) {
+        case NC_I8: sum_op<KeyT, int8_t>(P, pk, c, B, Rrow, u, all, valid); break;
+        case NC_I16: sum_op<KeyT, int16_t>(P, pk, c, B, Rrow, u, all, valid); break;
+        case NC_I32: sum_op<KeyT, int32_t>(P, pk, c, B, Rrow, u, all, valid); break;
+        case NC_I64: sum_op<KeyT, int64_t>(P, pk, c, B, Rrow, u, all, valid); break;
+        case NC_U8: sum_op<KeyT, uint8_t>(P, pk, c, B, Rrow, u, all, valid); break;
+        case NC_U16: sum_op<KeyT, uint16_t>(P, pk, c, B, Rrow, u, all, valid); break;
+        case NC_U32: sum_op<KeyT, uint32_t>(P, pk, c, B, Rrow, u, all, valid); break;
+        case NC_U64: sum_op<KeyT, uint64_t>(P, pk, c, B, Rrow, u, all, valid); break;
+        case NC_F32: sum_op<KeyT, float>(P, pk, c, B, Rrow, u, all, valid); break;
+        default: sum_op<KeyT, double>(P, pk, c, B, Rrow, u, all, valid); break;
+      }
+      // a key that no carrying file contains stays null (merge_operator.rs:61-62)
+      bool any = false;
+      for (int j = 0; j < B.k; ++j) any |= (present[j] && Rrow[j] != kNoRow);
+      valid = valid && any;
+      c.win_out[u] = (uint32_t)u;  // gather reads opval[u]
+    }
+  }
+  if (c.opvalid) {
+    const uint32_t word = __ballot_sync(0xffffffffu, active && valid);
+    if ((threadIdx.x & 31) == 0 && (u - (threadIdx.x & 31)) < U) c.opvalid[u >> 5] = word;
+  }
+}
+
+struct GeneralMerge {
+  MergePlan* plan = nullptr;
+  int C = 0;
+  int launches = 0;
+  uint32_t* d_R = nullptr;
+  int64_t* d_rofs = nullptr;
+  char* d_present = nullptr;
+  struct Col {
+    bool uses_plan_winners = true;
+    bool computed = false;
+    bool may_null = false;
+    uint32_t* win = nullptr;
+    void* opval = nullptr;
+    uint32_t* opvalid = nullptr;
+  };
+  std::vector<Col> cols;
+};
+
+void general_destroy(GeneralMerge* G) {
+  if (!G) return;
+  cudaFree(G->d_R); cudaFree(G->d_rofs); cudaFree(G->d_present);
+  for (auto& c : G->cols) { cudaFree(c.win); cudaFree(c.opval); cudaFree(c.opvalid); }
+  delete G;
+}
+
+GeneralMerge* general_create(MergePlan* P, const PkDesc& pk, const std::vector<GeneralColumnIn>& in,
+                             cudaStream_t stream) {
+  require_synced(P);
+  auto* G = new GeneralMerge();
+  try {
+    G->plan = P;
+    G->C = (int)in.size();
+    G->cols.resize(G->C);
+    const int nb = P->nb;
+    const int64_t U = P->out_base[nb];
+    // which columns need their own resolution
+    bool need_R = false;
+    for (int c = 0; c < G->C; ++c) {
+      bool all_present = true;
+      for (int f = 0; f < P->F; ++f) all_present &= in[c].present[f] != 0;
+      auto& col = G->cols[c];
+      col.uses_plan_winners = all_present && in[c].op == MergeOp::UseLast;
+      col.computed = in[c].op == MergeOp::SumAll || in[c].op == MergeOp::SumLast;
+      col.may_null = !all_present || in[c].validity != nullptr || in[c].op != MergeOp::UseLast;
+      if (in[c].op == MergeOp::JoinedLastByComma || in[c].op == MergeOp::JoinedLastBySemicolon ||
+          in[c].op == MergeOp::JoinedAllByComma || in[c].op == MergeOp::JoinedAllBySemicolon) {
+        g_last_error = "Joined* merge operators are not implemented by the GPU reader yet";
+        throw std::runtime_error(g_last_error);
+      }
+      if (col.computed && in[c].num_class == NC_NONE) {
+        g_last_error = "column type doesn't support MergeOperator::Sum";
+        throw std::runtime_error(g_last_error);
+      }
+      need_R |= !col.uses_plan_winners;
+    }
+    if (!need_R || U == 0) return G;
+
+    // presence matrix
+    std::vector<int64_t> rofs(nb + 1, 0);
+    for (int b = 0; b < nb; ++b)
+      rofs[b + 1] = rofs[b] + (P->out_base[b + 1] - P->out_base[b]) * P->buckets[b].k;
+    G->d_R = dev_alloc<uint32_t>(rofs[nb]);
+    G->d_rofs = dev_alloc<int64_t>(nb + 1);
+    LSB_CUDA(cudaMemsetAsync(G->d_R, 0xff, sizeof(uint32_t) * rofs[nb], stream));
+    LSB_CUDA(cudaMemcpyAsync(G->d_rofs, rofs.data(), sizeof(int64_t) * (nb + 1), cudaMemcpyHostToDevice, stream));
+    std::vector<char> present((size_t)G->C * P->F);
+    for (int c = 0; c < G->C; ++c) std::memcpy(present.data() + (size_t)c * P->F, in[c].present, P->F);
+    G->d_present = dev_alloc<char>(present.size());
+    LSB_CUDA(cudaMemcpyAsync(G->d_present, present.data(), present.size(), cudaMemcpyHostToDevice, stream));
+    LSB_CUDA(cudaStreamSynchronize(stream));  // host vectors go out of scope below
+
+    P->d_R = G->d_R;
+    P->d_rofs = G->d_rofs;
+    PlanDev D = plan_dev(P);
+    const int T0 = P->level_tile_cnt[0];
+    const int ofs0 = P->level_tile_ofs[0];
+    if (P->key128) tile_kernel<K128, true><<<T0, kTileThreads, P->smem_bytes, stream>>>(D, pk, 0, ofs0);
+    else tile_kernel<uint64_t, true><<<T0, kTileThreads, P->smem_bytes, stream>>>(D, pk, 0, ofs0);
+    ++G->launches;
+
+    for (int c = 0; c < G->C; ++c) {
+      auto& col = G->cols[c];
+      if (col.uses_plan_winners) continue;
+      col.win = dev_alloc<uint32_t>(U);
+      GenColDev gc{};
+      gc.values = in[c].values;
+      gc.validity = in[c].validity;
+      gc.present = G->d_present + (size_t)c * P->F;
+      gc.win_out = col.win;
+      gc.op = (int)in[c].op;
+      gc.width = in[c].kind.width;
+      gc.num_class = in[c].num_class;
+      if (col.computed) {
+        col.opval = dev_alloc<uint8_t>((size_t)U * std::max(in[c].kind.width, 1) + 32);
+        col.opvalid = dev_alloc<uint32_t>((U + 31) / 32 + 2);
+        gc.opval = col.opval;
+        gc.opvalid = col.opvalid;
+      }
+      const unsigned g = (unsigned)((U + 255) / 256);
+      if (P->key128) resolve_kernel<K128><<<g, 256, 0, stream>>>(D, pk, gc, U);
+      else resolve_kernel<uint64_t><<<g, 256, 0, stream>>>(D, pk, gc, U);
+      ++G->launches;
+    }
+    LSB_CUDA(cudaGetLastError());
+    P->d_R = nullptr;
+    P->d_rofs = nullptr;
+  } catch (...) {
+    P->d_R = nullptr;
+    P->d_rofs = nullptr;
+    general_destroy(G);
+    throw;
+  }
+  return G;
+}
+
+int general_launches(const GeneralMerge* G) { return G->launches; }
+const uint32_t* general_winners(const GeneralMerge* G, int c) { return G->cols[c].win; }
+const void* general_values(const GeneralMerge* G, int c, const void* dflt) {
+  return G->cols[c].computed && G->cols[c].opval ? G->cols[c].opval : dflt;
+}
+const uint8_t* general_validity(const GeneralMerge* G, int c, const uint8_t* dflt) {
+  return G->cols[c].computed && G->cols[c].opvalid ? reinterpret_cast<const uint8_t*>(G->cols[c].opvalid) : dflt;
+}
+const uint8_t* general_data(const GeneralMerge*, int, const uint8_t* dflt) { return dflt; }
+const int64_t* general_bucket_data(const GeneralMerge*, int, const int64_t* dflt) { return dflt; }
+int64_t general_data_bytes(const GeneralMerge*, int, int64_t dflt) { return dflt; }
+bool general_may_be_null(const GeneralMerge* G, int c) { return G->cols[c].may_null; }
+std::vector<uint32_t*> general_winner_lists(GeneralMerge* G) {
+  std::vector<uint32_t*> v;
+  for (auto& c : G->cols)
+    if (c.win) v.push_back(c.win);
+  return v;
+}
+
+}  // namespace lsb

@@ -1,0 +1,155 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// mor_engine.h -- device-level merge-on-read engine (internal C++ API).
+//
+// One MergePlan describes a *scan batch*: nb hash buckets, bucket b holding k_b
+// delta files (commit order = file order), every file sorted by primary key.
+// All columns of all files of the batch live in HBM as ONE concatenated array per
+// column ("global rows": file f occupies rows [file_row_base[f], +file_rows[f])).
+//
+// plan_merge()   : PK k-way merge + last-writer-wins selection for every bucket in
+//                  a handful of launches -> dense winner list win[] of global row ids
+//                  (replaces UseLastRangeCombiner::poll / loser tree,
+//                  reference rust/lakesoul-io/src/physical_plan/merge/sorted/combiner.rs:478-525,680-785
+//                  and SortKeyBatchRange::advance, sort_key_range.rs:99-113,182-187).
+// gather_*()     : out[u] = src[win[u]] into batch-segmented Arrow buffers
+//                  (replaces build_record_batch_full_merge + arrow interleave, combiner.rs:529-605).
+//
+// No torch / arrow types here: plain device pointers and sizes.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+
+namespace lsb {
+
+enum PkKind : uint8_t { PK_UNSIGNED = 0, PK_SIGNED = 1, PK_FLOAT = 2 };
+
+struct PkCol {
+  const void* values;       // `width` bytes per global row
+  const uint8_t* validity;  // Arrow validity bitmap over global rows, or nullptr (no nulls)
+  uint8_t width;            // 1, 2, 4, 8
+  uint8_t kind;             // PkKind
+  uint8_t pad[6];
+};
+
+constexpr int kMaxPkCols = 4;
+struct PkDesc {
+  int32_t ncols;
+  int32_t key_bits;  // sum(width*8 + (validity?1:0)); <=64 -> 64-bit keys, <=128 -> 128-bit keys
+  PkCol col[kMaxPkCols];
+};
+
+constexpr int kMaxLevels = 6;   // sampling levels above level 0
+constexpr int kMaxFilesPerBucket = 256;
+
+// Per-bucket plan record (host-built, copied to the device once per plan).
+struct BucketDesc {
+  int32_t file_begin;               // first global file id
+  int32_t k;                        // number of files
+  int32_t levels;                   // L_b: top sampling level (0 = bucket fits one tile)
+  int32_t m;                        // splitter stride, in samples of the level above
+  int64_t row_base;                 // global row of the bucket's first row
+  int64_t n_rows;                   // total input rows
+  int64_t split_ofs[kMaxLevels + 1];  // offset into splits[] of the (T_l+1) x k table
+  int64_t mlist_ofs[kMaxLevels + 1];  // offset into mlist[] of the merged level-l list (l>=1)
+  int32_t ntiles[kMaxLevels + 1];     // T_{b,l}
+  int32_t tile_base[kMaxLevels + 1];  // index of the bucket's first tile inside level l
+};
+
+struct MergeStats {
+  int64_t n_rows = 0;       // input rows
+  int64_t n_out = 0;        // output rows (valid after plan_sync_counts)
+  int32_t tiles_l0 = 0;
+  int32_t levels = 0;
+  int32_t log_s = 0;
+  int32_t tile_cap = 0;
+  int32_t launches = 0;     // kernels launched by the last plan_merge()
+};
+
+// Gather descriptors ---------------------------------------------------------
+constexpr uint32_t kNoRow = 0xffffffffu;  // winner slot "no source row" -> output null
+
+struct FixedCol {
+  const void* src;          // global-row indexed values (width bytes; bit-packed when width==0)
+  const uint8_t* src_valid; // bitmap over global rows or nullptr
+  void* dst;                // dense output values, (total_out) * width; width==0: batch-segmented bits
+  uint8_t* dst_valid;       // batch-segmented bitmap or nullptr (then no validity is produced)
+  const uint32_t* win;      // per-column winner list (partial merge / operators) or nullptr = plan winners
+  int32_t width;            // 0 (boolean bits),1,2,4,8,16,32
+  int32_t pad;
+};
+
+struct MergePlan;  // opaque
+
+// Build the plan (host work + descriptor upload on `stream`). Throws std::runtime_error on
+// unsupported shapes (too many files per bucket, > 2^32-2 rows per batch).
+// file_row_base (optional): global row of every file's first row (F entries, increasing, a file
+// never overlaps the next); nullptr = files packed back to back. row_span = one past the last
+// global row (ignored when file_row_base is null).
+MergePlan* plan_create(int nb, const int32_t* bucket_file_begin, const int64_t* file_rows,
+                       const int64_t* file_row_base, int64_t row_span, int key_bits, int batch_size,
+                       cudaStream_t stream);
+void plan_destroy(MergePlan*);
+
+// Run partition + tile merge + scan + compaction. Asynchronous on `stream`.
+void plan_merge(MergePlan*, const PkDesc& pk, cudaStream_t stream);
+
+// "No merge" variant (skip_merge_on_read / no primary key, merge/mod.rs:297-312): every input row
+// survives, in file order.
+void plan_identity(MergePlan*, cudaStream_t stream);
+
+// Keep only output rows with keep[u] != 0 (device array over the current output rows): compacts
+// the winner list and every list in `extra_lists` (device, same length), refreshes the per-bucket
+// bases. Call plan_sync_counts() afterwards.
+void plan_compact(MergePlan*, const uint8_t* keep, const std::vector<uint32_t*>& extra_lists,
+                  cudaStream_t stream);
+
+// Wait for the merge and fetch per-bucket output row counts (host vector of nb entries).
+const std::vector<int64_t>& plan_sync_counts(MergePlan*, cudaStream_t stream);
+
+const MergeStats& plan_stats(const MergePlan*);
+int64_t plan_total_rows(const MergePlan*);
+int plan_num_buckets(const MergePlan*);
+int plan_batch_size(const MergePlan*);
+
+// Device views (valid after plan_merge on the same stream).
+const uint32_t* plan_winners(const MergePlan*);      // dense winners, bucket b at [out_base[b], out_base[b+1])
+const int64_t* plan_out_base_dev(const MergePlan*);  // nb+1 entries (device)
+
+// Layout helpers for batch-segmented outputs, valid after plan_sync_counts():
+//   validity: every batch owns valid_stride_bytes() bytes; batch (b,i) is batch number
+//             batch_base(b)+i;  offsets: batch (b,i) starts at entry out_base[b]+i*bs + batch_base(b)+i.
+int64_t plan_valid_stride_bytes(const MergePlan*);
+const std::vector<int64_t>& plan_out_base(const MergePlan*);    // host copy, nb+1
+const std::vector<int64_t>& plan_batch_base(const MergePlan*);  // host, nb+1 (prefix of batches per bucket)
+
+// out[u] = src[win[u]] for a set of fixed-width columns in one launch.
+void gather_fixed(MergePlan*, const FixedCol* cols, int ncols, cudaStream_t stream);
+
+// Variable-width (Utf8/Binary) gather. src offsets are int32 indexed by global row (entries g and
+// g+1 delimit row g, so a file needs one spare global row after its last row, or the next file
+// must continue the same data run), relative to the bucket's data base `src_data_base[b]`
+// (int64, device array of nb).
+// Produces: dst_offsets (int32, batch-rebased, (rows+1) per batch), dst_data (dense bytes),
+// batch_data_start (int64 per batch + 1, device) = byte offset of each batch inside dst_data.
+struct VarCol {
+  const int32_t* src_offsets;
+  const uint8_t* src_data;
+  const int64_t* src_data_base;  // device, nb entries
+  const uint8_t* src_valid;      // or nullptr
+  const uint32_t* win;           // per-column winner list or nullptr
+  int32_t* dst_offsets;
+  uint8_t* dst_data;             // capacity must be >= total source bytes of the column
+  uint8_t* dst_valid;            // or nullptr
+  int64_t* batch_data_start;     // device, (total_batches + 1)
+};
+void gather_var(MergePlan*, const VarCol& col, cudaStream_t stream);
+
+// Scratch management for gather_var (lengths + scanned offsets); grows on demand.
+void plan_reserve_scratch(MergePlan*, cudaStream_t stream);
+
+std::string last_error();
+
+}  // namespace lsb

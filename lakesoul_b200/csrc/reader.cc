@@ -1,0 +1,463 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// reader.cc -- per-hash-bucket reader behind the lakesoul-io-c C-ABI.
+// Follows the observable behaviour of LakeSoulReader::start / next_rb
+// (rust/lakesoul-io/src/reader.rs:138-232, 355-363), LakeSoulIOSession::build_physical_plan
+// (session.rs:720-882), LakeSoulParquetFormat::create_physical_plan (file_format.rs:234-310),
+// MergeParquetExec (physical_plan/merge/mod.rs:61-120, 283-374) and DefaultColumnStream
+// (stream/default_column.rs:49-108) -- with the merge itself on the GPU (device_scan.cc).
+#include "reader.h"
+
+#include <arrow/compute/api.h>
+#include <arrow/io/file.h>
+#include <parquet/arrow/reader.h>
+#include <parquet/arrow/schema.h>
+#include <parquet/file_reader.h>
+#include <sys/stat.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <set>
+#include <stdexcept>
+
+#include "device_scan.h"
+#include "filter.h"
+
+namespace lsb {
+
+namespace {
+
+[[noreturn]] void fail(const std::string& m) { throw std::runtime_error(m); }
+
+constexpr const char* kNullString = "__L@KE$OUL_NULL__";         // constant.rs:18
+constexpr const char* kEmptyString = "__L@KE$OUL_EMPTY_STRING__";  // constant.rs:19
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+std::string upper(std::string s) {
+  for (auto& c : s) c = (char)toupper((unsigned char)c);
+  return s;
+}
+
+std::string strip_scheme(const std::string& path) {
+  // local files only: "file:///a/b" or "file:/a/b" or plain paths
+  if (path.rfind("file://", 0) == 0) return path.substr(7);
+  if (path.rfind("file:", 0) == 0) return path.substr(5);
+  if (path.find("://") != std::string::npos)
+    fail("object store '" + path.substr(0, path.find("://")) + "' is not supported by the GPU reader (local files only)");
+  return path;
+}
+
+// helpers/transform.rs:35-55 : timestamps with a zone are normalised to UTC
+std::shared_ptr<arrow::Field> uniform_field(const std::shared_ptr<arrow::Field>& f) {
+  if (f->type()->id() == arrow::Type::TIMESTAMP) {
+    const auto& t = static_cast<const arrow::TimestampType&>(*f->type());
+    if (!t.timezone().empty()) return f->WithType(arrow::timestamp(t.unit(), "UTC"));
+  }
+  return f;
+}
+
+// helpers/transform.rs:356-513 make_default_array
+std::shared_ptr<arrow::Array> make_default_array(const std::shared_ptr<arrow::DataType>& type,
+                                                 const std::string& value, int64_t rows) {
+  auto nulls = [&]() { return arrow::MakeArrayOfNull(type, rows).ValueOrDie(); };
+  if (value == kNullString) return nulls();
+  std::shared_ptr<arrow::Scalar> scalar;
+  auto parse_i64 = [&](int64_t* out) {
+    if (value.empty()) return false;
+    char* end = nullptr;
+    errno = 0;
+    long long v = strtoll(value.c_str(), &end, 10);
+    if (*end != 0 || errno != 0) return false;
+    *out = v;
+    return true;
+  };
+  switch (type->id()) {
+    case arrow::Type::STRING:
+      scalar = std::make_shared<arrow::StringScalar>(value == kEmptyString ? std::string() : value);
+      break;
+    case arrow::Type::INT32: {
+      int64_t v;
+      if (!parse_i64(&v) || v < INT32_MIN || v > INT32_MAX) fail("invalid digit found in string: " + value);
+      scalar = std::make_shared<arrow::Int32Scalar>((int32_t)v);
+    } break;
+    case arrow::Type::INT64: {
+      int64_t v;
+      if (!parse_i64(&v)) fail("invalid digit found in string: " + value);
+      scalar = std::make_shared<arrow::Int64Scalar>(v);
+    } break;
+    case arrow::Type::DATE32: {
+      int64_t v;
+      if (parse_i64(&v)) {
+        scalar = std::make_shared<arrow::Date32Scalar>((int32_t)v);
+      } else {
+        auto r = arrow::Scalar::Parse(type, value);  // YYYY-MM-DD
+        if (!r.ok()) fail("cannot parse date partition value '" + value + "'");
+        scalar = *r;
+      }
+    } break;
+    case arrow::Type::TIMESTAMP: {
+      int64_t v;
+      if (parse_i64(&v)) {
+        scalar = std::make_shared<arrow::TimestampScalar>(v, type);
+      } else {
+        std::string s = value;
+        auto r = arrow::Scalar::Parse(arrow::timestamp(static_cast<const arrow::TimestampType&>(*type).unit()), s);
+        if (!r.ok()) fail("cannot parse timestamp partition value '" + value + "'");
+        scalar = std::make_shared<arrow::TimestampScalar>(static_cast<const arrow::TimestampScalar&>(**r).value, type);
+      }
+    } break;
+    case arrow::Type::BOOL: {
+      if (value == "true") scalar = std::make_shared<arrow::BooleanScalar>(true);
+      else if (value == "false") scalar = std::make_shared<arrow::BooleanScalar>(false);
+      else fail("provided string was not `true` or `false`");
+    } break;
+    default: {
+      auto r = arrow::Scalar::Parse(type, value);
+      if (!r.ok()) {
+        fprintf(stderr, "[lakesoul_b200] make_default_array() datatype not match, datatype=%s, value=%s\n",
+                type->ToString().c_str(), value.c_str());
+        return nulls();
+      }
+      scalar = *r;
+    }
+  }
+  return arrow::MakeArrayFromScalar(*scalar, rows).ValueOrDie();
+}
+
+struct FileInfo {
+  std::string path;
+  std::unique_ptr<parquet::arrow::FileReader> reader;
+  std::shared_ptr<arrow::Schema> schema;  // partition columns removed
+  int64_t rows = 0;
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+bool IOConfig::option(const std::string& key, std::string* out) const {
+  auto it = options.find(key);
+  if (it != options.end()) { *out = it->second; return true; }
+  const std::string env = "LAKESOUL_" + upper(key);
+  if (const char* v = getenv(env.c_str())) { *out = v; return true; }
+  return false;
+}
+std::string IOConfig::cdc_column() const {
+  std::string v;
+  return option("cdc_column", &v) ? v : std::string();
+}
+bool IOConfig::is_compacted() const {
+  std::string v;
+  return option("is_compacted", &v) && v == "true";
+}
+bool IOConfig::skip_merge_on_read() const {
+  std::string v;
+  return option("skip_merge_on_read", &v) && v == "true";
+}
+
+int ensure_device() {
+  static int dev = -2;
+  static std::string err;
+  if (dev == -2) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      dev = -1;
+      err = std::string("lakesoul_b200: no CUDA device available (") +
+            (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") +
+            "); the merge-on-read engine has no CPU fallback";
+    } else {
+      int want = 0;
+      if (const char* v = getenv("LAKESOUL_B200_DEVICE")) want = atoi(v);
+      else if (const char* v2 = getenv("LOCAL_RANK")) want = atoi(v2) % n;
+      dev = want < n ? want : 0;
+      // keep freed blocks in the stream-ordered pool: readers are created per bucket
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      }
+    }
+  }
+  if (dev < 0) fail(err);
+  cudaSetDevice(dev);
+  return dev;
+}
+
+// ---------------------------------------------------------------------------------------
+struct Reader::Impl {
+  IOConfig cfg;
+  ReaderStats stats;
+  std::shared_ptr<arrow::Schema> out_schema;
+  std::unique_ptr<DeviceScan> scan;
+  int64_t next_batch = 0, n_batches = 0;
+  bool started = false;
+
+  // count-only reads (empty projection, nothing to merge)
+  bool count_only = false;
+  int64_t count_rows_left = 0;
+
+  struct OutField {
+    enum Kind { kPhysical, kDefault, kNull } kind = kNull;
+    int phys = -1;
+    std::shared_ptr<arrow::Array> constant;  // batch_size rows, sliced for the last batch
+    std::shared_ptr<arrow::DataType> type;
+  };
+  std::vector<OutField> out_fields;
+};
+
+Reader::Reader(IOConfig cfg) : impl_(new Impl()) {
+  if (cfg.files.empty()) fail("LakeSoulReader has the wrong number of files");  // reader.rs:108-110
+  impl_->cfg = std::move(cfg);
+}
+Reader::~Reader() = default;
+const ReaderStats& Reader::stats() const { return impl_->stats; }
+const IOConfig& Reader::config() const { return impl_->cfg; }
+std::shared_ptr<arrow::Schema> Reader::schema() const { return impl_->out_schema; }
+
+void Reader::Start() {
+  Impl& I = *impl_;
+  if (I.started) return;
+  const IOConfig& cfg = I.cfg;
+  if (cfg.filter_protos > 0)
+    fail("substrait filters (add_filter_proto) are not supported by the GPU reader; "
+         "refusing to read without applying a pushed filter");
+  ensure_device();
+
+  // ---- open files, read footers (session.rs:546-593) -----------------------------------------
+  const double t_dec0 = now_ms();
+  std::vector<FileInfo> files;
+  for (const auto& raw : cfg.files) {
+    const std::string path = strip_scheme(raw);
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0) fail("Object at location " + path + " not found");
+    if (st.st_size < 8) {  // session.rs:423-434
+      fprintf(stderr, "[lakesoul_b200] File %s, size %lld, is invalid\n", path.c_str(), (long long)st.st_size);
+      continue;
+    }
+    FileInfo fi;
+    fi.path = path;
+    auto in = arrow::io::ReadableFile::Open(path);
+    if (!in.ok()) fail(in.status().ToString());
+    auto rd = parquet::arrow::OpenFile(*in, arrow::default_memory_pool());
+    if (!rd.ok()) fail(rd.status().ToString());
+    fi.reader = std::move(*rd);
+    fi.reader->set_use_threads(false);
+    std::shared_ptr<arrow::Schema> fs;
+    auto st2 = fi.reader->GetSchema(&fs);
+    if (!st2.ok()) fail(st2.ToString());
+    std::vector<std::shared_ptr<arrow::Field>> kept;
+    for (const auto& f : fs->fields())
+      if (!cfg.partition_schema->GetFieldByName(f->name())) kept.push_back(f);
+    fi.schema = arrow::schema(kept);
+    fi.rows = fi.reader->parquet_reader()->metadata()->num_rows();
+    files.push_back(std::move(fi));
+  }
+
+  // ---- table schema = target (uniformed) + file-only fields (session.rs:596-626) ---------------
+  std::vector<std::shared_ptr<arrow::Field>> target_fields;
+  if (!cfg.inferring_schema)
+    for (const auto& f : cfg.target_schema->fields()) target_fields.push_back(uniform_field(f));
+  std::vector<std::shared_ptr<arrow::Field>> table_fields = target_fields;
+  auto in_fields = [](const std::vector<std::shared_ptr<arrow::Field>>& v, const std::string& n) {
+    for (const auto& f : v) if (f->name() == n) return true;
+    return false;
+  };
+  for (const auto& fi : files)
+    for (const auto& f : fi.schema->fields())
+      if (!in_fields(table_fields, f->name())) table_fields.push_back(f);
+  auto table_schema = arrow::schema(table_fields);
+  // requested columns: the target schema, or everything when inferring
+  std::vector<std::shared_ptr<arrow::Field>> requested = cfg.inferring_schema ? table_fields : target_fields;
+
+  // ---- filters (config/mod.rs:702-731) -------------------------------------------------------
+  std::vector<std::shared_ptr<FilterExpr>> fexprs;
+  for (const auto& s : cfg.filter_strs) fexprs.push_back(parse_filter(s, *table_schema));
+  std::shared_ptr<FilterExpr> filter = conjunction(fexprs);
+  std::set<std::string> fcols;
+  if (filter) filter_columns(*filter, &fcols);
+
+  // ---- merged schema: requested + filter + pk + cdc columns, table order (file_format.rs:254-265)
+  const std::string cdc = cfg.cdc_column();
+  auto is_pk = [&](const std::string& n) {
+    for (const auto& p : cfg.primary_keys) if (p == n) return true;
+    return false;
+  };
+  std::vector<std::shared_ptr<arrow::Field>> merged_fields;
+  for (const auto& f : table_fields) {
+    const std::string& n = f->name();
+    if (in_fields(requested, n) || fcols.count(n) || is_pk(n) || (!cdc.empty() && n == cdc))
+      merged_fields.push_back(f);
+  }
+  auto in_any_file = [&](const std::string& n) {
+    for (const auto& fi : files) if (fi.schema->GetFieldByName(n)) return true;
+    return false;
+  };
+
+  // ---- physical schema: merged minus default-valued and never-present columns ---------------
+  std::vector<std::shared_ptr<arrow::Field>> phys_fields;
+  for (const auto& f : merged_fields) {
+    if (cfg.default_column_value.count(f->name())) continue;  // merge/mod.rs:314-327
+    if (!in_any_file(f->name())) continue;                      // stays null
+    phys_fields.push_back(f);
+  }
+  auto physical_schema = arrow::schema(phys_fields);
+
+  // ---- output fields + nullability (merge/mod.rs:75-97) --------------------------------------
+  std::vector<std::shared_ptr<arrow::Field>> out_f;
+  for (const auto& f : requested) {
+    Impl::OutField of;
+    of.type = f->type();
+    bool nullable = f->nullable();
+    for (const auto& fi : files) {
+      auto ff = fi.schema->GetFieldByName(f->name());
+      nullable = nullable || !ff || ff->nullable();
+    }
+    auto dv = cfg.default_column_value.find(f->name());
+    const int pi = physical_schema->GetFieldIndex(f->name());
+    if (dv != cfg.default_column_value.end()) {
+      of.kind = Impl::OutField::kDefault;
+      of.constant = make_default_array(f->type(), dv->second, (int64_t)cfg.batch_size);
+    } else if (pi >= 0) {
+      of.kind = Impl::OutField::kPhysical;
+      of.phys = pi;
+    } else {
+      of.kind = Impl::OutField::kNull;
+      of.constant = arrow::MakeArrayOfNull(f->type(), (int64_t)cfg.batch_size).ValueOrDie();
+    }
+    I.out_fields.push_back(of);
+    out_f.push_back(f->WithNullable(nullable));
+  }
+  I.out_schema = arrow::schema(out_f);
+
+  // ---- merge decision (merge/mod.rs:297-304) --------------------------------------------------
+  bool merge_on_read;
+  if (cfg.skip_merge_on_read() || cfg.primary_keys.empty()) merge_on_read = false;
+  else merge_on_read = !(cfg.files.size() == 1 && cfg.merge_operators.empty() && cfg.is_compacted());
+
+  if (files.empty()) {  // no valid file: empty stream with the requested schema
+    I.started = true;
+    return;
+  }
+
+  // ---- count-only read with nothing to merge or filter ----------------------------------------
+  if (phys_fields.empty()) {
+    I.count_only = true;
+    for (const auto& fi : files) I.count_rows_left += fi.rows;
+    I.stats.rows_in = I.stats.rows_out = I.count_rows_left;
+    I.stats.path = "count";
+    I.started = true;
+    return;
+  }
+
+  // ---- decode every file (host Parquet decode; device page decode replaces this step) --------
+  BucketFiles bucket;
+  for (auto& fi : files) {
+    const auto& manifest = fi.reader->manifest();
+    std::vector<int> leaf;
+    std::vector<std::shared_ptr<arrow::Field>> want;
+    for (const auto& pf : phys_fields) {
+      const int idx = fi.schema->GetFieldIndex(pf->name());
+      if (idx < 0) continue;
+      // index inside the full parquet schema (partition columns may precede)
+      int full_idx = -1;
+      for (size_t s = 0; s < manifest.schema_fields.size(); ++s)
+        if (manifest.schema_fields[s].field->name() == pf->name()) { full_idx = (int)s; break; }
+      if (full_idx < 0 || manifest.schema_fields[full_idx].column_index < 0)
+        fail("nested column '" + pf->name() + "' is not supported by the GPU reader");
+      leaf.push_back(manifest.schema_fields[full_idx].column_index);
+      want.push_back(pf);
+    }
+    std::shared_ptr<arrow::Table> table;
+    if (leaf.empty()) {
+      table = arrow::Table::MakeEmpty(arrow::schema({})).ValueOrDie();
+      fail("file " + fi.path + " carries none of the requested columns");
+    }
+    auto st = fi.reader->ReadTable(leaf, &table);
+    if (!st.ok()) fail(st.ToString());
+    // a2: reorder to target order + cast to the target type (helpers/transform.rs:107-354)
+    std::vector<std::shared_ptr<arrow::ChunkedArray>> cols;
+    std::vector<std::shared_ptr<arrow::Field>> flds;
+    for (const auto& pf : want) {
+      auto col = table->GetColumnByName(pf->name());
+      if (!col) fail("column '" + pf->name() + "' missing after decode of " + fi.path);
+      if (!col->type()->Equals(*pf->type())) {
+        if (col->type()->id() == arrow::Type::TIMESTAMP && pf->type()->id() == arrow::Type::TIMESTAMP &&
+            static_cast<const arrow::TimestampType&>(*col->type()).unit() ==
+                static_cast<const arrow::TimestampType&>(*pf->type()).unit()) {
+          auto v = col->View(pf->type());
+          if (!v.ok()) fail(v.status().ToString());
+          col = *v;
+        } else {
+          auto r = arrow::compute::Cast(arrow::Datum(col), pf->type(), arrow::compute::CastOptions::Safe());
+          if (!r.ok())
+            fail("Failed to cast type from " + col->type()->ToString() + " to " + pf->type()->ToString() +
+                 ": " + r.status().ToString());
+          col = r->chunked_array();
+        }
+      }
+      cols.push_back(col);
+      flds.push_back(pf);
+    }
+    bucket.files.push_back(arrow::Table::Make(arrow::schema(flds), cols, table->num_rows()));
+    fi.reader.reset();
+  }
+  I.stats.decode_ms = now_ms() - t_dec0;
+
+  ScanSpec spec;
+  spec.physical_schema = physical_schema;
+  spec.primary_keys = cfg.primary_keys;
+  spec.merge = merge_on_read;
+  spec.batch_size = (int)cfg.batch_size;
+  spec.filter = filter;
+  for (const auto& f : phys_fields) {
+    auto it = cfg.merge_operators.find(f->name());
+    spec.ops.push_back(it == cfg.merge_operators.end() ? MergeOp::UseLast : merge_op_from_name(it->second));
+  }
+  std::vector<BucketFiles> buckets;
+  buckets.push_back(std::move(bucket));
+  I.scan.reset(new DeviceScan(std::move(spec), std::move(buckets)));
+  I.scan->Run();
+  I.n_batches = I.scan->num_batches(0);
+  const ScanCounters& c = I.scan->counters();
+  I.stats.rows_in = c.rows_in;
+  I.stats.rows_out = c.rows_out;
+  I.stats.h2d_bytes = c.h2d_bytes;
+  I.stats.d2h_bytes = c.d2h_bytes;
+  I.stats.kernel_launches = c.kernel_launches;
+  I.stats.upload_ms = c.upload_ms;
+  I.stats.merge_ms = c.merge_ms;
+  I.stats.gather_ms = c.gather_ms;
+  I.stats.download_ms = c.download_ms;
+  I.stats.path = c.path;
+  I.started = true;
+}
+
+std::shared_ptr<arrow::RecordBatch> Reader::Next() {
+  Impl& I = *impl_;
+  if (!I.started) fail("reader not started");
+  const int64_t bs = (int64_t)I.cfg.batch_size;
+  int64_t rows = 0;
+  std::shared_ptr<arrow::RecordBatch> phys;
+  if (I.count_only) {
+    if (I.count_rows_left <= 0) return nullptr;
+    rows = std::min(bs, I.count_rows_left);
+    I.count_rows_left -= rows;
+  } else {
+    if (!I.scan || I.next_batch >= I.n_batches) return nullptr;
+    phys = I.scan->Batch(0, I.next_batch++);
+    rows = phys->num_rows();
+  }
+  std::vector<std::shared_ptr<arrow::Array>> arrays;
+  for (const auto& of : I.out_fields) {
+    if (of.kind == Impl::OutField::kPhysical) arrays.push_back(phys->column(of.phys));
+    else arrays.push_back(rows == of.constant->length() ? of.constant : of.constant->Slice(0, rows));
+  }
+  return arrow::RecordBatch::Make(I.out_schema, rows, std::move(arrays));
+}
+
+}  // namespace lsb

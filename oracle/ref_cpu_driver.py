@@ -1,0 +1,36 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Driver of the CPU baseline (TEST/BENCH INFRASTRUCTURE ONLY -- never imported by lakesoul_b200/).
+
+Runs the reference-structured CPU reader over a list of buckets, one reader per host thread (the
+reference's deployment shape: one merge thread per reader, rust/lakesoul-io-c/src/lib.rs:1385-1391).
+Uses oracle/_build/ref_cpu (C++ port: Arrow C++ Parquet decode + loser-tree merge + interleave) when
+it has been built, else the vectorised pyarrow oracle."""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_CPU = os.path.join(HERE, "_build", "ref_cpu")
+
+
+def run(paths, schema, primary_keys, batch_size=8192, threads=None):
+    threads = threads or (os.cpu_count() or 1)
+    if os.path.exists(REF_CPU):
+        spec = {"buckets": paths, "primary_keys": list(primary_keys), "batch_size": batch_size, "threads": threads,
+                "columns": schema.names}
+        t0 = time.perf_counter()
+        out = subprocess.run([REF_CPU], input=json.dumps(spec), capture_output=True, text=True, check=True)
+        res = json.loads(out.stdout.strip().splitlines()[-1])
+        res.setdefault("seconds", time.perf_counter() - t0)
+        res.update(kind="port", impl="C++ port of rust/lakesoul-io SortedStreamMerger/UseLastRangeCombiner (oracle/ref_cpu.cc)")
+        return res
+    import mor_oracle as mo
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        rows = list(ex.map(lambda fs: mo.read_bucket(fs, schema, primary_keys).num_rows, paths))
+    return {"seconds": time.perf_counter() - t0, "threads": threads, "rows_out": sum(rows), "kind": "port",
+            "impl": "vectorised pyarrow restatement (oracle/mor_oracle.py)"}

@@ -1,0 +1,64 @@
+# SPDX-License-Identifier: Apache-2.0
+import json
+import os
+import sys
+
+import pyarrow as pa
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+_TYPES = {"int32": pa.int32(), "int64": pa.int64(), "float64": pa.float64(), "utf8": pa.string()}
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+def golden_cases():
+    with open(os.path.join(ROOT, "tests", "golden", "reference_unit_goldens.json")) as f:
+        return json.load(f)["cases"]
+
+
+def golden_schema(case) -> pa.Schema:
+    return pa.schema([pa.field(n, _TYPES[t], nullable) for n, t, nullable in case["schema"]])
+
+
+def golden_streams(case):
+    """[[RecordBatch, ...] per stream] with the stream's own column subset (partial merge cases)."""
+    schema = golden_schema(case)
+    streams = []
+    for s in case["streams"]:
+        batches = []
+        for b in s:
+            fields = [schema.field(n) for n in b.keys()]
+            batches.append(pa.RecordBatch.from_arrays([pa.array(v, type=f.type) for v, f in zip(b.values(), fields)],
+                                                      schema=pa.schema(fields)))
+        streams.append(batches)
+    return streams
+
+
+def golden_expected(case) -> pa.Table:
+    schema = golden_schema(case)
+    return pa.table({n: pa.array(case["expected"][n], type=schema.field(n).type) for n in schema.names}).cast(schema)
+
+
+def assert_tables_equal(got: pa.Table, want: pa.Table, what=""):
+    assert got.schema.names == want.schema.names, f"{what}: columns {got.schema.names} != {want.schema.names}"
+    assert got.num_rows == want.num_rows, f"{what}: rows {got.num_rows} != {want.num_rows}"
+    for name in want.schema.names:
+        g = got.column(name).combine_chunks()
+        w = want.column(name).combine_chunks().cast(g.type)
+        if not g.equals(w):
+            import pyarrow.compute as pc
+            bad = [i for i in range(len(g)) if g[i].as_py() != w[i].as_py()][:5]
+            raise AssertionError(f"{what}: column {name} differs at rows {bad}: "
+                                 f"got {[g[i].as_py() for i in bad]} want {[w[i].as_py() for i in bad]}")
+
+
+@pytest.fixture(scope="session")
+def lib():
+    from lakesoul_b200 import load_library
+    return load_library()

@@ -1,0 +1,72 @@
+# SPDX-License-Identifier: Apache-2.0
+"""The drop-in library loads and exports every symbol include/*.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = set()
+    for m in re.finditer(r"\b([a-z_0-9]+)\s*\(", text):
+        n = m.group(1)
+        if n.startswith(("lakesoul_", "lsb_", "new_", "create_", "check_", "start_", "next_", "free_", "write_",
+                         "export_", "flush_", "abort_", "apply_", "tokio_", "rust_logger")):
+            names.add(n)
+    return names
+
+
+def test_library_exports_every_declared_symbol(lib):
+    declared = _declared("lakesoul_c_bindings.h") | _declared("lakesoul_b200_ext.h")
+    assert len(declared) >= 60
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, f"symbols declared in include/*.h but not exported: {missing}"
+
+
+def test_python_binding_table_matches_header():
+    from lakesoul_b200 import _lib
+    declared = _declared("lakesoul_c_bindings.h")
+    assert set(_lib.REFERENCE_SYMBOLS) == declared
+
+
+def test_struct_layouts_match_reference(lib):
+    from lakesoul_b200._lib import CResult, CStatus
+    # CResult { ptr, err } (lib.rs:40-44); CStatus { err, status } (lib.rs:77-81)
+    assert ctypes.sizeof(CResult) == 16 and CResult.ptr.offset == 0 and CResult.err.offset == 8
+    assert ctypes.sizeof(CStatus) == 16 and CStatus.err.offset == 0 and CStatus.status.offset == 8
+
+
+def test_builder_lifecycle_without_gpu(lib):
+    b = lib.new_lakesoul_io_config_builder()
+    b = lib.lakesoul_config_builder_add_single_file(b, b"/nonexistent/part-0000.parquet")
+    b = lib.lakesoul_config_builder_set_batch_size(b, 128)
+    b = lib.lakesoul_config_builder_set_option(b, b"is_compacted", b"true")
+    cfg = lib.create_lakesoul_io_config_from_builder(b)
+    rt = lib.create_tokio_runtime_from_builder(lib.new_tokio_runtime_builder())
+    reader = lib.create_lakesoul_reader_from_config(cfg, rt)
+    assert lib.check_reader_created(reader) is None
+    st = lib.start_reader(reader)  # no GPU here or missing file: must be an error, never a silent success
+    assert st.contents.status == -1 and st.contents.err
+    lib.free_c_status(st)
+    lib.free_lakesoul_reader(reader)
+
+
+def test_empty_file_list_is_a_constructor_error(lib):
+    # reader.rs:108-110
+    cfg = lib.create_lakesoul_io_config_from_builder(lib.new_lakesoul_io_config_builder())
+    reader = lib.create_lakesoul_reader_from_config_with_global_runtime(cfg)
+    assert lib.check_reader_created(reader) == b"LakeSoulReader has the wrong number of files"
+    lib.free_lakesoul_reader(reader)
+
+
+def test_writer_entry_points_report_errors(lib):
+    cfg = lib.create_lakesoul_io_config_from_builder(lib.new_lakesoul_io_config_builder())
+    rt = lib.create_tokio_runtime_from_builder(lib.new_tokio_runtime_builder())
+    w = lib.create_lakesoul_writer_from_config(cfg, rt)
+    st = lib.check_writer_created(w)
+    assert st.contents.status == -1
+    lib.free_c_status(st)
+    lib.free_lakesoul_writer(w)

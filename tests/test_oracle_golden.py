@@ -1,0 +1,103 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Pins the CPU oracle against the reference's own golden vectors."""
+import numpy as np
+import pyarrow as pa
+import pytest
+
+import mor_oracle as mo
+from conftest import assert_tables_equal, golden_cases, golden_expected, golden_schema, golden_streams
+
+CASES = golden_cases()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_streaming_oracle_matches_reference_golden(case):
+    schema = golden_schema(case)
+    out = mo.streaming_merge(golden_streams(case), case["primary_keys"], schema, case["batch_size"],
+                             case["merge_ops"] or None)
+    for b in out:  # never an empty batch, never more than batch_size rows (SURVEY 8b contract 2/3)
+        assert 0 < b.num_rows <= case["batch_size"]
+    assert all(b.num_rows == case["batch_size"] for b in out[:-1])
+    got = pa.Table.from_batches(out, schema=schema) if out else schema.empty_table()
+    assert_tables_equal(got, golden_expected(case), case["name"])
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_vectorised_oracle_matches_reference_golden(case):
+    schema = golden_schema(case)
+    files = []
+    for s in golden_streams(case):
+        files.append(pa.Table.from_batches(s) if s else schema.empty_table())
+    ops = dict(zip(schema.names, case["merge_ops"])) if case["merge_ops"] else None
+    got = mo.merge_tables(files, case["primary_keys"], schema, ops)
+    assert_tables_equal(got, golden_expected(case), case["name"])
+
+
+def _random_streams(rng, k, schema, pk, max_rows, key_space, col_sets=None, batch_rows=7):
+    streams = []
+    for j in range(k):
+        n = int(rng.integers(0, max_rows + 1))
+        keys = np.sort(rng.integers(0, key_space, size=n))
+        names = [pk] + [c for c in schema.names if c != pk and (col_sets is None or c in col_sets[j])]
+        cols = {}
+        for name in names:
+            f = schema.field(name)
+            if name == pk:
+                cols[name] = pa.array(keys, type=f.type)
+            elif pa.types.is_string(f.type):
+                v = [None if rng.random() < 0.2 else "s%d" % rng.integers(0, 50) for _ in range(n)]
+                cols[name] = pa.array(v, type=f.type)
+            elif pa.types.is_floating(f.type):
+                v = rng.standard_normal(n)
+                cols[name] = pa.array(v, type=f.type, mask=rng.random(n) < 0.2)
+            else:
+                cols[name] = pa.array(rng.integers(-1000, 1000, size=n), type=f.type, mask=rng.random(n) < 0.2)
+        t = pa.table(cols)
+        cuts = sorted(set(rng.integers(0, n + 1, size=3).tolist() + [0, n]))
+        batches = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            batches.extend(t.slice(a, b - a).to_batches() or [pa.RecordBatch.from_pylist([], schema=t.schema)])
+        if not batches:
+            batches = [pa.RecordBatch.from_pylist([], schema=t.schema)]
+        streams.append(batches)
+    return streams
+
+
+SCHEMA = pa.schema([pa.field("id", pa.int32(), False), pa.field("a", pa.int32(), True), pa.field("b", pa.float64(), True),
+                    pa.field("c", pa.string(), True)])
+
+
+@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("mode", ["full", "partial", "ops"])
+def test_streaming_and_vectorised_oracles_agree(seed, mode):
+    rng = np.random.default_rng(1000 + seed)
+    k = int(rng.integers(1, 6))
+    col_sets = None
+    ops = None
+    if mode == "partial":
+        col_sets = [set(rng.choice(["a", "b", "c"], size=int(rng.integers(1, 4)), replace=False).tolist()) for _ in range(k)]
+        col_sets[0] = {"a"}  # make sure at least one stream is narrower than the schema
+    if mode == "ops":
+        ops = ["UseLast", str(rng.choice(["SumAll", "SumLast", "UseLast"])), str(rng.choice(["UseLastNotNull", "SumAll", "SumLast"])),
+               str(rng.choice(["UseLast", "UseLastNotNull", "JoinedLastByComma", "JoinedAllBySemicolon"]))]
+    streams = _random_streams(rng, k, SCHEMA, "id", 40, 25, col_sets)
+    out = mo.streaming_merge(streams, ["id"], SCHEMA, int(rng.integers(1, 9)), ops)
+    got = pa.Table.from_batches(out, schema=SCHEMA) if out else SCHEMA.empty_table()
+    files = [pa.Table.from_batches(s) for s in streams]
+    # SumLast/JoinedLast depend on decode batch boundaries only through runs that end a batch; the
+    # vectorised oracle treats a file as one batch, so give it whole-file batches for those modes
+    if ops and any(o in ("SumLast", "JoinedLastByComma") for o in ops):
+        streams1 = [[pa.Table.from_batches(s).combine_chunks().to_batches()[0]] if pa.Table.from_batches(s).num_rows else s[:1]
+                    for s in streams]
+        out = mo.streaming_merge(streams1, ["id"], SCHEMA, 8, ops)
+        got = pa.Table.from_batches(out, schema=SCHEMA) if out else SCHEMA.empty_table()
+    want = mo.merge_tables(files, ["id"], SCHEMA, dict(zip(SCHEMA.names, ops)) if ops else None)
+    assert_tables_equal(got, want, f"{mode}/{seed}")
+
+
+def test_hash_known_answers():
+    """G11: rust/lakesoul-datafusion/src/tests/hash_tests.rs:48-90."""
+    from lakesoul_b200 import hashing
+    assert hashing.hash_int32(np.array([1, 2, 3, 4]), 42).view(np.int32).tolist() == [-559580957, 1765031574, -1823081949, -397064898]
+    assert hashing.hash_int64(np.array([1, 2, 3, 4]), 42).view(np.int32).tolist() == [-1712319331, -797927272, 519220707, 1344313940]
+    assert hashing.hash_int32(np.array([49, 1065353216]), 42).view(np.int32).tolist() == [766678906, -466301895]
