@@ -86,9 +86,9 @@ class ScanPlan:
         class _Holder:
             pass
         h = _Holder()
-        h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<u4", "data": (ptr, True), "version": 2}
+        h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
         t = torch.as_tensor(h, device="cuda")
-        return t.to(torch.int64)
+        return t.to(torch.int64) & 0xFFFFFFFF
 
     @property
     def valid_stride(self) -> int:

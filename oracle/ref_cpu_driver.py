@@ -20,10 +20,10 @@ REF_CPU = os.path.join(HERE, "_build", "ref_cpu")
 def run(paths, schema, primary_keys, batch_size=8192, threads=None):
     threads = threads or (os.cpu_count() or 1)
     if os.path.exists(REF_CPU):
-        spec = {"buckets": paths, "primary_keys": list(primary_keys), "batch_size": batch_size, "threads": threads,
-                "columns": schema.names}
+        spec = (f"{threads} {batch_size} 0\n" + "\t".join(primary_keys) + "\n" + "\t".join(schema.names) + "\n" +
+                "\n".join("\t".join(p) for p in paths) + "\n")
         t0 = time.perf_counter()
-        out = subprocess.run([REF_CPU], input=json.dumps(spec), capture_output=True, text=True, check=True)
+        out = subprocess.run([REF_CPU], input=spec, capture_output=True, text=True, check=True)
         res = json.loads(out.stdout.strip().splitlines()[-1])
         res.setdefault("seconds", time.perf_counter() - t0)
         res.update(kind="port", impl="C++ port of rust/lakesoul-io SortedStreamMerger/UseLastRangeCombiner (oracle/ref_cpu.cc)")
