@@ -373,12 +373,12 @@ def merge_tables(files: Sequence[pa.Table], primary_keys: Sequence[str], schema:
                         bounds[1:] |= (rows_in_file[1:] // decode_batch_rows) != (rows_in_file[:-1] // decode_batch_rows)
                     bstarts = np.flatnonzero(bounds)
                     contrib = np.where(carry, vals, np_t(0))
-                    part = np.add.reduceat(contrib, bstarts) if np_t not in (np.float32, np.float64) else \
+                    part = np.add.reduceat(contrib, bstarts, dtype=np_t) if np_t not in (np.float32, np.float64) else \
                         np.array([_seq_sum(contrib[a:b], np_t) for a, b in zip(bstarts, np.append(bstarts[1:], n))], dtype=np_t)
                     part_gid = gid[bstarts]
                     gstarts = np.flatnonzero(np.append(True, part_gid[1:] != part_gid[:-1]))
                     total = np.array([_seq_sum(part[a:b], np_t) for a, b in zip(gstarts, np.append(gstarts[1:], len(part)))], dtype=np_t) \
-                        if np_t in (np.float32, np.float64) else np.add.reduceat(part, gstarts)
+                        if np_t in (np.float32, np.float64) else np.add.reduceat(part, gstarts, dtype=np_t)
                     anynull = np.maximum.reduceat((carry & ~valid).astype(np.int8), starts) > 0
                 else:
                     lastrow = sub_ends
@@ -387,7 +387,7 @@ def merge_tables(files: Sequence[pa.Table], primary_keys: Sequence[str], schema:
                     sg = gid[lastrow]
                     gstarts = np.flatnonzero(np.append(True, sg[1:] != sg[:-1]))
                     total = np.array([_seq_sum(contrib[a:b], np_t) for a, b in zip(gstarts, np.append(gstarts[1:], len(contrib)))], dtype=np_t) \
-                        if np_t in (np.float32, np.float64) else np.add.reduceat(contrib, gstarts)
+                        if np_t in (np.float32, np.float64) else np.add.reduceat(contrib, gstarts, dtype=np_t)
                     anynull = np.maximum.reduceat((c2 & ~valid[lastrow]).astype(np.int8), gstarts) > 0
             none = np.maximum.reduceat(carry.astype(np.int8), starts) == 0
             # a key with exactly one carrying row copies the cell (Extend)
