@@ -201,10 +201,13 @@ class Shard:
         dsts = [o["l_orderkey"], o["l_linenumber"]] + [o[n] for n, _ in FIXED_COLS]
         widths = [8, 4] + [w for _, w in FIXED_COLS]
         plan.gather_fixed(srcs, dsts, widths)
+        vcols = []
         for name, _, _ in STRING_COLS:
             offs, data, _ = self.strings[name]
             do, dd, db = o[name]
-            plan.gather_var(offs, data, self.zero_base, do, dd, db)
+            vcols.append(dict(src_offsets=offs, src_data=data, src_data_base=self.zero_base, dst_offsets=do, dst_data=dd,
+                              batch_data_start=db))
+        plan.gather_var_multi(vcols)
         if ev:
             ev[2].record()
             torch.cuda.synchronize()
@@ -361,7 +364,7 @@ def main():
         n, u, st = shard.step(rec)
         rows_in += n
         rows_out += u
-        launches += st["launches"] + 1 + 6 * len(STRING_COLS)
+        launches += st["launches"] + 1 + 3
     ev1.record()
     barrier()
     wall = time.perf_counter() - t_wall0

@@ -65,6 +65,12 @@ int32_t lsb_plan_gather_var(LsbPlan *plan, const void *src_offsets, const void *
                             const void *src_data_base, const void *src_valid, void *dst_offsets,
                             void *dst_data, void *dst_valid, void *batch_data_start, void *cuda_stream);
 
+/* n variable-width columns in 3 launches; every argument is an array of n device pointers */
+int32_t lsb_plan_gather_var_multi(LsbPlan *plan, int32_t ncols, const void *const *src_offsets,
+                                  const void *const *src_data, const void *const *src_data_base,
+                                  const void *const *src_valid, void *const *dst_offsets, void *const *dst_data,
+                                  void *const *dst_valid, void *const *batch_data_start, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,6 +107,7 @@ EXT_SYMBOLS = {
     "lsb_plan_stats": (c_int32, [c_void_p, c_void_p]),
     "lsb_plan_gather_fixed": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lsb_plan_gather_var": (c_int32, [c_void_p] * 10),
+    "lsb_plan_gather_var_multi": (c_int32, [c_void_p, c_int32] + [c_void_p] * 9),
 }
 
 

@@ -478,4 +478,26 @@ int32_t lsb_plan_gather_var(LsbPlan* plan, const void* src_offsets, const void* 
   });
 }
 
+int32_t lsb_plan_gather_var_multi(LsbPlan* plan, int32_t ncols, const void* const* src_offsets,
+                                  const void* const* src_data, const void* const* src_data_base,
+                                  const void* const* src_valid, void* const* dst_offsets, void* const* dst_data,
+                                  void* const* dst_valid, void* const* batch_data_start, void* stream) {
+  return guard([&] {
+    std::vector<lsb::VarCol> cols((size_t)ncols);
+    for (int i = 0; i < ncols; ++i) {
+      lsb::VarCol& vc = cols[i];
+      vc.src_offsets = static_cast<const int32_t*>(src_offsets[i]);
+      vc.src_data = static_cast<const uint8_t*>(src_data[i]);
+      vc.src_data_base = static_cast<const int64_t*>(src_data_base[i]);
+      vc.src_valid = static_cast<const uint8_t*>(src_valid ? src_valid[i] : nullptr);
+      vc.win = nullptr;
+      vc.dst_offsets = static_cast<int32_t*>(dst_offsets[i]);
+      vc.dst_data = static_cast<uint8_t*>(dst_data[i]);
+      vc.dst_valid = static_cast<uint8_t*>(dst_valid ? dst_valid[i] : nullptr);
+      vc.batch_data_start = static_cast<int64_t*>(batch_data_start[i]);
+    }
+    lsb::gather_var_multi(plan->p, cols.data(), ncols, static_cast<cudaStream_t>(stream));
+  });
+}
+
 }  // extern "C"

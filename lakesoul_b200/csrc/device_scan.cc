@@ -477,6 +477,7 @@ void DeviceScan::Impl::merge_and_gather() {
   struct DevOut { void *values = nullptr, *valid = nullptr, *offsets = nullptr, *data = nullptr, *bstart = nullptr; };
   std::vector<DevOut> dout(C);
   std::vector<FixedCol> fixed;
+  std::vector<VarCol> vars;
   for (int c = 0; c < C; ++c) {
     DevColumn& dc = cols[c];
     OutColumn& oc = outs[c];
@@ -507,8 +508,7 @@ void DeviceScan::Impl::merge_and_gather() {
       vc.dst_data = static_cast<uint8_t*>(dout[c].data);
       vc.dst_valid = static_cast<uint8_t*>(dout[c].valid);
       vc.batch_data_start = static_cast<int64_t*>(dout[c].bstart);
-      gather_var(plan, vc, stream);
-      ctr.kernel_launches += 6;
+      vars.push_back(vc);
     } else {
       const int w = dc.kind.width;
       dout[c].values = dalloc(w == 0 ? (size_t)(TB * vstride) : (size_t)U * w);
@@ -525,6 +525,10 @@ void DeviceScan::Impl::merge_and_gather() {
   if (!fixed.empty() && U > 0) {
     gather_fixed(plan, fixed.data(), (int)fixed.size(), stream);
     ctr.kernel_launches += 1;
+  }
+  if (!vars.empty() && U > 0) {
+    gather_var_multi(plan, vars.data(), (int)vars.size(), stream);
+    ctr.kernel_launches += 3 * (((int)vars.size() + 15) / 16);
   }
 
   // ---- download ---------------------------------------------------------------------------

@@ -330,16 +330,13 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(PlanDev P, PkDesc pk
     return;
   }
 
-  // ---- load keys: one warp per segment, coalesced at level 0 --------------------------
-  for (int j = warp; j < k; j += kTileThreads / 32) {
-    const int s0 = seg_start[j], len = seg_start[j + 1] - s0;
-    const int64_t fb = frb[j];
-    const int64_t p0 = seg_lo[j];
-    for (int x = lane; x < len; x += 32) {
-      const int64_t row = fb + (((p0 + x + 1) << sh) - 1);
-      K[s0 + x] = KeyLoader<KeyT>::load(pk, row);
-      idxA[s0 + x] = (uint16_t)(s0 + x);
-    }
+  // ---- load keys: elements strided over the whole CTA (independent loads in flight per thread;
+  // consecutive elements of a segment are consecutive rows, so warps stay coalesced at level 0)
+  for (int e = tid; e < L; e += kTileThreads) {
+    const int j = upper_idx(seg_start, k, e);
+    const int64_t row = frb[j] + ((((int64_t)seg_lo[j] + (e - seg_start[j]) + 1) << sh) - 1);
+    K[e] = KeyLoader<KeyT>::load(pk, row);
+    idxA[e] = (uint16_t)e;
   }
   if (level == 0 && warp == (kTileThreads / 32 - 1)) {
     // peek the first key after this tile (min over the k run heads)
@@ -368,51 +365,63 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(PlanDev P, PkDesc pk
   }
   __syncthreads();
 
-  // ---- pairwise rank-merge tree ------------------------------------------------------
+  // ---- pairwise merge tree, merge-path co-ranking ----------------------------------------
+  // Each pass merges adjacent run pairs (stable: the left run = lower files wins ties). A thread
+  // owns E consecutive OUTPUT positions: one diagonal binary search (co-rank) per pair it touches,
+  // then a sequential two-pointer merge with both heads cached in registers.
   uint16_t* in = idxA;
   uint16_t* out = idxB;
   int nr = k;
+  const int EM = (L + kTileThreads - 1) / kTileThreads;
+  const int mo0 = min(tid * EM, L), mo1 = min(mo0 + EM, L);
   for (int pass = 0; nr > 1; ++pass) {
     // run r of this pass spans original segments [r<<pass, (r+1)<<pass)
     auto rb = [&](int r) -> int {
       int s = r << pass;
       return seg_start[s < k ? s : k];
     };
-    for (int q = tid; q < L; q += kTileThreads) {
-      // find run containing q: largest r with rb(r) <= q
+    int q = mo0;
+    while (q < mo1) {
+      // run containing q: largest r with rb(r) <= q
       int lo = 0, hi = nr;
       while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
         if (rb(mid) <= q) lo = mid; else hi = mid;
       }
-      const int r = lo;
-      const int base = r & ~1;
-      const uint16_t e = in[q];
-      if (base + 1 >= nr) {  // unpaired last run
-        out[q] = e;
-        continue;
+      const int base = lo & ~1;
+      const int a0 = rb(base);
+      if (base + 1 >= nr) {  // unpaired last run: copy through
+        for (; q < mo1; ++q) out[q] = in[q];
+        break;
       }
-      const int a0 = rb(base), mid0 = rb(base + 1), end0 = rb(base + 2);
-      const KeyT key = K[e];
-      int dst;
-      if (r == base) {
-        // left run: count right elements strictly smaller
-        int l = mid0, h = end0;
-        while (l < h) {
-          int m2 = (l + h) >> 1;
-          if (key_lt(K[in[m2]], key)) l = m2 + 1; else h = m2;
-        }
-        dst = q + (l - mid0);
-      } else {
-        // right run: count left elements <= key
-        int l = a0, h = mid0;
-        while (l < h) {
-          int m2 = (l + h) >> 1;
-          if (key_le(K[in[m2]], key)) l = m2 + 1; else h = m2;
-        }
-        dst = a0 + (q - mid0) + (l - a0);
+      const int m0 = rb(base + 1), e0 = rb(base + 2);
+      const int stop = min(mo1, e0);
+      const int na = m0 - a0, nbb = e0 - m0;
+      const int d = q - a0;
+      int i = max(0, d - nbb), ihi = min(d, na);
+      while (i < ihi) {  // co-rank: number of left-run elements among the first d outputs
+        const int mid = (i + ihi) >> 1;
+        const KeyT ka = K[in[a0 + mid]];
+        const KeyT kb = K[in[m0 + d - 1 - mid]];
+        if (!key_lt(kb, ka)) i = mid + 1; else ihi = mid;
       }
-      out[dst] = e;
+      int j = d - i;
+      uint16_t ea = 0, eb = 0;
+      KeyT ka{}, kb{};
+      if (i < na) { ea = in[a0 + i]; ka = K[ea]; }
+      if (j < nbb) { eb = in[m0 + j]; kb = K[eb]; }
+      for (; q < stop; ++q) {
+        // predicated two-pointer step: no divergent branches, one index + one key load per output
+        const bool take_a = (j >= nbb) || (i < na && !key_lt(kb, ka));
+        out[q] = take_a ? ea : eb;
+        i += take_a ? 1 : 0;
+        j += take_a ? 0 : 1;
+        const int nxt = take_a ? (a0 + i) : (m0 + j);
+        const bool more = take_a ? (i < na) : (j < nbb);
+        const uint16_t en = in[more ? nxt : a0];
+        const KeyT kn = K[en];
+        if (take_a) { ea = en; ka = kn; } else { eb = en; kb = kn; }
+      }
     }
     __syncthreads();
     uint16_t* tmp = in; in = out; out = tmp;
@@ -636,101 +645,158 @@ __device__ __forceinline__ bool chunk_geometry(const GatherGeom& G, int64_t chun
   return r_begin < r_end;
 }
 
+constexpr int kRowsPerThread = kRowsPerChunk / kGatherThreads;  // 8
+
 __global__ void __launch_bounds__(kGatherThreads) gather_fixed_kernel(GatherGeom G,
-                                                                      const FixedCol* cols) {
-  const FixedCol col = cols[blockIdx.y];
+                                                                      const FixedCol* __restrict__ cols,
+                                                                      int ncols) {
   int b, r_begin, r_end, rows;
   int64_t gb, u0;
   if (!chunk_geometry(G, blockIdx.x, b, gb, u0, r_begin, r_end, rows)) return;
-  uint32_t* vwords =
-      col.dst_valid ? reinterpret_cast<uint32_t*>(col.dst_valid + gb * G.valid_stride) : nullptr;
-  const uint32_t* win = col.win ? col.win : G.win;
-  uint32_t* bwords =
-      col.width == 0 ? reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(col.dst) + gb * G.valid_stride)
-                     : nullptr;
-  for (int r = r_begin + threadIdx.x; r < r_end; r += kGatherThreads) {
-    const bool active = r < rows;
-    const int64_t u = u0 + r;
-    const uint32_t g = active ? win[u] : kNoRow;
-    const bool have = g != kNoRow;
+  // winners of this thread's rows (shared by every column unless a column brings its own list)
+  uint32_t g0[kRowsPerThread];
+#pragma unroll
+  for (int x = 0; x < kRowsPerThread; ++x) {
+    const int r = r_begin + threadIdx.x + x * kGatherThreads;
+    g0[x] = (r < rows) ? G.win[u0 + r] : kNoRow;
+  }
+  for (int c = 0; c < ncols; ++c) {
+    const FixedCol col = cols[c];
+    uint32_t g[kRowsPerThread];
+#pragma unroll
+    for (int x = 0; x < kRowsPerThread; ++x) {
+      const int r = r_begin + threadIdx.x + x * kGatherThreads;
+      g[x] = col.win ? ((r < rows) ? col.win[u0 + r] : kNoRow) : g0[x];
+    }
+    uint32_t* vwords =
+        col.dst_valid ? reinterpret_cast<uint32_t*>(col.dst_valid + gb * G.valid_stride) : nullptr;
     if (col.width == 0) {
-      bool v = false;
-      if (have) v = (reinterpret_cast<const uint8_t*>(col.src)[g >> 3] >> (g & 7)) & 1;
-      const uint32_t word = __ballot_sync(0xffffffffu, v);
-      if ((threadIdx.x & 31) == 0) bwords[r >> 5] = word;
-    } else if (active) {
+      uint32_t* bwords = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(col.dst) + gb * G.valid_stride);
+#pragma unroll
+      for (int x = 0; x < kRowsPerThread; ++x) {
+        const int r = r_begin + threadIdx.x + x * kGatherThreads;
+        if (r - (int)(threadIdx.x & 31) >= r_end) continue;  // warp-uniform
+        bool v = false;
+        if (g[x] != kNoRow) v = (reinterpret_cast<const uint8_t*>(col.src)[g[x] >> 3] >> (g[x] & 7)) & 1;
+        const uint32_t word = __ballot_sync(0xffffffffu, v);
+        if ((threadIdx.x & 31) == 0) bwords[r >> 5] = word;
+      }
+    } else {
+#define LSB_GATHER_CASE(T, ZERO)                                                             \
+  {                                                                                          \
+    T v[kRowsPerThread];                                                                     \
+    _Pragma("unroll") for (int x = 0; x < kRowsPerThread; ++x)                               \
+        v[x] = g[x] != kNoRow ? reinterpret_cast<const T*>(col.src)[g[x]] : ZERO;           \
+    _Pragma("unroll") for (int x = 0; x < kRowsPerThread; ++x) {                             \
+      const int r = r_begin + threadIdx.x + x * kGatherThreads;                              \
+      if (r < rows) reinterpret_cast<T*>(col.dst)[u0 + r] = v[x];                            \
+    }                                                                                        \
+  }
       switch (col.width) {
-        case 1: reinterpret_cast<uint8_t*>(col.dst)[u] = have ? reinterpret_cast<const uint8_t*>(col.src)[g] : 0; break;
-        case 2: reinterpret_cast<uint16_t*>(col.dst)[u] = have ? reinterpret_cast<const uint16_t*>(col.src)[g] : 0; break;
-        case 4: reinterpret_cast<uint32_t*>(col.dst)[u] = have ? reinterpret_cast<const uint32_t*>(col.src)[g] : 0; break;
-        case 8: reinterpret_cast<uint64_t*>(col.dst)[u] = have ? reinterpret_cast<const uint64_t*>(col.src)[g] : 0; break;
-        case 16: reinterpret_cast<uint4*>(col.dst)[u] = have ? reinterpret_cast<const uint4*>(col.src)[g] : make_uint4(0, 0, 0, 0); break;
+        case 1: LSB_GATHER_CASE(uint8_t, (uint8_t)0) break;
+        case 2: LSB_GATHER_CASE(uint16_t, (uint16_t)0) break;
+        case 4: LSB_GATHER_CASE(uint32_t, 0u) break;
+        case 8: LSB_GATHER_CASE(uint64_t, 0ull) break;
+        case 16: LSB_GATHER_CASE(uint4, make_uint4(0, 0, 0, 0)) break;
         default: {
           const uint4 z = make_uint4(0, 0, 0, 0);
-          reinterpret_cast<uint4*>(col.dst)[2 * u] = have ? reinterpret_cast<const uint4*>(col.src)[2 * (int64_t)g] : z;
-          reinterpret_cast<uint4*>(col.dst)[2 * u + 1] = have ? reinterpret_cast<const uint4*>(col.src)[2 * (int64_t)g + 1] : z;
+#pragma unroll
+          for (int x = 0; x < kRowsPerThread; ++x) {
+            const int r = r_begin + threadIdx.x + x * kGatherThreads;
+            if (r < rows) {
+              const bool have = g[x] != kNoRow;
+              reinterpret_cast<uint4*>(col.dst)[2 * (u0 + r)] = have ? reinterpret_cast<const uint4*>(col.src)[2 * (int64_t)g[x]] : z;
+              reinterpret_cast<uint4*>(col.dst)[2 * (u0 + r) + 1] = have ? reinterpret_cast<const uint4*>(col.src)[2 * (int64_t)g[x] + 1] : z;
+            }
+          }
         } break;
       }
+#undef LSB_GATHER_CASE
     }
     if (vwords) {
-      bool bit = have;
-      if (have && col.src_valid) bit = (col.src_valid[g >> 3] >> (g & 7)) & 1;
-      const uint32_t word = __ballot_sync(0xffffffffu, bit);
-      if ((threadIdx.x & 31) == 0) vwords[r >> 5] = word;
+#pragma unroll
+      for (int x = 0; x < kRowsPerThread; ++x) {
+        const int r = r_begin + threadIdx.x + x * kGatherThreads;
+        if (r - (int)(threadIdx.x & 31) >= r_end) continue;  // warp-uniform
+        bool bit = g[x] != kNoRow;
+        if (bit && col.src_valid) bit = (col.src_valid[g[x] >> 3] >> (g[x] & 7)) & 1;
+        const uint32_t word = __ballot_sync(0xffffffffu, bit);
+        if ((threadIdx.x & 31) == 0) vwords[r >> 5] = word;
+      }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// gather: variable width (Utf8 / Binary), two passes
+// gather: variable width (Utf8 / Binary): lengths -> chunk sums -> scan -> offsets + bytes
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGatherThreads) var_len_kernel(GatherGeom G, VarCol col,
-                                                                 int32_t* len_out) {
+__device__ __forceinline__ int var_row_len(const VarCol& col, uint32_t g, bool& valid) {
+  valid = g != kNoRow;
+  if (valid && col.src_valid) valid = (col.src_valid[g >> 3] >> (g & 7)) & 1;
+  return valid ? (col.src_offsets[(int64_t)g + 1] - col.src_offsets[g]) : 0;
+}
+
+// pass 1 (all variable-width columns in one launch): validity bitmaps + total string bytes of every
+// 2048-row chunk. chunk_sums is laid out column-major: [col][chunk] with a stride of (chunks + 1).
+constexpr int kMaxVarCols = 16;
+struct VarColSet {
+  int32_t n;
+  VarCol col[kMaxVarCols];
+};
+
+__global__ void __launch_bounds__(kGatherThreads) var_sum_kernel(GatherGeom G, const VarColSet* __restrict__ set,
+                                                                 int64_t* __restrict__ chunk_sums,
+                                                                 int64_t sums_stride) {
+  __shared__ int64_t ws[kGatherThreads / 32];
   int b, r_begin, r_end, rows;
   int64_t gb, u0;
-  if (!chunk_geometry(G, blockIdx.x, b, gb, u0, r_begin, r_end, rows)) return;
-  uint32_t* vwords =
-      col.dst_valid ? reinterpret_cast<uint32_t*>(col.dst_valid + gb * G.valid_stride) : nullptr;
-  for (int r = r_begin + threadIdx.x; r < r_end; r += kGatherThreads) {
-    const bool active = r < rows;
-    const int64_t u = u0 + r;
-    bool bit = active;
-    if (active) {
-      const uint32_t g = (col.win ? col.win : G.win)[u];
-      if (g == kNoRow) bit = false;
-      else if (col.src_valid) bit = (col.src_valid[g >> 3] >> (g & 7)) & 1;
-      len_out[u] = bit ? (col.src_offsets[(int64_t)g + 1] - col.src_offsets[g]) : 0;
+  const bool live = chunk_geometry(G, blockIdx.x, b, gb, u0, r_begin, r_end, rows);
+  uint32_t g0[kRowsPerThread];
+#pragma unroll
+  for (int x = 0; x < kRowsPerThread; ++x) {
+    const int r = r_begin + threadIdx.x + x * kGatherThreads;
+    g0[x] = (live && r < rows) ? G.win[u0 + r] : kNoRow;
+  }
+  const int ncols = set->n;
+  for (int c = 0; c < ncols; ++c) {
+    const VarCol col = set->col[c];
+    int64_t sum = 0;
+    if (live) {
+      uint32_t* vwords =
+          col.dst_valid ? reinterpret_cast<uint32_t*>(col.dst_valid + gb * G.valid_stride) : nullptr;
+#pragma unroll
+      for (int x = 0; x < kRowsPerThread; ++x) {
+        const int r = r_begin + threadIdx.x + x * kGatherThreads;
+        if (r - (int)(threadIdx.x & 31) >= r_end) continue;  // warp-uniform
+        bool valid = false;
+        if (r < rows) {
+          const uint32_t g = col.win ? col.win[u0 + r] : g0[x];
+          sum += var_row_len(col, g, valid);
+        }
+        if (vwords) {
+          const uint32_t word = __ballot_sync(0xffffffffu, valid);
+          if ((threadIdx.x & 31) == 0) vwords[r >> 5] = word;
+        }
+      }
     }
-    if (vwords) {
-      const uint32_t word = __ballot_sync(0xffffffffu, bit);
-      if ((threadIdx.x & 31) == 0) vwords[r >> 5] = word;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int64_t t = 0;
+      for (int i = 0; i < kGatherThreads / 32; ++i) t += ws[i];
+      chunk_sums[c * sums_stride + blockIdx.x] = t;
     }
   }
 }
 
-// device-wide exclusive scan int32 -> int64 (3 phases), chunk of 4096 per block
-constexpr int kScanChunk = 4096;
-__global__ void __launch_bounds__(256) scan_block_sums(const int32_t* in, int64_t n, int64_t* sums) {
-  const int64_t base = (int64_t)blockIdx.x * kScanChunk;
-  int64_t s = 0;
-  for (int x = threadIdx.x; x < kScanChunk; x += 256) {
-    const int64_t i = base + x;
-    if (i < n) s += in[i];
-  }
-  __shared__ int64_t ws[8];
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int64_t t = 0;
-    for (int i = 0; i < 8; ++i) t += ws[i];
-    sums[blockIdx.x] = t;
-  }
-}
-__global__ void __launch_bounds__(1024) scan_sums_inplace(int64_t* sums, int nblocks) {
+// exclusive scan in place; block b scans the segment sums[b*stride .. +nblocks] (+ total at [nblocks])
+__global__ void __launch_bounds__(1024) scan_sums_inplace(int64_t* sums_all, int nblocks, int64_t stride) {
   __shared__ int64_t wsum[32];
   __shared__ int64_t carry_s;
+  int64_t* sums = sums_all + blockIdx.x * stride;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid == 0) carry_s = 0;
   __syncthreads();
@@ -763,9 +829,154 @@ __global__ void __launch_bounds__(1024) scan_sums_inplace(int64_t* sums, int nbl
   }
   if (tid == 0) sums[nblocks] = carry_s;
 }
+
+// dst/src arbitrary alignment: byte head until dst is word aligned, then aligned word stores fed by
+// aligned word loads through a funnel shift, then a byte tail. Reads at most the aligned word that
+// holds the last source byte.
+__device__ __forceinline__ void copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int n) {
+  while (n > 0 && (reinterpret_cast<uintptr_t>(dst) & 3)) {
+    *dst++ = *src++;
+    --n;
+  }
+  const int nw = n >> 2;
+  if (nw > 0) {
+    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
+    if (sh == 0) {
+      for (int i = 0; i < nw; ++i) dw[i] = sw[i];
+    } else {
+      uint32_t lo = sw[0];
+      for (int i = 0; i < nw; ++i) {
+        const uint32_t hi = sw[i + 1];
+        dw[i] = __funnelshift_r(lo, hi, sh);
+        lo = hi;
+      }
+    }
+    src += nw * 4;
+    dst += nw * 4;
+    n &= 3;
+  }
+  while (n-- > 0) *dst++ = *src++;
+}
+
+// pass 2 (grid.y = column): batch-rebased offsets + the bytes of one chunk.
+// Thread t owns the 8 consecutive rows [8t, 8t+8) for the offsets; the bytes are staged through a
+// shared-memory window that is address-congruent (mod 16) with the destination, so the flush to HBM
+// is made of full, aligned 16-byte stores whatever the string lengths are.
+constexpr int kStageBytes = 24 * 1024;
+
+__global__ void __launch_bounds__(kGatherThreads) var_write_kernel(GatherGeom G, const VarColSet* __restrict__ set,
+                                                                   const int64_t* __restrict__ chunk_off_all,
+                                                                   int64_t sums_stride, int64_t total_batches) {
+  __shared__ int s_scan[kGatherThreads / 32 + 2];
+  __shared__ int32_t s_off[kRowsPerChunk + 1];   // chunk-relative destination offset of every row
+  __shared__ int32_t s_src[kRowsPerChunk];       // bucket-relative source offset of every row
+  __shared__ __align__(16) uint8_t s_stage[kStageBytes + 16];
+  int b, r_begin, r_end, rows;
+  int64_t gb, u0;
+  if (!chunk_geometry(G, blockIdx.x, b, gb, u0, r_begin, r_end, rows)) return;
+  const VarCol col = set->col[blockIdx.y];
+  const int64_t* chunk_off = chunk_off_all + blockIdx.y * sums_stride;
+  const uint32_t* win = col.win ? col.win : G.win;
+  const int c_in = (int)(blockIdx.x % G.chunks_per_batch);
+  const int64_t c0 = chunk_off[blockIdx.x];
+  const int64_t batch0 = chunk_off[blockIdx.x - c_in];
+  const uint8_t* src_base = col.src_data + col.src_data_base[b];
+  const int nloc = min(rows - r_begin, kRowsPerChunk);  // rows of this chunk
+  const int rl0 = threadIdx.x * kRowsPerThread;
+  int len[kRowsPerThread];
+  int mine = 0;
+#pragma unroll
+  for (int x = 0; x < kRowsPerThread; ++x) {
+    len[x] = 0;
+    if (rl0 + x < nloc) {
+      const uint32_t g = win[u0 + r_begin + rl0 + x];
+      bool valid;
+      len[x] = var_row_len(col, g, valid);
+      s_src[rl0 + x] = valid ? col.src_offsets[g] : 0;
+    }
+    mine += len[x];
+  }
+  int tot;
+  int run = block_exclusive_scan(mine, s_scan, tot);
+  // offsets (every earlier batch contributed one extra entry)
+  int32_t* dst_off = col.dst_offsets + u0 + gb + r_begin;
+  const int32_t rel = (int32_t)(c0 - batch0);
+#pragma unroll
+  for (int x = 0; x < kRowsPerThread; ++x) {
+    if (rl0 + x < nloc) {
+      dst_off[rl0 + x] = rel + run;
+      s_off[rl0 + x] = run;
+      run += len[x];
+    }
+  }
+  const bool last_chunk = r_begin + nloc == rows;
+  if (threadIdx.x == 0) {
+    s_off[nloc] = tot;
+    if (last_chunk) dst_off[nloc] = rel + tot;
+    if (c_in == 0) col.batch_data_start[gb] = batch0;
+    if (last_chunk && gb == total_batches - 1) col.batch_data_start[total_batches] = c0 + tot;
+  }
+  __syncthreads();
+  // ---- bytes: windows of the chunk's output range, staged in shared memory --------------------
+  uint8_t* dst_bytes = col.dst_data + c0;       // chunk-relative byte p lives at dst_bytes[p]
+  const int mis = (int)((reinterpret_cast<uintptr_t>(dst_bytes)) & 15);  // stage[mis + (p - w0)] <-> p
+  int w0 = 0;
+  while (w0 < tot) {
+    const int first_pad = (w0 == 0) ? mis : 0;   // later windows start on a 16-byte boundary
+    const int w1 = min(tot, w0 + kStageBytes - first_pad);
+    // rows intersecting [w0, w1)
+    const int r_lo = upper_idx(s_off, nloc + 1, w0);
+    const int r_hi = upper_idx(s_off, nloc + 1, w1 - 1);
+    for (int r = r_lo + threadIdx.x; r <= r_hi; r += kGatherThreads) {
+      const int a = max(s_off[r], w0), e = min(s_off[r + 1], w1);
+      if (e > a)
+        copy_bytes(s_stage + first_pad + (a - w0), src_base + s_src[r] + (a - s_off[r]), e - a);
+    }
+    __syncthreads();
+    // flush: global address of stage[first_pad] is dst_bytes + w0
+    uint8_t* gdst = dst_bytes + w0 - first_pad;  // 16-byte aligned
+    const int nbytes = first_pad + (w1 - w0);
+    const int nvec = nbytes >> 4;
+    for (int v = threadIdx.x; v < nvec; v += kGatherThreads) {
+      if (v == 0 && first_pad) {
+        for (int t = first_pad; t < 16; ++t) gdst[t] = s_stage[t];
+      } else {
+        reinterpret_cast<uint4*>(gdst)[v] = reinterpret_cast<const uint4*>(s_stage)[v];
+      }
+    }
+    if (threadIdx.x == 0) {
+      const int start = (nvec == 0) ? first_pad : (nvec << 4);
+      for (int t = start; t < nbytes; ++t) gdst[t] = s_stage[t];
+    }
+    __syncthreads();
+    w0 = w1;
+  }
+}
+
+// device-wide exclusive scan int32 -> int64 (used by the winner compaction), chunk of 4096 per block
+constexpr int kScanChunk = 4096;
+__global__ void __launch_bounds__(256) scan_block_sums(const int32_t* in, int64_t n, int64_t* sums) {
+  const int64_t base = (int64_t)blockIdx.x * kScanChunk;
+  int64_t s = 0;
+  for (int x = threadIdx.x; x < kScanChunk; x += 256) {
+    const int64_t i = base + x;
+    if (i < n) s += in[i];
+  }
+  __shared__ int64_t ws[8];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int64_t t = 0;
+    for (int i = 0; i < 8; ++i) t += ws[i];
+    sums[blockIdx.x] = t;
+  }
+}
 __global__ void __launch_bounds__(256) scan_apply(const int32_t* in, int64_t n, const int64_t* sums,
                                                   int64_t* out) {
-  // each block rescans its chunk serially per thread (16 items/thread), then block scan
   __shared__ int64_t ws[8];
   const int64_t base = (int64_t)blockIdx.x * kScanChunk;
   constexpr int per = kScanChunk / 256;
@@ -798,70 +1009,6 @@ __global__ void __launch_bounds__(256) scan_apply(const int32_t* in, int64_t n, 
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) out[n] = sums[gridDim.x];
 }
 
-__global__ void __launch_bounds__(kGatherThreads) var_offsets_kernel(GatherGeom G, VarCol col,
-                                                                     const int64_t* doff,
-                                                                     int64_t total_batches,
-                                                                     int64_t total_out) {
-  int b, r_begin, r_end, rows;
-  int64_t gb, u0;
-  if (!chunk_geometry(G, blockIdx.x, b, gb, u0, r_begin, r_end, rows)) return;
-  const int64_t first = doff[u0];
-  int32_t* dst = col.dst_offsets + u0 + gb;  // every earlier batch contributed one extra entry
-  for (int r = r_begin + threadIdx.x; r < r_end; r += kGatherThreads) {
-    if (r < rows) {
-      dst[r] = (int32_t)(doff[u0 + r] - first);
-      if (r == rows - 1) dst[rows] = (int32_t)(doff[u0 + rows] - first);
-    }
-  }
-  if (r_begin == 0 && threadIdx.x == 0) {
-    col.batch_data_start[gb] = first;
-    if (gb == total_batches - 1) col.batch_data_start[total_batches] = doff[total_out];
-  }
-}
-
-// copy string bytes: one block per 256 output rows; each thread produces 4 output bytes at a time
-constexpr int kCopyRows = 256;
-__global__ void __launch_bounds__(256) var_copy_kernel(GatherGeom G, VarCol col, const int64_t* doff,
-                                                       int64_t total_out) {
-  __shared__ int64_t s_doff[kCopyRows + 1];
-  __shared__ int64_t s_src[kCopyRows];
-  const int64_t u_begin = (int64_t)blockIdx.x * kCopyRows;
-  const int nrows = (int)min((int64_t)kCopyRows, total_out - u_begin);
-  if (nrows <= 0) return;
-  for (int r = threadIdx.x; r <= nrows; r += 256) s_doff[r] = doff[u_begin + r];
-  for (int r = threadIdx.x; r < nrows; r += 256) {
-    const int64_t u = u_begin + r;
-    const int b = upper_idx(G.out_base, G.nb + 1, u);
-    // out_base may repeat for empty buckets: upper_idx returns the last bucket starting at <= u,
-    // which is the one that owns row u.
-    const uint32_t g = (col.win ? col.win : G.win)[u];
-    s_src[r] = g == kNoRow ? 0 : col.src_data_base[b] + col.src_offsets[g];
-  }
-  __syncthreads();
-  const int64_t byte0 = s_doff[0], byte1 = s_doff[nrows];
-  // word-aligned sweep over [byte0, byte1)
-  const int64_t w0 = byte0 & ~3ll;
-  for (int64_t wpos = w0 + (int64_t)threadIdx.x * 4; wpos < byte1; wpos += 256 * 4) {
-    int64_t x = max(wpos, byte0);
-    const int64_t xe = min(wpos + 4, byte1);
-    if (x >= xe) continue;
-    // row containing byte x: largest r with s_doff[r] <= x, skipping empty rows
-    int r = upper_idx(s_doff, nrows + 1, x);
-    if (x == wpos && xe == wpos + 4 && s_doff[r + 1] >= xe) {
-      // fast path: whole word inside one row
-      const uint8_t* sp = col.src_data + s_src[r] + (x - s_doff[r]);
-      uint32_t v = (uint32_t)sp[0] | ((uint32_t)sp[1] << 8) | ((uint32_t)sp[2] << 16) |
-                   ((uint32_t)sp[3] << 24);
-      *reinterpret_cast<uint32_t*>(col.dst_data + wpos) = v;
-    } else {
-      for (; x < xe; ++x) {
-        while (s_doff[r + 1] <= x) ++r;
-        col.dst_data[x] = col.src_data[s_src[r] + (x - s_doff[r])];
-      }
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -892,7 +1039,10 @@ struct MergePlan {
   PkDesc last_pk{};
   int32_t* d_err = nullptr;
   // pinned host mirrors
-  int64_t* h_counts = nullptr;  // out_base (nb+1) + batch_base (nb+1) + err
+  int64_t* h_counts = nullptr;  // out_base (nb+1) + batch_base (nb+1) + err (thread-local pinned block)
+  cudaStream_t alloc_stream = nullptr;
+  std::vector<int64_t> h_frb, h_dense;
+  std::vector<int32_t> h_fr32, h_tb, h_ti;
   std::vector<int64_t> out_counts, out_base, batch_base;
   bool merged = false, synced = false;
   MergeStats stats;
@@ -902,6 +1052,10 @@ struct MergePlan {
   int64_t* d_sums = nullptr;
   FixedCol* d_cols = nullptr;
   int d_cols_cap = 0;
+  int64_t* d_chunk_sums = nullptr;
+  int64_t d_chunk_cap = 0;
+  struct VarColSet* d_varset = nullptr;
+  VarColSet h_varset;
   size_t smem_bytes = 0;
 };
 
@@ -911,11 +1065,32 @@ static size_t tile_smem_bytes(int C, bool key128) {
          (kMaxFilesPerBucket + 1) * 4 + kMaxFilesPerBucket * 4 + 16 * 4;
 }
 
+// stream-ordered pool allocations: plans are created per scan batch, cudaMalloc/cudaFree would
+// serialise the device every time
 template <typename T>
-static T* dev_alloc(size_t n) {
+static T* dev_alloc(size_t n, cudaStream_t stream) {
   T* p = nullptr;
-  LSB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  LSB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T), stream));
   return p;
+}
+static void dev_free(void* p, cudaStream_t stream) {
+  if (p) cudaFreeAsync(p, stream);
+}
+
+// small pinned staging blocks for the per-plan count read-back, recycled per thread
+struct PinnedCounts {
+  int64_t* p = nullptr;
+  size_t cap = 0;
+  ~PinnedCounts() { if (p) cudaFreeHost(p); }
+};
+static int64_t* pinned_counts(size_t n) {
+  static thread_local PinnedCounts pc;
+  if (pc.cap < n) {
+    if (pc.p) cudaFreeHost(pc.p);
+    pc.cap = std::max<size_t>(n * 2, 1024);
+    LSB_CUDA(cudaMallocHost(&pc.p, pc.cap * sizeof(int64_t)));
+  }
+  return pc.p;
 }
 
 MergePlan* plan_create(int nb, const int32_t* bucket_file_begin, const int64_t* file_rows,
@@ -931,6 +1106,7 @@ MergePlan* plan_create(int nb, const int32_t* bucket_file_begin, const int64_t* 
   }
   auto* P = new MergePlan();
   try {
+    P->alloc_stream = stream;
     P->nb = nb;
     P->F = bucket_file_begin[nb];
     P->batch_size = batch_size;
@@ -954,8 +1130,10 @@ MergePlan* plan_create(int nb, const int32_t* bucket_file_begin, const int64_t* 
       throw std::runtime_error(g_last_error);
     }
 
-    std::vector<int64_t> frb(P->F + 1, 0);
-    std::vector<int32_t> fr32(P->F);
+    std::vector<int64_t>& frb = P->h_frb;
+    std::vector<int32_t>& fr32 = P->h_fr32;
+    frb.assign(P->F + 1, 0);
+    fr32.assign(P->F, 0);
     for (int f = 0; f < P->F; ++f) {
       if (file_rows[f] < 0 || file_rows[f] > 0x7fffffff) {
         g_last_error = "file with more than 2^31-1 rows";
@@ -1027,7 +1205,8 @@ MergePlan* plan_create(int nb, const int32_t* bucket_file_begin, const int64_t* 
     // tiles per level, ordered by bucket then tile index
     P->level_tile_ofs.assign(max_level + 1, 0);
     P->level_tile_cnt.assign(max_level + 1, 0);
-    std::vector<int32_t> tb, ti;
+    std::vector<int32_t>& tb = P->h_tb;
+    std::vector<int32_t>& ti = P->h_ti;
     for (int l = 0; l <= max_level; ++l) {
       P->level_tile_ofs[l] = (int32_t)tb.size();
       for (int b = 0; b < nb; ++b) {
@@ -1044,27 +1223,27 @@ MergePlan* plan_create(int nb, const int32_t* bucket_file_begin, const int64_t* 
     P->total_tiles = (int32_t)tb.size();
     const int T0 = P->level_tile_cnt[0];
 
-    P->d_buckets = dev_alloc<BucketDesc>(nb);
-    P->d_file_rows = dev_alloc<int32_t>(P->F);
-    P->d_file_row_base = dev_alloc<int64_t>(P->F + 1);
-    P->d_splits = dev_alloc<int32_t>(split_total);
-    P->d_mlist = dev_alloc<uint2>(mlist_total);
-    P->d_tile_bucket = dev_alloc<int32_t>(tb.size());
-    P->d_tile_idx = dev_alloc<int32_t>(ti.size());
-    P->d_tile_cnt = dev_alloc<int32_t>(T0);
-    P->d_tile_gstart = dev_alloc<int64_t>(T0);
-    P->d_tile_out = dev_alloc<int64_t>(T0 + 1);
-    P->d_win_tmp = dev_alloc<uint32_t>(P->n_total);
-    P->d_win = dev_alloc<uint32_t>(P->n_total);
-    P->d_out_base = dev_alloc<int64_t>(nb + 1);
-    P->d_batch_base = dev_alloc<int64_t>(nb + 1);
-    P->d_err = dev_alloc<int32_t>(1);
-    P->d_dense_base = dev_alloc<int64_t>(P->F + 1);
-    std::vector<int64_t> dense(P->F + 1, 0);
+    P->d_buckets = dev_alloc<BucketDesc>(nb, stream);
+    P->d_file_rows = dev_alloc<int32_t>(P->F, stream);
+    P->d_file_row_base = dev_alloc<int64_t>(P->F + 1, stream);
+    P->d_splits = dev_alloc<int32_t>(split_total, stream);
+    P->d_mlist = dev_alloc<uint2>(mlist_total, stream);
+    P->d_tile_bucket = dev_alloc<int32_t>(tb.size(), stream);
+    P->d_tile_idx = dev_alloc<int32_t>(ti.size(), stream);
+    P->d_tile_cnt = dev_alloc<int32_t>(T0, stream);
+    P->d_tile_gstart = dev_alloc<int64_t>(T0, stream);
+    P->d_tile_out = dev_alloc<int64_t>(T0 + 1, stream);
+    P->d_win_tmp = dev_alloc<uint32_t>(P->n_total, stream);
+    P->d_win = dev_alloc<uint32_t>(P->n_total, stream);
+    P->d_out_base = dev_alloc<int64_t>(nb + 1, stream);
+    P->d_batch_base = dev_alloc<int64_t>(nb + 1, stream);
+    P->d_err = dev_alloc<int32_t>(1, stream);
+    P->d_dense_base = dev_alloc<int64_t>(P->F + 1, stream);
+    std::vector<int64_t>& dense = P->h_dense;
+    dense.assign(P->F + 1, 0);
     for (int f = 0; f < P->F; ++f) dense[f + 1] = dense[f] + file_rows[f];
     LSB_CUDA(cudaMemcpyAsync(P->d_dense_base, dense.data(), sizeof(int64_t) * (P->F + 1),
                              cudaMemcpyHostToDevice, stream));
-    LSB_CUDA(cudaMallocHost(&P->h_counts, sizeof(int64_t) * (2 * (nb + 1) + 1)));
     LSB_CUDA(cudaMemcpyAsync(P->d_buckets, P->buckets.data(), sizeof(BucketDesc) * nb,
                              cudaMemcpyHostToDevice, stream));
     LSB_CUDA(cudaMemcpyAsync(P->d_file_rows, fr32.data(), sizeof(int32_t) * P->F,
@@ -1076,10 +1255,14 @@ MergePlan* plan_create(int nb, const int32_t* bucket_file_begin, const int64_t* 
     LSB_CUDA(cudaMemcpyAsync(P->d_tile_idx, ti.data(), sizeof(int32_t) * ti.size(),
                              cudaMemcpyHostToDevice, stream));
     LSB_CUDA(cudaMemsetAsync(P->d_err, 0, sizeof(int32_t), stream));
-    // host vectors above die at scope exit: make the copies complete first
-    LSB_CUDA(cudaStreamSynchronize(stream));
+    // the host vectors are plan members: they outlive the asynchronous copies
 
     P->smem_bytes = tile_smem_bytes(C, P->key128);
+    static thread_local int attr_device = -1;
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (attr_device != cur_dev) {
+    attr_device = cur_dev;
     LSB_CUDA(cudaFuncSetAttribute(tile_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tile_smem_bytes(5632, false)));
     LSB_CUDA(cudaFuncSetAttribute(tile_kernel<K128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1088,6 +1271,7 @@ MergePlan* plan_create(int nb, const int32_t* bucket_file_begin, const int64_t* 
                                   (int)tile_smem_bytes(5632, false)));
     LSB_CUDA(cudaFuncSetAttribute(tile_kernel<K128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tile_smem_bytes(3328, true)));
+    }
     P->stats.n_rows = P->n_in;
     P->stats.tiles_l0 = T0;
     P->stats.levels = max_level;
@@ -1102,14 +1286,12 @@ MergePlan* plan_create(int nb, const int32_t* bucket_file_begin, const int64_t* 
 
 void plan_destroy(MergePlan* P) {
   if (!P) return;
-  cudaFree(P->d_buckets); cudaFree(P->d_file_rows); cudaFree(P->d_file_row_base);
-  cudaFree(P->d_splits); cudaFree(P->d_mlist); cudaFree(P->d_tile_bucket); cudaFree(P->d_tile_idx);
-  cudaFree(P->d_tile_cnt); cudaFree(P->d_tile_gstart); cudaFree(P->d_tile_out);
-  cudaFree(P->d_win_tmp); cudaFree(P->d_win); cudaFree(P->d_out_base); cudaFree(P->d_batch_base);
-  cudaFree(P->d_dense_base); cudaFree(P->d_ctmp);
-  cudaFree(P->d_err); cudaFree(P->d_len); cudaFree(P->d_doff); cudaFree(P->d_sums);
-  cudaFree(P->d_cols);
-  if (P->h_counts) cudaFreeHost(P->h_counts);
+  cudaStream_t st = P->alloc_stream;
+  void* ptrs[] = {P->d_buckets, P->d_file_rows, P->d_file_row_base, P->d_splits, P->d_mlist, P->d_tile_bucket,
+                  P->d_tile_idx, P->d_tile_cnt, P->d_tile_gstart, P->d_tile_out, P->d_win_tmp, P->d_win,
+                  P->d_out_base, P->d_batch_base, P->d_dense_base, P->d_ctmp, P->d_err, P->d_len, P->d_doff,
+                  P->d_sums, P->d_cols, P->d_chunk_sums, P->d_varset};
+  for (void* p : ptrs) dev_free(p, st);
   delete P;
 }
 
@@ -1205,6 +1387,7 @@ const std::vector<int64_t>& plan_sync_counts(MergePlan* P, cudaStream_t stream) 
   }
   if (!P->synced) {
     const int nb = P->nb;
+    P->h_counts = pinned_counts(2 * (size_t)(nb + 1) + 1);
     LSB_CUDA(cudaMemcpyAsync(P->h_counts, P->d_out_base, sizeof(int64_t) * (nb + 1),
                              cudaMemcpyDeviceToHost, stream));
     LSB_CUDA(cudaMemcpyAsync(P->h_counts + nb + 1, P->d_batch_base, sizeof(int64_t) * (nb + 1),
@@ -1264,49 +1447,56 @@ void gather_fixed(MergePlan* P, const FixedCol* cols, int ncols, cudaStream_t st
   const int64_t total_batches = P->batch_base[P->nb];
   if (total_batches == 0) return;
   if (P->d_cols_cap < ncols) {
-    cudaFree(P->d_cols);
-    P->d_cols = dev_alloc<FixedCol>(ncols);
+    dev_free(P->d_cols, stream);
+    P->d_cols = dev_alloc<FixedCol>(ncols, stream);
     P->d_cols_cap = ncols;
   }
   LSB_CUDA(cudaMemcpyAsync(P->d_cols, cols, sizeof(FixedCol) * ncols, cudaMemcpyHostToDevice, stream));
   GatherGeom G = make_geom(P);
   const int64_t chunks = total_batches * G.chunks_per_batch;
-  // grid.y <= 65535 columns; chunks in x (2^31-1)
-  for (int c0 = 0; c0 < ncols; c0 += 65535) {
-    dim3 grid((unsigned)chunks, (unsigned)std::min(65535, ncols - c0));
-    gather_fixed_kernel<<<grid, kGatherThreads, 0, stream>>>(G, P->d_cols + c0);
-  }
+  gather_fixed_kernel<<<(unsigned)chunks, kGatherThreads, 0, stream>>>(G, P->d_cols, ncols);
   LSB_CUDA(cudaGetLastError());
   // the descriptor table is reused by the next call: order the copy behind this launch
 }
 
-void plan_reserve_scratch(MergePlan* P, cudaStream_t) {
+void plan_reserve_scratch(MergePlan* P, cudaStream_t stream) {
   require_synced(P);
   const int64_t U = P->out_base[P->nb];
   if (!P->d_len) {
-    P->d_len = dev_alloc<int32_t>(U + 1);
-    P->d_doff = dev_alloc<int64_t>(U + 2);
-    P->d_sums = dev_alloc<int64_t>((U + kScanChunk - 1) / kScanChunk + 2);
+    P->d_len = dev_alloc<int32_t>(U + 1, stream);
+    P->d_doff = dev_alloc<int64_t>(U + 2, stream);
+    P->d_sums = dev_alloc<int64_t>((U + kScanChunk - 1) / kScanChunk + 2, stream);
   }
 }
 
-void gather_var(MergePlan* P, const VarCol& col, cudaStream_t stream) {
+void gather_var_multi(MergePlan* P, const VarCol* cols, int ncols, cudaStream_t stream) {
   require_synced(P);
-  plan_reserve_scratch(P, stream);
-  const int64_t U = P->out_base[P->nb];
   const int64_t total_batches = P->batch_base[P->nb];
-  if (total_batches == 0) return;
+  if (total_batches == 0 || ncols <= 0) return;
   GatherGeom G = make_geom(P);
   const int64_t chunks = total_batches * G.chunks_per_batch;
-  var_len_kernel<<<(unsigned)chunks, kGatherThreads, 0, stream>>>(G, col, P->d_len);
-  const int nblocks = (int)((U + kScanChunk - 1) / kScanChunk);
-  scan_block_sums<<<nblocks, 256, 0, stream>>>(P->d_len, U, P->d_sums);
-  scan_sums_inplace<<<1, 1024, 0, stream>>>(P->d_sums, nblocks);
-  scan_apply<<<nblocks, 256, 0, stream>>>(P->d_len, U, P->d_sums, P->d_doff);
-  var_offsets_kernel<<<(unsigned)chunks, kGatherThreads, 0, stream>>>(G, col, P->d_doff, total_batches, U);
-  var_copy_kernel<<<(unsigned)((U + kCopyRows - 1) / kCopyRows), 256, 0, stream>>>(G, col, P->d_doff, U);
+  const int64_t stride = chunks + 1;
+  for (int c0 = 0; c0 < ncols; c0 += kMaxVarCols) {
+    const int n = std::min(kMaxVarCols, ncols - c0);
+    if (P->d_chunk_cap < stride * n) {
+      dev_free(P->d_chunk_sums, stream);
+      P->d_chunk_sums = dev_alloc<int64_t>(stride * kMaxVarCols, stream);
+      P->d_chunk_cap = stride * kMaxVarCols;
+    }
+    if (!P->d_varset) P->d_varset = dev_alloc<VarColSet>(1, stream);
+    VarColSet& set = P->h_varset;
+    set.n = n;
+    for (int i = 0; i < n; ++i) set.col[i] = cols[c0 + i];
+    LSB_CUDA(cudaMemcpyAsync(P->d_varset, &set, sizeof(VarColSet), cudaMemcpyHostToDevice, stream));
+    var_sum_kernel<<<(unsigned)chunks, kGatherThreads, 0, stream>>>(G, P->d_varset, P->d_chunk_sums, stride);
+    scan_sums_inplace<<<n, 1024, 0, stream>>>(P->d_chunk_sums, (int)chunks, stride);
+    dim3 grid((unsigned)chunks, (unsigned)n);
+    var_write_kernel<<<grid, kGatherThreads, 0, stream>>>(G, P->d_varset, P->d_chunk_sums, stride, total_batches);
+  }
   LSB_CUDA(cudaGetLastError());
 }
+
+void gather_var(MergePlan* P, const VarCol& col, cudaStream_t stream) { gather_var_multi(P, &col, 1, stream); }
 
 // ---------------------------------------------------------------------------------------
 // winner compaction after the post-merge predicate
@@ -1335,12 +1525,12 @@ void plan_compact(MergePlan* P, const uint8_t* keep, const std::vector<uint32_t*
   const int64_t U = P->out_base[P->nb];
   if (U == 0) return;
   plan_reserve_scratch(P, stream);
-  if (!P->d_ctmp) P->d_ctmp = dev_alloc<uint32_t>(P->n_total);
+  if (!P->d_ctmp) P->d_ctmp = dev_alloc<uint32_t>(P->n_total, stream);
   const unsigned g = (unsigned)((U + 255) / 256);
   keep_to_i32<<<g, 256, 0, stream>>>(keep, U, P->d_len);
   const int nblocks = (int)((U + kScanChunk - 1) / kScanChunk);
   scan_block_sums<<<nblocks, 256, 0, stream>>>(P->d_len, U, P->d_sums);
-  scan_sums_inplace<<<1, 1024, 0, stream>>>(P->d_sums, nblocks);
+  scan_sums_inplace<<<1, 1024, 0, stream>>>(P->d_sums, nblocks, 0);
   scan_apply<<<nblocks, 256, 0, stream>>>(P->d_len, U, P->d_sums, P->d_doff);
   // plan winners: scatter into win_tmp, then swap roles
   scatter_kept<<<g, 256, 0, stream>>>(keep, P->d_doff, U, P->d_win, P->d_win_tmp);
@@ -1354,8 +1544,8 @@ void plan_compact(MergePlan* P, const uint8_t* keep, const std::vector<uint32_t*
   int64_t* nb_tmp = reinterpret_cast<int64_t*>(P->d_len);  // d_len no longer needed (>= (U+1)*4 bytes)
   if ((int64_t)(P->nb + 1) * 8 > (U + 1) * 4) {
     // tiny outputs with many buckets: use a dedicated buffer
-    cudaFree(P->d_sums);
-    P->d_sums = dev_alloc<int64_t>((U + kScanChunk - 1) / kScanChunk + 2 + P->nb + 1);
+    dev_free(P->d_sums, stream);
+    P->d_sums = dev_alloc<int64_t>((U + kScanChunk - 1) / kScanChunk + 2 + P->nb + 1, stream);
     nb_tmp = P->d_sums + (U + kScanChunk - 1) / kScanChunk + 2;
   }
   rebase_out<<<(P->nb + 1 + 255) / 256, 256, 0, stream>>>(D, P->d_doff, nb_tmp);
@@ -1495,8 +1685,9 @@ struct GeneralMerge {
 
 void general_destroy(GeneralMerge* G) {
   if (!G) return;
-  cudaFree(G->d_R); cudaFree(G->d_rofs); cudaFree(G->d_present);
-  for (auto& c : G->cols) { cudaFree(c.win); cudaFree(c.opval); cudaFree(c.opvalid); }
+  cudaStream_t st = G->plan ? G->plan->alloc_stream : nullptr;
+  dev_free(G->d_R, st); dev_free(G->d_rofs, st); dev_free(G->d_present, st);
+  for (auto& c : G->cols) { dev_free(c.win, st); dev_free(c.opval, st); dev_free(c.opvalid, st); }
   delete G;
 }
 
@@ -1536,13 +1727,13 @@ GeneralMerge* general_create(MergePlan* P, const PkDesc& pk, const std::vector<G
     std::vector<int64_t> rofs(nb + 1, 0);
     for (int b = 0; b < nb; ++b)
       rofs[b + 1] = rofs[b] + (P->out_base[b + 1] - P->out_base[b]) * P->buckets[b].k;
-    G->d_R = dev_alloc<uint32_t>(rofs[nb]);
-    G->d_rofs = dev_alloc<int64_t>(nb + 1);
+    G->d_R = dev_alloc<uint32_t>(rofs[nb], stream);
+    G->d_rofs = dev_alloc<int64_t>(nb + 1, stream);
     LSB_CUDA(cudaMemsetAsync(G->d_R, 0xff, sizeof(uint32_t) * rofs[nb], stream));
     LSB_CUDA(cudaMemcpyAsync(G->d_rofs, rofs.data(), sizeof(int64_t) * (nb + 1), cudaMemcpyHostToDevice, stream));
     std::vector<char> present((size_t)G->C * P->F);
     for (int c = 0; c < G->C; ++c) std::memcpy(present.data() + (size_t)c * P->F, in[c].present, P->F);
-    G->d_present = dev_alloc<char>(present.size());
+    G->d_present = dev_alloc<char>(present.size(), stream);
     LSB_CUDA(cudaMemcpyAsync(G->d_present, present.data(), present.size(), cudaMemcpyHostToDevice, stream));
     LSB_CUDA(cudaStreamSynchronize(stream));  // host vectors go out of scope below
 
@@ -1558,7 +1749,7 @@ GeneralMerge* general_create(MergePlan* P, const PkDesc& pk, const std::vector<G
     for (int c = 0; c < G->C; ++c) {
       auto& col = G->cols[c];
       if (col.uses_plan_winners) continue;
-      col.win = dev_alloc<uint32_t>(U);
+      col.win = dev_alloc<uint32_t>(U, stream);
       GenColDev gc{};
       gc.values = in[c].values;
       gc.validity = in[c].validity;
@@ -1568,8 +1759,8 @@ GeneralMerge* general_create(MergePlan* P, const PkDesc& pk, const std::vector<G
       gc.width = in[c].kind.width;
       gc.num_class = in[c].num_class;
       if (col.computed) {
-        col.opval = dev_alloc<uint8_t>((size_t)U * std::max(in[c].kind.width, 1) + 32);
-        col.opvalid = dev_alloc<uint32_t>((U + 31) / 32 + 2);
+        col.opval = dev_alloc<uint8_t>((size_t)U * std::max(in[c].kind.width, 1) + 32, stream);
+        col.opvalid = dev_alloc<uint32_t>((U + 31) / 32 + 2, stream);
         gc.opval = col.opval;
         gc.opvalid = col.opvalid;
       }

@@ -146,6 +146,8 @@ struct VarCol {
   int64_t* batch_data_start;     // device, (total_batches + 1)
 };
 void gather_var(MergePlan*, const VarCol& col, cudaStream_t stream);
+// same for several columns: 3 launches in total (the winner list is read once per pass)
+void gather_var_multi(MergePlan*, const VarCol* cols, int ncols, cudaStream_t stream);
 
 // Scratch management for gather_var (lengths + scanned offsets); grows on demand.
 void plan_reserve_scratch(MergePlan*, cudaStream_t stream);

@@ -116,6 +116,15 @@ class ScanPlan:
                                                  p(dst_offsets), p(dst_data), p(dst_valid), p(batch_data_start),
                                                  _stream_ptr(self.stream)))
 
+    def gather_var_multi(self, cols):
+        """cols: list of dicts with src_offsets, src_data, src_data_base, dst_offsets, dst_data,
+        batch_data_start and optional src_valid / dst_valid tensors."""
+        n = len(cols)
+        arr = lambda key: _ptr_array([(c.get(key).data_ptr() if c.get(key) is not None else None) for c in cols])  # noqa: E731
+        self._check(self.lib.lsb_plan_gather_var_multi(
+            self.h, n, arr("src_offsets"), arr("src_data"), arr("src_data_base"), arr("src_valid"), arr("dst_offsets"),
+            arr("dst_data"), arr("dst_valid"), arr("batch_data_start"), _stream_ptr(self.stream)))
+
     def close(self):
         if self.h:
             self.lib.lsb_plan_destroy(self.h)
