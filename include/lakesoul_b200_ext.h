@@ -30,6 +30,8 @@ typedef struct LsbReaderStats {
   int64_t rows_in, rows_out, h2d_bytes, d2h_bytes;
   int32_t kernel_launches, pad;
   double decode_ms, upload_ms, merge_ms, gather_ms, download_ms;
+  int64_t device_decoded_pages; /* Parquet data pages decoded by the GPU kernels */
+  int64_t host_decoded_files;   /* files that needed the Arrow C++ host decoder (unsupported encodings) */
 } LsbReaderStats;
 int32_t lsb_reader_get_stats(CResult_Reader *reader, LsbReaderStats *out);
 

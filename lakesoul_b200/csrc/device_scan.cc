@@ -9,8 +9,10 @@
 #include <mutex>
 #include <stdexcept>
 
-#include "general_merge.h"
+#include "decode_types.h"
 #include "filter_eval.h"
+#include "general_merge.h"
+#include "page_plan.h"
 
 namespace lsb {
 
@@ -76,6 +78,18 @@ class PinnedPool {
   std::map<size_t, std::vector<uint8_t*>> free_;
   size_t cached_ = 0;
 };
+
+}  // namespace
+
+std::shared_ptr<uint8_t> pinned_alloc(size_t bytes) { return PinnedPool::get().alloc(bytes); }
+
+void launch_dict_index(const DecodeArgs& A, cudaStream_t s);
+void launch_page_count(const DecodeArgs& A, cudaStream_t s);
+void launch_page_scan(const DecodeArgs& A, const int32_t* seg_start, const int64_t* seg_base, int nseg,
+                      int64_t* seg_total, cudaStream_t s);
+void launch_page_decode(const DecodeArgs& A, cudaStream_t s);
+
+namespace {
 
 class KeepAliveBuffer : public arrow::Buffer {
  public:
@@ -168,7 +182,7 @@ struct DeviceScan::Impl : std::enable_shared_from_this<DeviceScan::Impl> {
   int nb = 0, F = 0, C = 0;
   std::vector<int32_t> bucket_file_begin;
   std::vector<int64_t> file_rows, file_row_base;
-  std::vector<const arrow::Table*> file_table;
+  std::vector<const FileInput*> file_in;
   int64_t span = 0;
 
   struct DevColumn {
@@ -180,6 +194,7 @@ struct DeviceScan::Impl : std::enable_shared_from_this<DeviceScan::Impl> {
     int64_t data_bytes = 0;
     bool any_nulls = false;
     bool all_present = true;
+    bool has_raw = false;
   };
   std::vector<DevColumn> cols;
   std::vector<void*> dev_allocs;
@@ -230,7 +245,7 @@ struct DeviceScan::Impl : std::enable_shared_from_this<DeviceScan::Impl> {
 
   void layout();
   void upload();
-  void upload_column(int c);
+  void upload_host_file(int c, int b, int f, int64_t dpos);
   void merge_and_gather();
 };
 
@@ -243,138 +258,332 @@ void DeviceScan::Impl::layout() {
   F = bucket_file_begin[nb];
   file_rows.resize(F);
   file_row_base.resize(F);
-  file_table.resize(F);
+  file_in.resize(F);
   int64_t pos = 0;
   for (int b = 0, f = 0; b < nb; ++b) {
-    for (auto& t : buckets[b].files) {
-      file_table[f] = t.get();
-      file_rows[f] = t->num_rows();
+    for (auto& fi : buckets[b].files) {
+      file_in[f] = &fi;
+      file_rows[f] = fi.raw ? fi.raw->num_rows() : fi.table->num_rows();
       // 64-row alignment keeps validity bitmaps byte-copyable and 16-byte alignment for
       // every fixed width; the spare row after each file holds the closing string offset.
       file_row_base[f] = pos;
       pos = (pos + file_rows[f] + 1 + 63) & ~63ll;
       ctr.rows_in += file_rows[f];
+      if (!fi.raw) ctr.host_decoded_files += 1;
       ++f;
     }
   }
   span = pos;
 }
 
-void DeviceScan::Impl::upload_column(int c) {
+// Host-decoded file -> column buffers (used for files whose pages the device cannot decode).
+void DeviceScan::Impl::upload_host_file(int c, int b, int f, int64_t dpos) {
   const auto& field = spec.physical_schema->field(c);
   DevColumn& dc = cols[c];
-  dc.kind = classify_type(*field->type());
-  if (!dc.kind.ok) fail("unsupported column type for the GPU reader: " + field->ToString());
-  dc.present.assign(F, 0);
-  // pass 1: presence, nulls, var sizes
-  std::vector<int64_t> file_data_pos(F, 0);
-  dc.bucket_data.assign(nb, 0);
-  int64_t data_pos = 0;
-  for (int b = 0; b < nb; ++b) {
-    dc.bucket_data[b] = data_pos;
-    for (int f = bucket_file_begin[b]; f < bucket_file_begin[b + 1]; ++f) {
-      auto col = file_table[f]->GetColumnByName(field->name());
-      if (!col) { dc.all_present = false; continue; }
-      if (!col->type()->Equals(*field->type()))
-        fail("column '" + field->name() + "' has type " + col->type()->ToString() + " in a file but " +
-             field->type()->ToString() + " is expected");
-      dc.present[f] = 1;
-      if (col->null_count() > 0) dc.any_nulls = true;
-      if (dc.kind.var) {
-        file_data_pos[f] = data_pos;
-        for (const auto& ch : col->chunks()) {
-          const auto& ba = static_cast<const arrow::BinaryArray&>(*ch);
-          data_pos += ba.value_offset(ba.length()) - ba.value_offset(0);
-        }
-        if (data_pos - dc.bucket_data[b] > 0x7fffff00ll)
-          fail("variable-width column '" + field->name() + "' exceeds 2 GiB in one hash bucket");
-      }
-    }
-  }
-  dc.data_bytes = data_pos;
-
+  auto col = file_in[f]->table->GetColumnByName(field->name());
   const int w = dc.kind.width;
-  if (dc.kind.var) {
-    dc.values.bytes = (size_t)(span + 1) * 4;
-    dc.data.bytes = (size_t)data_pos;
-    dc.data.p = dalloc(dc.data.bytes);
-    dc.d_bucket_data.p = dalloc(sizeof(int64_t) * nb);
-    h2d(dc.d_bucket_data.p, dc.bucket_data.data(), sizeof(int64_t) * nb);
-  } else if (w == 0) {
-    dc.values.bytes = (size_t)(span / 8 + 8);
-  } else {
-    dc.values.bytes = (size_t)span * w;
-  }
-  dc.values.p = dalloc(dc.values.bytes);
-  if (dc.any_nulls) {
-    dc.validity.bytes = (size_t)(span / 8 + 8);
-    dc.validity.p = dalloc(dc.validity.bytes);
-    SCAN_CUDA(cudaMemsetAsync(dc.validity.p, 0xff, dc.validity.bytes, stream));
-  }
-
+  const int64_t base = file_row_base[f];
+  const int64_t n = file_rows[f];
   std::vector<uint8_t> bits;
   std::vector<int32_t> offs;
-  for (int b = 0; b < nb; ++b) {
-    for (int f = bucket_file_begin[b]; f < bucket_file_begin[b + 1]; ++f) {
-      if (!dc.present[f]) continue;
-      auto col = file_table[f]->GetColumnByName(field->name());
-      const int64_t base = file_row_base[f];
-      const int64_t n = file_rows[f];
-      // validity of the whole file, assembled at bit offset 0
-      if (dc.any_nulls && col->null_count() > 0) {
-        bits.assign((size_t)((n + 7) / 8), 0xff);
-        int64_t r0 = 0;
-        for (const auto& ch : col->chunks()) {
-          if (ch->null_count() > 0 && ch->null_bitmap_data())
-            arrow::internal::CopyBitmap(ch->null_bitmap_data(), ch->offset(), ch->length(), bits.data(), r0);
-          r0 += ch->length();
-        }
-        h2d(static_cast<uint8_t*>(dc.validity.p) + base / 8, bits.data(), bits.size());
-      }
-      int64_t r0 = 0;
-      int64_t dpos = file_data_pos[f];
-      if (w == 0 && !dc.kind.var) {
-        bits.assign((size_t)((n + 7) / 8), 0);
-        for (const auto& ch : col->chunks()) {
-          const auto& ba = static_cast<const arrow::BooleanArray&>(*ch);
-          arrow::internal::CopyBitmap(ba.values()->data(), ba.offset(), ba.length(), bits.data(), r0);
-          r0 += ch->length();
-        }
-        h2d(static_cast<uint8_t*>(dc.values.p) + base / 8, bits.data(), bits.size());
-        continue;
-      }
-      for (const auto& ch : col->chunks()) {
-        const int64_t len = ch->length();
-        if (len == 0) continue;
-        if (dc.kind.var) {
-          const auto& ba = static_cast<const arrow::BinaryArray&>(*ch);
-          const int32_t* o = ba.raw_value_offsets();  // already offset-adjusted
-          const int64_t first = o[0];
-          const int64_t nbytes = (int64_t)o[len] - first;
-          const int64_t delta = dpos - dc.bucket_data[b] - first;
-          offs.resize((size_t)len + 1);
-          for (int64_t i = 0; i <= len; ++i) offs[(size_t)i] = (int32_t)(o[i] + delta);
-          h2d(static_cast<int32_t*>(dc.values.p) + base + r0, offs.data(), sizeof(int32_t) * (size_t)(len + 1));
-          if (nbytes > 0)
-            h2d(static_cast<uint8_t*>(dc.data.p) + dpos, ba.value_data()->data() + first, (size_t)nbytes);
-          dpos += nbytes;
-        } else {
-          const uint8_t* src = ch->data()->buffers[1]->data() + (int64_t)ch->offset() * w;
-          h2d(static_cast<uint8_t*>(dc.values.p) + (base + r0) * w, src, (size_t)len * w);
-        }
-        r0 += len;
-      }
-      if (dc.kind.var && n == 0) {
-        const int32_t z = (int32_t)(dpos - dc.bucket_data[b]);
-        h2d(static_cast<int32_t*>(dc.values.p) + base, &z, sizeof(int32_t));
-      }
+  if (dc.validity.p) {  // zero-initialised bitmap: valid rows must be set explicitly
+    bits.assign((size_t)((n + 7) / 8), 0xff);
+    int64_t r0 = 0;
+    for (const auto& ch : col->chunks()) {
+      if (ch->null_count() > 0 && ch->null_bitmap_data())
+        arrow::internal::CopyBitmap(ch->null_bitmap_data(), ch->offset(), ch->length(), bits.data(), r0);
+      r0 += ch->length();
     }
+    if (n & 7) bits.back() &= (uint8_t)((1u << (n & 7)) - 1);
+    h2d(static_cast<uint8_t*>(dc.validity.p) + base / 8, bits.data(), bits.size());
+  }
+  int64_t r0 = 0;
+  if (w == 0 && !dc.kind.var) {
+    bits.assign((size_t)((n + 7) / 8), 0);
+    for (const auto& ch : col->chunks()) {
+      const auto& ba = static_cast<const arrow::BooleanArray&>(*ch);
+      arrow::internal::CopyBitmap(ba.values()->data(), ba.offset(), ba.length(), bits.data(), r0);
+      r0 += ch->length();
+    }
+    h2d(static_cast<uint8_t*>(dc.values.p) + base / 8, bits.data(), bits.size());
+    return;
+  }
+  for (const auto& ch : col->chunks()) {
+    const int64_t len = ch->length();
+    if (len == 0) continue;
+    if (dc.kind.var) {
+      const auto& ba = static_cast<const arrow::BinaryArray&>(*ch);
+      const int32_t* o = ba.raw_value_offsets();  // already offset-adjusted
+      const int64_t first = o[0];
+      const int64_t nbytes = (int64_t)o[len] - first;
+      const int64_t delta = dpos - dc.bucket_data[b] - first;
+      offs.resize((size_t)len + 1);
+      for (int64_t i = 0; i <= len; ++i) offs[(size_t)i] = (int32_t)(o[i] + delta);
+      h2d(static_cast<int32_t*>(dc.values.p) + base + r0, offs.data(), sizeof(int32_t) * (size_t)(len + 1));
+      if (nbytes > 0)
+        h2d(static_cast<uint8_t*>(dc.data.p) + dpos, ba.value_data()->data() + first, (size_t)nbytes);
+      dpos += nbytes;
+    } else {
+      const uint8_t* src = ch->data()->buffers[1]->data() + (int64_t)ch->offset() * w;
+      h2d(static_cast<uint8_t*>(dc.values.p) + (base + r0) * w, src, (size_t)len * w);
+    }
+    r0 += len;
+  }
+  if (dc.kind.var && n == 0) {
+    const int32_t z = (int32_t)(dpos - dc.bucket_data[b]);
+    h2d(static_cast<int32_t*>(dc.values.p) + base, &z, sizeof(int32_t));
   }
 }
 
 void DeviceScan::Impl::upload() {
   cols.resize(C);
-  for (int c = 0; c < C; ++c) upload_column(c);
+  // ---- pass 1 (host): presence, nullability, host-decoded string sizes ---------------------
+  std::vector<std::vector<int64_t>> host_bytes(C, std::vector<int64_t>(nb, 0));  // var: per bucket
+  std::vector<std::vector<int64_t>> file_host_bytes(C);
+  bool any_raw = false;
+  for (int c = 0; c < C; ++c) {
+    const auto& field = spec.physical_schema->field(c);
+    DevColumn& dc = cols[c];
+    dc.kind = classify_type(*field->type());
+    if (!dc.kind.ok) fail("unsupported column type for the GPU reader: " + field->ToString());
+    dc.present.assign(F, 0);
+    file_host_bytes[c].assign(F, 0);
+    for (int b = 0; b < nb; ++b) {
+      for (int f = bucket_file_begin[b]; f < bucket_file_begin[b + 1]; ++f) {
+        const FileInput& fi = *file_in[f];
+        if (fi.raw) {
+          any_raw = true;
+          const RawColumn& rc = fi.raw->columns()[c];
+          if (!rc.present) { dc.all_present = false; continue; }
+          dc.present[f] = 1;
+          dc.has_raw = true;
+          if (rc.may_have_nulls) dc.any_nulls = true;
+          continue;
+        }
+        auto col = fi.table->GetColumnByName(field->name());
+        if (!col) { dc.all_present = false; continue; }
+        if (!col->type()->Equals(*field->type()))
+          fail("column '" + field->name() + "' has type " + col->type()->ToString() + " in a file but " +
+               field->type()->ToString() + " is expected");
+        dc.present[f] = 1;
+        if (col->null_count() > 0) dc.any_nulls = true;
+        if (dc.kind.var) {
+          int64_t bytes = 0;
+          for (const auto& ch : col->chunks()) {
+            const auto& ba = static_cast<const arrow::BinaryArray&>(*ch);
+            bytes += ba.value_offset(ba.length()) - ba.value_offset(0);
+          }
+          file_host_bytes[c][f] = bytes;
+          host_bytes[c][b] += bytes;
+        }
+      }
+    }
+  }
+
+  // ---- raw files: image upload, page descriptors, string sizing -----------------------------
+  std::vector<PqChunk> chunks;
+  std::vector<PqPage> pages;
+  std::vector<int32_t> seg_start;
+  std::vector<int64_t> seg_base;
+  std::vector<int> seg_col, seg_bucket;
+  std::vector<int64_t> seg_total;
+  uint8_t* d_raw = nullptr;
+  PqChunk* d_chunks = nullptr;
+  PqPage* d_pages = nullptr;
+  int32_t* d_dict_pos = nullptr;
+  int32_t* d_err = nullptr;
+  DecodeArgs args{};
+  if (any_raw) {
+    // raw image layout: [file image | aux (decompressed pages)] per file, 64-byte aligned
+    std::vector<int64_t> img_off(F, 0), aux_off(F, 0);
+    int64_t raw_total = 0;
+    for (int f = 0; f < F; ++f) {
+      if (!file_in[f]->raw) continue;
+      img_off[f] = raw_total;
+      raw_total = (raw_total + file_in[f]->raw->image_bytes() + 63) & ~63ll;
+      aux_off[f] = raw_total;
+      raw_total = (raw_total + file_in[f]->raw->aux_bytes() + 63) & ~63ll;
+    }
+    d_raw = static_cast<uint8_t*>(dalloc((size_t)raw_total + 64));
+    for (int f = 0; f < F; ++f) {
+      if (!file_in[f]->raw) continue;
+      h2d(d_raw + img_off[f], file_in[f]->raw->image(), (size_t)file_in[f]->raw->image_bytes());
+      if (file_in[f]->raw->aux_bytes() > 0)
+        h2d(d_raw + aux_off[f], file_in[f]->raw->aux(), (size_t)file_in[f]->raw->aux_bytes());
+    }
+    int64_t dict_entries = 0;
+    for (int c = 0; c < C; ++c) {
+      if (!cols[c].has_raw) continue;
+      for (int b = 0; b < nb; ++b) {
+        const size_t seg_first_page = pages.size();
+        for (int f = bucket_file_begin[b]; f < bucket_file_begin[b + 1]; ++f) {
+          const FileInput& fi = *file_in[f];
+          if (!fi.raw) continue;
+          const RawColumn& rc = fi.raw->columns()[c];
+          if (!rc.present) continue;
+          // one chunk record per dictionary (plus one for the dictionary-less pages)
+          std::vector<int> chunk_of_dict(rc.dicts.size() + 1, -1);
+          for (size_t pi = 0; pi < rc.pages.size(); ++pi) {
+            const RawColumn::Page& rp = rc.pages[pi];
+            const int di = rc.page_dict[pi];
+            int& ci = chunk_of_dict[(size_t)(di + 1)];
+            if (ci < 0) {
+              PqChunk pc = rc.proto;
+              pc.col = c;
+              pc.bucket = b;
+              pc.dict_nvals = 0;
+              pc.dict_off = 0;
+              pc.dict_index = 0;
+              if (di >= 0) {
+                const RawColumn::Dict& d = rc.dicts[(size_t)di];
+                pc.dict_nvals = d.num_values;
+                pc.dict_off = (d.aux ? aux_off[f] : img_off[f]) + d.src_off;
+                if (pc.phys == PQ_BYTE_ARRAY) {
+                  pc.dict_index = dict_entries;
+                  dict_entries += d.num_values + 1;
+                }
+              }
+              chunks.push_back(pc);
+              ci = (int)chunks.size() - 1;
+            }
+            PqPage pg{};
+            pg.src_off = (rp.aux ? aux_off[f] : img_off[f]) + rp.src_off;
+            pg.size = rp.size;
+            pg.num_values = rp.num_values;
+            pg.encoding = rp.encoding;
+            pg.def_encoding = rp.def_encoding;
+            pg.v2_def_len = rp.v2_def_len;
+            pg.chunk = ci;
+            pg.closes_file = (pi + 1 == rc.pages.size()) ? 1 : 0;
+            pg.row_start = file_row_base[f] + rp.first_row;
+            pages.push_back(pg);
+          }
+          if (rc.pages.empty() && cols[c].kind.var) {
+            // empty file: its single offset entry is written by the host below
+          }
+        }
+        if (cols[c].kind.var && pages.size() > seg_first_page) {
+          seg_start.push_back((int32_t)seg_first_page);
+          seg_base.push_back(host_bytes[c][b]);
+          seg_col.push_back(c);
+          seg_bucket.push_back(b);
+        }
+      }
+    }
+    // explicit [start, end) page range of every (column, bucket) segment
+    std::vector<int32_t> seg_bounds;
+    for (size_t s = 0; s < seg_start.size(); ++s) {
+      seg_bounds.push_back(seg_start[s]);
+      // end = next page whose (col,bucket) differs
+      int32_t e = seg_start[s];
+      while (e < (int32_t)pages.size() && chunks[(size_t)pages[(size_t)e].chunk].col == seg_col[s] &&
+             chunks[(size_t)pages[(size_t)e].chunk].bucket == seg_bucket[s])
+        ++e;
+      seg_bounds.push_back(e);
+    }
+    ctr.device_decoded_pages += (int64_t)pages.size();
+    const int nseg = (int)seg_start.size();
+    d_chunks = static_cast<PqChunk*>(dalloc(sizeof(PqChunk) * chunks.size()));
+    d_pages = static_cast<PqPage*>(dalloc(sizeof(PqPage) * pages.size()));
+    d_dict_pos = static_cast<int32_t*>(dalloc(sizeof(int32_t) * (size_t)(dict_entries + 1)));
+    d_err = static_cast<int32_t*>(dalloc(sizeof(int32_t)));
+    SCAN_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int32_t), stream));
+    h2d(d_chunks, chunks.data(), sizeof(PqChunk) * chunks.size());
+    h2d(d_pages, pages.data(), sizeof(PqPage) * pages.size());
+    args.raw = d_raw;
+    args.chunks = d_chunks;
+    args.pages = d_pages;
+    args.dict_pos = d_dict_pos;
+    args.npages = (int32_t)pages.size();
+    args.nchunks = (int32_t)chunks.size();
+    args.err = d_err;
+    args.cols = nullptr;
+    seg_total.assign((size_t)nseg, 0);
+    if (nseg > 0) {
+      int32_t* d_bounds = static_cast<int32_t*>(dalloc(sizeof(int32_t) * seg_bounds.size()));
+      int64_t* d_base = static_cast<int64_t*>(dalloc(sizeof(int64_t) * (size_t)nseg));
+      int64_t* d_total = static_cast<int64_t*>(dalloc(sizeof(int64_t) * (size_t)nseg));
+      h2d(d_bounds, seg_bounds.data(), sizeof(int32_t) * seg_bounds.size());
+      h2d(d_base, seg_base.data(), sizeof(int64_t) * (size_t)nseg);
+      launch_dict_index(args, stream);
+      launch_page_count(args, stream);
+      launch_page_scan(args, d_bounds, d_base, nseg, d_total, stream);
+      ctr.kernel_launches += 3;
+      SCAN_CUDA(cudaMemcpyAsync(seg_total.data(), d_total, sizeof(int64_t) * (size_t)nseg, cudaMemcpyDeviceToHost, stream));
+      SCAN_CUDA(cudaStreamSynchronize(stream));
+    } else {
+      launch_dict_index(args, stream);
+      ctr.kernel_launches += 1;
+    }
+  }
+
+  // ---- allocate the column buffers, upload host-decoded files ---------------------------------
+  std::vector<PqColOut> colout((size_t)C);
+  for (int c = 0; c < C; ++c) {
+    DevColumn& dc = cols[c];
+    const int w = dc.kind.width;
+    dc.bucket_data.assign(nb, 0);
+    std::vector<int64_t> dev_bytes(nb, 0);
+    for (size_t s = 0; s < seg_col.size(); ++s)
+      if (seg_col[s] == c) dev_bytes[(size_t)seg_bucket[s]] = seg_total[s];
+    int64_t data_pos = 0;
+    for (int b = 0; b < nb; ++b) {
+      dc.bucket_data[b] = data_pos;
+      const int64_t bytes = host_bytes[c][b] + dev_bytes[(size_t)b];
+      if (bytes > 0x7fffff00ll)
+        fail("variable-width column '" + spec.physical_schema->field(c)->name() + "' exceeds 2 GiB in one hash bucket");
+      data_pos += bytes;
+    }
+    dc.data_bytes = data_pos;
+    if (dc.kind.var) {
+      dc.values.bytes = (size_t)(span + 1) * 4;
+      dc.data.bytes = (size_t)data_pos;
+      dc.data.p = dalloc(dc.data.bytes + 16);
+      dc.d_bucket_data.p = dalloc(sizeof(int64_t) * nb);
+      h2d(dc.d_bucket_data.p, dc.bucket_data.data(), sizeof(int64_t) * nb);
+    } else if (w == 0) {
+      dc.values.bytes = (size_t)(span / 8 + 8);
+    } else {
+      dc.values.bytes = (size_t)span * w;
+    }
+    dc.values.p = dalloc(dc.values.bytes);
+    if (w == 0 && !dc.kind.var && dc.has_raw) SCAN_CUDA(cudaMemsetAsync(dc.values.p, 0, dc.values.bytes, stream));
+    if (dc.any_nulls) {
+      dc.validity.bytes = (size_t)(span / 8 + 8);
+      dc.validity.p = dalloc(dc.validity.bytes);
+      SCAN_CUDA(cudaMemsetAsync(dc.validity.p, 0, dc.validity.bytes, stream));
+    }
+    for (int b = 0; b < nb; ++b) {
+      int64_t dpos = dc.bucket_data[b];
+      for (int f = bucket_file_begin[b]; f < bucket_file_begin[b + 1]; ++f) {
+        if (!dc.present[f]) continue;
+        if (file_in[f]->raw) {
+          if (dc.kind.var && file_rows[f] == 0) {
+            const int32_t z = 0;
+            h2d(static_cast<int32_t*>(dc.values.p) + file_row_base[f], &z, sizeof(int32_t));
+          }
+          continue;
+        }
+        upload_host_file(c, b, f, dpos);
+        dpos += file_host_bytes[c][f];
+      }
+    }
+    colout[(size_t)c].values = dc.values.p;
+    colout[(size_t)c].validity = static_cast<uint8_t*>(dc.validity.p);
+    colout[(size_t)c].data = static_cast<uint8_t*>(dc.data.p);
+    colout[(size_t)c].bucket_data = static_cast<const int64_t*>(dc.d_bucket_data.p);
+  }
+  if (any_raw && !pages.empty()) {
+    PqColOut* d_colout = static_cast<PqColOut*>(dalloc(sizeof(PqColOut) * (size_t)C));
+    h2d(d_colout, colout.data(), sizeof(PqColOut) * (size_t)C);
+    args.cols = d_colout;
+    launch_page_decode(args, stream);
+    ctr.kernel_launches += 1;
+    int32_t err = 0;
+    SCAN_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    SCAN_CUDA(cudaStreamSynchronize(stream));
+    if (err != 0) fail("device Parquet decode met a malformed or unsupported page (code " + std::to_string(err) + ")");
+  }
 }
 
 void DeviceScan::Impl::merge_and_gather() {
@@ -591,7 +800,7 @@ void DeviceScan::Run() {
   I.plan = nullptr;
   I.free_device();
   I.buckets.clear();  // drop the decoded inputs
-  I.file_table.clear();
+  I.file_in.clear();
   I.ran = true;
 }
 

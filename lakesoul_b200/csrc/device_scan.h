@@ -35,13 +35,23 @@ struct ScanSpec {
   std::shared_ptr<FilterExpr> filter;  // evaluated on the merged rows (session.rs:839-877), may be null
 };
 
+class RawParquetFile;
+
+// One delta file: either already decoded on the host (Arrow table; used for shapes the device
+// decoders do not cover) or a raw Parquet image whose pages are decoded on the GPU (page_plan.h).
+struct FileInput {
+  std::shared_ptr<arrow::Table> table;
+  std::shared_ptr<RawParquetFile> raw;
+};
+
 struct BucketFiles {
-  // one table per delta file (commit order); a table may lack some physical columns
-  std::vector<std::shared_ptr<arrow::Table>> files;
+  // commit order; a file may lack some physical columns
+  std::vector<FileInput> files;
 };
 
 struct ScanCounters {
   int64_t rows_in = 0, rows_out = 0, h2d_bytes = 0, d2h_bytes = 0;
+  int64_t device_decoded_pages = 0, host_decoded_files = 0;
   int32_t kernel_launches = 0;
   double upload_ms = 0, merge_ms = 0, gather_ms = 0, download_ms = 0;
   std::string path;

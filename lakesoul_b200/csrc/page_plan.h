@@ -1,0 +1,69 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// page_plan.h -- host-side framing of Parquet files for the device decoders: the file is read once
+// into pinned memory, footer + page headers are parsed (libparquet's thrift reader), compressed pages
+// are decompressed on the host (SNAPPY / ZSTD / ... through Arrow's codecs), and every data page is
+// described by a POD record that points into the raw image. Values are never touched on the host.
+#pragma once
+#include <arrow/api.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "decode_types.h"
+
+namespace lsb {
+
+std::shared_ptr<uint8_t> pinned_alloc(size_t bytes);  // recycled cudaMallocHost blocks (device_scan.cc)
+
+struct RawColumn {                    // one requested column of one file
+  std::string name;
+  bool present = false;
+  bool optional = false;              // max definition level 1
+  bool may_have_nulls = false;        // optional and statistics do not prove null_count == 0
+  PqChunk proto{};                    // phys/type_length/conv/out_width/max_def filled; col/bucket set later
+  struct Page {
+    int64_t src_off = 0;              // inside the file image (aux = false) or the aux arena (aux = true)
+    bool aux = false;
+    int32_t size = 0, num_values = 0, encoding = 0, def_encoding = 0, v2_def_len = -1;
+    int32_t row_group = 0;
+    int64_t first_row = 0;            // row inside the file
+  };
+  struct Dict { int64_t src_off = 0; bool aux = false; int32_t size = 0, num_values = 0; };
+  std::vector<Page> pages;
+  std::vector<Dict> dicts;            // one per row group (or size/num_values 0)
+  std::vector<int32_t> page_dict;     // page -> index into dicts, -1 none
+};
+
+class RawParquetFile {
+ public:
+  // reads the whole file into pinned memory and parses the footer; throws on IO / format errors
+  static std::shared_ptr<RawParquetFile> Open(const std::string& path);
+
+  int64_t num_rows() const { return rows_; }
+  const std::shared_ptr<arrow::Schema>& schema() const { return schema_; }  // full file schema (Arrow types)
+
+  // Frames the pages of the requested columns (missing columns are allowed: present = false).
+  // Returns false and fills `why` when some column chunk needs a decoder the device does not have;
+  // the caller then decodes this file on the host.
+  bool Plan(const std::vector<std::shared_ptr<arrow::Field>>& want, std::string* why);
+
+  const std::vector<RawColumn>& columns() const { return cols_; }
+  const uint8_t* image() const { return image_.get(); }
+  int64_t image_bytes() const { return image_bytes_; }
+  const uint8_t* aux() const { return aux_.get(); }
+  int64_t aux_bytes() const { return aux_used_; }
+  int64_t host_decompressed_bytes() const { return aux_used_; }
+
+ private:
+  int64_t aux_append(const uint8_t* p, int64_t n);
+  std::string path_;
+  std::shared_ptr<uint8_t> image_, aux_;
+  int64_t image_bytes_ = 0, aux_cap_ = 0, aux_used_ = 0, rows_ = 0;
+  std::shared_ptr<arrow::Schema> schema_;
+  std::shared_ptr<void> reader_;  // parquet::ParquetFileReader
+  std::vector<RawColumn> cols_;
+};
+
+}  // namespace lsb

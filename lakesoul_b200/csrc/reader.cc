@@ -21,8 +21,11 @@
 #include <set>
 #include <stdexcept>
 
+#include <arrow/io/memory.h>
+
 #include "device_scan.h"
 #include "filter.h"
+#include "page_plan.h"
 
 namespace lsb {
 
@@ -131,10 +134,15 @@ std::shared_ptr<arrow::Array> make_default_array(const std::shared_ptr<arrow::Da
 
 struct FileInfo {
   std::string path;
-  std::unique_ptr<parquet::arrow::FileReader> reader;
+  std::shared_ptr<RawParquetFile> raw;    // whole file in pinned memory + parsed footer
   std::shared_ptr<arrow::Schema> schema;  // partition columns removed
   int64_t rows = 0;
 };
+
+bool force_host_decode() {
+  const char* v = getenv("LAKESOUL_B200_HOST_DECODE");
+  return v && (v[0] == '1' || v[0] == 't');
+}
 
 }  // namespace
 
@@ -241,20 +249,12 @@ void Reader::Start() {
     }
     FileInfo fi;
     fi.path = path;
-    auto in = arrow::io::ReadableFile::Open(path);
-    if (!in.ok()) fail(in.status().ToString());
-    auto rd = parquet::arrow::OpenFile(*in, arrow::default_memory_pool());
-    if (!rd.ok()) fail(rd.status().ToString());
-    fi.reader = std::move(*rd);
-    fi.reader->set_use_threads(false);
-    std::shared_ptr<arrow::Schema> fs;
-    auto st2 = fi.reader->GetSchema(&fs);
-    if (!st2.ok()) fail(st2.ToString());
+    fi.raw = RawParquetFile::Open(path);
     std::vector<std::shared_ptr<arrow::Field>> kept;
-    for (const auto& f : fs->fields())
+    for (const auto& f : fi.raw->schema()->fields())
       if (!cfg.partition_schema->GetFieldByName(f->name())) kept.push_back(f);
     fi.schema = arrow::schema(kept);
-    fi.rows = fi.reader->parquet_reader()->metadata()->num_rows();
+    fi.rows = fi.raw->num_rows();
     files.push_back(std::move(fi));
   }
 
@@ -354,31 +354,44 @@ void Reader::Start() {
     return;
   }
 
-  // ---- decode every file (host Parquet decode; device page decode replaces this step) --------
+  // ---- frame every file for the device decoders; host Arrow decode only where they do not apply
   BucketFiles bucket;
+  const bool host_only = force_host_decode();
   for (auto& fi : files) {
-    const auto& manifest = fi.reader->manifest();
+    bool any = false;
+    for (const auto& pf : phys_fields) any = any || fi.schema->GetFieldByName(pf->name());
+    if (!any) fail("file " + fi.path + " carries none of the requested columns");
+    std::string why;
+    if (!host_only && fi.raw->Plan(phys_fields, &why)) {
+      FileInput in;
+      in.raw = fi.raw;
+      bucket.files.push_back(std::move(in));
+      continue;
+    }
+    if (!host_only && getenv("LAKESOUL_B200_VERBOSE"))
+      fprintf(stderr, "[lakesoul_b200] %s: host decode (%s)\n", fi.path.c_str(), why.c_str());
+    // host fallback: Arrow C++ decode from the pinned image already in memory
+    auto buf = std::make_shared<arrow::Buffer>(fi.raw->image(), fi.raw->image_bytes());
+    auto rd = parquet::arrow::OpenFile(std::make_shared<arrow::io::BufferReader>(buf), arrow::default_memory_pool());
+    if (!rd.ok()) fail(rd.status().ToString());
+    std::unique_ptr<parquet::arrow::FileReader> reader = std::move(*rd);
+    reader->set_use_threads(false);
+    const auto& manifest = reader->manifest();
     std::vector<int> leaf;
     std::vector<std::shared_ptr<arrow::Field>> want;
     for (const auto& pf : phys_fields) {
-      const int idx = fi.schema->GetFieldIndex(pf->name());
-      if (idx < 0) continue;
-      // index inside the full parquet schema (partition columns may precede)
+      if (fi.schema->GetFieldIndex(pf->name()) < 0) continue;
       int full_idx = -1;
-      for (size_t s = 0; s < manifest.schema_fields.size(); ++s)
-        if (manifest.schema_fields[s].field->name() == pf->name()) { full_idx = (int)s; break; }
+      for (size_t s2 = 0; s2 < manifest.schema_fields.size(); ++s2)
+        if (manifest.schema_fields[s2].field->name() == pf->name()) { full_idx = (int)s2; break; }
       if (full_idx < 0 || manifest.schema_fields[full_idx].column_index < 0)
         fail("nested column '" + pf->name() + "' is not supported by the GPU reader");
       leaf.push_back(manifest.schema_fields[full_idx].column_index);
       want.push_back(pf);
     }
-    std::shared_ptr<arrow::Table> table;
-    if (leaf.empty()) {
-      table = arrow::Table::MakeEmpty(arrow::schema({})).ValueOrDie();
-      fail("file " + fi.path + " carries none of the requested columns");
-    }
-    auto st = fi.reader->ReadTable(leaf, &table);
-    if (!st.ok()) fail(st.ToString());
+    auto tr = reader->ReadTable(leaf);
+    if (!tr.ok()) fail(tr.status().ToString());
+    std::shared_ptr<arrow::Table> table = *tr;
     // a2: reorder to target order + cast to the target type (helpers/transform.rs:107-354)
     std::vector<std::shared_ptr<arrow::ChunkedArray>> cols;
     std::vector<std::shared_ptr<arrow::Field>> flds;
@@ -403,8 +416,9 @@ void Reader::Start() {
       cols.push_back(col);
       flds.push_back(pf);
     }
-    bucket.files.push_back(arrow::Table::Make(arrow::schema(flds), cols, table->num_rows()));
-    fi.reader.reset();
+    FileInput in;
+    in.table = arrow::Table::Make(arrow::schema(flds), cols, table->num_rows());
+    bucket.files.push_back(std::move(in));
   }
   I.stats.decode_ms = now_ms() - t_dec0;
 
@@ -429,6 +443,8 @@ void Reader::Start() {
   I.stats.h2d_bytes = c.h2d_bytes;
   I.stats.d2h_bytes = c.d2h_bytes;
   I.stats.kernel_launches = c.kernel_launches;
+  I.stats.device_decoded_pages = c.device_decoded_pages;
+  I.stats.host_decoded_files = c.host_decoded_files;
   I.stats.upload_ms = c.upload_ms;
   I.stats.merge_ms = c.merge_ms;
   I.stats.gather_ms = c.gather_ms;

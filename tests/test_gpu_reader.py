@@ -48,6 +48,8 @@ def _roundtrip(spec, tmp_path, encoding="E1", batch_size=1000, buckets=None, nbu
         assert_tables_equal(got, want, f"{spec.name} bucket {b}")
         assert stats["kernel_launches"] > 0, "no CUDA kernel ran: a CPU/library fallback is not acceptable"
         assert stats["rows_out"] == want.num_rows
+        if not os.environ.get("LAKESOUL_B200_HOST_DECODE"):
+            assert stats["device_decoded_pages"] > 0 and stats["host_decoded_files"] == 0, stats
 
 
 def test_config1_int64_pk(tmp_path):
@@ -141,3 +143,47 @@ def test_reference_sample_parquet_fixture(tmp_path):
         got = read_bucket([p], want.schema, [], batch_size=256)
         assert got.num_rows == 1000
         assert_tables_equal(got, want, name)
+
+
+def test_host_decode_fallback_gives_the_same_table(tmp_path, monkeypatch):
+    """Files the device decoders cannot frame go through Arrow C++ on the host; forcing that path
+    must not change the result."""
+    from lakesoul_b200 import datagen
+    monkeypatch.setenv("LAKESOUL_B200_HOST_DECODE", "1")
+    _roundtrip(datagen.config_spec(3, 0.2), tmp_path, buckets=[0])
+
+
+def test_device_decode_nulls_dictionary_and_v2_pages(tmp_path):
+    """Optional columns with nulls, dictionary-encoded strings/ints, booleans, data page v2, several
+    row groups and small pages: every device decoder against pyarrow's decode of the same file."""
+    from lakesoul_b200 import datagen, read_bucket
+    rng = np.random.default_rng(11)
+    n = 50_000
+    words = np.array(["alpha", "beta", "", "gamma-delta-epsilon", "z"], dtype=object)
+    t = pa.table({
+        "id": pa.array(np.arange(n, dtype=np.int64)),
+        "i32": pa.array(rng.integers(-5, 5, n).astype(np.int32), mask=rng.random(n) < 0.3),
+        "i8": pa.array(rng.integers(-100, 100, n).astype(np.int8)),
+        "f64": pa.array(rng.standard_normal(n), mask=rng.random(n) < 0.1),
+        "f32": pa.array(rng.standard_normal(n).astype(np.float32)),
+        "flag": pa.array(rng.random(n) < 0.5, mask=rng.random(n) < 0.2),
+        "s": pa.array(words[rng.integers(0, 5, n)], type=pa.string(), mask=rng.random(n) < 0.25),
+        "u": pa.array([("k%d" % v) * (v % 7) for v in rng.integers(0, 10**6, n)], type=pa.string()),
+        "dec": datagen._decimal(rng, n, -10**9, 10**9),
+        "d": pa.array(rng.integers(0, 20000, n).astype(np.int32)).cast(pa.date32()),
+        "ts": pa.array(rng.integers(0, 2**50, n)).cast(pa.timestamp("us", "UTC")),
+    })
+    variants = {
+        "v1_dict_snappy": dict(data_page_version="1.0", use_dictionary=True, compression="SNAPPY", data_page_size=4096, row_group_size=17_000),
+        "v2_dict_zstd": dict(data_page_version="2.0", use_dictionary=True, compression="ZSTD", data_page_size=8192, row_group_size=50_000),
+        "v1_plain_none": dict(data_page_version="1.0", use_dictionary=False, compression="NONE", data_page_size=1 << 20, row_group_size=20_000),
+        "v2_plain_none": dict(data_page_version="2.0", use_dictionary=False, compression="NONE", data_page_size=1000, row_group_size=50_000),
+    }
+    for name, opts in variants.items():
+        p = str(tmp_path / f"part-{name}_0000.parquet")
+        pq.write_table(t, p, **opts)
+        got, reader = read_bucket([p], t.schema, ["id"], batch_size=4096, return_reader=True)
+        st = reader.stats()
+        reader.close()
+        assert st["device_decoded_pages"] > 0 and st["host_decoded_files"] == 0, (name, st)
+        assert_tables_equal(got, pq.read_table(p), name)
