@@ -42,13 +42,14 @@ BATCH_SIZE = 8192
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--buckets", type=int, default=BUCKETS, help="hash buckets per GPU")
     ap.add_argument("--e2e-buckets", type=int, default=32, help="buckets written as Parquet for the e2e leg")
     ap.add_argument("--e2e-threads", type=int, default=16, help="concurrent per-bucket readers (Spark task slots)")
-    ap.add_argument("--cpu-buckets", type=int, default=8, help="buckets in the bounded CPU baseline sample")
+    ap.add_argument("--cpu-buckets", type=int, default=32, help="distinct buckets in the bounded CPU baseline sample")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="CPU baseline reader threads (0 = usable host cores)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--data-dir", default=None)
@@ -70,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -261,6 +262,8 @@ def run_e2e(spec, paths, threads: int):
         r.close()
         return rows, st
 
+    from lakesoul_b200 import load_library
+    load_library()
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:
         res = list(ex.map(read_one, paths))
@@ -269,20 +272,39 @@ def run_e2e(spec, paths, threads: int):
     h2d = sum(s["h2d_bytes"] for _, s in res)
     d2h = sum(s["d2h_bytes"] for _, s in res)
     launches = sum(s["kernel_launches"] for _, s in res)
+    run_e2e.last_decode = (sum(s["device_decoded_pages"] for _, s in res), sum(s["host_decoded_files"] for _, s in res))
     return dt, out_rows, h2d, d2h, launches
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the reference-structured CPU reader (oracle/) on a bounded sample
 # ------------------------------------------------------------------------------------------------
-def run_cpu_baseline(spec, paths, rows, nb: int):
+def usable_cores() -> int:
+    """Cores this process may run on (affinity mask, then the cgroup CPU quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
+def run_cpu_baseline(spec, paths, rows, nb: int, threads: int = 0):
+    """The reference-structured CPU reader (oracle/ref_cpu) with one reader per usable host core.
+    The bounded sample = `nb` distinct buckets, replicated so that every thread owns at least one."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref_cpu_driver
+    threads = threads or usable_cores()
     paths, rows = paths[:nb], rows[:nb]
-    res = ref_cpu_driver.run(paths, spec.schema, spec.primary_keys, batch_size=BATCH_SIZE)
-    return {"value": sum(rows) / res["seconds"], "unit": "rows/s", "cores": res["threads"], "kind": res["kind"],
-            "sample": f"{len(paths)} buckets x {K} files of the config-2 table ({sum(rows)} input rows), "
-                      f"{res['impl']}, one reader per host thread"}, res
+    reps = max(1, -(-threads // len(paths)))
+    res = ref_cpu_driver.run(paths * reps, spec.schema, spec.primary_keys, batch_size=BATCH_SIZE, threads=threads)
+    total = sum(rows) * reps
+    return {"value": total / res["seconds"], "unit": "rows/s", "cores": res["threads"], "kind": res["kind"],
+            "sample": f"{len(paths)} distinct config-2 buckets x {K} files read {reps}x ({total} input rows, "
+                      f"{res['seconds']:.2f} s), {res['impl']}, one reader per host thread "
+                      f"({res['threads']} threads on {os.cpu_count()} logical CPUs)"}, res
 
 
 def main():
@@ -304,7 +326,7 @@ def main():
         spec, paths, rows = make_e2e_files(args.cpu_buckets, tmp)
         vals = []
         for i in range(args.warmup + args.steps):
-            cb, res = run_cpu_baseline(spec, paths, rows, args.cpu_buckets)
+            cb, res = run_cpu_baseline(spec, paths, rows, args.cpu_buckets, args.cpu_threads)
             if i >= args.warmup:
                 vals.append((cb, res))
         cb = vals[-1][0]
@@ -390,7 +412,13 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         ach = (mb + gb) / ((merge_ms + gather_ms) / 1e3) / 1e9
-        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic = tj["dram_bytes_per_step"]
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "6650 GB/s (of fallback)",
                     "kernels": "PK merge (part+tile+scan+compact) + winner gather (fixed + var)",
                     "merge_ms": merge_ms, "gather_ms": gather_ms,
@@ -417,13 +445,15 @@ def main():
             dt, out_rows, h2d, d2h, e_launch = best
             line["e2e"] = {"value": sum(rows_e) / dt, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                            "rows_in": sum(rows_e), "rows_out": out_rows, "seconds": dt, "gpu_launches": e_launch,
+                           "device_decoded_pages": run_e2e.last_decode[0], "host_decoded_files": run_e2e.last_decode[1],
                            "how": f"{len(paths_e)} config-2 buckets (Parquet PLAIN, uncompressed) read through the "
-                                  f"lakesoul-io-c C-ABI by {args.e2e_threads} concurrent per-bucket readers; "
-                                  "host Parquet decode + H2D + merge/gather kernels + D2H into Arrow batches, best of 3"}
+                                  f"lakesoul-io-c C-ABI by {args.e2e_threads} concurrent per-bucket readers (one per task slot); "
+                                  "pread into pinned memory + H2D + device page decode + merge/gather kernels + D2H "
+                                  "into Arrow batches consumed by the caller, best of 3"}
         if not args.no_cpu:
             spec, paths, rows = e2e_ctx
             try:
-                cb, _ = run_cpu_baseline(spec, paths, rows, args.cpu_buckets)
+                cb, _ = run_cpu_baseline(spec, paths, rows, args.cpu_buckets, args.cpu_threads)
                 line["cpu_baseline"] = cb
             except Exception as e:  # the baseline is reporting only
                 line["cpu_baseline"] = {"value": None, "unit": "rows/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}

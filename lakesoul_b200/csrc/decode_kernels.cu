@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(128) page_decode_kernel(DecodeArgs A) {
   if (dict) hybrid_init(idx, v.values + 1, v.values_end, v.values < v.values_end ? v.values[0] : 0);
   if (rle_bool) {  // <4-byte length> <hybrid runs, bit width 1>
     const uint32_t len = v.values + 4 <= v.values_end ? load_le32(v.values) : 0;
-    hybrid_init(idx, v.values + 4, min(v.values + 4 + len, v.values_end), 1);
+    hybrid_init(idx, v.values + 4, (v.values + 4 + len < v.values_end) ? (v.values + 4 + len) : v.values_end, 1);
   }
   const int pw = phys_width(ch);
   const uint8_t* dict_base = A.raw + ch.dict_off;
