@@ -62,3 +62,21 @@ def assert_tables_equal(got: pa.Table, want: pa.Table, what=""):
 def lib():
     from lakesoul_b200 import load_library
     return load_library()
+
+
+def upsert_cases():
+    with open(os.path.join(ROOT, "tests", "golden", "reference_upsert_goldens.json")) as f:
+        return json.load(f)["cases"]
+
+
+def upsert_case_files(case, tmp_path):
+    import pyarrow.parquet as pq
+    paths = []
+    for j, cols in enumerate(case["files"]):
+        t = pa.table({k: pa.array(v, type=pa.int32()) for k, v in cols.items()})
+        p = str(tmp_path / f"part-{j:016d}_0000.parquet")
+        pq.write_table(t, p)
+        paths.append(p)
+    schema = pa.schema([pa.field(n, _TYPES[t], nl) for n, t, nl in case["schema"]])
+    expected = pa.table({n: pa.array(case["expected"][n], type=schema.field(n).type) for n in schema.names})
+    return paths, schema, expected

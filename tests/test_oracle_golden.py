@@ -101,3 +101,16 @@ def test_hash_known_answers():
     assert hashing.hash_int32(np.array([1, 2, 3, 4]), 42).view(np.int32).tolist() == [-559580957, 1765031574, -1823081949, -397064898]
     assert hashing.hash_int64(np.array([1, 2, 3, 4]), 42).view(np.int32).tolist() == [-1712319331, -797927272, 519220707, 1344313940]
     assert hashing.hash_int32(np.array([49, 1065353216]), 42).view(np.int32).tolist() == [766678906, -466301895]
+
+
+from conftest import upsert_case_files, upsert_cases  # noqa: E402
+
+UPSERTS = upsert_cases()
+
+
+@pytest.mark.parametrize("case", UPSERTS, ids=[c["name"] for c in UPSERTS])
+def test_reader_level_oracle_matches_reference_upsert_golden(case, tmp_path):
+    """G9: rust/lakesoul-datafusion/src/tests/upsert_tests.rs scenarios at reader level."""
+    paths, schema, expected = upsert_case_files(case, tmp_path)
+    got = mo.read_bucket(paths, schema, case["primary_keys"], default_columns=case["partition"], filters=case["filters"])
+    assert_tables_equal(got, expected, case["name"])
