@@ -420,6 +420,8 @@ int32_t lsb_plan_merge(LsbPlan* plan, int32_t n_pk, const void* const* pk_values
       pk.col[i].validity = static_cast<const uint8_t*>(pk_validity ? pk_validity[i] : nullptr);
       pk.col[i].width = (uint8_t)pk_width[i];
       pk.col[i].kind = (uint8_t)pk_kind[i];
+      pk.col[i].data = nullptr;
+      pk.col[i].bucket_data = nullptr;
       bits += pk_width[i] * 8 + (pk.col[i].validity ? 1 : 0);
     }
     pk.key_bits = bits;

@@ -607,10 +607,22 @@ void DeviceScan::Impl::merge_and_gather() {
       const int c = spec.physical_schema->GetFieldIndex(spec.primary_keys[i]);
       if (c < 0) fail("primary key column '" + spec.primary_keys[i] + "' is not in the schema");
       const DevColumn& dc = cols[c];
+      if (!dc.all_present) fail("primary key column '" + spec.primary_keys[i] + "' is missing from a file");
+      if (dc.kind.var && pk.ncols == 1) {
+        // Utf8 / Binary key: prefix + full byte-wise compare on the device
+        pk.col[i].values = dc.values.p;
+        pk.col[i].validity = static_cast<const uint8_t*>(dc.validity.p);
+        pk.col[i].width = 0;
+        pk.col[i].kind = PK_BYTES;
+        pk.col[i].data = static_cast<const uint8_t*>(dc.data.p);
+        pk.col[i].bucket_data = static_cast<const int64_t*>(dc.d_bucket_data.p);
+        key_bits = 128;
+        continue;
+      }
       if (!dc.kind.pk_ok)
         fail("primary key column '" + spec.primary_keys[i] + "' of type " +
-             spec.physical_schema->field(c)->type()->ToString() + " is not supported by the GPU reader yet");
-      if (!dc.all_present) fail("primary key column '" + spec.primary_keys[i] + "' is missing from a file");
+             spec.physical_schema->field(c)->type()->ToString() +
+             (dc.kind.var ? " inside a composite key" : "") + " is not supported by the GPU reader yet");
       pk.col[i].values = dc.values.p;
       pk.col[i].validity = static_cast<const uint8_t*>(dc.validity.p);
       pk.col[i].width = (uint8_t)dc.kind.width;

@@ -125,6 +125,81 @@ struct KeyLoader<K128> {
   }
 };
 
+// Utf8 / Binary primary key (single column; reference typed fast path sorted_stream_merger.rs:311-315,
+// byte-wise unsigned compare cursor.rs:283-324): 8-byte big-endian prefix in shared memory, the rest
+// of the string is fetched from HBM only when two prefixes tie.
+struct StrKey {
+  uint64_t prefix;
+  uint32_t row;   // global row, kNoRow for a null key (nulls sort first and are equal, cursor.rs:444-476)
+  uint32_t len;
+};
+
+template <typename KeyT>
+struct KeyOps {
+  PkDesc pk;
+  __device__ __forceinline__ KeyOps(const PkDesc& p, int) : pk(p) {}
+  __device__ __forceinline__ KeyT load(int64_t row) const { return KeyLoader<KeyT>::load(pk, row); }
+  __device__ __forceinline__ bool lt(const KeyT& a, const KeyT& b) const { return key_lt(a, b); }
+  __device__ __forceinline__ bool le(const KeyT& a, const KeyT& b) const { return key_le(a, b); }
+  __device__ __forceinline__ bool ne(const KeyT& a, const KeyT& b) const { return key_ne(a, b); }
+};
+
+template <>
+struct KeyOps<StrKey> {
+  const int32_t* offs;
+  const uint8_t* valid;
+  const uint8_t* data;  // bucket's bytes
+  __device__ __forceinline__ KeyOps(const PkDesc& p, int bucket)
+      : offs(reinterpret_cast<const int32_t*>(p.col[0].values)), valid(p.col[0].validity),
+        data(p.col[0].data + p.col[0].bucket_data[bucket]) {}
+  __device__ __forceinline__ StrKey load(int64_t row) const {
+    StrKey k{0, (uint32_t)row, 0};
+    if (valid && !((valid[row >> 3] >> (row & 7)) & 1)) { k.row = kNoRow; return k; }
+    const int32_t o0 = offs[row], o1 = offs[row + 1];
+    k.len = (uint32_t)(o1 - o0);
+    const uint8_t* p = data + o0;
+    const int n = k.len < 8 ? (int)k.len : 8;
+    uint64_t v = 0;
+    for (int i = 0; i < n; ++i) v |= (uint64_t)p[i] << (56 - 8 * i);
+    k.prefix = v;
+    return k;
+  }
+  // <0, 0, >0
+  __device__ __forceinline__ int cmp(const StrKey& a, const StrKey& b) const {
+    const bool an = a.row == kNoRow, bn = b.row == kNoRow;
+    if (an || bn) return an == bn ? 0 : (an ? -1 : 1);
+    if (a.prefix != b.prefix) return a.prefix < b.prefix ? -1 : 1;
+    const uint32_t m = a.len < b.len ? a.len : b.len;
+    if (m > 8) {
+      const uint8_t* pa = data + offs[a.row];
+      const uint8_t* pb = data + offs[b.row];
+      for (uint32_t i = 8; i < m; ++i) {
+        const int d = (int)pa[i] - (int)pb[i];
+        if (d) return d;
+      }
+    }
+    return a.len == b.len ? 0 : (a.len < b.len ? -1 : 1);
+  }
+  __device__ __forceinline__ bool lt(const StrKey& a, const StrKey& b) const { return cmp(a, b) < 0; }
+  __device__ __forceinline__ bool le(const StrKey& a, const StrKey& b) const { return cmp(a, b) <= 0; }
+  __device__ __forceinline__ bool ne(const StrKey& a, const StrKey& b) const { return cmp(a, b) != 0; }
+};
+
+__device__ __forceinline__ uint64_t shfl_xor_key(uint64_t k, int d) { return __shfl_xor_sync(0xffffffffu, k, d); }
+__device__ __forceinline__ K128 shfl_xor_key(const K128& k, int d) {
+  K128 r;
+  r.hi = __shfl_xor_sync(0xffffffffu, k.hi, d);
+  r.lo = __shfl_xor_sync(0xffffffffu, k.lo, d);
+  return r;
+}
+__device__ __forceinline__ StrKey shfl_xor_key(const StrKey& k, int d) {
+  StrKey r;
+  r.prefix = __shfl_xor_sync(0xffffffffu, k.prefix, d);
+  r.row = __shfl_xor_sync(0xffffffffu, k.row, d);
+  r.len = __shfl_xor_sync(0xffffffffu, k.len, d);
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------
 // device plan view
 // ---------------------------------------------------------------------------------------
@@ -182,6 +257,7 @@ __global__ void __launch_bounds__(128) part_kernel(PlanDev P, PkDesc pk, int lev
   const int b = P.tile_bucket[t];
   const int i = P.tile_idx[t];
   const BucketDesc& B = P.buckets[b];
+  const KeyOps<KeyT> ops(pk, b);
   const int k = B.k;
   const int T = B.ntiles[level];
   int32_t* sp = P.splits + B.split_ofs[level];
@@ -196,7 +272,7 @@ __global__ void __launch_bounds__(128) part_kernel(PlanDev P, PkDesc pk, int lev
     const int64_t ps = s.y;
     const int64_t rowS =
         P.file_row_base[B.file_begin + js] + (((ps + 1) << (sh + P.log_s)) - 1);
-    keyS = KeyLoader<KeyT>::load(pk, rowS);
+    keyS = ops.load(rowS);
     pprime = ((ps + 1) << P.log_s) - 1;
   }
   for (int j = lane; j < k; j += 32) {
@@ -212,14 +288,14 @@ __global__ void __launch_bounds__(128) part_kernel(PlanDev P, PkDesc pk, int lev
         if (j < js) {  // count of elements with key <= keyS
           while (lo < hi) {
             int mid = (lo + hi) >> 1;
-            KeyT km = KeyLoader<KeyT>::load(pk, fb + ((((int64_t)mid + 1) << sh) - 1));
-            if (key_le(km, keyS)) lo = mid + 1; else hi = mid;
+            KeyT km = ops.load(fb + ((((int64_t)mid + 1) << sh) - 1));
+            if (ops.le(km, keyS)) lo = mid + 1; else hi = mid;
           }
         } else {  // count of elements with key < keyS
           while (lo < hi) {
             int mid = (lo + hi) >> 1;
-            KeyT km = KeyLoader<KeyT>::load(pk, fb + ((((int64_t)mid + 1) << sh) - 1));
-            if (key_lt(km, keyS)) lo = mid + 1; else hi = mid;
+            KeyT km = ops.load(fb + ((((int64_t)mid + 1) << sh) - 1));
+            if (ops.lt(km, keyS)) lo = mid + 1; else hi = mid;
           }
         }
         v = lo;
@@ -284,6 +360,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(PlanDev P, PkDesc pk
   const int b = P.tile_bucket[t];
   const int i = P.tile_idx[t];
   const BucketDesc& B = P.buckets[b];
+  const KeyOps<KeyT> ops(pk, b);
   const int k = B.k;
   const int32_t* sp_lo = P.splits + B.split_ofs[level] + (int64_t)i * k;
   const int32_t* sp_hi = sp_lo + k;
@@ -347,7 +424,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(PlanDev P, PkDesc pk
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (e0 + u * kTileThreads < L) kv[u] = KeyLoader<KeyT>::load(pk, row[u]);
+      if (e0 + u * kTileThreads < L) kv[u] = ops.load(row[u]);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int e = e0 + u * kTileThreads;
@@ -364,21 +441,15 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(PlanDev P, PkDesc pk
     for (int j = lane; j < k; j += 32) {
       const int32_t h = sp_hi[j];
       if (h < P.file_rows[B.file_begin + j]) {
-        KeyT kk = KeyLoader<KeyT>::load(pk, frb[j] + h);
-        if (!have || key_lt(kk, best)) { best = kk; have = true; }
+        KeyT kk = ops.load(frb[j] + h);
+        if (!have || ops.lt(kk, best)) { best = kk; have = true; }
       }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
       bool oh = __shfl_xor_sync(0xffffffffu, (int)have, d);
-      KeyT ob;
-      if constexpr (sizeof(KeyT) == 8) {
-        ob = __shfl_xor_sync(0xffffffffu, best, d);
-      } else {
-        ob.hi = __shfl_xor_sync(0xffffffffu, best.hi, d);
-        ob.lo = __shfl_xor_sync(0xffffffffu, best.lo, d);
-      }
-      if (oh && (!have || key_lt(ob, best))) { best = ob; have = true; }
+      const KeyT ob = shfl_xor_key(best, d);
+      if (oh && (!have || ops.lt(ob, best))) { best = ob; have = true; }
     }
     if (lane == 0) { s_has_next = have; s_next_key = best; }
   }
@@ -422,7 +493,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(PlanDev P, PkDesc pk
         const int mid = (i + ihi) >> 1;
         const KeyT ka = K[in[a0 + mid]];
         const KeyT kb = K[in[m0 + d - 1 - mid]];
-        if (!key_lt(kb, ka)) i = mid + 1; else ihi = mid;
+        if (!ops.lt(kb, ka)) i = mid + 1; else ihi = mid;
       }
       int j = d - i;
       uint16_t ea = 0, eb = 0;
@@ -431,7 +502,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(PlanDev P, PkDesc pk
       if (j < nbb) { eb = in[m0 + j]; kb = K[eb]; }
       for (; q < stop; ++q) {
         // predicated two-pointer step: no divergent branches, one index + one key load per output
-        const bool take_a = (j >= nbb) || (i < na && !key_lt(kb, ka));
+        const bool take_a = (j >= nbb) || (i < na && !ops.lt(kb, ka));
         out[q] = take_a ? ea : eb;
         i += take_a ? 1 : 0;
         j += take_a ? 0 : 1;
@@ -467,8 +538,8 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(PlanDev P, PkDesc pk
   for (int q = q0; q < q1; ++q) {
     const KeyT kq = K[in[q]];
     bool end;
-    if (q + 1 < L) end = key_ne(kq, K[in[q + 1]]);
-    else end = has_next ? key_ne(kq, next_key) : true;
+    if (q + 1 < L) end = ops.ne(kq, K[in[q + 1]]);
+    else end = has_next ? ops.ne(kq, next_key) : true;
     cnt += end ? 1 : 0;
   }
   int total;
@@ -485,15 +556,15 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(PlanDev P, PkDesc pk
       bool end, sub_last;
       if (q + 1 < L) {
         const int e2 = in[q + 1];
-        end = key_ne(kq, K[e2]);
+        end = ops.ne(kq, K[e2]);
         sub_last = end || upper_idx(seg_start, k, e2) != j;
       } else {
-        end = has_next ? key_ne(kq, next_key) : true;
+        end = has_next ? ops.ne(kq, next_key) : true;
         const int32_t h = sp_hi[j];
         sub_last = true;
         if (h < P.file_rows[B.file_begin + j]) {
-          const KeyT kn = KeyLoader<KeyT>::load(pk, frb[j] + h);
-          sub_last = key_ne(kn, kq);
+          const KeyT kn = ops.load(frb[j] + h);
+          sub_last = ops.ne(kn, kq);
         }
       }
       if (sub_last) Rb[u_run * k + j] = (uint32_t)(frb[j] + seg_lo[j] + (e - seg_start[j]));
@@ -507,8 +578,8 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(PlanDev P, PkDesc pk
     const int e = in[q];
     const KeyT kq = K[e];
     bool end;
-    if (q + 1 < L) end = key_ne(kq, K[in[q + 1]]);
-    else end = has_next ? key_ne(kq, next_key) : true;
+    if (q + 1 < L) end = ops.ne(kq, K[in[q + 1]]);
+    else end = has_next ? ops.ne(kq, next_key) : true;
     if (end) {
       const int j = upper_idx(seg_start, k, e);
       wt[off++] = (uint32_t)(frb[j] + seg_lo[j] + (e - seg_start[j]));
@@ -1051,6 +1122,7 @@ struct MergePlan {
   int nb = 0, F = 0;
   int batch_size = 8192;
   bool key128 = false;
+  bool key_bytes = false;  // last merge used a Utf8/Binary key
   int log_s = 6, tile_cap = 0, max_level = 0;
   int64_t n_total = 0;  // global row span (>= input rows when files are padded apart)
   int64_t n_in = 0;     // input rows
@@ -1306,6 +1378,10 @@ MergePlan* plan_create(int nb, const int32_t* bucket_file_begin, const int64_t* 
                                   (int)tile_smem_bytes(5632, false)));
     LSB_CUDA(cudaFuncSetAttribute(tile_kernel<K128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tile_smem_bytes(3328, true)));
+    LSB_CUDA(cudaFuncSetAttribute(tile_kernel<StrKey, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tile_smem_bytes(3328, true)));
+    LSB_CUDA(cudaFuncSetAttribute(tile_kernel<StrKey, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tile_smem_bytes(3328, true)));
     }
     P->stats.n_rows = P->n_in;
     P->stats.tiles_l0 = T0;
@@ -1381,7 +1457,9 @@ void plan_merge(MergePlan* P, const PkDesc& pk, cudaStream_t stream) {
   }
   int launches = 0;
   if (P->n_total > 0) {
-    launches += P->key128 ? run_levels<K128>(P, pk, stream) : run_levels<uint64_t>(P, pk, stream);
+    P->key_bytes = pk.ncols == 1 && pk.col[0].kind == PK_BYTES;
+    if (P->key_bytes) launches += run_levels<StrKey>(P, pk, stream);
+    else launches += P->key128 ? run_levels<K128>(P, pk, stream) : run_levels<uint64_t>(P, pk, stream);
   }
   PlanDev D = plan_dev(P);
   const int T0 = P->level_tile_cnt[0];
@@ -1610,11 +1688,11 @@ __device__ __forceinline__ T ld(const void* p, int64_t i) { return reinterpret_c
 __device__ __forceinline__ bool bit_at(const uint8_t* bm, int64_t i) { return !bm || ((bm[i >> 3] >> (i & 7)) & 1); }
 
 template <typename KeyT>
-__device__ __forceinline__ int64_t run_first(const PkDesc& pk, int64_t file_first, int64_t last) {
+__device__ __forceinline__ int64_t run_first(const KeyOps<KeyT>& ops, int64_t file_first, int64_t last) {
   // in-file run of equal keys ending at `last` (sort_key_range.rs:99-113)
-  const KeyT kl = KeyLoader<KeyT>::load(pk, last);
+  const KeyT kl = ops.load(last);
   int64_t r = last;
-  while (r > file_first && !key_ne(KeyLoader<KeyT>::load(pk, r - 1), kl)) --r;
+  while (r > file_first && !ops.ne(ops.load(r - 1), kl)) --r;
   return r;
 }
 
@@ -1622,7 +1700,7 @@ template <typename T>
 __device__ __forceinline__ void store_val(void* p, int64_t i, T v) { reinterpret_cast<T*>(p)[i] = v; }
 
 template <typename KeyT, typename T>
-__device__ void sum_op(const PlanDev& P, const PkDesc& pk, const GenColDev& c, const BucketDesc& B,
+__device__ void sum_op(const PlanDev& P, const KeyOps<KeyT>& ops, const GenColDev& c, const BucketDesc& B,
                        const uint32_t* Rrow, int64_t u, bool sum_all, bool& valid) {
   T res = T(0);
   valid = true;
@@ -1631,7 +1709,7 @@ __device__ void sum_op(const PlanDev& P, const PkDesc& pk, const GenColDev& c, c
     const uint32_t last = Rrow[j];
     if (last == kNoRow) continue;
     if (sum_all) {
-      const int64_t first = run_first<KeyT>(pk, P.file_row_base[B.file_begin + j], last);
+      const int64_t first = run_first<KeyT>(ops, P.file_row_base[B.file_begin + j], last);
       T part = T(0);
       for (int64_t r = first; r <= (int64_t)last; ++r) {
         if (!bit_at(c.validity, r)) { valid = false; break; }
@@ -1654,6 +1732,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(PlanDev P, PkDesc pk, GenC
   if (active) {
     const int b = upper_idx(P.out_base, P.nb + 1, u);
     const BucketDesc& B = P.buckets[b];
+    const KeyOps<KeyT> ops(pk, b);
     const uint32_t* Rrow = P.R + P.rofs[b] + (u - P.out_base[b]) * B.k;
     const char* present = c.present + B.file_begin;
     if (c.op == (int)MergeOp::UseLast) {
@@ -1667,7 +1746,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(PlanDev P, PkDesc pk, GenC
       for (int j = B.k - 1; j >= 0 && w == kNoRow; --j) {
         if (!present[j] || Rrow[j] == kNoRow) continue;
         const int64_t last = Rrow[j];
-        const int64_t first = run_first<KeyT>(pk, P.file_row_base[B.file_begin + j], last);
+        const int64_t first = run_first<KeyT>(ops, P.file_row_base[B.file_begin + j], last);
         for (int64_t r = last; r >= first; --r) {
           if (bit_at(c.validity, r)) { w = (uint32_t)r; break; }
         }
@@ -1676,16 +1755,16 @@ __global__ void __launch_bounds__(256) resolve_kernel(PlanDev P, PkDesc pk, GenC
     } else {
       const bool all = c.op == (int)MergeOp::SumAll;
       switch (c.num_class) {
-        case NC_I8: sum_op<KeyT, int8_t>(P, pk, c, B, Rrow, u, all, valid); break;
-        case NC_I16: sum_op<KeyT, int16_t>(P, pk, c, B, Rrow, u, all, valid); break;
-        case NC_I32: sum_op<KeyT, int32_t>(P, pk, c, B, Rrow, u, all, valid); break;
-        case NC_I64: sum_op<KeyT, int64_t>(P, pk, c, B, Rrow, u, all, valid); break;
-        case NC_U8: sum_op<KeyT, uint8_t>(P, pk, c, B, Rrow, u, all, valid); break;
-        case NC_U16: sum_op<KeyT, uint16_t>(P, pk, c, B, Rrow, u, all, valid); break;
-        case NC_U32: sum_op<KeyT, uint32_t>(P, pk, c, B, Rrow, u, all, valid); break;
-        case NC_U64: sum_op<KeyT, uint64_t>(P, pk, c, B, Rrow, u, all, valid); break;
-        case NC_F32: sum_op<KeyT, float>(P, pk, c, B, Rrow, u, all, valid); break;
-        default: sum_op<KeyT, double>(P, pk, c, B, Rrow, u, all, valid); break;
+        case NC_I8: sum_op<KeyT, int8_t>(P, ops, c, B, Rrow, u, all, valid); break;
+        case NC_I16: sum_op<KeyT, int16_t>(P, ops, c, B, Rrow, u, all, valid); break;
+        case NC_I32: sum_op<KeyT, int32_t>(P, ops, c, B, Rrow, u, all, valid); break;
+        case NC_I64: sum_op<KeyT, int64_t>(P, ops, c, B, Rrow, u, all, valid); break;
+        case NC_U8: sum_op<KeyT, uint8_t>(P, ops, c, B, Rrow, u, all, valid); break;
+        case NC_U16: sum_op<KeyT, uint16_t>(P, ops, c, B, Rrow, u, all, valid); break;
+        case NC_U32: sum_op<KeyT, uint32_t>(P, ops, c, B, Rrow, u, all, valid); break;
+        case NC_U64: sum_op<KeyT, uint64_t>(P, ops, c, B, Rrow, u, all, valid); break;
+        case NC_F32: sum_op<KeyT, float>(P, ops, c, B, Rrow, u, all, valid); break;
+        default: sum_op<KeyT, double>(P, ops, c, B, Rrow, u, all, valid); break;
       }
       // a key that no carrying file contains stays null (merge_operator.rs:61-62)
       bool any = false;
@@ -1777,7 +1856,8 @@ GeneralMerge* general_create(MergePlan* P, const PkDesc& pk, const std::vector<G
     PlanDev D = plan_dev(P);
     const int T0 = P->level_tile_cnt[0];
     const int ofs0 = P->level_tile_ofs[0];
-    if (P->key128) tile_kernel<K128, true><<<T0, kTileThreads, P->smem_bytes, stream>>>(D, pk, 0, ofs0);
+    if (P->key_bytes) tile_kernel<StrKey, true><<<T0, kTileThreads, P->smem_bytes, stream>>>(D, pk, 0, ofs0);
+    else if (P->key128) tile_kernel<K128, true><<<T0, kTileThreads, P->smem_bytes, stream>>>(D, pk, 0, ofs0);
     else tile_kernel<uint64_t, true><<<T0, kTileThreads, P->smem_bytes, stream>>>(D, pk, 0, ofs0);
     ++G->launches;
 
@@ -1800,7 +1880,8 @@ GeneralMerge* general_create(MergePlan* P, const PkDesc& pk, const std::vector<G
         gc.opvalid = col.opvalid;
       }
       const unsigned g = (unsigned)((U + 255) / 256);
-      if (P->key128) resolve_kernel<K128><<<g, 256, 0, stream>>>(D, pk, gc, U);
+      if (P->key_bytes) resolve_kernel<StrKey><<<g, 256, 0, stream>>>(D, pk, gc, U);
+      else if (P->key128) resolve_kernel<K128><<<g, 256, 0, stream>>>(D, pk, gc, U);
       else resolve_kernel<uint64_t><<<g, 256, 0, stream>>>(D, pk, gc, U);
       ++G->launches;
     }

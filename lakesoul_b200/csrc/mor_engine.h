@@ -24,20 +24,23 @@
 
 namespace lsb {
 
-enum PkKind : uint8_t { PK_UNSIGNED = 0, PK_SIGNED = 1, PK_FLOAT = 2 };
+enum PkKind : uint8_t { PK_UNSIGNED = 0, PK_SIGNED = 1, PK_FLOAT = 2, PK_BYTES = 3 };
 
 struct PkCol {
-  const void* values;       // `width` bytes per global row
+  const void* values;       // `width` bytes per global row; PK_BYTES: int32 offsets (bucket relative)
   const uint8_t* validity;  // Arrow validity bitmap over global rows, or nullptr (no nulls)
-  uint8_t width;            // 1, 2, 4, 8
+  uint8_t width;            // 1, 2, 4, 8 (PK_BYTES: 0)
   uint8_t kind;             // PkKind
   uint8_t pad[6];
+  const uint8_t* data;          // PK_BYTES: byte buffer of the column
+  const int64_t* bucket_data;   // PK_BYTES: data base of every bucket (device, nb entries)
 };
 
 constexpr int kMaxPkCols = 4;
 struct PkDesc {
   int32_t ncols;
-  int32_t key_bits;  // sum(width*8 + (validity?1:0)); <=64 -> 64-bit keys, <=128 -> 128-bit keys
+  int32_t key_bits;  // sum(width*8 + (validity?1:0)); <=64 -> 64-bit keys, <=128 -> 128-bit keys;
+                     // a single Utf8/Binary key column (PK_BYTES) uses 8-byte prefixes + full compares: pass 128
   PkCol col[kMaxPkCols];
 };
 

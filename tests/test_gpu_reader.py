@@ -238,3 +238,33 @@ def test_schema_evolution_cast_and_missing_column(tmp_path):
     assert got.column("id").to_pylist() == [1, 2, 3, 4]
     assert got.column("qty").to_pylist() == [10, 200, 30, 400]
     assert got.column("tag").to_pylist() == [None, "b", None, "d"]
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_string_primary_key(tmp_path, binary):
+    """Utf8 / Binary single-column PK (reference typed fast path sorted_stream_merger.rs:311-315):
+    byte-wise unsigned order, long common prefixes, empty and null keys, duplicates inside a file."""
+    from lakesoul_b200 import read_bucket
+    rng = np.random.default_rng(21)
+    typ = pa.binary() if binary else pa.string()
+    schema = pa.schema([pa.field("k", typ, True), pa.field("v", pa.int64()), pa.field("s", pa.string())])
+
+    def keys(n):
+        pool = ["user_%08d" % i for i in range(3000)] + ["", "a", "ab", "ab\x00", "user_", "zz", "été", "user_00000001x"]
+        ks = [pool[i] for i in rng.integers(0, len(pool), n)]
+        if binary:
+            return sorted(k.encode() for k in ks)
+        return sorted(ks, key=lambda x: x.encode())
+    paths = []
+    for j, n in enumerate((4000, 700, 700, 50)):
+        ks = keys(n)
+        if j == 1:
+            ks = [None, None] + ks
+        t = pa.table({"k": pa.array(ks, type=typ), "v": pa.array(rng.integers(0, 10**9, len(ks))),
+                      "s": pa.array(["f%d_%d" % (j, i) for i in range(len(ks))])}).cast(schema)
+        p = str(tmp_path / f"part-{j:016d}_0000.parquet")
+        pq.write_table(t, p)
+        paths.append(p)
+    got = read_bucket(paths, schema, ["k"], batch_size=1000)
+    want = mo.read_bucket(paths, schema, ["k"])
+    assert_tables_equal(got, want, "string pk")
