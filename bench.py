@@ -276,6 +276,21 @@ def run_e2e(spec, paths, threads: int):
     return dt, out_rows, h2d, d2h, launches
 
 
+def run_e2e_native(spec, paths, threads: int, repeat: int = 3):
+    """Same call sequence from a native task executor (tools/cabi_driver.cc): T threads, one reader per
+    bucket through the C-ABI, every batch released by the consumer. No Python in the timed path."""
+    drv = os.path.join(ROOT, "lakesoul_b200", "lib", "cabi_driver")
+    if not os.path.exists(drv):
+        return None
+    inp = (f"{threads} {BATCH_SIZE} {repeat}\n" + "\t".join(spec.primary_keys) + "\n\n\n" +
+           "\n".join("\t".join(p) for p in paths) + "\n")
+    env = dict(os.environ)
+    out = subprocess.run([drv], input=inp, capture_output=True, text=True, env=env)
+    if out.returncode != 0:
+        raise RuntimeError("cabi_driver failed: " + out.stderr[-500:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the reference-structured CPU reader (oracle/) on a bounded sample
 # ------------------------------------------------------------------------------------------------
@@ -443,9 +458,18 @@ def main():
                 if best is None or r[0] < best[0]:
                     best = r
             dt, out_rows, h2d, d2h, e_launch = best
+            py_val = sum(rows_e) / dt
+            dec = run_e2e.last_decode
+            harness = "python ctypes harness (lakesoul_b200.NativeIOReader)"
+            nat = run_e2e_native(spec, paths_e, args.e2e_threads)
+            if nat is not None and nat["rows_out"] == out_rows:
+                dt, h2d, d2h, e_launch = nat["seconds"], nat["h2d_bytes"], nat["d2h_bytes"], nat["kernel_launches"]
+                dec = (nat["device_decoded_pages"], nat["host_decoded_files"])
+                harness = "native task executor tools/cabi_driver.cc (C-ABI calls only)"
             line["e2e"] = {"value": sum(rows_e) / dt, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                            "rows_in": sum(rows_e), "rows_out": out_rows, "seconds": dt, "gpu_launches": e_launch,
-                           "device_decoded_pages": run_e2e.last_decode[0], "host_decoded_files": run_e2e.last_decode[1],
+                           "device_decoded_pages": dec[0], "host_decoded_files": dec[1],
+                           "consumer": harness, "python_harness_value": py_val,
                            "how": f"{len(paths_e)} config-2 buckets (Parquet PLAIN, uncompressed) read through the "
                                   f"lakesoul-io-c C-ABI by {args.e2e_threads} concurrent per-bucket readers (one per task slot); "
                                   "pread into pinned memory + H2D + device page decode + merge/gather kernels + D2H "

@@ -920,50 +920,71 @@ __global__ void __launch_bounds__(1024) scan_sums_inplace(int64_t* sums_all, int
   if (tid == 0) sums[nblocks] = carry_s;
 }
 
-// Row copy global -> shared with many loads in flight: byte head until dst is word aligned (at most
-// 3, predicated), then chunks of 8 destination words fed by 9 INDEPENDENT aligned source-word loads
-// (issued before any store) through a funnel shift, then a byte tail (at most 3, predicated).
-// Reads at most the aligned word that holds the last source byte.
-// (A sub-warp "G lanes per row" variant was measured slower: 6.2 ms vs 4.4 ms on the bench step.)
-__device__ __forceinline__ void copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int n) {
-  const int head = min(n, (int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3));
-  {
-    uint8_t b0 = 0, b1 = 0, b2 = 0;
-    if (head > 0) b0 = src[0];
-    if (head > 1) b1 = src[1];
-    if (head > 2) b2 = src[2];
-    if (head > 0) dst[0] = b0;
-    if (head > 1) dst[1] = b1;
-    if (head > 2) dst[2] = b2;
-  }
-  src += head;
-  dst += head;
-  n -= head;
-  const int nw = n >> 2;
-  const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
-  const uint32_t* sw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
-  uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
-  for (int base = 0; base < nw; base += 8) {
-    const int cnt = min(8, nw - base);
+// Row copy global -> shared, split into a LOAD phase and a STORE phase so that every global load of a
+// row (and of the next row of the same thread) is in flight before the first dependent store:
+// byte head until dst is word aligned (<= 3), 8 destination words fed by 9 aligned source words through
+// a funnel shift, byte tail (<= 3); rows longer than head + 32 bytes continue with further 8-word
+// chunks. Reads at most the aligned word that holds the last source byte.
+// (Profile r01: with loads and stores interleaved per piece the kernel sat on 3 serialized DRAM
+//  latencies per row -- 54 % long-scoreboard stalls; a "G lanes per row" variant was slower still.)
+struct RowCopy {
+  uint8_t* dst;
+  const uint8_t* src;
+  int n, head, nw, tail;
+  unsigned sh;
+  const uint32_t* sw;
+  uint8_t h0, h1, h2, t0, t1, t2;
+  uint32_t w[9];
+};
+
+__device__ __forceinline__ void row_load(RowCopy& rc, uint8_t* dst, const uint8_t* src, int n) {
+  rc.dst = dst;
+  rc.src = src;
+  rc.n = n;
+  rc.head = min(n, (int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3));
+  const int body = n - rc.head;
+  rc.nw = body >> 2;
+  rc.tail = body & 3;
+  const uint8_t* bsrc = src + rc.head;
+  rc.sh = (unsigned)(reinterpret_cast<uintptr_t>(bsrc) & 3) * 8;
+  rc.sw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(bsrc) & ~(uintptr_t)3);
+  const uint8_t* tsrc = bsrc + rc.nw * 4;
+  rc.h0 = rc.h1 = rc.h2 = rc.t0 = rc.t1 = rc.t2 = 0;
+  if (rc.head > 0) rc.h0 = src[0];
+  if (rc.head > 1) rc.h1 = src[1];
+  if (rc.head > 2) rc.h2 = src[2];
+  const int cnt = min(8, rc.nw);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) rc.w[i] = (i < cnt || (i == cnt && rc.sh != 0 && cnt > 0)) ? rc.sw[i] : 0u;
+  if (rc.tail > 0) rc.t0 = tsrc[0];
+  if (rc.tail > 1) rc.t1 = tsrc[1];
+  if (rc.tail > 2) rc.t2 = tsrc[2];
+}
+
+__device__ __forceinline__ void row_store(RowCopy& rc) {
+  if (rc.n <= 0) return;
+  uint8_t* dst = rc.dst;
+  if (rc.head > 0) dst[0] = rc.h0;
+  if (rc.head > 1) dst[1] = rc.h1;
+  if (rc.head > 2) dst[2] = rc.h2;
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst + rc.head);
+  const int cnt = min(8, rc.nw);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < cnt) dw[i] = __funnelshift_r(rc.w[i], rc.w[i + 1], rc.sh);
+  for (int base = 8; base < rc.nw; base += 8) {  // long rows
+    const int c2 = min(8, rc.nw - base);
     uint32_t w[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) w[i] = (i < cnt || (i == cnt && sh != 0)) ? sw[base + i] : 0u;
+    for (int i = 0; i < 9; ++i) w[i] = (i < c2 || (i == c2 && rc.sh != 0)) ? rc.sw[base + i] : 0u;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      if (i < cnt) dw[base + i] = __funnelshift_r(w[i], w[i + 1], sh);
+      if (i < c2) dw[base + i] = __funnelshift_r(w[i], w[i + 1], rc.sh);
   }
-  src += nw * 4;
-  dst += nw * 4;
-  n &= 3;
-  {
-    uint8_t b0 = 0, b1 = 0, b2 = 0;
-    if (n > 0) b0 = src[0];
-    if (n > 1) b1 = src[1];
-    if (n > 2) b2 = src[2];
-    if (n > 0) dst[0] = b0;
-    if (n > 1) dst[1] = b1;
-    if (n > 2) dst[2] = b2;
-  }
+  uint8_t* td = dst + rc.head + rc.nw * 4;
+  if (rc.tail > 0) td[0] = rc.t0;
+  if (rc.tail > 1) td[1] = rc.t1;
+  if (rc.tail > 2) td[2] = rc.t2;
 }
 
 // pass 2 (grid.y = column): batch-rebased offsets + the bytes of one chunk.
@@ -1035,10 +1056,21 @@ __global__ void __launch_bounds__(kGatherThreads) var_write_kernel(GatherGeom G,
     // rows intersecting [w0, w1)
     const int r_lo = upper_idx(s_off, nloc + 1, w0);
     const int r_hi = upper_idx(s_off, nloc + 1, w1 - 1);
-    for (int r = r_lo + threadIdx.x; r <= r_hi; r += kGatherThreads) {
-      const int a = max(s_off[r], w0), e = min(s_off[r + 1], w1);
-      if (e > a)
-        copy_bytes(s_stage + first_pad + (a - w0), src_base + s_src[r] + (a - s_off[r]), e - a);
+    for (int r = r_lo + threadIdx.x; r <= r_hi; r += 2 * kGatherThreads) {
+      // two rows per trip: all loads of both rows are issued before the first store
+      RowCopy c0r, c1r;
+      {
+        const int a = max(s_off[r], w0), e = min(s_off[r + 1], w1);
+        row_load(c0r, s_stage + first_pad + (a - w0), src_base + s_src[r] + (a - s_off[r]), max(e - a, 0));
+      }
+      const int r2 = r + kGatherThreads;
+      c1r.n = 0;
+      if (r2 <= r_hi) {
+        const int a = max(s_off[r2], w0), e = min(s_off[r2 + 1], w1);
+        row_load(c1r, s_stage + first_pad + (a - w0), src_base + s_src[r2] + (a - s_off[r2]), max(e - a, 0));
+      }
+      row_store(c0r);
+      row_store(c1r);
     }
     __syncthreads();
     // flush: global address of stage[first_pad] is dst_bytes + w0
