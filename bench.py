@@ -201,14 +201,13 @@ class Shard:
         srcs = [self.l_orderkey, self.l_linenumber] + [self.fixed[n] for n, _ in FIXED_COLS]
         dsts = [o["l_orderkey"], o["l_linenumber"]] + [o[n] for n, _ in FIXED_COLS]
         widths = [8, 4] + [w for _, w in FIXED_COLS]
-        plan.gather_fixed(srcs, dsts, widths)
         vcols = []
         for name, _, _ in STRING_COLS:
             offs, data, _ = self.strings[name]
             do, dd, db = o[name]
             vcols.append(dict(src_offsets=offs, src_data=data, src_data_base=self.zero_base, dst_offsets=do, dst_data=dd,
                               batch_data_start=db))
-        plan.gather_var_multi(vcols)
+        plan.gather_all(srcs, dsts, widths, vcols)
         if ev:
             ev[2].record()
             torch.cuda.synchronize()

@@ -73,6 +73,14 @@ int32_t lsb_plan_gather_var_multi(LsbPlan *plan, int32_t ncols, const void *cons
                                   const void *const *src_valid, void *const *dst_offsets, void *const *dst_data,
                                   void *const *dst_valid, void *const *batch_data_start, void *cuda_stream);
 
+/* fixed-width + variable-width columns of one scan (1 + 3 launches) */
+int32_t lsb_plan_gather_all(LsbPlan *plan, int32_t nfixed, const void *const *src, const void *const *src_valid,
+                            void *const *dst, void *const *dst_valid, const int32_t *width, int32_t nvars,
+                            const void *const *v_src_offsets, const void *const *v_src_data,
+                            const void *const *v_src_data_base, const void *const *v_src_valid,
+                            void *const *v_dst_offsets, void *const *v_dst_data, void *const *v_dst_valid,
+                            void *const *v_batch_data_start, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,6 +109,7 @@ EXT_SYMBOLS = {
     "lsb_plan_gather_fixed": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lsb_plan_gather_var": (c_int32, [c_void_p] * 10),
     "lsb_plan_gather_var_multi": (c_int32, [c_void_p, c_int32] + [c_void_p] * 9),
+    "lsb_plan_gather_all": (c_int32, [c_void_p, c_int32] + [c_void_p] * 5 + [c_int32] + [c_void_p] * 9),
 }
 
 

@@ -503,4 +503,36 @@ int32_t lsb_plan_gather_var_multi(LsbPlan* plan, int32_t ncols, const void* cons
   });
 }
 
+int32_t lsb_plan_gather_all(LsbPlan* plan, int32_t nfixed, const void* const* src, const void* const* src_valid,
+                            void* const* dst, void* const* dst_valid, const int32_t* width, int32_t nvars,
+                            const void* const* v_src_offsets, const void* const* v_src_data,
+                            const void* const* v_src_data_base, const void* const* v_src_valid,
+                            void* const* v_dst_offsets, void* const* v_dst_data, void* const* v_dst_valid,
+                            void* const* v_batch_data_start, void* stream) {
+  return guard([&] {
+    std::vector<lsb::FixedCol> fc((size_t)nfixed);
+    for (int i = 0; i < nfixed; ++i) {
+      fc[i].src = src[i];
+      fc[i].src_valid = static_cast<const uint8_t*>(src_valid ? src_valid[i] : nullptr);
+      fc[i].dst = dst[i];
+      fc[i].dst_valid = static_cast<uint8_t*>(dst_valid ? dst_valid[i] : nullptr);
+      fc[i].win = nullptr;
+      fc[i].width = width[i];
+    }
+    std::vector<lsb::VarCol> vc((size_t)nvars);
+    for (int i = 0; i < nvars; ++i) {
+      vc[i].src_offsets = static_cast<const int32_t*>(v_src_offsets[i]);
+      vc[i].src_data = static_cast<const uint8_t*>(v_src_data[i]);
+      vc[i].src_data_base = static_cast<const int64_t*>(v_src_data_base[i]);
+      vc[i].src_valid = static_cast<const uint8_t*>(v_src_valid ? v_src_valid[i] : nullptr);
+      vc[i].win = nullptr;
+      vc[i].dst_offsets = static_cast<int32_t*>(v_dst_offsets[i]);
+      vc[i].dst_data = static_cast<uint8_t*>(v_dst_data[i]);
+      vc[i].dst_valid = static_cast<uint8_t*>(v_dst_valid ? v_dst_valid[i] : nullptr);
+      vc[i].batch_data_start = static_cast<int64_t*>(v_batch_data_start[i]);
+    }
+    lsb::gather_all(plan->p, fc.data(), nfixed, vc.data(), nvars, static_cast<cudaStream_t>(stream));
+  });
+}
+
 }  // extern "C"

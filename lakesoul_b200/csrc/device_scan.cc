@@ -743,13 +743,9 @@ void DeviceScan::Impl::merge_and_gather() {
       fixed.push_back(fc);
     }
   }
-  if (!fixed.empty() && U > 0) {
-    gather_fixed(plan, fixed.data(), (int)fixed.size(), stream);
-    ctr.kernel_launches += 1;
-  }
-  if (!vars.empty() && U > 0) {
-    gather_var_multi(plan, vars.data(), (int)vars.size(), stream);
-    ctr.kernel_launches += 3 * (((int)vars.size() + 15) / 16);
+  if (U > 0 && (!fixed.empty() || !vars.empty())) {
+    gather_all(plan, fixed.data(), (int)fixed.size(), vars.data(), (int)vars.size(), stream);
+    ctr.kernel_launches += (fixed.empty() ? 0 : 1) + 3 * (((int)vars.size() + 15) / 16);
   }
 
   // ---- download ---------------------------------------------------------------------------

@@ -737,6 +737,21 @@ __device__ __forceinline__ bool chunk_geometry(const GatherGeom& G, int64_t chun
 
 constexpr int kRowsPerThread = kRowsPerChunk / kGatherThreads;  // 8
 
+constexpr int kMaxVarCols = 16;
+struct VarColSet {
+  int32_t n;
+  VarCol col[kMaxVarCols];
+};
+
+__device__ __forceinline__ int var_row_len(const VarCol& col, uint32_t g, bool& valid) {
+  valid = g != kNoRow;
+  if (valid && col.src_valid) valid = (col.src_valid[g >> 3] >> (g & 7)) & 1;
+  return valid ? (col.src_offsets[(int64_t)g + 1] - col.src_offsets[g]) : 0;
+}
+
+// One block = 2048 output rows of one batch x ALL fixed-width columns.
+// (Fusing pass 1 of the string gather in here was measured slower: the latency-bound string sizing
+//  then runs at this kernel's 2 blocks/SM instead of 8 -- gather 7.99 ms vs 7.2 ms per bench step.)
 __global__ void __launch_bounds__(kGatherThreads) gather_fixed_kernel(GatherGeom G,
                                                                       const FixedCol* __restrict__ cols,
                                                                       int ncols) {
@@ -820,19 +835,9 @@ __global__ void __launch_bounds__(kGatherThreads) gather_fixed_kernel(GatherGeom
 // ---------------------------------------------------------------------------------------
 // gather: variable width (Utf8 / Binary): lengths -> chunk sums -> scan -> offsets + bytes
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ int var_row_len(const VarCol& col, uint32_t g, bool& valid) {
-  valid = g != kNoRow;
-  if (valid && col.src_valid) valid = (col.src_valid[g >> 3] >> (g & 7)) & 1;
-  return valid ? (col.src_offsets[(int64_t)g + 1] - col.src_offsets[g]) : 0;
-}
 
 // pass 1 (all variable-width columns in one launch): validity bitmaps + total string bytes of every
 // 2048-row chunk. chunk_sums is laid out column-major: [col][chunk] with a stride of (chunks + 1).
-constexpr int kMaxVarCols = 16;
-struct VarColSet {
-  int32_t n;
-  VarCol col[kMaxVarCols];
-};
 
 __global__ void __launch_bounds__(kGatherThreads) var_sum_kernel(GatherGeom G, const VarColSet* __restrict__ set,
                                                                  int64_t* __restrict__ chunk_sums,
@@ -1604,6 +1609,23 @@ void gather_fixed(MergePlan* P, const FixedCol* cols, int ncols, cudaStream_t st
   // the descriptor table is reused by the next call: order the copy behind this launch
 }
 
+void gather_var_multi(MergePlan* P, const VarCol* cols, int ncols, cudaStream_t stream);
+
+static void ensure_var_scratch(MergePlan* P, int64_t stride, cudaStream_t stream) {
+  if (P->d_chunk_cap < stride * kMaxVarCols) {
+    dev_free(P->d_chunk_sums, stream);
+    P->d_chunk_sums = dev_alloc<int64_t>(stride * kMaxVarCols, stream);
+    P->d_chunk_cap = stride * kMaxVarCols;
+  }
+  if (!P->d_varset) P->d_varset = dev_alloc<VarColSet>(1, stream);
+}
+
+// Fixed-width and variable-width columns of one scan: 1 + 3 launches.
+void gather_all(MergePlan* P, const FixedCol* fixed, int nfixed, const VarCol* vars, int nvars, cudaStream_t stream) {
+  if (nfixed > 0) gather_fixed(P, fixed, nfixed, stream);
+  if (nvars > 0) gather_var_multi(P, vars, nvars, stream);
+}
+
 void plan_reserve_scratch(MergePlan* P, cudaStream_t stream) {
   require_synced(P);
   const int64_t U = P->out_base[P->nb];
@@ -1623,12 +1645,7 @@ void gather_var_multi(MergePlan* P, const VarCol* cols, int ncols, cudaStream_t 
   const int64_t stride = chunks + 1;
   for (int c0 = 0; c0 < ncols; c0 += kMaxVarCols) {
     const int n = std::min(kMaxVarCols, ncols - c0);
-    if (P->d_chunk_cap < stride * n) {
-      dev_free(P->d_chunk_sums, stream);
-      P->d_chunk_sums = dev_alloc<int64_t>(stride * kMaxVarCols, stream);
-      P->d_chunk_cap = stride * kMaxVarCols;
-    }
-    if (!P->d_varset) P->d_varset = dev_alloc<VarColSet>(1, stream);
+    ensure_var_scratch(P, stride, stream);
     VarColSet& set = P->h_varset;
     set.n = n;
     for (int i = 0; i < n; ++i) set.col[i] = cols[c0 + i];

@@ -152,6 +152,9 @@ void gather_var(MergePlan*, const VarCol& col, cudaStream_t stream);
 // same for several columns: 3 launches in total (the winner list is read once per pass)
 void gather_var_multi(MergePlan*, const VarCol* cols, int ncols, cudaStream_t stream);
 
+// Everything at once: 1 launch for the fixed-width columns + 3 for the string columns.
+void gather_all(MergePlan*, const FixedCol* fixed, int nfixed, const VarCol* vars, int nvars, cudaStream_t stream);
+
 // Scratch management for gather_var (lengths + scanned offsets); grows on demand.
 void plan_reserve_scratch(MergePlan*, cudaStream_t stream);
 

@@ -125,6 +125,20 @@ class ScanPlan:
             self.h, n, arr("src_offsets"), arr("src_data"), arr("src_data_base"), arr("src_valid"), arr("dst_offsets"),
             arr("dst_data"), arr("dst_valid"), arr("batch_data_start"), _stream_ptr(self.stream)))
 
+    def gather_all(self, srcs, dsts, widths, vcols, src_valid=None, dst_valid=None):
+        """Fixed-width columns (as in gather_fixed) + string columns (as in gather_var_multi), 3 launches."""
+        n = len(srcs)
+        nv = len(vcols)
+        arr = lambda key: _ptr_array([(c.get(key).data_ptr() if c.get(key) is not None else None) for c in vcols])  # noqa: E731
+        self._check(self.lib.lsb_plan_gather_all(
+            self.h, n, _ptr_array([t.data_ptr() for t in srcs]),
+            _ptr_array([(v.data_ptr() if v is not None else None) for v in (src_valid or [None] * n)]),
+            _ptr_array([t.data_ptr() for t in dsts]),
+            _ptr_array([(v.data_ptr() if v is not None else None) for v in (dst_valid or [None] * n)]),
+            (ctypes.c_int32 * n)(*widths), nv, arr("src_offsets"), arr("src_data"), arr("src_data_base"),
+            arr("src_valid"), arr("dst_offsets"), arr("dst_data"), arr("dst_valid"), arr("batch_data_start"),
+            _stream_ptr(self.stream)))
+
     def close(self):
         if self.h:
             self.lib.lsb_plan_destroy(self.h)
