@@ -228,7 +228,7 @@ struct PlanDev {
   int32_t batch_size;
 };
 
-constexpr int kTileThreads = 256;
+constexpr int kTileThreads = 512;
 constexpr int kErrTileOverflow = 1;
 
 // largest r in [0, n) with arr[r] <= q   (arr non-decreasing, arr[0] <= q)
@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(128) part_kernel(PlanDev P, PkDesc pk, int lev
 // ---------------------------------------------------------------------------------------
 // block scan helper (exclusive), blockDim.x == kTileThreads
 // ---------------------------------------------------------------------------------------
+template <int kThreads>
 __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int& total) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int x = v;
@@ -320,17 +321,17 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int& 
   if (lane == 31) warp_sums[w] = x;
   __syncthreads();
   if (w == 0) {
-    int s = lane < (kTileThreads / 32) ? warp_sums[lane] : 0;
+    int s = lane < (kThreads / 32) ? warp_sums[lane] : 0;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       int y = __shfl_up_sync(0xffffffffu, s, d);
       if (lane >= d) s += y;
     }
-    if (lane < (kTileThreads / 32)) warp_sums[lane] = s;  // inclusive warp totals
+    if (lane < (kThreads / 32)) warp_sums[lane] = s;  // inclusive warp totals
   }
   __syncthreads();
   const int base = w == 0 ? 0 : warp_sums[w - 1];
-  total = warp_sums[kTileThreads / 32 - 1];
+  total = warp_sums[kThreads / 32 - 1];
   return base + x - v;
 }
 
@@ -340,7 +341,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int& 
 //   level == 0: mark group ends, write winners (global rows) -> win_tmp, count -> tile_cnt
 // ---------------------------------------------------------------------------------------
 template <typename KeyT, bool kGeneral>
-__global__ void __launch_bounds__(kTileThreads) tile_kernel(PlanDev P, PkDesc pk, int level,
+__global__ void __launch_bounds__(kTileThreads, 3) tile_kernel(PlanDev P, PkDesc pk, int level,
                                                             int tile_ofs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = P.tile_cap;
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_kernel(PlanDev P, PkDesc pk
     cnt += end ? 1 : 0;
   }
   int total;
-  int off = block_exclusive_scan(cnt, scan_tmp, total);
+  int off = block_exclusive_scan<kTileThreads>(cnt, scan_tmp, total);
   const int t0 = blockIdx.x;  // level-0 tiles start at tile_ofs
   if constexpr (kGeneral) {
     // second pass: R[u][j] = last row of output key u inside file j
@@ -996,9 +997,9 @@ __device__ __forceinline__ void row_store(RowCopy& rc) {
 // Thread t owns the 8 consecutive rows [8t, 8t+8) for the offsets; the bytes are staged through a
 // shared-memory window that is address-congruent (mod 16) with the destination, so the flush to HBM
 // is made of full, aligned 16-byte stores whatever the string lengths are.
-constexpr int kStageBytes = 24 * 1024;
+constexpr int kStageBytes = 16 * 1024;
 
-__global__ void __launch_bounds__(kGatherThreads) var_write_kernel(GatherGeom G, const VarColSet* __restrict__ set,
+__global__ void __launch_bounds__(kGatherThreads, 6) var_write_kernel(GatherGeom G, const VarColSet* __restrict__ set,
                                                                    const int64_t* __restrict__ chunk_off_all,
                                                                    int64_t sums_stride, int64_t total_batches) {
   __shared__ int s_scan[kGatherThreads / 32 + 2];
@@ -1031,7 +1032,7 @@ __global__ void __launch_bounds__(kGatherThreads) var_write_kernel(GatherGeom G,
     mine += len[x];
   }
   int tot;
-  int run = block_exclusive_scan(mine, s_scan, tot);
+  int run = block_exclusive_scan<kGatherThreads>(mine, s_scan, tot);
   // offsets (every earlier batch contributed one extra entry)
   int32_t* dst_off = col.dst_offsets + u0 + gb + r_begin;
   const int32_t rel = (int32_t)(c0 - batch0);
