@@ -997,9 +997,9 @@ __device__ __forceinline__ void row_store(RowCopy& rc) {
 // Thread t owns the 8 consecutive rows [8t, 8t+8) for the offsets; the bytes are staged through a
 // shared-memory window that is address-congruent (mod 16) with the destination, so the flush to HBM
 // is made of full, aligned 16-byte stores whatever the string lengths are.
-constexpr int kStageBytes = 16 * 1024;
+constexpr int kStageBytes = 24 * 1024;
 
-__global__ void __launch_bounds__(kGatherThreads, 6) var_write_kernel(GatherGeom G, const VarColSet* __restrict__ set,
+__global__ void __launch_bounds__(kGatherThreads) var_write_kernel(GatherGeom G, const VarColSet* __restrict__ set,
                                                                    const int64_t* __restrict__ chunk_off_all,
                                                                    int64_t sums_stride, int64_t total_batches) {
   __shared__ int s_scan[kGatherThreads / 32 + 2];
