@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--buckets", type=int, default=BUCKETS, help="hash buckets per GPU")
-    ap.add_argument("--e2e-buckets", type=int, default=32, help="buckets written as Parquet for the e2e leg")
+    ap.add_argument("--e2e-buckets", type=int, default=64, help="buckets written as Parquet for the e2e leg")
     ap.add_argument("--e2e-threads", type=int, default=16, help="concurrent per-bucket readers (Spark task slots)")
     ap.add_argument("--cpu-buckets", type=int, default=32, help="distinct buckets in the bounded CPU baseline sample")
     ap.add_argument("--cpu-threads", type=int, default=0, help="CPU baseline reader threads (0 = usable host cores)")
