@@ -1774,6 +1774,11 @@ __device__ void sum_op(const PlanDev& P, const KeyOps<KeyT>& ops, const GenColDe
   store_val<T>(c.opval, u, valid ? res : T(0));
 }
 
+__global__ void __launch_bounds__(256) iota_u32(uint32_t* out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)i;
+}
+
 template <typename KeyT>
 __global__ void __launch_bounds__(256) resolve_kernel(PlanDev P, PkDesc pk, GenColDev c, int64_t U) {
   const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1829,6 +1834,75 @@ __global__ void __launch_bounds__(256) resolve_kernel(PlanDev P, PkDesc pk, GenC
   }
 }
 
+// Joined* operators (merge_operator.rs:389-487): the result is a new Utf8 cell per output key.
+// Pass 1 (kWrite=false): one thread per output key sizes the cell and decides its validity;
+// pass 2 (kWrite=true): one warp per output key copies the pieces to their scanned position.
+struct JoinedDev {
+  const int32_t* src_offsets;   // global-row offsets of the source column
+  const uint8_t* src_data;
+  const int64_t* bucket_data;   // per-bucket base of src_data
+  int32_t* len;                 // U (pass 1 out)
+  const int64_t* ooff;          // U+1 scanned (pass 2 in)
+  int32_t* ooff32;              // U+1 (pass 2 out): offsets of the computed column
+  uint8_t* out;                 // computed column bytes
+  char delim;
+  bool all;                     // JoinedAll*: every row of every run, and never a delimiter (:402-406)
+};
+
+template <typename KeyT, bool kWrite>
+__global__ void __launch_bounds__(256) joined_kernel(PlanDev P, PkDesc pk, GenColDev c, JoinedDev J, int64_t U) {
+  const int lane = threadIdx.x & 31;
+  const int64_t u = kWrite ? ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5))
+                           : ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  const bool active = u < U;
+  bool valid = false;
+  if (active) {
+    const int b = upper_idx(P.out_base, P.nb + 1, u);
+    const BucketDesc& B = P.buckets[b];
+    const KeyOps<KeyT> ops(pk, b);
+    const uint32_t* Rrow = P.R + P.rofs[b] + (u - P.out_base[b]) * B.k;
+    const char* present = c.present + B.file_begin;
+    const uint8_t* data = J.src_data + J.bucket_data[b];
+    int64_t pos = kWrite ? J.ooff[u] : 0;
+    const int64_t cell_len = kWrite ? (J.ooff[u + 1] - pos) : 0;
+    if (kWrite && lane == 0) {
+      J.ooff32[u] = (int32_t)pos;
+      if (u == U - 1) J.ooff32[U] = (int32_t)J.ooff[U];
+    }
+    int64_t len = 0;
+    bool any = false, ok = true, first = true;
+    if (!kWrite || cell_len > 0) {
+      for (int j = 0; j < B.k && ok; ++j) {
+        if (!present[j] || Rrow[j] == kNoRow) continue;
+        any = true;
+        const int64_t last = Rrow[j];
+        const int64_t r0 = J.all ? run_first<KeyT>(ops, P.file_row_base[B.file_begin + j], last) : last;
+        for (int64_t r = r0; r <= last; ++r) {
+          if (!bit_at(c.validity, r)) { ok = false; break; }
+          if (!J.all && !first) {
+            if (kWrite) { if (lane == 0) J.out[pos] = (uint8_t)J.delim; ++pos; }
+            else ++len;
+          }
+          first = false;
+          const int32_t o0 = J.src_offsets[r], o1 = J.src_offsets[r + 1];
+          if (kWrite) {
+            for (int32_t x = lane; x < o1 - o0; x += 32) J.out[pos + x] = data[o0 + x];
+            pos += o1 - o0;
+          } else {
+            len += o1 - o0;
+          }
+        }
+      }
+    }
+    valid = ok && any;
+    if (!kWrite) J.len[u] = valid ? (int32_t)min(len, (int64_t)INT32_MAX) : 0;
+  }
+  if (!kWrite && c.opvalid) {
+    const uint32_t word = __ballot_sync(0xffffffffu, active && valid);
+    if (lane == 0 && (u - lane) < U) c.opvalid[u >> 5] = word;
+  }
+}
+
 struct GeneralMerge {
   MergePlan* plan = nullptr;
   int C = 0;
@@ -1841,9 +1915,13 @@ struct GeneralMerge {
     bool computed = false;
     bool may_null = false;
     uint32_t* win = nullptr;
-    void* opval = nullptr;
+    void* opval = nullptr;       // computed values (Sum*) or int32 offsets (Joined*)
     uint32_t* opvalid = nullptr;
+    uint8_t* opdata = nullptr;   // Joined*: bytes of the computed column
+    int64_t opdata_bytes = 0;
+    bool joined = false;
   };
+  int64_t* d_zero_base = nullptr;  // nb zeros: the computed string columns are addressed scan-wide
   std::vector<Col> cols;
 };
 
@@ -1851,7 +1929,8 @@ void general_destroy(GeneralMerge* G) {
   if (!G) return;
   cudaStream_t st = G->plan ? G->plan->alloc_stream : nullptr;
   dev_free(G->d_R, st); dev_free(G->d_rofs, st); dev_free(G->d_present, st);
-  for (auto& c : G->cols) { dev_free(c.win, st); dev_free(c.opval, st); dev_free(c.opvalid, st); }
+  for (auto& c : G->cols) { dev_free(c.win, st); dev_free(c.opval, st); dev_free(c.opvalid, st); dev_free(c.opdata, st); }
+  dev_free(G->d_zero_base, st);
   delete G;
 }
 
@@ -1874,12 +1953,14 @@ GeneralMerge* general_create(MergePlan* P, const PkDesc& pk, const std::vector<G
       col.uses_plan_winners = all_present && in[c].op == MergeOp::UseLast;
       col.computed = in[c].op == MergeOp::SumAll || in[c].op == MergeOp::SumLast;
       col.may_null = !all_present || in[c].validity != nullptr || in[c].op != MergeOp::UseLast;
-      if (in[c].op == MergeOp::JoinedLastByComma || in[c].op == MergeOp::JoinedLastBySemicolon ||
-          in[c].op == MergeOp::JoinedAllByComma || in[c].op == MergeOp::JoinedAllBySemicolon) {
-        g_last_error = "Joined* merge operators are not implemented by the GPU reader yet";
+      col.joined = in[c].op == MergeOp::JoinedLastByComma || in[c].op == MergeOp::JoinedLastBySemicolon ||
+                   in[c].op == MergeOp::JoinedAllByComma || in[c].op == MergeOp::JoinedAllBySemicolon;
+      if (col.joined && !in[c].kind.var) {
+        g_last_error = "column type doesn't support MergeOperator::Joined (Utf8 only)";  // as_string_array, :399
         throw std::runtime_error(g_last_error);
       }
-      if (col.computed && in[c].num_class == NC_NONE) {
+      col.computed |= col.joined;
+      if (col.computed && !col.joined && in[c].num_class == NC_NONE) {
         g_last_error = "column type doesn't support MergeOperator::Sum";
         throw std::runtime_error(g_last_error);
       }
@@ -1923,6 +2004,59 @@ GeneralMerge* general_create(MergePlan* P, const PkDesc& pk, const std::vector<G
       gc.op = (int)in[c].op;
       gc.width = in[c].kind.width;
       gc.num_class = in[c].num_class;
+      if (col.joined) {
+        // size -> scan -> write; the computed column is addressed scan-wide with int32 offsets
+        col.opval = dev_alloc<int32_t>(U + 2, stream);
+        col.opvalid = dev_alloc<uint32_t>((U + 31) / 32 + 2, stream);
+        gc.opvalid = col.opvalid;
+        if (!G->d_zero_base) {
+          G->d_zero_base = dev_alloc<int64_t>(nb, stream);
+          LSB_CUDA(cudaMemsetAsync(G->d_zero_base, 0, sizeof(int64_t) * nb, stream));
+        }
+        const int nblocks = (int)((U + kScanChunk - 1) / kScanChunk);
+        int32_t* d_len = dev_alloc<int32_t>(U, stream);
+        int64_t* d_sums = dev_alloc<int64_t>(nblocks + 2, stream);
+        int64_t* d_ooff = dev_alloc<int64_t>(U + 1, stream);
+        JoinedDev J{};
+        J.src_offsets = static_cast<const int32_t*>(in[c].values);
+        J.src_data = in[c].data;
+        J.bucket_data = in[c].bucket_data;
+        J.len = d_len;
+        J.ooff = d_ooff;
+        J.ooff32 = static_cast<int32_t*>(col.opval);
+        J.delim = (in[c].op == MergeOp::JoinedLastByComma || in[c].op == MergeOp::JoinedAllByComma) ? ',' : ';';
+        J.all = in[c].op == MergeOp::JoinedAllByComma || in[c].op == MergeOp::JoinedAllBySemicolon;
+        const unsigned g1 = (unsigned)((U + 255) / 256), g2 = (unsigned)((U + 7) / 8);
+        int64_t total = 0;
+        try {
+          if (P->key_bytes) joined_kernel<StrKey, false><<<g1, 256, 0, stream>>>(D, pk, gc, J, U);
+          else if (P->key128) joined_kernel<K128, false><<<g1, 256, 0, stream>>>(D, pk, gc, J, U);
+          else joined_kernel<uint64_t, false><<<g1, 256, 0, stream>>>(D, pk, gc, J, U);
+          scan_block_sums<<<nblocks, 256, 0, stream>>>(d_len, U, d_sums);
+          scan_sums_inplace<<<1, 1024, 0, stream>>>(d_sums, nblocks, 0);
+          scan_apply<<<nblocks, 256, 0, stream>>>(d_len, U, d_sums, d_ooff);
+          LSB_CUDA(cudaMemcpyAsync(&total, d_ooff + U, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+          LSB_CUDA(cudaStreamSynchronize(stream));
+          if (total > (int64_t)INT32_MAX) {
+            g_last_error = "Joined* merge operator: the joined column exceeds 2 GiB in one scan";
+            throw std::runtime_error(g_last_error);
+          }
+          col.opdata = dev_alloc<uint8_t>((size_t)total + 64, stream);
+          col.opdata_bytes = total;
+          J.out = col.opdata;
+          if (P->key_bytes) joined_kernel<StrKey, true><<<g2, 256, 0, stream>>>(D, pk, gc, J, U);
+          else if (P->key128) joined_kernel<K128, true><<<g2, 256, 0, stream>>>(D, pk, gc, J, U);
+          else joined_kernel<uint64_t, true><<<g2, 256, 0, stream>>>(D, pk, gc, J, U);
+          G->launches += 5;
+        } catch (...) {
+          dev_free(d_len, stream); dev_free(d_sums, stream); dev_free(d_ooff, stream);
+          throw;
+        }
+        dev_free(d_len, stream); dev_free(d_sums, stream); dev_free(d_ooff, stream);
+        iota_u32<<<g1, 256, 0, stream>>>(col.win, U);
+        ++G->launches;
+        continue;
+      }
       if (col.computed) {
         col.opval = dev_alloc<uint8_t>((size_t)U * std::max(in[c].kind.width, 1) + 32, stream);
         col.opvalid = dev_alloc<uint32_t>((U + 31) / 32 + 2, stream);
@@ -1955,9 +2089,15 @@ const void* general_values(const GeneralMerge* G, int c, const void* dflt) {
 const uint8_t* general_validity(const GeneralMerge* G, int c, const uint8_t* dflt) {
   return G->cols[c].computed && G->cols[c].opvalid ? reinterpret_cast<const uint8_t*>(G->cols[c].opvalid) : dflt;
 }
-const uint8_t* general_data(const GeneralMerge*, int, const uint8_t* dflt) { return dflt; }
-const int64_t* general_bucket_data(const GeneralMerge*, int, const int64_t* dflt) { return dflt; }
-int64_t general_data_bytes(const GeneralMerge*, int, int64_t dflt) { return dflt; }
+const uint8_t* general_data(const GeneralMerge* G, int c, const uint8_t* dflt) {
+  return G->cols[c].joined && G->cols[c].opdata ? G->cols[c].opdata : dflt;
+}
+const int64_t* general_bucket_data(const GeneralMerge* G, int c, const int64_t* dflt) {
+  return G->cols[c].joined && G->cols[c].opdata ? G->d_zero_base : dflt;
+}
+int64_t general_data_bytes(const GeneralMerge* G, int c, int64_t dflt) {
+  return G->cols[c].joined && G->cols[c].opdata ? G->cols[c].opdata_bytes : dflt;
+}
 bool general_may_be_null(const GeneralMerge* G, int c) { return G->cols[c].may_null; }
 std::vector<uint32_t*> general_winner_lists(GeneralMerge* G) {
   std::vector<uint32_t*> v;

@@ -130,6 +130,36 @@ def test_merge_operators_sum_and_not_null(tmp_path):
     assert_tables_equal(got, want, "ops")
 
 
+@pytest.mark.parametrize("with_filter", [False, True])
+def test_merge_operators_joined_strings(tmp_path, with_filter):
+    """JoinedLast* / JoinedAll* (merge_operator.rs:389-487) incl. the reference's quirk that JoinedAll never
+    emits its delimiter, nulls poisoning the cell, in-file duplicate keys and a file that lacks the column."""
+    from lakesoul_b200 import read_bucket
+    rng = np.random.default_rng(11)
+    schema = pa.schema([("id", pa.int64()), ("a", pa.string()), ("b", pa.string()), ("c", pa.string()), ("v", pa.int32())])
+    paths = []
+    for f in range(4):
+        n = 3000
+        ids = np.sort(rng.integers(0, 2500, n))  # duplicates inside a file
+        def strs(p_null):
+            vals = ["s%d_%d" % (f, x) * int(rng.integers(0, 3)) for x in rng.integers(0, 1000, n)]
+            mask = rng.random(n) < p_null
+            return pa.array([None if m else v for v, m in zip(vals, mask)], pa.string())
+        cols = {"id": pa.array(ids, pa.int64()), "a": strs(0.02), "b": strs(0.0), "c": strs(0.3),
+                "v": pa.array(rng.integers(0, 100, n), pa.int32())}
+        names = [x for x in schema.names if not (f == 2 and x == "b")]  # file 2 lacks column b
+        t = pa.table({k: cols[k] for k in names})
+        path = os.path.join(str(tmp_path), "part-%016d_0000.parquet" % f)
+        pq.write_table(t, path, row_group_size=1024)
+        paths.append(path)
+    ops = {"a": "JoinedLastByComma", "b": "JoinedAllBySemicolon", "c": "JoinedLastBySemicolon", "v": "SumAll"}
+    filters = ["gt(v, 150)"] if with_filter else []
+    got = read_bucket(paths, schema, ["id"], batch_size=500, merge_ops=ops, filters=filters)
+    want = mo.read_bucket(paths, schema, ["id"], merge_ops=ops, filters=filters)
+    assert want.num_rows > 0 and want.column("a").null_count > 0
+    assert_tables_equal(got, want, "joined")
+
+
 def test_reference_sample_parquet_fixture(tmp_path):
     """G12: Spark-written snappy files with PLAIN_DICTIONARY / RLE / BIT_PACKED pages (row count 1000 each,
     reader.rs:421-441). The fixtures travel as a copy under tests/golden/sample-parquet-files if present."""
