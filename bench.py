@@ -232,12 +232,12 @@ class Shard:
 # ------------------------------------------------------------------------------------------------
 # e2e leg: Parquet files -> C-ABI readers -> host Arrow batches
 # ------------------------------------------------------------------------------------------------
-def make_e2e_files(nb: int, root: str):
+def make_e2e_files(nb: int, root: str, encoding: str = "E1"):
     from lakesoul_b200 import datagen
     spec = datagen.config_spec(2, 1.0)
     spec.buckets = nb
     tables = datagen.generate_table(spec)
-    paths = datagen.write_table(root, spec, tables, encoding="E1")
+    paths = datagen.write_table(root, spec, tables, encoding=encoding)
     rows = [sum(t.num_rows for t in b) for b in tables]
     return spec, paths, rows
 
@@ -287,6 +287,8 @@ def run_e2e_native(spec, paths, threads: int, repeat: int = 3):
     out = subprocess.run([drv], input=inp, capture_output=True, text=True, env=env)
     if out.returncode != 0:
         raise RuntimeError("cabi_driver failed: " + out.stderr[-500:])
+    if os.environ.get("LAKESOUL_B200_TRACE") == "1":
+        sys.stderr.write(out.stderr)
     return json.loads(out.stdout.strip().splitlines()[-1])
 
 

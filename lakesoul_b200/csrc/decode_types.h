@@ -44,6 +44,8 @@ struct PqChunk {         // one column chunk (file x column x row group)
   int64_t dict_index;    // BYTE_ARRAY dictionaries: first entry of this chunk in the dict_pos table
 };
 
+constexpr int kDecodeBlockRows = 1024;  // rows per decode work unit (one warp)
+
 struct PqPage {
   int64_t src_off;       // payload (after the thrift header, decompressed) inside the raw image
   int32_t size;
@@ -53,10 +55,35 @@ struct PqPage {
   int32_t v2_def_len;    // DATA_PAGE_V2: bytes of definition levels (no length prefix); -1 for v1 pages
   int32_t chunk;
   int32_t closes_file;   // 1: also write the closing string offset after the page's last row
-  int32_t pad;
+  int32_t first_block;   // the page's first entry in the block table (ceil(num_values / kDecodeBlockRows) entries)
   int64_t row_start;     // global row of the page's first value
-  int64_t str_base;      // var: first byte of the page inside the bucket's data (after the scan)
-  int64_t str_bytes;     // var: bytes produced by the page (count pass)
+  int64_t vpos_base;     // PLAIN BYTE_ARRAY: first entry of the page in the vpos table (nonnull + 1 entries)
+  int32_t nonnull;       // index pass: non-null values of the page
+  int32_t values_off;    // index pass: offset of the value section inside the page payload
+};
+
+// State of one RLE / bit-packed hybrid stream at a block boundary (all offsets relative to the page payload).
+struct PqStreamCk {
+  int32_t pos;           // next run header
+  int32_t base;          // payload of the current bit-packed run
+  int32_t run_left;
+  int32_t mode;          // 0 rle, 1 bit-packed, 2 legacy BIT_PACKED
+  int32_t idx;           // position inside the bit-packed run
+  uint32_t val;          // value of the current RLE run
+};
+
+// One decode work unit: rows [row0, row0 + kDecodeBlockRows) of a page. Filled by the index pass
+// (one warp per page walks the run headers / length prefixes once), consumed by the decode pass
+// (one warp per block, all blocks of all pages in parallel).
+struct PqBlock {
+  int32_t page;
+  int32_t row0;          // first row of the block inside the page
+  int32_t vbase;         // non-null values of the page before the block
+  int32_t pad;
+  PqStreamCk levels;     // definition levels at row0
+  PqStreamCk index;      // dictionary indices / RLE booleans at value vbase
+  int64_t str_bytes;     // var: bytes produced by the block
+  int64_t str_base;      // var: first byte of the block inside the bucket's data (after the scan)
 };
 
 struct DecodeArgs {
@@ -65,8 +92,11 @@ struct DecodeArgs {
   const PqChunk* chunks;
   PqPage* pages;
   int32_t* dict_pos;         // start of every dictionary string inside its dictionary page (+1 closing entry per chunk)
+  PqBlock* blocks;
+  int32_t* vpos;             // PLAIN BYTE_ARRAY pages: string bytes of the page before every non-null value
   int32_t npages;
   int32_t nchunks;
+  int32_t nblocks;
   int32_t* err;              // device error flag (unsupported page shape met at decode time)
 };
 

@@ -83,11 +83,87 @@ class PinnedPool {
 
 std::shared_ptr<uint8_t> pinned_alloc(size_t bytes) { return PinnedPool::get().alloc(bytes); }
 
+// ---------------------------------------------------------------------------------------
+// scan slots: a stream + a device scratch arena, checked out by one reader for the duration of
+// its scan and recycled afterwards (readers come and go per bucket; their threads usually persist)
+// ---------------------------------------------------------------------------------------
+namespace {
+struct ScanSlot {
+  cudaStream_t stream = nullptr;
+  DeviceArena arena;
+  int device = -1;
+};
+class SlotPool {
+ public:
+  static SlotPool& get() {
+    static SlotPool* p = new SlotPool();  // leaked on purpose (no CUDA calls at process teardown)
+    return *p;
+  }
+  ScanSlot* acquire() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      for (size_t i = 0; i < free_.size(); ++i) {
+        if (free_[i]->device == dev) {
+          ScanSlot* s = free_[i];
+          free_.erase(free_.begin() + (long)i);
+          return s;
+        }
+      }
+    }
+    auto* s = new ScanSlot();
+    s->device = dev;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete s;
+      fail(std::string("cudaStreamCreate failed: ") + cudaGetErrorString(e));
+    }
+    return s;
+  }
+  void release(ScanSlot* s) {
+    s->arena.reset();
+    std::lock_guard<std::mutex> g(mu_);
+    free_.push_back(s);
+  }
+ private:
+  std::mutex mu_;
+  std::vector<ScanSlot*> free_;
+};
+}  // namespace
+
+namespace {
+bool trace_on() {
+  static const bool on = [] { const char* v = getenv("LAKESOUL_B200_TRACE"); return v && *v == '1'; }();
+  return on;
+}
+struct TraceBuf { std::vector<std::pair<const char*, double>> marks; };
+thread_local TraceBuf t_trace;
+}  // namespace
+void trace_mark(const char* phase) {
+  if (trace_on()) t_trace.marks.emplace_back(phase, now_ms());
+}
+void trace_flush(const char* tag) {
+  if (!trace_on() || t_trace.marks.empty()) return;
+  std::string line = std::string("LSBTRACE ") + tag;
+  char buf[96];
+  snprintf(buf, sizeof(buf), " t0=%.3f", t_trace.marks.front().second);
+  line += buf;
+  for (size_t i = 1; i < t_trace.marks.size(); ++i) {
+    snprintf(buf, sizeof(buf), " %s=%.3f", t_trace.marks[i].first, t_trace.marks[i].second - t_trace.marks[i - 1].second);
+    line += buf;
+  }
+  line += "\n";
+  fputs(line.c_str(), stderr);
+  t_trace.marks.clear();
+}
+
 void launch_dict_index(const DecodeArgs& A, cudaStream_t s);
-void launch_page_count(const DecodeArgs& A, cudaStream_t s);
-void launch_page_scan(const DecodeArgs& A, const int32_t* seg_start, const int64_t* seg_base, int nseg,
-                      int64_t* seg_total, cudaStream_t s);
-void launch_page_decode(const DecodeArgs& A, cudaStream_t s);
+void launch_page_index(const DecodeArgs& A, cudaStream_t s);
+void launch_block_count(const DecodeArgs& A, cudaStream_t s);
+void launch_block_scan(const DecodeArgs& A, const int32_t* seg_bounds, const int64_t* seg_base, int nseg,
+                       int64_t* seg_total, cudaStream_t s);
+void launch_block_decode(const DecodeArgs& A, cudaStream_t s);
 
 namespace {
 
@@ -197,7 +273,6 @@ struct DeviceScan::Impl : std::enable_shared_from_this<DeviceScan::Impl> {
     bool has_raw = false;
   };
   std::vector<DevColumn> cols;
-  std::vector<void*> dev_allocs;
 
   MergePlan* plan = nullptr;
   GeneralMerge* general = nullptr;
@@ -214,23 +289,27 @@ struct DeviceScan::Impl : std::enable_shared_from_this<DeviceScan::Impl> {
   int64_t vstride = 0;
   bool ran = false;
 
-  ~Impl() {
-    if (general) general_destroy(general);
-    if (plan) plan_destroy(plan);
-    free_device();
-    if (stream) cudaStreamDestroy(stream);
-  }
+  ScanSlot* slot = nullptr;
 
-  void* dalloc(size_t bytes) {
-    void* p = nullptr;
-    SCAN_CUDA(cudaMallocAsync(&p, std::max<size_t>(bytes, 16), stream));
-    dev_allocs.push_back(p);
-    return p;
+  ~Impl() { end_device(); }
+
+  // every device buffer of the scan lives in the slot's arena (no per-buffer driver calls)
+  void* dalloc(size_t bytes) { return slot->arena.alloc(std::max<size_t>(bytes, 16)); }
+  void begin_device() {
+    slot = SlotPool::get().acquire();
+    stream = slot->stream;
+    arena_install(&slot->arena);
   }
-  void free_device() {
-    for (void* p : dev_allocs) cudaFreeAsync(p, stream);
-    dev_allocs.clear();
-    if (stream) cudaStreamSynchronize(stream);
+  // must run on the thread that called begin_device(), with all results already on the host
+  void end_device() {
+    if (!slot) return;
+    if (general) { general_destroy(general); general = nullptr; }
+    if (plan) { plan_destroy(plan); plan = nullptr; }
+    stream_wait(stream);
+    arena_install(nullptr);
+    SlotPool::get().release(slot);
+    slot = nullptr;
+    stream = nullptr;
   }
   void h2d(void* dst, const void* src, size_t n) {
     if (n == 0) return;
@@ -411,7 +490,8 @@ void DeviceScan::Impl::upload() {
       if (file_in[f]->raw->aux_bytes() > 0)
         h2d(d_raw + aux_off[f], file_in[f]->raw->aux(), (size_t)file_in[f]->raw->aux_bytes());
     }
-    int64_t dict_entries = 0;
+    int64_t dict_entries = 0, nblocks = 0, vpos_entries = 0;
+    bool any_dict_var = false;
     for (int c = 0; c < C; ++c) {
       if (!cols[c].has_raw) continue;
       for (int b = 0; b < nb; ++b) {
@@ -456,6 +536,16 @@ void DeviceScan::Impl::upload() {
             pg.chunk = ci;
             pg.closes_file = (pi + 1 == rc.pages.size()) ? 1 : 0;
             pg.row_start = file_row_base[f] + rp.first_row;
+            pg.first_block = (int32_t)nblocks;
+            nblocks += (rp.num_values + kDecodeBlockRows - 1) / kDecodeBlockRows;
+            if (rc.proto.conv == CONV_VAR) {
+              if (rp.encoding == ENC_PLAIN) {
+                pg.vpos_base = vpos_entries;
+                vpos_entries += (int64_t)rp.num_values + 1;
+              } else {
+                any_dict_var = true;
+              }
+            }
             pages.push_back(pg);
           }
           if (rc.pages.empty() && cols[c].kind.var) {
@@ -487,6 +577,8 @@ void DeviceScan::Impl::upload() {
     d_pages = static_cast<PqPage*>(dalloc(sizeof(PqPage) * pages.size()));
     d_dict_pos = static_cast<int32_t*>(dalloc(sizeof(int32_t) * (size_t)(dict_entries + 1)));
     d_err = static_cast<int32_t*>(dalloc(sizeof(int32_t)));
+    PqBlock* d_blocks = static_cast<PqBlock*>(dalloc(sizeof(PqBlock) * (size_t)(nblocks + 1)));
+    int32_t* d_vpos = static_cast<int32_t*>(dalloc(sizeof(int32_t) * (size_t)(vpos_entries + 1)));
     SCAN_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int32_t), stream));
     h2d(d_chunks, chunks.data(), sizeof(PqChunk) * chunks.size());
     h2d(d_pages, pages.data(), sizeof(PqPage) * pages.size());
@@ -494,8 +586,11 @@ void DeviceScan::Impl::upload() {
     args.chunks = d_chunks;
     args.pages = d_pages;
     args.dict_pos = d_dict_pos;
+    args.blocks = d_blocks;
+    args.vpos = d_vpos;
     args.npages = (int32_t)pages.size();
     args.nchunks = (int32_t)chunks.size();
+    args.nblocks = (int32_t)nblocks;
     args.err = d_err;
     args.cols = nullptr;
     seg_total.assign((size_t)nseg, 0);
@@ -505,15 +600,19 @@ void DeviceScan::Impl::upload() {
       int64_t* d_total = static_cast<int64_t*>(dalloc(sizeof(int64_t) * (size_t)nseg));
       h2d(d_bounds, seg_bounds.data(), sizeof(int32_t) * seg_bounds.size());
       h2d(d_base, seg_base.data(), sizeof(int64_t) * (size_t)nseg);
+      trace_mark("up_enqueue");
       launch_dict_index(args, stream);
-      launch_page_count(args, stream);
-      launch_page_scan(args, d_bounds, d_base, nseg, d_total, stream);
-      ctr.kernel_launches += 3;
+      launch_page_index(args, stream);
+      if (any_dict_var) launch_block_count(args, stream);
+      launch_block_scan(args, d_bounds, d_base, nseg, d_total, stream);
+      ctr.kernel_launches += any_dict_var ? 4 : 3;
       SCAN_CUDA(cudaMemcpyAsync(seg_total.data(), d_total, sizeof(int64_t) * (size_t)nseg, cudaMemcpyDeviceToHost, stream));
-      SCAN_CUDA(cudaStreamSynchronize(stream));
+      SCAN_CUDA(stream_wait(stream));
+      trace_mark("wait_index");
     } else {
       launch_dict_index(args, stream);
-      ctr.kernel_launches += 1;
+      launch_page_index(args, stream);
+      ctr.kernel_launches += 2;
     }
   }
 
@@ -577,11 +676,13 @@ void DeviceScan::Impl::upload() {
     PqColOut* d_colout = static_cast<PqColOut*>(dalloc(sizeof(PqColOut) * (size_t)C));
     h2d(d_colout, colout.data(), sizeof(PqColOut) * (size_t)C);
     args.cols = d_colout;
-    launch_page_decode(args, stream);
+    launch_block_decode(args, stream);
     ctr.kernel_launches += 1;
     int32_t err = 0;
     SCAN_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-    SCAN_CUDA(cudaStreamSynchronize(stream));
+    trace_mark("dec_enqueue");
+    SCAN_CUDA(stream_wait(stream));
+    trace_mark("wait_decode");
     if (err != 0) fail("device Parquet decode met a malformed or unsupported page (code " + std::to_string(err) + ")");
   }
 }
@@ -684,6 +785,7 @@ void DeviceScan::Impl::merge_and_gather() {
     ctr.kernel_launches += apply_filter(plan, *spec.filter, fin, extra, stream);
   }
   ctr.merge_ms += now_ms() - t0;
+  trace_mark("merge");
 
   out_base = plan_out_base(plan);
   batch_base = plan_batch_base(plan);
@@ -767,7 +869,9 @@ void DeviceScan::Impl::merge_and_gather() {
       d2h(oc.h_values.get(), dout[c].values, n);
     }
   }
-  SCAN_CUDA(cudaStreamSynchronize(stream));
+  trace_mark("gather_enqueue");
+  SCAN_CUDA(stream_wait(stream));
+  trace_mark("wait_gather");
   ctr.gather_ms += now_ms() - t1;
   const double t2 = now_ms();
   for (int c = 0; c < C && U > 0; ++c) {
@@ -780,7 +884,8 @@ void DeviceScan::Impl::merge_and_gather() {
     oc.h_data = pool.alloc((size_t)std::max<int64_t>(total, 1));
     d2h(oc.h_data.get(), dout[c].data, (size_t)total);
   }
-  SCAN_CUDA(cudaStreamSynchronize(stream));
+  SCAN_CUDA(stream_wait(stream));
+  trace_mark("wait_strings");
   ctr.download_ms += now_ms() - t2;
 }
 
@@ -795,18 +900,19 @@ DeviceScan::~DeviceScan() = default;
 void DeviceScan::Run() {
   Impl& I = *impl_;
   if (I.ran) return;
-  SCAN_CUDA(cudaStreamCreateWithFlags(&I.stream, cudaStreamNonBlocking));
-  I.layout();
-  const double t0 = now_ms();
-  I.upload();
-  SCAN_CUDA(cudaStreamSynchronize(I.stream));
-  I.ctr.upload_ms += now_ms() - t0;
-  I.merge_and_gather();
+  I.begin_device();
+  try {
+    I.layout();
+    const double t0 = now_ms();
+    I.upload();
+    I.ctr.upload_ms += now_ms() - t0;
+    I.merge_and_gather();
+  } catch (...) {
+    I.end_device();
+    throw;
+  }
   // device memory is no longer needed: only the pinned host copy backs the exported batches
-  if (I.general) { general_destroy(I.general); I.general = nullptr; }
-  plan_destroy(I.plan);
-  I.plan = nullptr;
-  I.free_device();
+  I.end_device();
   I.buckets.clear();  // drop the decoded inputs
   I.file_in.clear();
   I.ran = true;

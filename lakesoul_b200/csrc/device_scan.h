@@ -23,6 +23,11 @@ namespace lsb {
 
 ColumnKind classify_type(const arrow::DataType& t);
 
+// Development trace (LAKESOUL_B200_TRACE=1): phase marks of the calling thread's current reader,
+// printed to stderr as one line per reader by trace_flush(). No-ops when the variable is unset.
+void trace_mark(const char* phase);
+void trace_flush(const char* tag);
+
 // merge_operator.rs:41-53 -- unknown names are an error (the reference panics)
 MergeOp merge_op_from_name(const std::string& name);
 

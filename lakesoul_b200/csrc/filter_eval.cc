@@ -144,9 +144,9 @@ int apply_filter(MergePlan* plan, const FilterExpr& expr, const std::vector<Filt
   auto check = [](cudaError_t e, const char* what) {
     if (e != cudaSuccess) fail(std::string(what) + ": " + cudaGetErrorString(e));
   };
-  check(cudaMallocAsync(reinterpret_cast<void**>(&d_pool), b.pool.size() + 16, stream), "cudaMallocAsync");
-  check(cudaMallocAsync(reinterpret_cast<void**>(&d_prog), sizeof(FilterProgram), stream), "cudaMallocAsync");
-  check(cudaMallocAsync(reinterpret_cast<void**>(&d_keep), (size_t)U, stream), "cudaMallocAsync");
+  d_pool = static_cast<uint8_t*>(device_alloc_bytes(b.pool.size() + 16, stream));
+  d_prog = static_cast<FilterProgram*>(device_alloc_bytes(sizeof(FilterProgram), stream));
+  d_keep = static_cast<uint8_t*>(device_alloc_bytes((size_t)U, stream));
   if (!b.pool.empty())
     check(cudaMemcpyAsync(d_pool, b.pool.data(), b.pool.size(), cudaMemcpyHostToDevice, stream), "memcpy pool");
   b.prog.lit_pool = d_pool;
@@ -154,9 +154,9 @@ int apply_filter(MergePlan* plan, const FilterExpr& expr, const std::vector<Filt
   launch_filter_kernel(d_prog, plan_winners(plan), plan_out_base_dev(plan), nb, U, d_keep, stream);
   plan_compact(plan, d_keep, extra_lists, stream);
   plan_sync_counts(plan, stream);
-  cudaFreeAsync(d_pool, stream);
-  cudaFreeAsync(d_prog, stream);
-  cudaFreeAsync(d_keep, stream);
+  device_free_bytes(d_pool, stream);
+  device_free_bytes(d_prog, stream);
+  device_free_bytes(d_keep, stream);
   return 1 + 8 + 2 * (int)extra_lists.size();
 }
 

@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -27,6 +28,31 @@ namespace lsb {
 
 static thread_local std::string g_last_error;
 std::string last_error() { return g_last_error; }
+
+cudaError_t stream_wait(cudaStream_t stream) {
+  static const bool spin = [] { const char* v = getenv("LAKESOUL_B200_SPIN_SYNC"); return v && *v == '1'; }();
+  if (spin) return cudaStreamSynchronize(stream);
+  struct Ev {
+    cudaEvent_t e = nullptr;
+    int dev = -1;
+    ~Ev() { if (e) cudaEventDestroy(e); }
+  };
+  thread_local Ev ev;
+  int dev = 0;
+  cudaError_t rc = cudaGetDevice(&dev);
+  if (rc != cudaSuccess) return rc;
+  if (!ev.e || ev.dev != dev) {
+    if (ev.e) cudaEventDestroy(ev.e);
+    ev.e = nullptr;
+    rc = cudaEventCreateWithFlags(&ev.e, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (rc != cudaSuccess) return rc;
+    ev.dev = dev;
+  }
+  rc = cudaEventRecord(ev.e, stream);
+  if (rc != cudaSuccess) return rc;
+  return cudaEventSynchronize(ev.e);
+}
+
 
 #define LSB_CUDA(x)                                                                   \
   do {                                                                                \
@@ -1212,15 +1238,72 @@ static size_t tile_smem_bytes(int C, bool key128) {
 
 // stream-ordered pool allocations: plans are created per scan batch, cudaMalloc/cudaFree would
 // serialise the device every time
-template <typename T>
-static T* dev_alloc(size_t n, cudaStream_t stream) {
-  T* p = nullptr;
-  LSB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T), stream));
+static thread_local DeviceArena* t_arena = nullptr;
+void arena_install(DeviceArena* a) { t_arena = a; }
+DeviceArena* arena_current() { return t_arena; }
+
+DeviceArena::~DeviceArena() {
+  for (auto& b : blocks_) cudaFree(b.p);
+}
+size_t DeviceArena::capacity() const {
+  size_t c = 0;
+  for (auto& b : blocks_) c += b.cap;
+  return c;
+}
+void* DeviceArena::alloc(size_t bytes) {
+  bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+  while (true) {
+    if (cur_ < blocks_.size() && off_ + bytes <= blocks_[cur_].cap) {
+      void* p = blocks_[cur_].p + off_;
+      off_ += bytes;
+      used_ += bytes;
+      return p;
+    }
+    if (cur_ + 1 < blocks_.size()) {  // later block left over from an earlier reader
+      ++cur_;
+      off_ = 0;
+      continue;
+    }
+    size_t cap = std::max<size_t>(bytes, (size_t)64 << 20);
+    if (!blocks_.empty()) cap = std::max(cap, blocks_.back().cap * 2);
+    uint8_t* p = nullptr;
+    LSB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), cap));
+    blocks_.push_back({p, cap});
+    cur_ = blocks_.size() - 1;
+    off_ = 0;
+  }
+}
+void DeviceArena::reset() {
+  high_ = std::max(high_, used_);
+  // several blocks = the arena had to grow: fold them into one block that fits the largest reader so far
+  if (blocks_.size() > 1) {
+    for (auto& b : blocks_) cudaFree(b.p);
+    blocks_.clear();
+    uint8_t* p = nullptr;
+    const size_t cap = ((high_ + high_ / 4) + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1);
+    if (cudaMalloc(reinterpret_cast<void**>(&p), cap) == cudaSuccess) blocks_.push_back({p, cap});
+    else cudaGetLastError();
+  }
+  cur_ = 0;
+  off_ = 0;
+  used_ = 0;
+}
+
+void* device_alloc_bytes(size_t bytes, cudaStream_t stream) {
+  if (t_arena) return t_arena->alloc(bytes);
+  void* p = nullptr;
+  LSB_CUDA(cudaMallocAsync(&p, std::max<size_t>(bytes, 16), stream));
   return p;
 }
-static void dev_free(void* p, cudaStream_t stream) {
-  if (p) cudaFreeAsync(p, stream);
+void device_free_bytes(void* p, cudaStream_t stream) {
+  if (p && !t_arena) cudaFreeAsync(p, stream);
 }
+
+template <typename T>
+static T* dev_alloc(size_t n, cudaStream_t stream) {
+  return static_cast<T*>(device_alloc_bytes(std::max<size_t>(n, 1) * sizeof(T), stream));
+}
+static void dev_free(void* p, cudaStream_t stream) { device_free_bytes(p, stream); }
 
 // small pinned staging blocks for the per-plan count read-back, recycled per thread
 struct PinnedCounts {
@@ -1545,7 +1628,7 @@ const std::vector<int64_t>& plan_sync_counts(MergePlan* P, cudaStream_t stream) 
                              cudaMemcpyDeviceToHost, stream));
     LSB_CUDA(cudaMemcpyAsync(P->h_counts + 2 * (nb + 1), P->d_err, sizeof(int32_t),
                              cudaMemcpyDeviceToHost, stream));
-    LSB_CUDA(cudaStreamSynchronize(stream));
+    LSB_CUDA(stream_wait(stream));
     const int32_t err = *reinterpret_cast<int32_t*>(P->h_counts + 2 * (nb + 1));
     if (err != 0) {
       g_last_error = "merge kernel reported error code " + std::to_string(err);
@@ -1980,7 +2063,7 @@ GeneralMerge* general_create(MergePlan* P, const PkDesc& pk, const std::vector<G
     for (int c = 0; c < G->C; ++c) std::memcpy(present.data() + (size_t)c * P->F, in[c].present, P->F);
     G->d_present = dev_alloc<char>(present.size(), stream);
     LSB_CUDA(cudaMemcpyAsync(G->d_present, present.data(), present.size(), cudaMemcpyHostToDevice, stream));
-    LSB_CUDA(cudaStreamSynchronize(stream));  // host vectors go out of scope below
+    LSB_CUDA(stream_wait(stream));  // host vectors go out of scope below
 
     P->d_R = G->d_R;
     P->d_rofs = G->d_rofs;
@@ -2036,7 +2119,7 @@ GeneralMerge* general_create(MergePlan* P, const PkDesc& pk, const std::vector<G
           scan_sums_inplace<<<1, 1024, 0, stream>>>(d_sums, nblocks, 0);
           scan_apply<<<nblocks, 256, 0, stream>>>(d_len, U, d_sums, d_ooff);
           LSB_CUDA(cudaMemcpyAsync(&total, d_ooff + U, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-          LSB_CUDA(cudaStreamSynchronize(stream));
+          LSB_CUDA(stream_wait(stream));
           if (total > (int64_t)INT32_MAX) {
             g_last_error = "Joined* merge operator: the joined column exceeds 2 GiB in one scan";
             throw std::runtime_error(g_last_error);

@@ -160,4 +160,30 @@ void plan_reserve_scratch(MergePlan*, cudaStream_t stream);
 
 std::string last_error();
 
+// Scratch arena for one reader at a time: device memory is handed out by bumping a pointer, nothing
+// is returned until reset(). While a thread has an arena installed (arena_install), every device
+// allocation of the engine on that thread comes from it and frees are no-ops -- per-bucket readers
+// then make no cudaMallocAsync / cudaFreeAsync calls at all (measured ~100 us each under 16 concurrent
+// readers, the largest host-side cost of a bucket).
+class DeviceArena {
+ public:
+  ~DeviceArena();
+  void* alloc(size_t bytes);   // 256-byte aligned; grows with cudaMalloc when the current block is full
+  void reset();                // all GPU work on the arena must have completed
+  size_t capacity() const;
+ private:
+  struct Block { uint8_t* p; size_t cap; };
+  std::vector<Block> blocks_;
+  size_t cur_ = 0, off_ = 0, high_ = 0, used_ = 0;
+};
+void arena_install(DeviceArena* a);   // nullptr restores cudaMallocAsync / cudaFreeAsync
+DeviceArena* arena_current();
+void* device_alloc_bytes(size_t bytes, cudaStream_t stream);  // arena if installed, else cudaMallocAsync
+void device_free_bytes(void* p, cudaStream_t stream);
+
+// Wait for `stream` without spinning: the calling thread sleeps on a blocking-sync event, so task
+// slots that wait for the GPU leave their core to the slots that are reading files
+// (LAKESOUL_B200_SPIN_SYNC=1 restores cudaStreamSynchronize).
+cudaError_t stream_wait(cudaStream_t stream);
+
 }  // namespace lsb

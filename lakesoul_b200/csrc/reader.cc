@@ -238,6 +238,7 @@ void Reader::Start() {
 
   // ---- open files, read footers (session.rs:546-593) -----------------------------------------
   const double t_dec0 = now_ms();
+  trace_mark("start");
   std::vector<FileInfo> files;
   for (const auto& raw : cfg.files) {
     const std::string path = strip_scheme(raw);
@@ -257,6 +258,7 @@ void Reader::Start() {
     fi.rows = fi.raw->num_rows();
     files.push_back(std::move(fi));
   }
+  trace_mark("open_read");
 
   // ---- table schema = target (uniformed) + file-only fields (session.rs:596-626) ---------------
   std::vector<std::shared_ptr<arrow::Field>> target_fields;
@@ -421,6 +423,7 @@ void Reader::Start() {
     bucket.files.push_back(std::move(in));
   }
   I.stats.decode_ms = now_ms() - t_dec0;
+  trace_mark("frame");
 
   ScanSpec spec;
   spec.physical_schema = physical_schema;
@@ -436,6 +439,8 @@ void Reader::Start() {
   buckets.push_back(std::move(bucket));
   I.scan.reset(new DeviceScan(std::move(spec), std::move(buckets)));
   I.scan->Run();
+  trace_mark("cleanup");
+  trace_flush("reader");
   I.n_batches = I.scan->num_batches(0);
   const ScanCounters& c = I.scan->counters();
   I.stats.rows_in = c.rows_in;
