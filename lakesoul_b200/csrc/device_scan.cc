@@ -132,6 +132,34 @@ class SlotPool {
 };
 }  // namespace
 
+class ScanSession {
+ public:
+  ScanSlot* slot = nullptr;
+  int64_t h2d_bytes = 0;
+  ~ScanSession() {
+    if (!slot) return;
+    stream_wait(slot->stream);
+    if (arena_current() == &slot->arena) arena_install(nullptr);
+    SlotPool::get().release(slot);
+  }
+};
+std::shared_ptr<ScanSession> begin_scan_session() {
+  auto s = std::make_shared<ScanSession>();
+  s->slot = SlotPool::get().acquire();
+  arena_install(&s->slot->arena);
+  return s;
+}
+uint8_t* session_upload(ScanSession& s, const uint8_t* pinned, size_t bytes) {
+  uint8_t* d = static_cast<uint8_t*>(s.slot->arena.alloc(bytes + 64));
+  if (bytes > 0) {
+    cudaError_t e = cudaMemcpyAsync(d, pinned, bytes, cudaMemcpyHostToDevice, s.slot->stream);
+    if (e != cudaSuccess) fail(std::string("cudaMemcpyAsync failed: ") + cudaGetErrorString(e));
+    s.h2d_bytes += (int64_t)bytes;
+  }
+  return d;
+}
+int64_t session_h2d_bytes(const ScanSession& s) { return s.h2d_bytes; }
+
 namespace {
 bool trace_on() {
   static const bool on = [] { const char* v = getenv("LAKESOUL_B200_TRACE"); return v && *v == '1'; }();
@@ -282,13 +310,14 @@ struct DeviceScan::Impl : std::enable_shared_from_this<DeviceScan::Impl> {
     ColumnKind kind;
     bool has_valid = false;
     std::shared_ptr<uint8_t> h_values, h_valid, h_offsets, h_data;
-    std::vector<int64_t> batch_data_start;
+    std::shared_ptr<int64_t> h_bstart;  // per-batch start of the string bytes (+ closing entry)
   };
   std::vector<OutColumn> outs;
   std::vector<int64_t> out_base, batch_base;
   int64_t vstride = 0;
   bool ran = false;
 
+  std::shared_ptr<ScanSession> session;
   ScanSlot* slot = nullptr;
 
   ~Impl() { end_device(); }
@@ -296,18 +325,16 @@ struct DeviceScan::Impl : std::enable_shared_from_this<DeviceScan::Impl> {
   // every device buffer of the scan lives in the slot's arena (no per-buffer driver calls)
   void* dalloc(size_t bytes) { return slot->arena.alloc(std::max<size_t>(bytes, 16)); }
   void begin_device() {
-    slot = SlotPool::get().acquire();
+    if (!session) session = begin_scan_session();
+    slot = session->slot;
     stream = slot->stream;
-    arena_install(&slot->arena);
+    ctr.h2d_bytes += session->h2d_bytes;
   }
-  // must run on the thread that called begin_device(), with all results already on the host
+  // must run on the thread that opened the session, with all results already on the host
   void end_device() {
-    if (!slot) return;
     if (general) { general_destroy(general); general = nullptr; }
     if (plan) { plan_destroy(plan); plan = nullptr; }
-    stream_wait(stream);
-    arena_install(nullptr);
-    SlotPool::get().release(slot);
+    session.reset();  // waits for the stream, uninstalls the arena, recycles the slot
     slot = nullptr;
     stream = nullptr;
   }
@@ -322,6 +349,9 @@ struct DeviceScan::Impl : std::enable_shared_from_this<DeviceScan::Impl> {
     ctr.d2h_bytes += (int64_t)n;
   }
 
+  std::shared_ptr<uint8_t> h_small;  // pinned: [decode error flag | string segment totals]
+  bool decode_err_pending = false;
+  void check_decode_error();
   void layout();
   void upload();
   void upload_host_file(int c, int b, int f, int64_t dpos);
@@ -466,29 +496,29 @@ void DeviceScan::Impl::upload() {
   std::vector<int64_t> seg_base;
   std::vector<int> seg_col, seg_bucket;
   std::vector<int64_t> seg_total;
-  uint8_t* d_raw = nullptr;
   PqChunk* d_chunks = nullptr;
   PqPage* d_pages = nullptr;
   int32_t* d_dict_pos = nullptr;
   int32_t* d_err = nullptr;
   DecodeArgs args{};
   if (any_raw) {
-    // raw image layout: [file image | aux (decompressed pages)] per file, 64-byte aligned
+    // device copies of the file images (already sent by the reader, or sent now) and of the
+    // decompressed pages; page offsets below are absolute device addresses (args.raw = nullptr)
     std::vector<int64_t> img_off(F, 0), aux_off(F, 0);
-    int64_t raw_total = 0;
     for (int f = 0; f < F; ++f) {
-      if (!file_in[f]->raw) continue;
-      img_off[f] = raw_total;
-      raw_total = (raw_total + file_in[f]->raw->image_bytes() + 63) & ~63ll;
-      aux_off[f] = raw_total;
-      raw_total = (raw_total + file_in[f]->raw->aux_bytes() + 63) & ~63ll;
-    }
-    d_raw = static_cast<uint8_t*>(dalloc((size_t)raw_total + 64));
-    for (int f = 0; f < F; ++f) {
-      if (!file_in[f]->raw) continue;
-      h2d(d_raw + img_off[f], file_in[f]->raw->image(), (size_t)file_in[f]->raw->image_bytes());
-      if (file_in[f]->raw->aux_bytes() > 0)
-        h2d(d_raw + aux_off[f], file_in[f]->raw->aux(), (size_t)file_in[f]->raw->aux_bytes());
+      RawParquetFile* rf = file_in[f]->raw.get();
+      if (!rf) continue;
+      uint8_t* d_img = rf->device_image();
+      if (!d_img) {
+        d_img = static_cast<uint8_t*>(dalloc((size_t)rf->image_bytes() + 64));
+        h2d(d_img, rf->image(), (size_t)rf->image_bytes());
+      }
+      img_off[f] = (int64_t)reinterpret_cast<uintptr_t>(d_img);
+      if (rf->aux_bytes() > 0) {
+        uint8_t* d_aux = static_cast<uint8_t*>(dalloc((size_t)rf->aux_bytes() + 64));
+        h2d(d_aux, rf->aux(), (size_t)rf->aux_bytes());
+        aux_off[f] = (int64_t)reinterpret_cast<uintptr_t>(d_aux);
+      }
     }
     int64_t dict_entries = 0, nblocks = 0, vpos_entries = 0;
     bool any_dict_var = false;
@@ -582,7 +612,7 @@ void DeviceScan::Impl::upload() {
     SCAN_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int32_t), stream));
     h2d(d_chunks, chunks.data(), sizeof(PqChunk) * chunks.size());
     h2d(d_pages, pages.data(), sizeof(PqPage) * pages.size());
-    args.raw = d_raw;
+    args.raw = nullptr;
     args.chunks = d_chunks;
     args.pages = d_pages;
     args.dict_pos = d_dict_pos;
@@ -606,8 +636,23 @@ void DeviceScan::Impl::upload() {
       if (any_dict_var) launch_block_count(args, stream);
       launch_block_scan(args, d_bounds, d_base, nseg, d_total, stream);
       ctr.kernel_launches += any_dict_var ? 4 : 3;
-      SCAN_CUDA(cudaMemcpyAsync(seg_total.data(), d_total, sizeof(int64_t) * (size_t)nseg, cudaMemcpyDeviceToHost, stream));
-      SCAN_CUDA(stream_wait(stream));
+      bool host_var = false;
+      for (size_t s2 = 0; s2 < seg_base.size(); ++s2) host_var |= seg_base[s2] != 0;
+      if (nb == 1 && !any_dict_var && !host_var) {
+        // one bucket of PLAIN strings: the page payload bounds the string bytes, so the column buffers
+        // can be sized without waiting for the index pass (one GPU round trip less per reader)
+        for (int s2 = 0; s2 < nseg; ++s2) {
+          int64_t bound = 0;
+          for (int32_t i = seg_bounds[2 * (size_t)s2]; i < seg_bounds[2 * (size_t)s2 + 1]; ++i) bound += pages[(size_t)i].size;
+          seg_total[(size_t)s2] = bound;
+        }
+      } else {
+        h_small = pinned_alloc(sizeof(int64_t) * (size_t)nseg + 64);
+        int64_t* h_total = reinterpret_cast<int64_t*>(h_small.get() + 64);
+        SCAN_CUDA(cudaMemcpyAsync(h_total, d_total, sizeof(int64_t) * (size_t)nseg, cudaMemcpyDeviceToHost, stream));
+        SCAN_CUDA(stream_wait(stream));
+        for (int s2 = 0; s2 < nseg; ++s2) seg_total[(size_t)s2] = h_total[s2];
+      }
       trace_mark("wait_index");
     } else {
       launch_dict_index(args, stream);
@@ -678,13 +723,20 @@ void DeviceScan::Impl::upload() {
     args.cols = d_colout;
     launch_block_decode(args, stream);
     ctr.kernel_launches += 1;
-    int32_t err = 0;
-    SCAN_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    // the error flag is read back with the merge counts (check_decode_error), not with a sync of its own
+    if (!h_small) h_small = pinned_alloc(64);
+    *reinterpret_cast<int32_t*>(h_small.get()) = 0;
+    SCAN_CUDA(cudaMemcpyAsync(h_small.get(), d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    decode_err_pending = true;
     trace_mark("dec_enqueue");
-    SCAN_CUDA(stream_wait(stream));
-    trace_mark("wait_decode");
-    if (err != 0) fail("device Parquet decode met a malformed or unsupported page (code " + std::to_string(err) + ")");
   }
+}
+
+void DeviceScan::Impl::check_decode_error() {
+  if (!decode_err_pending) return;
+  decode_err_pending = false;
+  const int32_t err = *reinterpret_cast<const int32_t*>(h_small.get());
+  if (err != 0) fail("device Parquet decode met a malformed or unsupported page (code " + std::to_string(err) + ")");
 }
 
 void DeviceScan::Impl::merge_and_gather() {
@@ -740,6 +792,7 @@ void DeviceScan::Impl::merge_and_gather() {
   if (do_merge) plan_merge(plan, pk, stream);
   else plan_identity(plan, stream);
   plan_sync_counts(plan, stream);
+  check_decode_error();  // same stream, enqueued before the merge
   ctr.kernel_launches += plan_stats(plan).launches;
 
   // per-column winner lists / operator results (partial merge, non-UseLast operators)
@@ -795,53 +848,74 @@ void DeviceScan::Impl::merge_and_gather() {
   ctr.rows_out = U;
 
   // ---- gather ---------------------------------------------------------------------------
+  // Every fixed-size output (validity, values, string offsets, per-batch data starts) of every column
+  // lives in ONE device region mirrored by ONE pinned host block: a single D2H copy brings them back.
   const double t1 = now_ms();
   outs.resize(C);
-  struct DevOut { void *values = nullptr, *valid = nullptr, *offsets = nullptr, *data = nullptr, *bstart = nullptr; };
-  std::vector<DevOut> dout(C);
-  std::vector<FixedCol> fixed;
-  std::vector<VarCol> vars;
+  struct Seg { size_t valid = 0, main = 0, bstart = 0; size_t valid_n = 0, main_n = 0, bstart_n = 0; };
+  std::vector<Seg> seg(C);
+  size_t region = 0;
+  auto take = [&](size_t n) { const size_t o = region; region = (region + n + 255) & ~(size_t)255; return o; };
+  std::vector<const uint32_t*> wins(C, nullptr);
+  std::vector<const void*> src_values(C, nullptr);
+  std::vector<const uint8_t*> src_valid(C, nullptr);
   for (int c = 0; c < C; ++c) {
     DevColumn& dc = cols[c];
     OutColumn& oc = outs[c];
     oc.kind = dc.kind;
-    const uint32_t* win = general ? general_winners(general, c) : nullptr;
-    const void* src_values = general ? general_values(general, c, dc.values.p) : dc.values.p;
-    const uint8_t* src_valid = general ? general_validity(general, c, static_cast<const uint8_t*>(dc.validity.p))
-                                       : static_cast<const uint8_t*>(dc.validity.p);
-    oc.has_valid = src_valid != nullptr || (general && general_may_be_null(general, c));
+    wins[c] = general ? general_winners(general, c) : nullptr;
+    src_values[c] = general ? general_values(general, c, dc.values.p) : dc.values.p;
+    src_valid[c] = general ? general_validity(general, c, static_cast<const uint8_t*>(dc.validity.p))
+                           : static_cast<const uint8_t*>(dc.validity.p);
+    oc.has_valid = src_valid[c] != nullptr || (general && general_may_be_null(general, c));
     if (U == 0) continue;
-    if (oc.has_valid) dout[c].valid = dalloc((size_t)(TB * vstride));
+    Seg& sg = seg[c];
+    if (oc.has_valid) { sg.valid_n = (size_t)(TB * vstride); sg.valid = take(sg.valid_n); }
+    if (dc.kind.var) {
+      sg.main_n = (size_t)(U + TB) * 4;
+      sg.main = take(sg.main_n);
+      sg.bstart_n = (size_t)(TB + 1) * 8;
+      sg.bstart = take(sg.bstart_n);
+    } else {
+      const int w = dc.kind.width;
+      sg.main_n = w == 0 ? (size_t)(TB * vstride) : (size_t)U * w;
+      sg.main = take(sg.main_n);
+    }
+  }
+  uint8_t* d_region = U > 0 ? static_cast<uint8_t*>(dalloc(region + 256)) : nullptr;
+  std::vector<void*> d_data(C, nullptr);
+  std::vector<FixedCol> fixed;
+  std::vector<VarCol> vars;
+  for (int c = 0; c < C && U > 0; ++c) {
+    DevColumn& dc = cols[c];
+    const Seg& sg = seg[c];
+    uint8_t* d_valid = outs[c].has_valid ? d_region + sg.valid : nullptr;
     if (dc.kind.var) {
       const uint8_t* src_data = general ? general_data(general, c, static_cast<const uint8_t*>(dc.data.p))
                                         : static_cast<const uint8_t*>(dc.data.p);
       const int64_t* bdata = general ? general_bucket_data(general, c, static_cast<const int64_t*>(dc.d_bucket_data.p))
                                      : static_cast<const int64_t*>(dc.d_bucket_data.p);
       const int64_t cap = general ? general_data_bytes(general, c, dc.data_bytes) : dc.data_bytes;
-      dout[c].offsets = dalloc((size_t)(U + TB) * 4);
-      dout[c].data = dalloc((size_t)cap);
-      dout[c].bstart = dalloc((size_t)(TB + 1) * 8);
+      d_data[c] = dalloc((size_t)cap);
       VarCol vc{};
-      vc.src_offsets = static_cast<const int32_t*>(src_values);
+      vc.src_offsets = static_cast<const int32_t*>(src_values[c]);
       vc.src_data = src_data;
       vc.src_data_base = bdata;
-      vc.src_valid = src_valid;
-      vc.win = win;
-      vc.dst_offsets = static_cast<int32_t*>(dout[c].offsets);
-      vc.dst_data = static_cast<uint8_t*>(dout[c].data);
-      vc.dst_valid = static_cast<uint8_t*>(dout[c].valid);
-      vc.batch_data_start = static_cast<int64_t*>(dout[c].bstart);
+      vc.src_valid = src_valid[c];
+      vc.win = wins[c];
+      vc.dst_offsets = reinterpret_cast<int32_t*>(d_region + sg.main);
+      vc.dst_data = static_cast<uint8_t*>(d_data[c]);
+      vc.dst_valid = d_valid;
+      vc.batch_data_start = reinterpret_cast<int64_t*>(d_region + sg.bstart);
       vars.push_back(vc);
     } else {
-      const int w = dc.kind.width;
-      dout[c].values = dalloc(w == 0 ? (size_t)(TB * vstride) : (size_t)U * w);
       FixedCol fc{};
-      fc.src = src_values;
-      fc.src_valid = src_valid;
-      fc.dst = dout[c].values;
-      fc.dst_valid = static_cast<uint8_t*>(dout[c].valid);
-      fc.win = win;
-      fc.width = w;
+      fc.src = src_values[c];
+      fc.src_valid = src_valid[c];
+      fc.dst = d_region + sg.main;
+      fc.dst_valid = d_valid;
+      fc.win = wins[c];
+      fc.width = dc.kind.width;
       fixed.push_back(fc);
     }
   }
@@ -852,21 +926,20 @@ void DeviceScan::Impl::merge_and_gather() {
 
   // ---- download ---------------------------------------------------------------------------
   auto& pool = PinnedPool::get();
-  for (int c = 0; c < C && U > 0; ++c) {
-    OutColumn& oc = outs[c];
-    if (oc.has_valid) {
-      oc.h_valid = pool.alloc((size_t)(TB * vstride));
-      d2h(oc.h_valid.get(), dout[c].valid, (size_t)(TB * vstride));
-    }
-    if (oc.kind.var) {
-      oc.h_offsets = pool.alloc((size_t)(U + TB) * 4);
-      d2h(oc.h_offsets.get(), dout[c].offsets, (size_t)(U + TB) * 4);
-      oc.batch_data_start.resize((size_t)TB + 1);
-      d2h(oc.batch_data_start.data(), dout[c].bstart, (size_t)(TB + 1) * 8);
-    } else {
-      const size_t n = oc.kind.width == 0 ? (size_t)(TB * vstride) : (size_t)U * oc.kind.width;
-      oc.h_values = pool.alloc(n);
-      d2h(oc.h_values.get(), dout[c].values, n);
+  std::shared_ptr<uint8_t> h_region;
+  if (U > 0) {
+    h_region = pool.alloc(region + 256);
+    d2h(h_region.get(), d_region, region);
+    for (int c = 0; c < C; ++c) {
+      OutColumn& oc = outs[c];
+      const Seg& sg = seg[c];
+      if (oc.has_valid) oc.h_valid = std::shared_ptr<uint8_t>(h_region, h_region.get() + sg.valid);
+      if (oc.kind.var) {
+        oc.h_offsets = std::shared_ptr<uint8_t>(h_region, h_region.get() + sg.main);
+        oc.h_bstart = std::shared_ptr<int64_t>(h_region, reinterpret_cast<int64_t*>(h_region.get() + sg.bstart));
+      } else {
+        oc.h_values = std::shared_ptr<uint8_t>(h_region, h_region.get() + sg.main);
+      }
     }
   }
   trace_mark("gather_enqueue");
@@ -874,22 +947,38 @@ void DeviceScan::Impl::merge_and_gather() {
   trace_mark("wait_gather");
   ctr.gather_ms += now_ms() - t1;
   const double t2 = now_ms();
+  // string bytes: exact sizes are known now; one pinned block for all columns
+  size_t str_total = 0;
+  std::vector<size_t> str_off(C, 0);
   for (int c = 0; c < C && U > 0; ++c) {
     OutColumn& oc = outs[c];
     if (!oc.kind.var) continue;
-    const int64_t total = oc.batch_data_start[(size_t)TB];
+    const int64_t* bs = oc.h_bstart.get();
     for (int64_t g = 0; g < TB; ++g)
-      if (oc.batch_data_start[(size_t)g + 1] - oc.batch_data_start[(size_t)g] > 0x7fffffffll)
-        fail("string data of one output batch exceeds 2 GiB");
-    oc.h_data = pool.alloc((size_t)std::max<int64_t>(total, 1));
-    d2h(oc.h_data.get(), dout[c].data, (size_t)total);
+      if (bs[g + 1] - bs[g] > 0x7fffffffll) fail("string data of one output batch exceeds 2 GiB");
+    str_off[c] = str_total;
+    str_total = (str_total + (size_t)bs[TB] + 255) & ~(size_t)255;
   }
-  SCAN_CUDA(stream_wait(stream));
+  if (str_total > 0) {
+    std::shared_ptr<uint8_t> h_str = pool.alloc(str_total);
+    for (int c = 0; c < C; ++c) {
+      OutColumn& oc = outs[c];
+      if (!oc.kind.var) continue;
+      oc.h_data = std::shared_ptr<uint8_t>(h_str, h_str.get() + str_off[c]);
+      d2h(oc.h_data.get(), d_data[c], (size_t)oc.h_bstart.get()[TB]);
+    }
+    SCAN_CUDA(stream_wait(stream));
+  } else {
+    for (int c = 0; c < C && U > 0; ++c)
+      if (outs[c].kind.var) outs[c].h_data = h_region;  // empty strings only: any valid pointer
+  }
   trace_mark("wait_strings");
   ctr.download_ms += now_ms() - t2;
 }
 
-DeviceScan::DeviceScan(ScanSpec spec, std::vector<BucketFiles> buckets) : impl_(std::make_shared<Impl>()) {
+DeviceScan::DeviceScan(ScanSpec spec, std::vector<BucketFiles> buckets, std::shared_ptr<ScanSession> session)
+    : impl_(std::make_shared<Impl>()) {
+  impl_->session = std::move(session);
   impl_->spec = std::move(spec);
   impl_->buckets = std::move(buckets);
   if (impl_->spec.ops.empty())
@@ -946,7 +1035,7 @@ std::shared_ptr<arrow::RecordBatch> DeviceScan::Batch(int b, int64_t i) const {
     std::shared_ptr<arrow::ArrayData> data;
     if (oc.kind.var) {
       const uint8_t* op = oc.h_offsets.get() + (u0 + gb) * 4;
-      const int64_t d0 = oc.batch_data_start[(size_t)gb], d1 = oc.batch_data_start[(size_t)gb + 1];
+      const int64_t d0 = oc.h_bstart.get()[gb], d1 = oc.h_bstart.get()[gb + 1];
       auto offsets = std::make_shared<KeepAliveBuffer>(op, (rows + 1) * 4, owner);
       auto bytes = std::make_shared<KeepAliveBuffer>(oc.h_data.get() + d0, d1 - d0, owner);
       data = arrow::ArrayData::Make(type, rows, {valid, offsets, bytes}, null_count, 0);

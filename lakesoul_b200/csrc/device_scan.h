@@ -62,9 +62,18 @@ struct ScanCounters {
   std::string path;
 };
 
+// A checked-out scan slot (stream + device scratch arena), installed on the calling thread until the
+// session is destroyed. A reader opens one before it reads its files so that every file image
+// travels to the GPU while the next file is still being read.
+class ScanSession;
+std::shared_ptr<ScanSession> begin_scan_session();
+// copies a pinned host block to fresh device memory of the session (asynchronous on its stream)
+uint8_t* session_upload(ScanSession& s, const uint8_t* pinned, size_t bytes);
+int64_t session_h2d_bytes(const ScanSession& s);
+
 class DeviceScan {
  public:
-  DeviceScan(ScanSpec spec, std::vector<BucketFiles> buckets);
+  DeviceScan(ScanSpec spec, std::vector<BucketFiles> buckets, std::shared_ptr<ScanSession> session = nullptr);
   ~DeviceScan();
   // runs upload -> merge -> (filter) -> gather -> download; synchronous on return
   void Run();

@@ -55,6 +55,9 @@ class RawParquetFile {
   const uint8_t* aux() const { return aux_.get(); }
   int64_t aux_bytes() const { return aux_used_; }
   int64_t host_decompressed_bytes() const { return aux_used_; }
+  // device copy of image() when the reader already sent it (session_upload), else nullptr
+  uint8_t* device_image() const { return device_image_; }
+  void set_device_image(uint8_t* p) { device_image_ = p; }
 
  private:
   int64_t aux_append(const uint8_t* p, int64_t n);
@@ -64,6 +67,7 @@ class RawParquetFile {
   std::shared_ptr<arrow::Schema> schema_;
   std::shared_ptr<void> reader_;  // parquet::ParquetFileReader
   std::vector<RawColumn> cols_;
+  uint8_t* device_image_ = nullptr;
 };
 
 }  // namespace lsb

@@ -239,6 +239,10 @@ void Reader::Start() {
   // ---- open files, read footers (session.rs:546-593) -----------------------------------------
   const double t_dec0 = now_ms();
   trace_mark("start");
+  // the scan slot (stream + device arena) is taken now: every file image is sent to the GPU as soon as
+  // it is in pinned memory, overlapping the read of the next file
+  std::shared_ptr<ScanSession> session = begin_scan_session();
+  const bool early_upload = !force_host_decode();
   std::vector<FileInfo> files;
   for (const auto& raw : cfg.files) {
     const std::string path = strip_scheme(raw);
@@ -251,6 +255,8 @@ void Reader::Start() {
     FileInfo fi;
     fi.path = path;
     fi.raw = RawParquetFile::Open(path);
+    if (early_upload)
+      fi.raw->set_device_image(session_upload(*session, fi.raw->image(), (size_t)fi.raw->image_bytes()));
     std::vector<std::shared_ptr<arrow::Field>> kept;
     for (const auto& f : fi.raw->schema()->fields())
       if (!cfg.partition_schema->GetFieldByName(f->name())) kept.push_back(f);
@@ -437,7 +443,7 @@ void Reader::Start() {
   }
   std::vector<BucketFiles> buckets;
   buckets.push_back(std::move(bucket));
-  I.scan.reset(new DeviceScan(std::move(spec), std::move(buckets)));
+  I.scan.reset(new DeviceScan(std::move(spec), std::move(buckets), std::move(session)));
   I.scan->Run();
   trace_mark("cleanup");
   trace_flush("reader");

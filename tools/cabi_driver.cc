@@ -14,6 +14,7 @@
 // The requested schema is inferred from the files (set_inferring_schema), i.e. all columns.
 // stdout: one JSON line.
 #include <dlfcn.h>
+#include <sys/resource.h>
 
 #include <atomic>
 #include <chrono>
@@ -69,7 +70,12 @@ int main() {
   }
   std::string error;
   std::mutex mu;
-  double best = 1e30;
+  double best = 1e30, best_cpu = 0;
+  auto cpu_seconds = [] {
+    struct rusage ru;
+    getrusage(RUSAGE_SELF, &ru);
+    return ru.ru_utime.tv_sec + ru.ru_stime.tv_sec + 1e-6 * (ru.ru_utime.tv_usec + ru.ru_stime.tv_usec);
+  };
   int64_t rows_out = 0, rows_in = 0, h2d = 0, d2h = 0, launches = 0, dev_pages = 0, host_files = 0, batches = 0;
   uint64_t checksum = 0;
   for (int rep = 0; rep < repeat; ++rep) {
@@ -77,6 +83,7 @@ int main() {
     std::atomic<int64_t> a_out{0}, a_in{0}, a_h2d{0}, a_d2h{0}, a_l{0}, a_dp{0}, a_hf{0}, a_b{0};
     std::atomic<uint64_t> a_ck{0};
     auto t0 = std::chrono::steady_clock::now();
+    const double cpu0 = cpu_seconds();
     auto worker = [&]() {
       while (true) {
         const size_t b = next.fetch_add(1);
@@ -148,7 +155,7 @@ int main() {
     for (auto& t : pool) t.join();
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (!error.empty()) break;
-    if (secs < best) best = secs;
+    if (secs < best) { best = secs; best_cpu = cpu_seconds() - cpu0; }
     rows_out = a_out; rows_in = a_in; h2d = a_h2d; d2h = a_d2h; launches = a_l; dev_pages = a_dp; host_files = a_hf;
     batches = a_b; checksum = a_ck;
   }
@@ -156,10 +163,10 @@ int main() {
     fprintf(stderr, "cabi_driver: %s\n", error.c_str());
     return 1;
   }
-  printf("{\"seconds\": %.6f, \"threads\": %d, \"repeat\": %d, \"rows_in\": %lld, \"rows_out\": %lld, \"batches\": %lld, "
+  printf("{\"seconds\": %.6f, \"cpu_seconds\": %.6f, \"threads\": %d, \"repeat\": %d, \"rows_in\": %lld, \"rows_out\": %lld, \"batches\": %lld, "
          "\"h2d_bytes\": %lld, \"d2h_bytes\": %lld, \"kernel_launches\": %lld, \"device_decoded_pages\": %lld, "
          "\"host_decoded_files\": %lld, \"checksum\": %llu}\n",
-         best, threads, repeat, (long long)rows_in, (long long)rows_out, (long long)batches, (long long)h2d,
+         best, best_cpu, threads, repeat, (long long)rows_in, (long long)rows_out, (long long)batches, (long long)h2d,
          (long long)d2h, (long long)launches, (long long)dev_pages, (long long)host_files, (unsigned long long)checksum);
   return 0;
 }

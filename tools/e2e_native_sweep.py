@@ -13,4 +13,4 @@ print("usable cores", bench.usable_cores(), "buckets", nb, "rows", sum(rows), "e
 for th in threads:
     r = bench.run_e2e_native(spec, paths, th, repeat=3)
     print(th, "slots:", round(sum(rows) / r["seconds"] / 1e6, 1), "Mrows/s", round(r["seconds"] * 1e3, 1), "ms",
-          "h2d GB/s", round(r["h2d_bytes"] / r["seconds"] / 1e9, 1), flush=True)
+          "h2d GB/s", round(r["h2d_bytes"] / r["seconds"] / 1e9, 1), "cpu cores busy", round(r.get("cpu_seconds", 0) / r["seconds"], 1), flush=True)
