@@ -863,57 +863,6 @@ __global__ void __launch_bounds__(kGatherThreads) gather_fixed_kernel(GatherGeom
 // gather: variable width (Utf8 / Binary): lengths -> chunk sums -> scan -> offsets + bytes
 // ---------------------------------------------------------------------------------------
 
-// pass 1 (all variable-width columns in one launch): validity bitmaps + total string bytes of every
-// 2048-row chunk. chunk_sums is laid out column-major: [col][chunk] with a stride of (chunks + 1).
-
-__global__ void __launch_bounds__(kGatherThreads) var_sum_kernel(GatherGeom G, const VarColSet* __restrict__ set,
-                                                                 int64_t* __restrict__ chunk_sums,
-                                                                 int64_t sums_stride) {
-  __shared__ int64_t ws[kGatherThreads / 32];
-  int b, r_begin, r_end, rows;
-  int64_t gb, u0;
-  const bool live = chunk_geometry(G, blockIdx.x, b, gb, u0, r_begin, r_end, rows);
-  uint32_t g0[kRowsPerThread];
-#pragma unroll
-  for (int x = 0; x < kRowsPerThread; ++x) {
-    const int r = r_begin + threadIdx.x + x * kGatherThreads;
-    g0[x] = (live && r < rows) ? G.win[u0 + r] : kNoRow;
-  }
-  const int ncols = set->n;
-  for (int c = 0; c < ncols; ++c) {
-    const VarCol col = set->col[c];
-    int64_t sum = 0;
-    if (live) {
-      uint32_t* vwords =
-          col.dst_valid ? reinterpret_cast<uint32_t*>(col.dst_valid + gb * G.valid_stride) : nullptr;
-#pragma unroll
-      for (int x = 0; x < kRowsPerThread; ++x) {
-        const int r = r_begin + threadIdx.x + x * kGatherThreads;
-        if (r - (int)(threadIdx.x & 31) >= r_end) continue;  // warp-uniform
-        bool valid = false;
-        if (r < rows) {
-          const uint32_t g = col.win ? col.win[u0 + r] : g0[x];
-          sum += var_row_len(col, g, valid);
-        }
-        if (vwords) {
-          const uint32_t word = __ballot_sync(0xffffffffu, valid);
-          if ((threadIdx.x & 31) == 0) vwords[r >> 5] = word;
-        }
-      }
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int64_t t = 0;
-      for (int i = 0; i < kGatherThreads / 32; ++i) t += ws[i];
-      chunk_sums[c * sums_stride + blockIdx.x] = t;
-    }
-  }
-}
-
 // exclusive scan in place; block b scans the segment sums[b*stride .. +nblocks] (+ total at [nblocks])
 __global__ void __launch_bounds__(1024) scan_sums_inplace(int64_t* sums_all, int nblocks, int64_t stride) {
   __shared__ int64_t wsum[32];
@@ -1025,27 +974,97 @@ __device__ __forceinline__ void row_store(RowCopy& rc) {
 // is made of full, aligned 16-byte stores whatever the string lengths are.
 constexpr int kStageBytes = 24 * 1024;
 
+// The byte position of a chunk is resolved inside the kernel with a decoupled look-back scan over the
+// per-chunk totals of the column (status word = bit 63 "published" | bytes): no separate sizing pass.
+// Chunks look back at lower-numbered chunks of their column, which the hardware dispatches first (blocks
+// are dispatched in index order -- the assumption CUB's single-pass scan makes); the column is the
+// fastest-moving index so that the chunks in flight span few chunk numbers.
+struct VarScan {
+  unsigned long long* agg;    // [col][chunk]: bytes of the chunk
+  unsigned long long* incl;   // [col][chunk]: bytes up to and including the chunk
+  int64_t stride;             // chunks per column
+  int32_t ncols;
+};
+constexpr unsigned long long kScanFlag = 1ull << 63;
+__device__ __forceinline__ unsigned long long ld_scan(const unsigned long long* p) {
+  return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ void st_scan(unsigned long long* p, unsigned long long v) {
+  *reinterpret_cast<volatile unsigned long long*>(p) = v;
+}
+
+// Executed by one warp: publishes `tot` for `chunk`, returns the bytes before the chunk (*c0) and the bytes
+// of the chunk's batch before it (*rel; the c_in preceding chunks belong to the same batch).
+__device__ __forceinline__ void scan_lookback(unsigned long long* agg, unsigned long long* incl, int64_t chunk, int c_in,
+                                              int tot, long long* c0, long long* rel) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) st_scan(agg + chunk, kScanFlag | (unsigned long long)tot);
+  unsigned long long excl = 0, relv = 0;
+  int64_t idx = chunk - 1;
+  int rel_left = c_in;  // totals still to be added to relv, nearest chunk first
+  bool have_excl = chunk == 0;
+  while (!have_excl || rel_left > 0) {
+    // 32 predecessors per round trip: both status words of each, so that one trip usually settles everything
+    const int64_t my = idx - lane;
+    const unsigned long long vi = my >= 0 ? ld_scan(incl + my) : 0;
+    const unsigned long long va = my >= 0 ? ld_scan(agg + my) : 0;
+    const unsigned m_incl = __ballot_sync(0xffffffffu, my >= 0 && (vi & kScanFlag));
+    const unsigned m_agg = __ballot_sync(0xffffffffu, my < 0 || (va & kScanFlag));
+    const int first_incl = (!have_excl && m_incl) ? (__ffs(m_incl) - 1) : 32;
+    // totals needed from this group: lanes before the first inclusive prefix (for excl) and the batch's chunks
+    const int n_excl = have_excl ? 0 : first_incl;
+    const int n_need = max(n_excl, min(rel_left, 32));
+    const unsigned need = n_need >= 32 ? 0xffffffffu : ((1u << n_need) - 1);
+    if ((m_agg & need) != need) { __nanosleep(40); continue; }  // a predecessor has not published yet
+    unsigned long long c = 0, r = 0;
+    if (my >= 0) {
+      if (!have_excl) {
+        if (lane < first_incl) c = va & ~kScanFlag;
+        else if (lane == first_incl) c = vi & ~kScanFlag;
+      }
+      if (lane < rel_left) r = va & ~kScanFlag;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      c += __shfl_xor_sync(0xffffffffu, c, d);
+      r += __shfl_xor_sync(0xffffffffu, r, d);
+    }
+    excl += c;
+    relv += r;
+    rel_left = max(rel_left - 32, 0);
+    idx -= 32;
+    if (first_incl < 32 || idx < 0) have_excl = true;
+  }
+  if (lane == 0) {
+    st_scan(incl + chunk, kScanFlag | (excl + (unsigned long long)tot));
+    *c0 = (long long)excl;
+    *rel = (long long)relv;
+  }
+}
+
 __global__ void __launch_bounds__(kGatherThreads) var_write_kernel(GatherGeom G, const VarColSet* __restrict__ set,
-                                                                   const int64_t* __restrict__ chunk_off_all,
-                                                                   int64_t sums_stride, int64_t total_batches) {
+                                                                   VarScan S, int64_t total_batches) {
   __shared__ int s_scan[kGatherThreads / 32 + 2];
   __shared__ int32_t s_off[kRowsPerChunk + 1];   // chunk-relative destination offset of every row
   __shared__ int32_t s_src[kRowsPerChunk];       // bucket-relative source offset of every row
   __shared__ __align__(16) uint8_t s_stage[kStageBytes + 16];
+  __shared__ long long s_c0, s_rel;
   int b, r_begin, r_end, rows;
   int64_t gb, u0;
-  if (!chunk_geometry(G, blockIdx.x, b, gb, u0, r_begin, r_end, rows)) return;
-  const VarCol col = set->col[blockIdx.y];
-  const int64_t* chunk_off = chunk_off_all + blockIdx.y * sums_stride;
+  const int ci = (int)(blockIdx.x % (unsigned)S.ncols);
+  const int64_t chunk = blockIdx.x / (unsigned)S.ncols;
+  const bool live = chunk_geometry(G, chunk, b, gb, u0, r_begin, r_end, rows);
+  const VarCol col = set->col[ci];
+  unsigned long long* agg = S.agg + (int64_t)ci * S.stride;
+  unsigned long long* incl = S.incl + (int64_t)ci * S.stride;
   const uint32_t* win = col.win ? col.win : G.win;
-  const int c_in = (int)(blockIdx.x % G.chunks_per_batch);
-  const int64_t c0 = chunk_off[blockIdx.x];
-  const int64_t batch0 = chunk_off[blockIdx.x - c_in];
+  const int c_in = (int)(chunk % G.chunks_per_batch);
   const uint8_t* src_base = col.src_data + col.src_data_base[b];
-  const int nloc = min(rows - r_begin, kRowsPerChunk);  // rows of this chunk
+  const int nloc = live ? min(rows - r_begin, kRowsPerChunk) : 0;  // rows of this chunk
   const int rl0 = threadIdx.x * kRowsPerThread;
   int len[kRowsPerThread];
   int mine = 0;
+  unsigned vbits = 0;
 #pragma unroll
   for (int x = 0; x < kRowsPerThread; ++x) {
     len[x] = 0;
@@ -1054,30 +1073,40 @@ __global__ void __launch_bounds__(kGatherThreads) var_write_kernel(GatherGeom G,
       bool valid;
       len[x] = var_row_len(col, g, valid);
       s_src[rl0 + x] = valid ? col.src_offsets[g] : 0;
+      vbits |= valid ? (1u << x) : 0u;
     }
     mine += len[x];
   }
+  // validity: a thread owns 8 consecutive rows = one byte of the batch's bitmap (words are completed up to
+  // the 32-row boundary after the last row)
+  if (col.dst_valid && rl0 < ((nloc + 31) & ~31))
+    (col.dst_valid + gb * G.valid_stride)[(r_begin + rl0) >> 3] = (uint8_t)vbits;
   int tot;
   int run = block_exclusive_scan<kGatherThreads>(mine, s_scan, tot);
-  // offsets (every earlier batch contributed one extra entry)
-  int32_t* dst_off = col.dst_offsets + u0 + gb + r_begin;
-  const int32_t rel = (int32_t)(c0 - batch0);
+  // chunk-relative offsets first (shared memory), so that nothing but `tot` is live across the look-back
 #pragma unroll
   for (int x = 0; x < kRowsPerThread; ++x) {
     if (rl0 + x < nloc) {
-      dst_off[rl0 + x] = rel + run;
       s_off[rl0 + x] = run;
       run += len[x];
     }
   }
+  if (threadIdx.x == 0) s_off[nloc] = tot;
+  // publish the chunk total, then resolve the chunk's position by looking back
+  if (threadIdx.x < 32) scan_lookback(agg, incl, chunk, c_in, tot, &s_c0, &s_rel);
+  __syncthreads();
+  if (!live) return;
+  const int64_t c0 = s_c0;
+  const int32_t rel = (int32_t)s_rel;
+  // offsets (every earlier batch contributed one extra entry)
+  int32_t* dst_off = col.dst_offsets + u0 + gb + r_begin;
+  for (int r = threadIdx.x; r < nloc; r += kGatherThreads) dst_off[r] = rel + s_off[r];
   const bool last_chunk = r_begin + nloc == rows;
   if (threadIdx.x == 0) {
-    s_off[nloc] = tot;
     if (last_chunk) dst_off[nloc] = rel + tot;
-    if (c_in == 0) col.batch_data_start[gb] = batch0;
+    if (c_in == 0) col.batch_data_start[gb] = c0 - rel;
     if (last_chunk && gb == total_batches - 1) col.batch_data_start[total_batches] = c0 + tot;
   }
-  __syncthreads();
   // ---- bytes: windows of the chunk's output range, staged in shared memory --------------------
   uint8_t* dst_bytes = col.dst_data + c0;       // chunk-relative byte p lives at dst_bytes[p]
   const int mis = (int)((reinterpret_cast<uintptr_t>(dst_bytes)) & 15);  // stage[mis + (p - w0)] <-> p
@@ -1695,11 +1724,11 @@ void gather_fixed(MergePlan* P, const FixedCol* cols, int ncols, cudaStream_t st
 
 void gather_var_multi(MergePlan* P, const VarCol* cols, int ncols, cudaStream_t stream);
 
-static void ensure_var_scratch(MergePlan* P, int64_t stride, cudaStream_t stream) {
-  if (P->d_chunk_cap < stride * kMaxVarCols) {
+static void ensure_var_scratch(MergePlan* P, int64_t words, cudaStream_t stream) {
+  if (P->d_chunk_cap < words) {
     dev_free(P->d_chunk_sums, stream);
-    P->d_chunk_sums = dev_alloc<int64_t>(stride * kMaxVarCols, stream);
-    P->d_chunk_cap = stride * kMaxVarCols;
+    P->d_chunk_sums = dev_alloc<int64_t>(words, stream);
+    P->d_chunk_cap = words;
   }
   if (!P->d_varset) P->d_varset = dev_alloc<VarColSet>(1, stream);
 }
@@ -1726,18 +1755,26 @@ void gather_var_multi(MergePlan* P, const VarCol* cols, int ncols, cudaStream_t 
   if (total_batches == 0 || ncols <= 0) return;
   GatherGeom G = make_geom(P);
   const int64_t chunks = total_batches * G.chunks_per_batch;
-  const int64_t stride = chunks + 1;
   for (int c0 = 0; c0 < ncols; c0 += kMaxVarCols) {
     const int n = std::min(kMaxVarCols, ncols - c0);
-    ensure_var_scratch(P, stride, stream);
+    if (chunks * n > 0x7fffffffll) {
+      g_last_error = "too many string chunks in one scan";
+      throw std::runtime_error(g_last_error);
+    }
+    // look-back scan state: two status words per (column, chunk), zeroed = "not published"
+    const int64_t words = 2 * chunks * n;
+    ensure_var_scratch(P, words, stream);
+    LSB_CUDA(cudaMemsetAsync(P->d_chunk_sums, 0, sizeof(int64_t) * words, stream));
+    VarScan S{};
+    S.agg = reinterpret_cast<unsigned long long*>(P->d_chunk_sums);
+    S.incl = S.agg + chunks * n;
+    S.stride = chunks;
+    S.ncols = n;
     VarColSet& set = P->h_varset;
     set.n = n;
     for (int i = 0; i < n; ++i) set.col[i] = cols[c0 + i];
     LSB_CUDA(cudaMemcpyAsync(P->d_varset, &set, sizeof(VarColSet), cudaMemcpyHostToDevice, stream));
-    var_sum_kernel<<<(unsigned)chunks, kGatherThreads, 0, stream>>>(G, P->d_varset, P->d_chunk_sums, stride);
-    scan_sums_inplace<<<n, 1024, 0, stream>>>(P->d_chunk_sums, (int)chunks, stride);
-    dim3 grid((unsigned)chunks, (unsigned)n);
-    var_write_kernel<<<grid, kGatherThreads, 0, stream>>>(G, P->d_varset, P->d_chunk_sums, stride, total_batches);
+    var_write_kernel<<<(unsigned)(chunks * n), kGatherThreads, 0, stream>>>(G, P->d_varset, S, total_batches);
   }
   LSB_CUDA(cudaGetLastError());
 }

@@ -3,7 +3,9 @@
 usage: python profiles/ncu_digest.py <file.ncu-rep>"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# optional 3rd argument: index of the launch inside the report (default 0)
+sel = ["--launch-skip", sys.argv[3], "--launch-count", "1"] if len(sys.argv) > 3 else ["--launch-count", "1"]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
 want = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread", "launch__occupancy_limit_shared_mem",
@@ -18,9 +20,13 @@ print("==", vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "")
 for h, u, v in zip(hdr, units, vals):
     if h in want:
         print(f"{h:80s} {v} {u}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-h = rows[1]; data = rows[2:]
+# one section per kernel: a "Kernel Name" row, a header row, then one row per SASS instruction
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] or [0]
+k = min(int(sys.argv[3]) if len(sys.argv) > 3 else 0, len(starts) - 1) if len(starts) > 1 else 0
+lo = starts[k]; hi = starts[k + 1] if k + 1 < len(starts) else len(rows)
+h = rows[lo + 1]; data = [r for r in rows[lo + 2:hi] if len(r) == len(h)]
 idx = {n: i for i, n in enumerate(h)}
 stalls = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
 tot = {s: sum(int(r[idx[s]] or 0) for r in data) for s in stalls}
