@@ -219,6 +219,63 @@ def test_device_decode_nulls_dictionary_and_v2_pages(tmp_path):
         assert_tables_equal(got, pq.read_table(p), name)
 
 
+def test_device_decode_long_strings_and_all_null_blocks(tmp_path):
+    """PLAIN BYTE_ARRAY values longer than the walker's 4 KiB window and than the gather's 24 KiB stage,
+    empty strings, blocks and whole pages of nulls, one-row row groups; plain and dictionary pages."""
+    from lakesoul_b200 import read_bucket
+    rng = np.random.default_rng(5)
+    n = 6000
+    lens = rng.choice([0, 1, 7, 300, 5000, 30000], size=n, p=[0.2, 0.3, 0.3, 0.15, 0.04, 0.01])
+    alphabet = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz0123456789", dtype=np.uint8)
+    big = [bytes(alphabet[rng.integers(0, len(alphabet), int(l))]).decode() for l in lens]
+    null_run = np.zeros(n, dtype=bool)
+    null_run[1000:4100] = True  # three whole 1024-row blocks of nulls inside one page
+    t = pa.table({
+        "id": pa.array(np.arange(n, dtype=np.int64)),
+        "big": pa.array(big, type=pa.string(), mask=rng.random(n) < 0.3),
+        "sparse": pa.array(["x%d" % v for v in rng.integers(0, 50, n)], type=pa.string(), mask=null_run),
+        "n32": pa.array(rng.integers(0, 1000, n).astype(np.int32), mask=null_run),
+        "allnull": pa.array([None] * n, type=pa.int64()),
+    })
+    variants = {
+        "plain_big_pages": dict(use_dictionary=False, compression="NONE", data_page_size=8 << 20, row_group_size=n),
+        "dict_small_groups": dict(use_dictionary=True, compression="SNAPPY", data_page_size=2048, row_group_size=1500),
+        "plain_v2_one_row_groups": dict(use_dictionary=False, compression="NONE", data_page_version="2.0", row_group_size=997),
+    }
+    for name, opts in variants.items():
+        p = str(tmp_path / f"part-{name}_0000.parquet")
+        pq.write_table(t, p, **opts)
+        # one more tiny file in front: a single row that is overridden by the big file
+        p0 = str(tmp_path / f"part-{name}_tiny_0000.parquet")
+        pq.write_table(t.slice(17, 1), p0, row_group_size=1)
+        got, reader = read_bucket([p0, p], t.schema, ["id"], batch_size=257, return_reader=True)
+        st = reader.stats()
+        reader.close()
+        assert st["device_decoded_pages"] > 0 and st["host_decoded_files"] == 0, (name, st)
+        assert_tables_equal(got, pq.read_table(p), name)
+
+
+def test_corrupt_files_fail_cleanly(tmp_path):
+    """A truncated file and a file that is not Parquet at all are start_reader errors (status < 0 + message),
+    never a crash; the reader object stays usable for free_lakesoul_reader."""
+    from lakesoul_b200 import datagen, read_bucket
+    spec = datagen.config_spec(1, 0.01)
+    paths = datagen.write_table(str(tmp_path), spec)[0]
+    raw = open(paths[0], "rb").read()
+    cut = str(tmp_path / "part-cut_0000.parquet")
+    open(cut, "wb").write(raw[: len(raw) // 2])
+    junk = str(tmp_path / "part-junk_0000.parquet")
+    open(junk, "wb").write(b"PAR1" + bytes(range(256)) * 8 + b"PAR1")
+    for bad in (cut, junk):
+        with pytest.raises(Exception) as ei:
+            read_bucket([paths[1], bad], spec.schema, spec.primary_keys)
+        assert "parquet" in str(ei.value).lower() or "invalid" in str(ei.value).lower(), str(ei.value)
+    # the good files still read after the failures (slots and arenas were released)
+    got = read_bucket(paths, spec.schema, spec.primary_keys)
+    want = mo.read_bucket(paths, spec.schema, spec.primary_keys)
+    assert_tables_equal(got, want, "after failures")
+
+
 from conftest import upsert_case_files, upsert_cases  # noqa: E402
 
 UPSERTS = upsert_cases()
