@@ -8,6 +8,6 @@ so the parity tests read like the reference's own.  There is no Python or CPU im
 the merge in this package: without the compiled library and a GPU every reader fails loudly.
 """
 from ._lib import load_library, library_path  # noqa: F401
-from .native_io import NativeIOReader, LakeSoulArrowReader, read_bucket  # noqa: F401
+from .native_io import NativeIOReader, LakeSoulArrowReader, open_bucket, read_bucket  # noqa: F401
 
-__all__ = ["load_library", "library_path", "NativeIOReader", "LakeSoulArrowReader", "read_bucket"]
+__all__ = ["load_library", "library_path", "NativeIOReader", "LakeSoulArrowReader", "open_bucket", "read_bucket"]

@@ -194,18 +194,41 @@ class LakeSoulArrowReader:
         batches = list(self)
         return pa.Table.from_batches(batches, schema=self.reader.getSchema())
 
+    def to_reader(self) -> pa.RecordBatchReader:
+        """pyarrow RecordBatchReader over the native reader (what python/src/dataset.rs:32-70 hands to
+        pyarrow.dataset through PyO3 in the reference); it also provides __arrow_c_stream__."""
+        return pa.RecordBatchReader.from_batches(self.reader.getSchema(), iter(self))
+
+    def __arrow_c_stream__(self, requested_schema=None):
+        return self.to_reader().__arrow_c_stream__(requested_schema)
+
     def close(self):
         self.finished = True
         self.reader.close()
 
 
-def read_bucket(files: List[str], schema: pa.Schema, primary_keys: Iterable[str] = (), *,
-                batch_size: int = 8192, default_columns: Optional[Dict[str, str]] = None,
-                merge_ops: Optional[Dict[str, str]] = None, options: Optional[Dict[str, str]] = None,
-                filters: Iterable[str] = (), partition_schema: Optional[pa.Schema] = None,
-                return_reader: bool = False):
-    """Convenience wrapper: configure a NativeIOReader the way the connectors do
-    (lakesoul-spark NativeVectorizedReader.java:224-269) and read the whole bucket."""
+def open_bucket(files: List[str], schema: pa.Schema, primary_keys: Iterable[str] = (), *, batch_size: int = 8192,
+                default_columns: Optional[Dict[str, str]] = None, merge_ops: Optional[Dict[str, str]] = None,
+                options: Optional[Dict[str, str]] = None, filters: Iterable[str] = (),
+                partition_schema: Optional[pa.Schema] = None) -> pa.RecordBatchReader:
+    """One hash bucket as a streaming pyarrow.RecordBatchReader (Arrow C stream capable): the Python surface the
+    reference exposes with `python/src/dataset.rs`. The native reader is freed when the stream ends."""
+    r = _configure(files, schema, primary_keys, batch_size, default_columns, merge_ops, options, filters, partition_schema)
+    r.initializeReader()
+    ar = LakeSoulArrowReader(r)
+
+    def batches():
+        try:
+            yield from ar
+        finally:
+            r.close()
+
+    return pa.RecordBatchReader.from_batches(r.getSchema(), batches())
+
+
+def _configure(files, schema, primary_keys, batch_size, default_columns, merge_ops, options, filters,
+               partition_schema) -> NativeIOReader:
+    """the builder calls of lakesoul-spark NativeVectorizedReader.java:224-269"""
     r = NativeIOReader()
     for f in files:
         r.addFile(f)
@@ -222,6 +245,17 @@ def read_bucket(files: List[str], schema: pa.Schema, primary_keys: Iterable[str]
         r.addFilter(flt)
     if merge_ops:
         r.addMergeOps(merge_ops)
+    return r
+
+
+def read_bucket(files: List[str], schema: pa.Schema, primary_keys: Iterable[str] = (), *,
+                batch_size: int = 8192, default_columns: Optional[Dict[str, str]] = None,
+                merge_ops: Optional[Dict[str, str]] = None, options: Optional[Dict[str, str]] = None,
+                filters: Iterable[str] = (), partition_schema: Optional[pa.Schema] = None,
+                return_reader: bool = False):
+    """Convenience wrapper: configure a NativeIOReader the way the connectors do
+    (lakesoul-spark NativeVectorizedReader.java:224-269) and read the whole bucket."""
+    r = _configure(files, schema, primary_keys, batch_size, default_columns, merge_ops, options, filters, partition_schema)
     r.initializeReader()
     ar = LakeSoulArrowReader(r)
     table = ar.read_all()

@@ -276,6 +276,23 @@ def test_corrupt_files_fail_cleanly(tmp_path):
     assert_tables_equal(got, want, "after failures")
 
 
+def test_record_batch_reader_and_arrow_c_stream(tmp_path):
+    """the bucket as a streaming pyarrow.RecordBatchReader / Arrow C stream."""
+    from lakesoul_b200 import datagen, open_bucket
+    spec = datagen.config_spec(1, 0.01)
+    paths = datagen.write_table(str(tmp_path), spec)[0]
+    want = mo.read_bucket(paths, spec.schema, spec.primary_keys)
+    rdr = open_bucket(paths, spec.schema, spec.primary_keys, batch_size=1000)
+    assert isinstance(rdr, pa.RecordBatchReader) and rdr.schema.names == spec.schema.names
+    first = rdr.read_next_batch()
+    assert first.num_rows == min(1000, want.num_rows)
+    rest = rdr.read_all()
+    assert_tables_equal(pa.concat_tables([pa.Table.from_batches([first]), rest]), want, "stream")
+    # the same through the C stream interface
+    got = pa.table(open_bucket(paths, spec.schema, spec.primary_keys, batch_size=777))
+    assert_tables_equal(got, want, "c stream")
+
+
 from conftest import upsert_case_files, upsert_cases  # noqa: E402
 
 UPSERTS = upsert_cases()
