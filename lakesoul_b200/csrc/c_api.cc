@@ -385,6 +385,7 @@ int32_t lsb_reader_get_stats(CResult_Reader* reader, LsbReaderStats* out) {
   out->decode_ms = s.decode_ms; out->upload_ms = s.upload_ms; out->merge_ms = s.merge_ms;
   out->gather_ms = s.gather_ms; out->download_ms = s.download_ms;
   out->device_decoded_pages = s.device_decoded_pages; out->host_decoded_files = s.host_decoded_files;
+  out->pruned_row_groups = s.pruned_row_groups;
   return 0;
 }
 

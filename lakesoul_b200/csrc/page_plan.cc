@@ -13,6 +13,7 @@
 #include <unistd.h>
 
 #include <cstring>
+#include <functional>
 #include <stdexcept>
 
 namespace lsb {
@@ -61,6 +62,8 @@ std::shared_ptr<RawParquetFile> RawParquetFile::Open(const std::string& path) {
   auto st2 = parquet::arrow::FromParquetSchema(md->schema(), parquet::default_arrow_reader_properties(),
                                                md->key_value_metadata(), &f->schema_);
   if (!st2.ok()) fail(st2.ToString());
+  f->kept_rg_.resize((size_t)md->num_row_groups());
+  for (int rg = 0; rg < md->num_row_groups(); ++rg) f->kept_rg_[(size_t)rg] = rg;
   f->reader_ = std::shared_ptr<parquet::ParquetFileReader>(std::move(rd));
   return f;
 }
@@ -77,6 +80,173 @@ int64_t RawParquetFile::aux_append(const uint8_t* p, int64_t n) {
   memcpy(aux_.get() + off, p, (size_t)n);
   aux_used_ = (aux_used_ + n + 15) & ~15ll;
   return off;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// row-group pruning by primary-key statistics
+// ---------------------------------------------------------------------------------------
+namespace {
+
+// what a predicate can evaluate to over the rows of one row group (NULL results never keep a row)
+struct Possible { bool t, f; };
+
+struct Bound {          // min / max of one column chunk, comparable with a literal of the same family
+  enum Fam { kNone, kInt, kReal, kBytes } fam = kNone;
+  int64_t imin = 0, imax = 0;
+  double rmin = 0, rmax = 0;
+  std::string bmin, bmax;
+};
+
+Bound chunk_bound(const parquet::ColumnChunkMetaData& ccm, const parquet::ColumnDescriptor& cd, const arrow::DataType& type) {
+  Bound b;
+  if (!ccm.is_stats_set()) return b;
+  auto st = ccm.statistics();
+  if (!st || !st->HasMinMax()) return b;
+  using AT = arrow::Type;
+  switch (cd.physical_type()) {
+    case parquet::Type::INT32: {
+      if (!arrow::is_integer(type.id()) && type.id() != AT::DATE32 && type.id() != AT::TIME32) return b;
+      auto ts = std::static_pointer_cast<parquet::Int32Statistics>(st);
+      const bool uns = arrow::is_unsigned_integer(type.id());
+      b.imin = uns ? (int64_t)(uint32_t)ts->min() : ts->min();
+      b.imax = uns ? (int64_t)(uint32_t)ts->max() : ts->max();
+      b.fam = Bound::kInt;
+    } break;
+    case parquet::Type::INT64: {
+      if (type.id() == AT::UINT64) return b;  // would need unsigned 64-bit compares: not worth a special case
+      if (!arrow::is_integer(type.id()) && type.id() != AT::TIMESTAMP && type.id() != AT::TIME64) return b;
+      auto ts = std::static_pointer_cast<parquet::Int64Statistics>(st);
+      b.imin = ts->min(); b.imax = ts->max(); b.fam = Bound::kInt;
+    } break;
+    case parquet::Type::FLOAT: {
+      auto ts = std::static_pointer_cast<parquet::FloatStatistics>(st);
+      b.rmin = ts->min(); b.rmax = ts->max(); b.fam = Bound::kReal;
+    } break;
+    case parquet::Type::DOUBLE: {
+      auto ts = std::static_pointer_cast<parquet::DoubleStatistics>(st);
+      b.rmin = ts->min(); b.rmax = ts->max(); b.fam = Bound::kReal;
+    } break;
+    case parquet::Type::BYTE_ARRAY: {
+      if (type.id() != AT::STRING && type.id() != AT::BINARY) return b;
+      auto ts = std::static_pointer_cast<parquet::ByteArrayStatistics>(st);
+      b.bmin.assign(reinterpret_cast<const char*>(ts->min().ptr), ts->min().len);
+      b.bmax.assign(reinterpret_cast<const char*>(ts->max().ptr), ts->max().len);
+      b.fam = Bound::kBytes;
+    } break;
+    default: break;
+  }
+  if (b.fam == Bound::kReal && (b.rmin != b.rmin || b.rmax != b.rmax)) b.fam = Bound::kNone;  // NaN bounds
+  return b;
+}
+
+// sign of (bound value - literal) for min and max; false when the literal is not comparable
+bool compare_literal(const Bound& b, const arrow::Scalar& lit, int* cmin, int* cmax) {
+  if (!lit.is_valid) return false;
+  using AT = arrow::Type;
+  auto sgn = [](auto a, auto c) { return a < c ? -1 : (a > c ? 1 : 0); };
+  if (b.fam == Bound::kInt) {
+    int64_t v;
+    switch (lit.type->id()) {
+      case AT::INT8: v = static_cast<const arrow::Int8Scalar&>(lit).value; break;
+      case AT::INT16: v = static_cast<const arrow::Int16Scalar&>(lit).value; break;
+      case AT::INT32: v = static_cast<const arrow::Int32Scalar&>(lit).value; break;
+      case AT::INT64: v = static_cast<const arrow::Int64Scalar&>(lit).value; break;
+      case AT::UINT8: v = static_cast<const arrow::UInt8Scalar&>(lit).value; break;
+      case AT::UINT16: v = static_cast<const arrow::UInt16Scalar&>(lit).value; break;
+      case AT::UINT32: v = static_cast<const arrow::UInt32Scalar&>(lit).value; break;
+      case AT::DATE32: v = static_cast<const arrow::Date32Scalar&>(lit).value; break;
+      case AT::TIMESTAMP: v = static_cast<const arrow::TimestampScalar&>(lit).value; break;
+      default: return false;
+    }
+    *cmin = sgn(b.imin, v); *cmax = sgn(b.imax, v);
+    return true;
+  }
+  if (b.fam == Bound::kReal) {
+    double v;
+    if (lit.type->id() == AT::FLOAT) v = static_cast<const arrow::FloatScalar&>(lit).value;
+    else if (lit.type->id() == AT::DOUBLE) v = static_cast<const arrow::DoubleScalar&>(lit).value;
+    else return false;
+    if (v != v) return false;
+    *cmin = sgn(b.rmin, v); *cmax = sgn(b.rmax, v);
+    return true;
+  }
+  if (b.fam == Bound::kBytes) {
+    if (lit.type->id() != AT::STRING && lit.type->id() != AT::BINARY) return false;
+    const auto& bs = static_cast<const arrow::BaseBinaryScalar&>(lit);
+    if (!bs.value) return false;
+    const std::string v = bs.value->ToString();
+    *cmin = sgn(b.bmin.compare(v), 0); *cmax = sgn(b.bmax.compare(v), 0);
+    return true;
+  }
+  return false;
+}
+
+using BoundFn = std::function<Bound(const std::string&)>;
+
+Possible possible(const FilterExpr& e, const BoundFn& bound_of) {
+  const Possible unknown{true, true};
+  switch (e.kind) {
+    case FilterExpr::kTrue: return {true, false};
+    case FilterExpr::kFalse: return {false, true};
+    case FilterExpr::kAnd: {
+      const Possible l = possible(*e.left, bound_of), r = possible(*e.right, bound_of);
+      return {l.t && r.t, l.f || r.f};
+    }
+    case FilterExpr::kOr: {
+      const Possible l = possible(*e.left, bound_of), r = possible(*e.right, bound_of);
+      return {l.t || r.t, l.f && r.f};
+    }
+    case FilterExpr::kNot: {
+      const Possible x = possible(*e.right, bound_of);
+      return {x.f, x.t};
+    }
+    case FilterExpr::kCmp: {
+      if (!e.literal) return unknown;
+      const Bound b = bound_of(e.column);
+      int cmin = 0, cmax = 0;
+      if (b.fam == Bound::kNone || !compare_literal(b, *e.literal, &cmin, &cmax)) return unknown;
+      // values of the chunk lie in [min, max]; cmin/cmax = sign(min - lit), sign(max - lit)
+      switch (e.op) {
+        case FilterExpr::kEq: return {cmin <= 0 && cmax >= 0, !(cmin == 0 && cmax == 0)};
+        case FilterExpr::kNe: return {!(cmin == 0 && cmax == 0), cmin <= 0 && cmax >= 0};
+        case FilterExpr::kGt: return {cmax > 0, cmin <= 0};
+        case FilterExpr::kGe: return {cmax >= 0, cmin < 0};
+        case FilterExpr::kLt: return {cmin < 0, cmax >= 0};
+        case FilterExpr::kLe: return {cmin <= 0, cmax > 0};
+      }
+      return unknown;
+    }
+    default: return unknown;  // null tests: statistics of key columns say nothing useful here
+  }
+}
+
+}  // namespace
+
+int RawParquetFile::PruneRowGroups(const FilterExpr& filter, const std::set<std::string>& pk_columns) {
+  auto* rd = static_cast<parquet::ParquetFileReader*>(reader_.get());
+  auto md = rd->metadata();
+  const auto* sd = md->schema();
+  if (sd->num_columns() != schema_->num_fields()) return 0;  // nested schema: leaf index != field index
+  std::vector<int> kept;
+  int64_t rows = 0;
+  for (int rg : kept_rg_) {
+    auto rgm = md->RowGroup(rg);
+    BoundFn bound_of = [&](const std::string& name) -> Bound {
+      if (!pk_columns.count(name)) return Bound{};
+      const int ci = schema_->GetFieldIndex(name);
+      if (ci < 0) return Bound{};
+      return chunk_bound(*rgm->ColumnChunk(ci), *sd->Column(ci), *schema_->field(ci)->type());
+    };
+    if (possible(filter, bound_of).t) {
+      kept.push_back(rg);
+      rows += rgm->num_rows();
+    }
+  }
+  const int dropped = (int)(kept_rg_.size() - kept.size());
+  kept_rg_ = std::move(kept);
+  rows_ = rows;
+  return dropped;
 }
 
 bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want, std::string* why) {
@@ -145,7 +315,7 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
     }
     // pages
     int64_t first_row = 0;
-    for (int rg = 0; rg < md->num_row_groups(); ++rg) {
+    for (int rg : kept_rg_) {
       auto rgm = md->RowGroup(rg);
       auto ccm = rgm->ColumnChunk(ci);
       for (auto e : ccm->encodings())

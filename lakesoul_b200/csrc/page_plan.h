@@ -8,10 +8,12 @@
 #include <arrow/api.h>
 
 #include <memory>
+#include <set>
 #include <string>
 #include <vector>
 
 #include "decode_types.h"
+#include "filter.h"
 
 namespace lsb {
 
@@ -44,6 +46,14 @@ class RawParquetFile {
   int64_t num_rows() const { return rows_; }
   const std::shared_ptr<arrow::Schema>& schema() const { return schema_; }  // full file schema (Arrow types)
 
+  // PK-filter pushdown (reference file_format.rs:234-265 pushes PK-only conjuncts below the merge as Inexact
+  // filters): drops the row groups in which `filter` cannot be TRUE judging by the min/max
+  // statistics of the `pk_columns` only -- every version of a key carries the same key, so a row group pruned
+  // by a key predicate is pruned in every file alike and the merge result is unchanged. Call before Plan();
+  // num_rows() then counts the kept row groups. Returns the number of row groups dropped.
+  int PruneRowGroups(const FilterExpr& filter, const std::set<std::string>& pk_columns);
+  const std::vector<int>& kept_row_groups() const { return kept_rg_; }  // indices, ascending (all by default)
+
   // Frames the pages of the requested columns (missing columns are allowed: present = false).
   // Returns false and fills `why` when some column chunk needs a decoder the device does not have;
   // the caller then decodes this file on the host.
@@ -67,6 +77,7 @@ class RawParquetFile {
   std::shared_ptr<arrow::Schema> schema_;
   std::shared_ptr<void> reader_;  // parquet::ParquetFileReader
   std::vector<RawColumn> cols_;
+  std::vector<int> kept_rg_;
   uint8_t* device_image_ = nullptr;
 };
 

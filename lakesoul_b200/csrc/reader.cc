@@ -288,6 +288,18 @@ void Reader::Start() {
   std::shared_ptr<FilterExpr> filter = conjunction(fexprs);
   std::set<std::string> fcols;
   if (filter) filter_columns(*filter, &fcols);
+  // key predicates prune whole row groups by their min/max statistics before anything is decoded
+  if (filter && !cfg.primary_keys.empty() && getenv("LAKESOUL_B200_NO_PRUNING") == nullptr) {
+    const std::set<std::string> pk_set(cfg.primary_keys.begin(), cfg.primary_keys.end());
+    bool touches_pk = false;
+    for (const auto& c : fcols) touches_pk = touches_pk || pk_set.count(c) > 0;
+    if (touches_pk) {
+      for (auto& fi : files) {
+        I.stats.pruned_row_groups += fi.raw->PruneRowGroups(*filter, pk_set);
+        fi.rows = fi.raw->num_rows();
+      }
+    }
+  }
 
   // ---- merged schema: requested + filter + pk + cdc columns, table order (file_format.rs:254-265)
   const std::string cdc = cfg.cdc_column();
@@ -397,7 +409,7 @@ void Reader::Start() {
       leaf.push_back(manifest.schema_fields[full_idx].column_index);
       want.push_back(pf);
     }
-    auto tr = reader->ReadTable(leaf);
+    auto tr = reader->ReadRowGroups(fi.raw->kept_row_groups(), leaf);
     if (!tr.ok()) fail(tr.status().ToString());
     std::shared_ptr<arrow::Table> table = *tr;
     // a2: reorder to target order + cast to the target type (helpers/transform.rs:107-354)

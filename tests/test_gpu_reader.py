@@ -293,6 +293,44 @@ def test_record_batch_reader_and_arrow_c_stream(tmp_path):
     assert_tables_equal(got, want, "c stream")
 
 
+@pytest.mark.parametrize("key_type", ["int64", "string"])
+def test_key_filters_prune_row_groups(tmp_path, key_type):
+    """conjuncts on primary-key columns skip row groups by min/max statistics; the result is the
+    one the post-merge filter alone gives (the oracle never prunes)."""
+    from lakesoul_b200 import read_bucket
+    rng = np.random.default_rng(3)
+    def keys(v):
+        return pa.array(v.astype(np.int64)) if key_type == "int64" else pa.array(["k%08d" % x for x in v], pa.string())
+    # string literals arrive in parquet-mr's toString form (filter/parser.rs:220-223)
+    lit = (lambda x: str(x)) if key_type == "int64" else (lambda x: 'Binary{"k%08d"}' % x)
+    schema = pa.schema([pa.field("id", pa.int64() if key_type == "int64" else pa.string(), False), ("v", pa.int32()), ("s", pa.string())])
+    paths, total_rows = [], 0
+    for f, n in enumerate((40_000, 9_000, 9_000)):
+        ids = np.sort(rng.choice(100_000, n, replace=False))
+        t = pa.table({"id": keys(ids), "v": pa.array(rng.integers(0, 10, n).astype(np.int32)),
+                      "s": pa.array(["f%d_%d" % (f, x) for x in ids], pa.string())}).cast(schema)
+        p = os.path.join(str(tmp_path), "part-%016d_0000.parquet" % f)
+        pq.write_table(t, p, row_group_size=2_000, use_dictionary=(f == 1))
+        paths.append(p)
+        total_rows += n
+    cases = [f"gt(id, {lit(90_000)})", f"and(gteq(id, {lit(30_000)}), lt(id, {lit(33_000)}))", f"eq(id, {lit(int(1234))})",
+             f"or(lt(id, {lit(2_000)}), gt(id, {lit(98_000)}))", f"not(lt(id, {lit(95_000)}))",
+             f"and(gt(id, {lit(50_000)}), gt(v, 5))", f"and(noteq(id, {lit(7)}), lteq(id, {lit(1_000)}))",
+             f"gt(id, {lit(200_000)})"]
+    for flt in cases:
+        got, reader = read_bucket(paths, schema, ["id"], batch_size=1024, filters=[flt], return_reader=True)
+        st = reader.stats()
+        reader.close()
+        want = mo.read_bucket(paths, schema, ["id"], filters=[flt])
+        assert_tables_equal(got, want, flt)
+        assert st["pruned_row_groups"] > 0 and st["rows_in"] < total_rows, (flt, st)
+    # a predicate on a payload column alone must not prune anything
+    got, reader = read_bucket(paths, schema, ["id"], filters=["gt(v, 8)"], return_reader=True)
+    assert reader.stats()["pruned_row_groups"] == 0
+    reader.close()
+    assert_tables_equal(got, mo.read_bucket(paths, schema, ["id"], filters=["gt(v, 8)"]), "payload filter")
+
+
 from conftest import upsert_case_files, upsert_cases  # noqa: E402
 
 UPSERTS = upsert_cases()
