@@ -298,21 +298,60 @@ __device__ __forceinline__ void copy_bytes(uint8_t* dst, const uint8_t* src, int
 
 }  // namespace
 
-// start of every BYTE_ARRAY dictionary entry's payload, one thread per chunk
-__global__ void dict_index_kernel(DecodeArgs A) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// start of every BYTE_ARRAY dictionary entry's payload, one warp per chunk: the length-prefix chain of the
+// dictionary page is walked by lane 0 inside a shared-memory window refilled by the whole warp (same scheme as
+// the PLAIN BYTE_ARRAY walk of the index pass)
+__global__ void __launch_bounds__(128) dict_index_kernel(DecodeArgs A) {
+  __shared__ __align__(16) uint8_t s_win_all[4][kWalkWindow];
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= A.nchunks) return;
-  const PqChunk& ch = A.chunks[c];
+  const PqChunk ch = A.chunks[c];
   if (ch.dict_nvals <= 0 || ch.phys != PQ_BYTE_ARRAY) return;
+  uint8_t* s_win = s_win_all[threadIdx.x >> 5];
   const uint8_t* base = A.raw + ch.dict_off;
-  const uint8_t* p = base;
+  const int64_t avail = ch.dict_size;
+  const uintptr_t vaddr = reinterpret_cast<uintptr_t>(base);
   int32_t* pos = A.dict_pos + ch.dict_index;
-  for (int i = 0; i < ch.dict_nvals; ++i) {
-    const uint32_t len = load_le32(p);
-    pos[i] = (int32_t)(p + 4 - base);
-    p += 4 + len;
+  const int n = ch.dict_nvals;
+  int64_t cursor = 0;
+  int j = 0, bad = 0;
+  while (j < n && !bad) {
+    const uintptr_t wbeg = (vaddr + (uintptr_t)cursor) & ~(uintptr_t)15;
+    const uintptr_t vend = vaddr + (uintptr_t)avail;
+#pragma unroll
+    for (int i = 0; i < kWalkWindow / 512; ++i) {
+      const uintptr_t a = wbeg + (uintptr_t)(lane + 32 * i) * 16;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (a < vend) q = *reinterpret_cast<const uint4*>(a);
+      reinterpret_cast<uint4*>(s_win)[lane + 32 * i] = q;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const int64_t wofs = (int64_t)(wbeg - vaddr);
+      const int64_t lim = min(wofs + (int64_t)kWalkWindow, avail) - 4;
+      if (cursor > lim) bad = 1;  // a fresh window always holds the prefix at `cursor` unless the page ends
+      while (j < n && cursor <= lim) {
+        const uint8_t* q = s_win + (cursor - wofs);
+        const uint32_t len = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+        pos[j] = (int32_t)(cursor + 4);
+        cursor += 4 + (int64_t)len;
+        ++j;
+      }
+    }
+    cursor = __shfl_sync(0xffffffffu, cursor, 0);
+    j = __shfl_sync(0xffffffffu, j, 0);
+    bad = __shfl_sync(0xffffffffu, bad, 0);
+    __syncwarp();
   }
-  pos[ch.dict_nvals] = (int32_t)(p + 4 - base);
+  if (lane == 0) {
+    if (bad || cursor > avail) {
+      atomicExch(A.err, kErrBadPage);
+      for (int t = 0; t <= n; ++t) pos[t] = 4;  // every entry reads as empty
+    } else {
+      pos[n] = (int32_t)(cursor + 4);
+    }
+  }
 }
 
 // ---- index pass: one warp per page ------------------------------------------------------------
@@ -656,7 +695,7 @@ __global__ void __launch_bounds__(128) block_decode_kernel(DecodeArgs A) {
 
 // ---- launchers (called from device_scan.cc) -----------------------------------------------------
 void launch_dict_index(const DecodeArgs& A, cudaStream_t s) {
-  if (A.nchunks > 0) dict_index_kernel<<<(A.nchunks + 127) / 128, 128, 0, s>>>(A);
+  if (A.nchunks > 0) dict_index_kernel<<<(A.nchunks + 3) / 4, 128, 0, s>>>(A);
 }
 void launch_page_index(const DecodeArgs& A, cudaStream_t s) {
   if (A.npages > 0) page_index_kernel<<<(A.npages + 3) / 4, 128, 0, s>>>(A);

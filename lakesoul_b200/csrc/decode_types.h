@@ -40,6 +40,8 @@ struct PqChunk {         // one column chunk (file x column x row group)
   int32_t max_def;       // 0 required, 1 optional
   int32_t bucket;
   int32_t dict_nvals;    // 0 = no dictionary page
+  int32_t dict_size;     // payload bytes of the dictionary page
+  int32_t pad;
   int64_t dict_off;      // payload offset of the dictionary page inside the raw image
   int64_t dict_index;    // BYTE_ARRAY dictionaries: first entry of this chunk in the dict_pos table
 };

@@ -542,11 +542,13 @@ void DeviceScan::Impl::upload() {
               pc.col = c;
               pc.bucket = b;
               pc.dict_nvals = 0;
+              pc.dict_size = 0;
               pc.dict_off = 0;
               pc.dict_index = 0;
               if (di >= 0) {
                 const RawColumn::Dict& d = rc.dicts[(size_t)di];
                 pc.dict_nvals = d.num_values;
+                pc.dict_size = d.size;
                 pc.dict_off = (d.aux ? aux_off[f] : img_off[f]) + d.src_off;
                 if (pc.phys == PQ_BYTE_ARRAY) {
                   pc.dict_index = dict_entries;

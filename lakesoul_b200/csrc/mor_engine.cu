@@ -1304,14 +1304,32 @@ void* DeviceArena::alloc(size_t bytes) {
 }
 void DeviceArena::reset() {
   high_ = std::max(high_, used_);
+  const size_t cap = capacity();
   // several blocks = the arena had to grow: fold them into one block that fits the largest reader so far
-  if (blocks_.size() > 1) {
+  bool rebuild = blocks_.size() > 1;
+  size_t want = high_ + high_ / 4;
+  // one huge bucket must not pin its footprint forever: after 8 readers in a row that used less than a quarter
+  // of a large arena, shrink it to twice the recent need
+  if (cap > ((size_t)256 << 20) && used_ * 4 < cap) {
+    recent_ = std::max(recent_, used_);
+    if (++idle_ >= 8) {
+      rebuild = true;
+      want = 2 * recent_;
+      high_ = recent_;
+    }
+  } else {
+    idle_ = 0;
+    recent_ = 0;
+  }
+  if (rebuild) {
     for (auto& b : blocks_) cudaFree(b.p);
     blocks_.clear();
     uint8_t* p = nullptr;
-    const size_t cap = ((high_ + high_ / 4) + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1);
-    if (cudaMalloc(reinterpret_cast<void**>(&p), cap) == cudaSuccess) blocks_.push_back({p, cap});
+    const size_t bytes = std::max<size_t>((want + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1), (size_t)64 << 20);
+    if (cudaMalloc(reinterpret_cast<void**>(&p), bytes) == cudaSuccess) blocks_.push_back({p, bytes});
     else cudaGetLastError();
+    idle_ = 0;
+    recent_ = 0;
   }
   cur_ = 0;
   off_ = 0;

@@ -174,7 +174,8 @@ class DeviceArena {
  private:
   struct Block { uint8_t* p; size_t cap; };
   std::vector<Block> blocks_;
-  size_t cur_ = 0, off_ = 0, high_ = 0, used_ = 0;
+  size_t cur_ = 0, off_ = 0, high_ = 0, used_ = 0, recent_ = 0;
+  int idle_ = 0;
 };
 void arena_install(DeviceArena* a);   // nullptr restores cudaMallocAsync / cudaFreeAsync
 DeviceArena* arena_current();
