@@ -68,13 +68,13 @@ int32_t lsb_plan_gather_var(LsbPlan *plan, const void *src_offsets, const void *
                             const void *src_data_base, const void *src_valid, void *dst_offsets,
                             void *dst_data, void *dst_valid, void *batch_data_start, void *cuda_stream);
 
-/* n variable-width columns in 3 launches; every argument is an array of n device pointers */
+/* n variable-width columns in one launch (per 16 columns); every argument is an array of n device pointers */
 int32_t lsb_plan_gather_var_multi(LsbPlan *plan, int32_t ncols, const void *const *src_offsets,
                                   const void *const *src_data, const void *const *src_data_base,
                                   const void *const *src_valid, void *const *dst_offsets, void *const *dst_data,
                                   void *const *dst_valid, void *const *batch_data_start, void *cuda_stream);
 
-/* fixed-width + variable-width columns of one scan (1 + 3 launches) */
+/* fixed-width + variable-width columns of one scan (2 launches) */
 int32_t lsb_plan_gather_all(LsbPlan *plan, int32_t nfixed, const void *const *src, const void *const *src_valid,
                             void *const *dst, void *const *dst_valid, const int32_t *width, int32_t nvars,
                             const void *const *v_src_offsets, const void *const *v_src_data,

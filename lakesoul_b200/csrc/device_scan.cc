@@ -923,7 +923,7 @@ void DeviceScan::Impl::merge_and_gather() {
   }
   if (U > 0 && (!fixed.empty() || !vars.empty())) {
     gather_all(plan, fixed.data(), (int)fixed.size(), vars.data(), (int)vars.size(), stream);
-    ctr.kernel_launches += (fixed.empty() ? 0 : 1) + 3 * (((int)vars.size() + 15) / 16);
+    ctr.kernel_launches += (fixed.empty() ? 0 : 1) + (((int)vars.size() + 15) / 16);
   }
 
   // ---- download ---------------------------------------------------------------------------

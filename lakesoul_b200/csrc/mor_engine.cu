@@ -1751,7 +1751,7 @@ static void ensure_var_scratch(MergePlan* P, int64_t words, cudaStream_t stream)
   if (!P->d_varset) P->d_varset = dev_alloc<VarColSet>(1, stream);
 }
 
-// Fixed-width and variable-width columns of one scan: 1 + 3 launches.
+// Fixed-width and variable-width columns of one scan: 2 launches.
 void gather_all(MergePlan* P, const FixedCol* fixed, int nfixed, const VarCol* vars, int nvars, cudaStream_t stream) {
   if (nfixed > 0) gather_fixed(P, fixed, nfixed, stream);
   if (nvars > 0) gather_var_multi(P, vars, nvars, stream);

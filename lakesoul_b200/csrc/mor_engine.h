@@ -149,10 +149,10 @@ struct VarCol {
   int64_t* batch_data_start;     // device, (total_batches + 1)
 };
 void gather_var(MergePlan*, const VarCol& col, cudaStream_t stream);
-// same for several columns: 3 launches in total (the winner list is read once per pass)
+// same for several columns: one launch per 16 columns (chunk positions by a look-back scan inside the kernel)
 void gather_var_multi(MergePlan*, const VarCol* cols, int ncols, cudaStream_t stream);
 
-// Everything at once: 1 launch for the fixed-width columns + 3 for the string columns.
+// Everything at once: 1 launch for the fixed-width columns + 1 for the string columns.
 void gather_all(MergePlan*, const FixedCol* fixed, int nfixed, const VarCol* vars, int nvars, cudaStream_t stream);
 
 // Scratch management for gather_var (lengths + scanned offsets); grows on demand.

@@ -126,7 +126,7 @@ class ScanPlan:
             arr("dst_data"), arr("dst_valid"), arr("batch_data_start"), _stream_ptr(self.stream)))
 
     def gather_all(self, srcs, dsts, widths, vcols, src_valid=None, dst_valid=None):
-        """Fixed-width columns (as in gather_fixed) + string columns (as in gather_var_multi), 3 launches."""
+        """Fixed-width columns (as in gather_fixed) + string columns (as in gather_var_multi), 2 launches."""
         n = len(srcs)
         nv = len(vcols)
         arr = lambda key: _ptr_array([(c.get(key).data_ptr() if c.get(key) is not None else None) for c in vcols])  # noqa: E731
