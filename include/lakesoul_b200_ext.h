@@ -33,6 +33,7 @@ typedef struct LsbReaderStats {
   int64_t device_decoded_pages; /* Parquet data pages decoded by the GPU kernels */
   int64_t host_decoded_files;   /* files that needed the Arrow C++ host decoder (unsupported encodings) */
   int64_t pruned_row_groups;    /* row groups skipped by primary-key min/max statistics (pushed key filters) */
+  int64_t device_decompressed_pages; /* ZSTD page payloads expanded by the GPU (the rest is decompressed on the host) */
 } LsbReaderStats;
 int32_t lsb_reader_get_stats(CResult_Reader *reader, LsbReaderStats *out);
 

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include "decode_types.h"
+#include "zstd_decode.h"
 
 namespace lsb {
 
@@ -691,6 +692,328 @@ __global__ void __launch_bounds__(128) block_decode_kernel(DecodeArgs A) {
     const int64_t end_off = dict ? blk.str_base + sbytes : blk.str_base + ((int64_t)vpos[pg.nonnull] - vpos0);
     offs[pg.row_start + pg.num_values] = (int32_t)end_off;
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// ZSTD page payloads (the LakeSoul writer compresses every page with ZSTD, multipart_writer.rs:128): one warp
+// per page. The format is sequential inside a frame (entropy-coded bit streams read backwards, matches that
+// reference earlier output), so one lane parses while the warp does what is parallel: the four Huffman
+// streams of a block's literals are decoded by four lanes, literal and match copies by all 32. The tables
+// live in shared memory; zstd_decode.h holds the format logic (shared with the host unit test).
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+// backward bit reader for the hot loops: the stream sits inside the file image, which is padded, so the four
+// bytes after any in-range position may be read; going below the start is caught through bits_left < 0
+struct FastBack {
+  const uint8_t* p;
+  int64_t bits_left;
+  __device__ __forceinline__ bool init(const uint8_t* src, int64_t size) {
+    p = src;
+    if (size <= 0 || src[size - 1] == 0) return false;
+    bits_left = size * 8 - (8 - (31 - __clz((unsigned)src[size - 1])));
+    return true;
+  }
+  __device__ __forceinline__ uint32_t peek(int n) const {  // n <= 24
+    int64_t lo = bits_left - n;
+    int drop = 0;
+    if (lo < 0) { drop = (int)-lo; lo = 0; }  // over-read: the missing low bits are zeros
+    const uint8_t* q = p + (lo >> 3);
+    const uint64_t v = (uint64_t)q[0] | ((uint64_t)q[1] << 8) | ((uint64_t)q[2] << 16) | ((uint64_t)q[3] << 24) |
+                       ((uint64_t)q[4] << 32);
+    const uint32_t got = (uint32_t)(v >> (lo & 7)) & ((1u << (n - drop)) - 1);
+    return n == 0 ? 0u : (drop >= n ? 0u : (got << drop));
+  }
+  __device__ __forceinline__ uint32_t read(int n) {
+    const uint32_t v = peek(n);
+    bits_left -= n;
+    return v;
+  }
+};
+
+__device__ __forceinline__ int64_t huf_stream_device(const ZstdWork& W, const uint8_t* src, int64_t size, uint8_t* dst, int64_t n) {
+  FastBack bb;
+  if (!bb.init(src, size)) return ZSTD_E_CORRUPT;
+  const int log = W.huf_log;
+  for (int64_t i = 0; i < n; ++i) {
+    const uint16_t e = W.huf[bb.peek(log)];
+    dst[i] = (uint8_t)e;
+    bb.bits_left -= e >> 8;
+  }
+  return bb.bits_left == 0 ? n : (int64_t)ZSTD_E_CORRUPT;
+}
+
+// Decodes one frame with the whole warp; every lane returns the same value (bytes written or < 0).
+__device__ int64_t zstd_frame_warp(ZstdWork& W, const uint8_t* src, int64_t size, uint8_t* dst, int64_t dst_cap, uint8_t* lit) {
+  using namespace zstd_detail;
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) zstd_work_init(W);
+  __syncwarp();
+  if (size < 5) return ZSTD_E_TRUNCATED;
+  if (!(src[0] == 0x28 && src[1] == 0xB5 && src[2] == 0x2F && src[3] == 0xFD)) return ZSTD_E_MAGIC;
+  const int fhd = src[4];
+  const int fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, has_checksum = (fhd >> 2) & 1, did = fhd & 3;
+  if ((fhd & 0x08) || did != 0) return ZSTD_E_UNSUPPORTED;
+  int64_t ip = 5 + (single ? 0 : 1);
+  ip += fcs_flag == 0 ? (single ? 1 : 0) : (fcs_flag == 1 ? 2 : (fcs_flag == 2 ? 4 : 8));
+  if (ip > size) return ZSTD_E_TRUNCATED;
+  int64_t op = 0;
+  while (true) {
+    if (ip + 3 > size) return ZSTD_E_TRUNCATED;
+    const uint32_t bh = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8) | ((uint32_t)src[ip + 2] << 16);
+    ip += 3;
+    const int last = bh & 1, type = (bh >> 1) & 3;
+    const int64_t bsize = bh >> 3;
+    if (type == 0) {
+      if (ip + bsize > size) return ZSTD_E_TRUNCATED;
+      if (op + bsize > dst_cap) return ZSTD_E_DST_SMALL;
+      for (int64_t i = lane; i < bsize; i += 32) dst[op + i] = src[ip + i];
+      ip += bsize; op += bsize;
+    } else if (type == 1) {
+      if (ip + 1 > size) return ZSTD_E_TRUNCATED;
+      if (op + bsize > dst_cap) return ZSTD_E_DST_SMALL;
+      const uint8_t v = src[ip++];
+      for (int64_t i = lane; i < bsize; i += 32) dst[op + i] = v;
+      op += bsize;
+    } else if (type == 2) {
+      if (bsize > kZstdBlockMax || ip + bsize > size) return ZSTD_E_TRUNCATED;
+      const uint8_t* b = src + ip;
+      const int64_t bend = bsize;
+      int64_t bp = 0;
+      if (bend < 1) return ZSTD_E_CORRUPT;
+      // ---- literals ---------------------------------------------------------------------------
+      const int ltype = b[0] & 3, lfmt = (b[0] >> 2) & 3;
+      int64_t regen = 0, lcomp = 0;
+      int streams = 1;
+      const uint8_t* lits = lit;
+      if (ltype <= 1) {
+        int hs;
+        if (lfmt == 0 || lfmt == 2) { hs = 1; regen = b[0] >> 3; }
+        else if (lfmt == 1) { hs = 2; if (bend < 2) return ZSTD_E_TRUNCATED; regen = (b[0] >> 4) | ((int64_t)b[1] << 4); }
+        else { hs = 3; if (bend < 3) return ZSTD_E_TRUNCATED; regen = (b[0] >> 4) | ((int64_t)b[1] << 4) | ((int64_t)b[2] << 12); }
+        bp = hs;
+        if (regen > kZstdBlockMax) return ZSTD_E_CORRUPT;
+        if (ltype == 0) {
+          if (bp + regen > bend) return ZSTD_E_TRUNCATED;
+          lits = b + bp;
+          bp += regen;
+        } else {
+          if (bp + 1 > bend) return ZSTD_E_TRUNCATED;
+          const uint8_t v = b[bp++];
+          for (int64_t i = lane; i < regen; i += 32) lit[i] = v;
+        }
+      } else {
+        int hs;
+        if (lfmt == 0 || lfmt == 1) {
+          hs = 3; if (bend < 3) return ZSTD_E_TRUNCATED;
+          const uint32_t v = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16);
+          regen = (v >> 4) & 0x3ff; lcomp = (v >> 14) & 0x3ff;
+          streams = lfmt == 0 ? 1 : 4;
+        } else if (lfmt == 2) {
+          hs = 4; if (bend < 4) return ZSTD_E_TRUNCATED;
+          const uint32_t v = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+          regen = (v >> 4) & 0x3fff; lcomp = (v >> 18) & 0x3fff;
+          streams = 4;
+        } else {
+          hs = 5; if (bend < 5) return ZSTD_E_TRUNCATED;
+          const uint64_t v = (uint64_t)b[0] | ((uint64_t)b[1] << 8) | ((uint64_t)b[2] << 16) | ((uint64_t)b[3] << 24) | ((uint64_t)b[4] << 32);
+          regen = (v >> 4) & 0x3ffff; lcomp = (v >> 22) & 0x3ffff;
+          streams = 4;
+        }
+        bp = hs;
+        if (regen > kZstdBlockMax || bp + lcomp > bend) return ZSTD_E_CORRUPT;
+        const uint8_t* lp = b + bp;
+        int64_t lsize = lcomp;
+        if (ltype == 2) {
+          int64_t t = 0;
+          if (lane == 0) t = huf_read_table(W, lp, lsize);
+          t = __shfl_sync(0xffffffffu, t, 0);
+          if (t < 0) return t;
+          lp += t; lsize -= t;
+        } else if (W.huf_log == 0) {
+          return ZSTD_E_CORRUPT;
+        }
+        __syncwarp();
+        int64_t r = 0;
+        if (streams == 1) {
+          if (lane == 0) r = huf_stream_device(W, lp, lsize, lit, regen);
+        } else {
+          if (lsize < 6) return ZSTD_E_CORRUPT;
+          const int64_t s1 = lp[0] | (lp[1] << 8), s2 = lp[2] | (lp[3] << 8), s3 = lp[4] | (lp[5] << 8);
+          const int64_t s4 = lsize - 6 - s1 - s2 - s3;
+          const int64_t per = (regen + 3) / 4;
+          const int64_t n4 = regen - 3 * per;
+          if (s4 < 1 || n4 < 0) return ZSTD_E_CORRUPT;
+          const uint8_t* sp = lp + 6;
+          if (lane == 0) r = huf_stream_device(W, sp, s1, lit, per);
+          else if (lane == 1) r = huf_stream_device(W, sp + s1, s2, lit + per, per);
+          else if (lane == 2) r = huf_stream_device(W, sp + s1 + s2, s3, lit + 2 * per, per);
+          else if (lane == 3) r = huf_stream_device(W, sp + s1 + s2 + s3, s4, lit + 3 * per, n4);
+        }
+        if (__any_sync(0xffffffffu, r < 0)) return ZSTD_E_CORRUPT;
+        bp += lcomp;
+      }
+      __syncwarp();
+      // ---- sequences --------------------------------------------------------------------------
+      if (bp + 1 > bend) return ZSTD_E_TRUNCATED;
+      int64_t nseq = b[bp++];
+      if (nseq >= 128) {
+        if (nseq == 255) {
+          if (bp + 2 > bend) return ZSTD_E_TRUNCATED;
+          nseq = (int64_t)b[bp] + ((int64_t)b[bp + 1] << 8) + 0x7F00;
+          bp += 2;
+        } else {
+          if (bp + 1 > bend) return ZSTD_E_TRUNCATED;
+          nseq = ((nseq - 128) << 8) + b[bp++];
+        }
+      }
+      int64_t lpos = 0;
+      if (nseq > 0) {
+        if (bp + 1 > bend) return ZSTD_E_TRUNCATED;
+        const int modes = b[bp++];
+        if (modes & 3) return ZSTD_E_CORRUPT;
+        // tables: built by lane 0 (short, serial), the new read position is broadcast
+        int64_t st = 0;
+        if (lane == 0) {
+          const int mode[3] = {(modes >> 6) & 3, (modes >> 4) & 3, (modes >> 2) & 3};
+          for (int t = 0; t < 3 && st >= 0; ++t) {
+            FseEntry* tab = t == 0 ? W.ll : (t == 1 ? W.of : W.ml);
+            int* tlog = t == 0 ? &W.ll_log : (t == 1 ? &W.of_log : &W.ml_log);
+            const int max_sym = t == 0 ? 35 : (t == 1 ? 31 : 52);
+            const int max_log = t == 0 ? kLLLogMax : (t == 1 ? kOFLogMax : kMLLogMax);
+            if (mode[t] == 0) {
+              const int n = t == 0 ? 36 : (t == 1 ? 29 : 53);
+              for (int i = 0; i < n; ++i) W.norm[i] = t == 0 ? ll_default(i) : (t == 1 ? of_default(i) : ml_default(i));
+              *tlog = t == 1 ? 5 : 6;
+              fse_build(tab, *tlog, W.norm, n, W.next);
+            } else if (mode[t] == 1) {
+              if (bp + 1 > bend) { st = ZSTD_E_TRUNCATED; break; }
+              if (b[bp] > max_sym) { st = ZSTD_E_CORRUPT; break; }
+              fse_build_rle(tab, b[bp++]);
+              *tlog = 0;
+            } else if (mode[t] == 2) {
+              int nsym = 0, al = 0;
+              const int64_t u = fse_read_ncount(b + bp, bend - bp, max_sym, max_log, W.norm, &nsym, &al);
+              if (u < 0) { st = u; break; }
+              bp += u;
+              fse_build(tab, al, W.norm, nsym, W.next);
+              *tlog = al;
+            } else if (*tlog < 0) {
+              st = ZSTD_E_CORRUPT;
+            }
+          }
+          if (st >= 0) st = bp;
+        }
+        st = __shfl_sync(0xffffffffu, st, 0);
+        if (st < 0) return st;
+        bp = st;
+        __syncwarp();
+        FastBack bb;
+        bb.p = nullptr; bb.bits_left = 0;
+        uint32_t sl = 0, so = 0, sm = 0;
+        int ok = 1;
+        if (lane == 0) {
+          ok = bb.init(b + bp, bend - bp) ? 1 : 0;
+          if (ok) { sl = bb.read(W.ll_log); so = bb.read(W.of_log); sm = bb.read(W.ml_log); }
+        }
+        if (!__shfl_sync(0xffffffffu, ok, 0)) return ZSTD_E_CORRUPT;
+        for (int64_t q = 0; q < nseq; ++q) {
+          uint32_t ll = 0, ml = 0, offset = 0;
+          int bad = 0;
+          if (lane == 0) {
+            const int oc = W.of[so].symbol, mc = W.ml[sm].symbol, lc = W.ll[sl].symbol;
+            if (oc > 31 || mc > 52 || lc > 35) bad = 1;
+            else {
+              uint32_t ov;
+              if (oc > 24) {
+                const uint32_t hi = bb.read(oc - 16);
+                ov = (1u << oc) + (hi << 16) + bb.read(16);
+              } else {
+                ov = (1u << oc) + bb.read(oc);
+              }
+              ml = ml_base(mc) + bb.read(ml_bits(mc));
+              ll = ll_base(lc) + bb.read(ll_bits(lc));
+              if (q + 1 < nseq) {
+                sl = W.ll[sl].baseline + bb.read(W.ll[sl].nbits);
+                sm = W.ml[sm].baseline + bb.read(W.ml[sm].nbits);
+                so = W.of[so].baseline + bb.read(W.of[so].nbits);
+              }
+              if (bb.bits_left < 0) bad = 1;
+              if (ov > 3) {
+                offset = ov - 3;
+                W.rep[2] = W.rep[1]; W.rep[1] = W.rep[0]; W.rep[0] = offset;
+              } else {
+                const uint32_t idx = ov - 1 + (ll == 0 ? 1 : 0);
+                if (idx == 0) {
+                  offset = W.rep[0];
+                } else {
+                  offset = idx == 3 ? W.rep[0] - 1 : W.rep[idx];
+                  if (idx > 1) W.rep[2] = W.rep[1];
+                  W.rep[1] = W.rep[0];
+                  W.rep[0] = offset;
+                }
+              }
+              if (offset == 0) bad = 1;
+              if (q + 1 == nseq && bb.bits_left != 0) bad = 1;
+            }
+          }
+          ll = __shfl_sync(0xffffffffu, ll, 0);
+          ml = __shfl_sync(0xffffffffu, ml, 0);
+          offset = __shfl_sync(0xffffffffu, offset, 0);
+          if (__shfl_sync(0xffffffffu, bad, 0)) return ZSTD_E_CORRUPT;
+          if (lpos + ll > regen) return ZSTD_E_CORRUPT;
+          if (op + ll + ml > dst_cap) return ZSTD_E_DST_SMALL;
+          for (uint32_t i = lane; i < ll; i += 32) dst[op + i] = lits[lpos + i];
+          op += ll; lpos += ll;
+          if ((int64_t)offset > op) return ZSTD_E_CORRUPT;
+          __syncwarp();  // the literals just written may be the match source
+          const uint8_t* m = dst + op - offset;
+          if (offset >= ml) {
+            for (uint32_t i = lane; i < ml; i += 32) dst[op + i] = m[i];
+          } else {  // overlapping match: only bytes that existed before this sequence are read
+            for (uint32_t i = lane; i < ml; i += 32) dst[op + i] = m[i % offset];
+          }
+          op += ml;
+          __syncwarp();
+        }
+      }
+      const int64_t rest = regen - lpos;
+      if (rest < 0) return ZSTD_E_CORRUPT;
+      if (op + rest > dst_cap) return ZSTD_E_DST_SMALL;
+      for (int64_t i = lane; i < rest; i += 32) dst[op + i] = lits[lpos + i];
+      op += rest;
+      ip += bsize;
+      __syncwarp();
+    } else {
+      return ZSTD_E_CORRUPT;
+    }
+    if (last) break;
+  }
+  if (has_checksum) ip += 4;
+  if (ip > size) return ZSTD_E_TRUNCATED;
+  return op;
+}
+
+}  // namespace
+
+constexpr int kZstdWarpsPerBlock = 2;
+__global__ void __launch_bounds__(32 * kZstdWarpsPerBlock) zstd_pages_kernel(const PqZstdPage* pages, int npages, uint8_t* lit_scratch,
+                                                                             int32_t* err) {
+  __shared__ ZstdWork s_work[kZstdWarpsPerBlock];
+  const int w = threadIdx.x >> 5;
+  const int pi = blockIdx.x * kZstdWarpsPerBlock + w;
+  if (pi >= npages) return;
+  const PqZstdPage pg = pages[pi];
+  const int64_t r = zstd_frame_warp(s_work[w], reinterpret_cast<const uint8_t*>(pg.src_off), pg.comp_size,
+                                    reinterpret_cast<uint8_t*>(pg.dst_off), pg.raw_size,
+                                    lit_scratch + (int64_t)pi * kZstdBlockMax);
+  if (r != pg.raw_size && (threadIdx.x & 31) == 0) atomicExch(err, kErrBadPage);
+}
+
+void launch_zstd_pages(const PqZstdPage* pages, int npages, uint8_t* lit_scratch, int32_t* err, cudaStream_t s) {
+  if (npages > 0)
+    zstd_pages_kernel<<<(npages + kZstdWarpsPerBlock - 1) / kZstdWarpsPerBlock, 32 * kZstdWarpsPerBlock, 0, s>>>(pages, npages, lit_scratch, err);
 }
 
 // ---- launchers (called from device_scan.cc) -----------------------------------------------------

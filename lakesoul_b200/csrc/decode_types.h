@@ -88,6 +88,14 @@ struct PqBlock {
   int64_t str_base;      // var: first byte of the block inside the bucket's data (after the scan)
 };
 
+// One ZSTD-compressed page payload to expand on the device before the index pass.
+struct PqZstdPage {
+  int64_t src_off;       // compressed bytes (absolute device address, like PqPage.src_off)
+  int64_t dst_off;       // where the decompressed payload goes (absolute device address)
+  int32_t comp_size;
+  int32_t raw_size;      // uncompressed_page_size of the page header
+};
+
 struct DecodeArgs {
   const uint8_t* raw;        // device image of the files / decompressed pages
   const PqColOut* cols;

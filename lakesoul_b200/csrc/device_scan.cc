@@ -12,6 +12,7 @@
 #include "decode_types.h"
 #include "filter_eval.h"
 #include "general_merge.h"
+#include "zstd_decode.h"
 #include "page_plan.h"
 
 namespace lsb {
@@ -192,6 +193,7 @@ void launch_block_count(const DecodeArgs& A, cudaStream_t s);
 void launch_block_scan(const DecodeArgs& A, const int32_t* seg_bounds, const int64_t* seg_base, int nseg,
                        int64_t* seg_total, cudaStream_t s);
 void launch_block_decode(const DecodeArgs& A, cudaStream_t s);
+void launch_zstd_pages(const PqZstdPage* pages, int npages, uint8_t* lit_scratch, int32_t* err, cudaStream_t s);
 
 namespace {
 
@@ -520,8 +522,10 @@ void DeviceScan::Impl::upload() {
         aux_off[f] = (int64_t)reinterpret_cast<uintptr_t>(d_aux);
       }
     }
-    int64_t dict_entries = 0, nblocks = 0, vpos_entries = 0;
+    int64_t dict_entries = 0, nblocks = 0, vpos_entries = 0, zstd_bytes = 0;
     bool any_dict_var = false;
+    std::vector<PqZstdPage> zpages;
+    std::vector<int32_t> zstd_page_of;
     for (int c = 0; c < C; ++c) {
       if (!cols[c].has_raw) continue;
       for (int b = 0; b < nb; ++b) {
@@ -561,6 +565,16 @@ void DeviceScan::Impl::upload() {
             PqPage pg{};
             pg.src_off = (rp.aux ? aux_off[f] : img_off[f]) + rp.src_off;
             pg.size = rp.size;
+            if (rp.zstd) {  // expanded on the device: the decoders read the expansion, not the file image
+              PqZstdPage zp{};
+              zp.src_off = img_off[f] + rp.src_off;
+              zp.comp_size = rp.comp_size;
+              zp.raw_size = rp.size;
+              zp.dst_off = zstd_bytes;  // relative for now; the buffer is allocated once the total is known
+              zstd_bytes = (zstd_bytes + rp.size + 64 + 63) & ~63ll;
+              zstd_page_of.push_back((int32_t)pages.size());
+              zpages.push_back(zp);
+            }
             pg.num_values = rp.num_values;
             pg.encoding = rp.encoding;
             pg.def_encoding = rp.def_encoding;
@@ -612,6 +626,20 @@ void DeviceScan::Impl::upload() {
     PqBlock* d_blocks = static_cast<PqBlock*>(dalloc(sizeof(PqBlock) * (size_t)(nblocks + 1)));
     int32_t* d_vpos = static_cast<int32_t*>(dalloc(sizeof(int32_t) * (size_t)(vpos_entries + 1)));
     SCAN_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int32_t), stream));
+    if (!zpages.empty()) {
+      // ZSTD frames -> plain page payloads, one warp per page, before anything reads the pages
+      uint8_t* d_zout = static_cast<uint8_t*>(dalloc((size_t)zstd_bytes + 64));
+      uint8_t* d_zlit = static_cast<uint8_t*>(dalloc((size_t)zpages.size() * kZstdBlockMax));
+      for (size_t z = 0; z < zpages.size(); ++z) {
+        zpages[z].dst_off += (int64_t)reinterpret_cast<uintptr_t>(d_zout);
+        pages[(size_t)zstd_page_of[z]].src_off = zpages[z].dst_off;
+      }
+      PqZstdPage* d_zpages = static_cast<PqZstdPage*>(dalloc(sizeof(PqZstdPage) * zpages.size()));
+      h2d(d_zpages, zpages.data(), sizeof(PqZstdPage) * zpages.size());
+      launch_zstd_pages(d_zpages, (int)zpages.size(), d_zlit, d_err, stream);
+      ctr.kernel_launches += 1;
+      ctr.device_decompressed_pages += (int64_t)zpages.size();
+    }
     h2d(d_chunks, chunks.data(), sizeof(PqChunk) * chunks.size());
     h2d(d_pages, pages.data(), sizeof(PqPage) * pages.size());
     args.raw = nullptr;

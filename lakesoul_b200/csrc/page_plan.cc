@@ -12,6 +12,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <stdexcept>
@@ -20,6 +21,17 @@ namespace lsb {
 
 namespace {
 [[noreturn]] void fail(const std::string& m) { throw std::runtime_error(m); }
+
+// ZSTD page payloads: expanded by the GPU (zstd_pages_kernel) or by Arrow's codec on the host.
+// LAKESOUL_B200_DEVICE_ZSTD=1|0 selects; see kDeviceZstdDefault.
+constexpr bool kDeviceZstdDefault = false;
+bool device_zstd() {
+  static const bool on = [] {
+    const char* v = getenv("LAKESOUL_B200_DEVICE_ZSTD");
+    return v ? (*v == '1') : kDeviceZstdDefault;
+  }();
+  return on;
+}
 
 int32_t map_encoding(parquet::Encoding::type e) {
   switch (e) {
@@ -329,8 +341,20 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
         if (!proven) rc.may_have_nulls = true;
       }
       std::unique_ptr<parquet::PageReader> pr;
+      // ZSTD chunks without a dictionary page (what the LakeSoul writer emits): the pages stay compressed in the
+      // file image and are expanded by the GPU (zstd_pages_kernel); everything else is decompressed here
+      bool raw_zstd = device_zstd() && ccm->compression() == parquet::Compression::ZSTD && !ccm->has_dictionary_page() &&
+                            ccm->data_page_offset() > 0 &&
+                            ccm->data_page_offset() + ccm->total_compressed_size() <= image_bytes_;
       try {
-        pr = rd->RowGroup(rg)->GetColumnPageReader(ci);
+        if (raw_zstd) {
+          auto whole = std::make_shared<arrow::Buffer>(image_.get(), image_bytes_);
+          auto chunk = arrow::SliceBuffer(whole, ccm->data_page_offset(), ccm->total_compressed_size());
+          pr = parquet::PageReader::Open(std::make_shared<arrow::io::BufferReader>(chunk), ccm->num_values(),
+                                         parquet::Compression::UNCOMPRESSED);
+        } else {
+          pr = rd->RowGroup(rg)->GetColumnPageReader(ci);
+        }
       } catch (const std::exception& e) {
         *why = std::string("page reader: ") + e.what();
         return false;
@@ -393,6 +417,28 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
           if (pc.conv == CONV_BOOL && is_dict) { *why = "dictionary coded boolean"; return false; }
           place(&pg.src_off, &pg.aux);
           pg.size = (int32_t)size;
+          if (raw_zstd && page->type() == parquet::PageType::DATA_PAGE_V2 && row_in_rg == 0) {
+            // v2 pages keep their levels outside the compressed section: let libparquet decompress this chunk
+            raw_zstd = false;
+            try {
+              pr = rd->RowGroup(rg)->GetColumnPageReader(ci);
+            } catch (const std::exception& e) {
+              *why = std::string("page reader: ") + e.what();
+              return false;
+            }
+            continue;
+          }
+          if (raw_zstd) {
+            auto* dp = static_cast<parquet::DataPage*>(page.get());
+            if (page->type() != parquet::PageType::DATA_PAGE || pg.aux || dp->uncompressed_size() <= 0 ||
+                dp->uncompressed_size() > (int64_t)1 << 30) {
+              *why = "ZSTD page shape in column " + rc.name;
+              return false;
+            }
+            pg.zstd = true;
+            pg.comp_size = (int32_t)size;
+            pg.size = (int32_t)dp->uncompressed_size();
+          }
           pg.row_group = rg;
           pg.first_row = first_row + row_in_rg;
           row_in_rg += pg.num_values;

@@ -28,6 +28,8 @@ struct RawColumn {                    // one requested column of one file
   struct Page {
     int64_t src_off = 0;              // inside the file image (aux = false) or the aux arena (aux = true)
     bool aux = false;
+    bool zstd = false;                // src_off/comp_size = ZSTD frame inside the file image, expanded on the device
+    int32_t comp_size = 0;
     int32_t size = 0, num_values = 0, encoding = 0, def_encoding = 0, v2_def_len = -1;
     int32_t row_group = 0;
     int64_t first_row = 0;            // row inside the file

@@ -467,6 +467,7 @@ void Reader::Start() {
   I.stats.d2h_bytes = c.d2h_bytes;
   I.stats.kernel_launches = c.kernel_launches;
   I.stats.device_decoded_pages = c.device_decoded_pages;
+  I.stats.device_decompressed_pages = c.device_decompressed_pages;
   I.stats.host_decoded_files = c.host_decoded_files;
   I.stats.upload_ms = c.upload_ms;
   I.stats.merge_ms = c.merge_ms;

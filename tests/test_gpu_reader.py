@@ -331,6 +331,37 @@ def test_key_filters_prune_row_groups(tmp_path, key_type):
     assert_tables_equal(got, mo.read_bucket(paths, schema, ["id"], filters=["gt(v, 8)"]), "payload filter")
 
 
+def test_zstd_pages_are_expanded_on_the_device(tmp_path):
+    """PLAIN + ZSTD without dictionaries is what the LakeSoul writer emits (multipart_writer.rs:128-129): the page
+    payloads stay compressed on the host and are expanded by zstd_pages_kernel; same table as the host codec path."""
+    from lakesoul_b200 import datagen, read_bucket
+    spec = datagen.config_spec(2, 0.05)
+    spec.buckets = 2
+    paths = datagen.write_table(str(tmp_path), spec, encoding="E3")
+    for b in range(2):
+        got, reader = read_bucket(paths[b], spec.schema, spec.primary_keys, batch_size=4096, return_reader=True)
+        st = reader.stats()
+        reader.close()
+        assert st["device_decompressed_pages"] > 0 and st["host_decoded_files"] == 0, st
+        assert_tables_equal(got, mo.read_bucket(paths[b], spec.schema, spec.primary_keys), f"zstd bucket {b}")
+    # large pages (several 128 KiB ZSTD blocks per page), several compression levels, nulls
+    rng = np.random.default_rng(9)
+    n = 120_000
+    t = pa.table({"id": pa.array(np.arange(n, dtype=np.int64)),
+                  "txt": pa.array(["row %d %s" % (i, "lorem ipsum dolor sit amet " * int(rng.integers(0, 4))) for i in range(n)], pa.string()),
+                  "f": pa.array(rng.standard_normal(n), mask=rng.random(n) < 0.2),
+                  "k": pa.array(rng.integers(0, 50, n).astype(np.int32))})
+    for level in (1, 3, 12):
+        p = str(tmp_path / f"part-lvl{level}_0000.parquet")
+        pq.write_table(t, p, use_dictionary=False, compression="ZSTD", compression_level=level, data_page_size=2 << 20,
+                       row_group_size=60_000)
+        got, reader = read_bucket([p], t.schema, ["id"], return_reader=True)
+        st = reader.stats()
+        reader.close()
+        assert st["device_decompressed_pages"] > 0, st
+        assert_tables_equal(got, pq.read_table(p), f"zstd level {level}")
+
+
 from conftest import upsert_case_files, upsert_cases  # noqa: E402
 
 UPSERTS = upsert_cases()
