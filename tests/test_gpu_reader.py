@@ -332,8 +332,27 @@ def test_key_filters_prune_row_groups(tmp_path, key_type):
 
 
 def test_zstd_pages_are_expanded_on_the_device(tmp_path):
-    """PLAIN + ZSTD without dictionaries is what the LakeSoul writer emits (multipart_writer.rs:128-129): the page
-    payloads stay compressed on the host and are expanded by zstd_pages_kernel; same table as the host codec path."""
+    """PLAIN + ZSTD without dictionaries is what the LakeSoul writer emits (multipart_writer.rs:128-129): with
+    LAKESOUL_B200_DEVICE_ZSTD=1 the page payloads stay compressed on the host and are expanded by
+    zstd_pages_kernel; same table as the host codec path. (The variable is read once per process: the test runs
+    the reader in a child process.)"""
+    import subprocess
+    import sys
+    import textwrap
+    if os.environ.get("LAKESOUL_B200_DEVICE_ZSTD") != "1":
+        here = os.path.dirname(os.path.abspath(__file__))
+        root = os.path.dirname(here)
+        env = dict(os.environ, LAKESOUL_B200_DEVICE_ZSTD="1")
+        code = textwrap.dedent(f"""
+            import sys, pathlib
+            sys.path[:0] = [{here!r}, {os.path.join(root, "oracle")!r}, {root!r}]
+            import test_gpu_reader as t
+            t.test_zstd_pages_are_expanded_on_the_device(pathlib.Path({str(tmp_path)!r}))
+            print("child ok")
+        """)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+        assert out.returncode == 0 and "child ok" in out.stdout, out.stdout[-1500:] + out.stderr[-3000:]
+        return
     from lakesoul_b200 import datagen, read_bucket
     spec = datagen.config_spec(2, 0.05)
     spec.buckets = 2
