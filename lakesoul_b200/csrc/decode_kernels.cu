@@ -704,26 +704,43 @@ __global__ void __launch_bounds__(128) block_decode_kernel(DecodeArgs A) {
 // ---------------------------------------------------------------------------------------------------
 namespace {
 
-// backward bit reader for the hot loops: the stream sits inside the file image, which is padded, so the four
-// bytes after any in-range position may be read; going below the start is caught through bits_left < 0
+// backward bit reader for the hot loops: a 64-bit register window over the stream, refilled with byte loads only
+// when fewer than 32 unread bits are left in it. The stream sits inside the (padded) file image; going below its
+// start is caught through bits_left < 0 (the missing low bits read as zeros).
 struct FastBack {
   const uint8_t* p;
-  int64_t bits_left;
+  int64_t bits_left;   // unread bits of the stream
+  uint64_t win;        // bits [wlo, wlo + 64) of the stream, little-endian bit numbering
+  int64_t wlo;
+  __device__ __forceinline__ void refill() {
+    // window ending at the unread position: its top bit is bit (bits_left - 1) when possible
+    int64_t lo = ((bits_left + 7) & ~(int64_t)7) - 64;  // the window's top byte is the last byte with unread bits
+    if (lo < 0) lo = 0;
+    const uint8_t* q = p + (lo >> 3);
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v |= (uint64_t)q[i] << (8 * i);  // at most 7 bytes past the stream end: image padding
+    win = v;
+    wlo = lo;
+  }
   __device__ __forceinline__ bool init(const uint8_t* src, int64_t size) {
     p = src;
     if (size <= 0 || src[size - 1] == 0) return false;
     bits_left = size * 8 - (8 - (31 - __clz((unsigned)src[size - 1])));
+    refill();
     return true;
   }
-  __device__ __forceinline__ uint32_t peek(int n) const {  // n <= 24
+  __device__ __forceinline__ uint32_t peek(int n) {  // n <= 24
+    if (n == 0) return 0u;
     int64_t lo = bits_left - n;
-    int drop = 0;
-    if (lo < 0) { drop = (int)-lo; lo = 0; }  // over-read: the missing low bits are zeros
-    const uint8_t* q = p + (lo >> 3);
-    const uint64_t v = (uint64_t)q[0] | ((uint64_t)q[1] << 8) | ((uint64_t)q[2] << 16) | ((uint64_t)q[3] << 24) |
-                       ((uint64_t)q[4] << 32);
-    const uint32_t got = (uint32_t)(v >> (lo & 7)) & ((1u << (n - drop)) - 1);
-    return n == 0 ? 0u : (drop >= n ? 0u : (got << drop));
+    if (lo < 0) {  // over-read: zeros below the start
+      const int drop = (int)-lo;
+      if (drop >= n) return 0u;
+      if (wlo != 0) refill();
+      return ((uint32_t)win & ((1u << (n - drop)) - 1)) << drop;
+    }
+    if (lo < wlo) refill();
+    return (uint32_t)(win >> (lo - wlo)) & ((1u << n) - 1);
   }
   __device__ __forceinline__ uint32_t read(int n) {
     const uint32_t v = peek(n);
@@ -732,8 +749,28 @@ struct FastBack {
   }
 };
 
+// n bytes src -> dst by one lane, ranges do not overlap: eight loads are in flight before the first store (a
+// plain byte loop waits for every load, the compiler cannot move loads above possibly aliasing stores)
+__device__ __forceinline__ void copy_lane(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, uint32_t n) {
+  uint32_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint8_t t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = s[i + k];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[i + k] = t[k];
+  }
+  const uint32_t r = n - i;
+  uint8_t t[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) if ((uint32_t)k < r) t[k] = s[i + k];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) if ((uint32_t)k < r) d[i + k] = t[k];
+}
+
 __device__ __forceinline__ int64_t huf_stream_device(const ZstdWork& W, const uint8_t* src, int64_t size, uint8_t* dst, int64_t n) {
   FastBack bb;
+  bb.win = 0; bb.wlo = 0;
   if (!bb.init(src, size)) return ZSTD_E_CORRUPT;
   const int log = W.huf_log;
   for (int64_t i = 0; i < n; ++i) {
@@ -745,7 +782,8 @@ __device__ __forceinline__ int64_t huf_stream_device(const ZstdWork& W, const ui
 }
 
 // Decodes one frame with the whole warp; every lane returns the same value (bytes written or < 0).
-__device__ int64_t zstd_frame_warp(ZstdWork& W, const uint8_t* src, int64_t size, uint8_t* dst, int64_t dst_cap, uint8_t* lit) {
+__device__ int64_t zstd_frame_warp(ZstdWork& W, uint32_t* seq /* 96 words of shared memory */, const uint8_t* src, int64_t size,
+                                   uint8_t* dst, int64_t dst_cap, uint8_t* lit) {
   using namespace zstd_detail;
   const int lane = threadIdx.x & 31;
   if (lane == 0) zstd_work_init(W);
@@ -910,7 +948,7 @@ __device__ int64_t zstd_frame_warp(ZstdWork& W, const uint8_t* src, int64_t size
         bp = st;
         __syncwarp();
         FastBack bb;
-        bb.p = nullptr; bb.bits_left = 0;
+        bb.p = nullptr; bb.bits_left = 0; bb.win = 0; bb.wlo = 0;
         uint32_t sl = 0, so = 0, sm = 0;
         int ok = 1;
         if (lane == 0) {
@@ -918,13 +956,16 @@ __device__ int64_t zstd_frame_warp(ZstdWork& W, const uint8_t* src, int64_t size
           if (ok) { sl = bb.read(W.ll_log); so = bb.read(W.of_log); sm = bb.read(W.ml_log); }
         }
         if (!__shfl_sync(0xffffffffu, ok, 0)) return ZSTD_E_CORRUPT;
-        for (int64_t q = 0; q < nseq; ++q) {
-          uint32_t ll = 0, ml = 0, offset = 0;
+        // 32 sequences at a time: lane 0 decodes them (the bit stream and the FSE states are serial), then the
+        // warp executes them: output positions by a scan, literal runs in parallel, matches whose source lies
+        // entirely before the chunk's output in parallel, the rest (and the long ones) one by one with 32 lanes
+        for (int64_t q0 = 0; q0 < nseq; q0 += 32) {
+          const int cnt = (int)min((int64_t)32, nseq - q0);
           int bad = 0;
           if (lane == 0) {
-            const int oc = W.of[so].symbol, mc = W.ml[sm].symbol, lc = W.ll[sl].symbol;
-            if (oc > 31 || mc > 52 || lc > 35) bad = 1;
-            else {
+            for (int i = 0; i < cnt && !bad; ++i) {
+              const int oc = W.of[so].symbol, mc = W.ml[sm].symbol, lc = W.ll[sl].symbol;
+              if (oc > 31 || mc > 52 || lc > 35) { bad = 1; break; }
               uint32_t ov;
               if (oc > 24) {
                 const uint32_t hi = bb.read(oc - 16);
@@ -932,14 +973,15 @@ __device__ int64_t zstd_frame_warp(ZstdWork& W, const uint8_t* src, int64_t size
               } else {
                 ov = (1u << oc) + bb.read(oc);
               }
-              ml = ml_base(mc) + bb.read(ml_bits(mc));
-              ll = ll_base(lc) + bb.read(ll_bits(lc));
-              if (q + 1 < nseq) {
+              const uint32_t ml = ml_base(mc) + bb.read(ml_bits(mc));
+              const uint32_t ll = ll_base(lc) + bb.read(ll_bits(lc));
+              if (q0 + i + 1 < nseq) {
                 sl = W.ll[sl].baseline + bb.read(W.ll[sl].nbits);
                 sm = W.ml[sm].baseline + bb.read(W.ml[sm].nbits);
                 so = W.of[so].baseline + bb.read(W.of[so].nbits);
               }
               if (bb.bits_left < 0) bad = 1;
+              uint32_t offset;
               if (ov > 3) {
                 offset = ov - 3;
                 W.rep[2] = W.rep[1]; W.rep[1] = W.rep[0]; W.rep[0] = offset;
@@ -955,27 +997,60 @@ __device__ int64_t zstd_frame_warp(ZstdWork& W, const uint8_t* src, int64_t size
                 }
               }
               if (offset == 0) bad = 1;
-              if (q + 1 == nseq && bb.bits_left != 0) bad = 1;
+              if (q0 + i + 1 == nseq && bb.bits_left != 0) bad = 1;
+              seq[i] = ll; seq[32 + i] = ml; seq[64 + i] = offset;
             }
           }
-          ll = __shfl_sync(0xffffffffu, ll, 0);
-          ml = __shfl_sync(0xffffffffu, ml, 0);
-          offset = __shfl_sync(0xffffffffu, offset, 0);
           if (__shfl_sync(0xffffffffu, bad, 0)) return ZSTD_E_CORRUPT;
-          if (lpos + ll > regen) return ZSTD_E_CORRUPT;
-          if (op + ll + ml > dst_cap) return ZSTD_E_DST_SMALL;
-          for (uint32_t i = lane; i < ll; i += 32) dst[op + i] = lits[lpos + i];
-          op += ll; lpos += ll;
-          if ((int64_t)offset > op) return ZSTD_E_CORRUPT;
-          __syncwarp();  // the literals just written may be the match source
-          const uint8_t* m = dst + op - offset;
-          if (offset >= ml) {
-            for (uint32_t i = lane; i < ml; i += 32) dst[op + i] = m[i];
-          } else {  // overlapping match: only bytes that existed before this sequence are read
-            for (uint32_t i = lane; i < ml; i += 32) dst[op + i] = m[i % offset];
-          }
-          op += ml;
           __syncwarp();
+          const uint32_t ll = lane < cnt ? seq[lane] : 0u, ml = lane < cnt ? seq[32 + lane] : 0u;
+          const uint32_t offset = lane < cnt ? seq[64 + lane] : 1u;
+          __syncwarp();  // seq[] may be rewritten by lane 0 in the next round
+          // positions
+          uint32_t io = ll + ml, il = ll;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t yo = __shfl_up_sync(0xffffffffu, io, d), yl = __shfl_up_sync(0xffffffffu, il, d);
+            if (lane >= d) { io += yo; il += yl; }
+          }
+          const uint32_t tot_out = __shfl_sync(0xffffffffu, io, 31), tot_lit = __shfl_sync(0xffffffffu, il, 31);
+          if (lpos + tot_lit > regen) return ZSTD_E_CORRUPT;
+          if (op + tot_out > dst_cap) return ZSTD_E_DST_SMALL;
+          const int64_t my_out = op + (io - ll - ml);   // where this sequence's literals go
+          const int64_t my_lit = lpos + (il - ll);
+          const int64_t my_match = my_out + ll;
+          if (__any_sync(0xffffffffu, lane < cnt && (int64_t)offset > my_match)) return ZSTD_E_CORRUPT;
+          // literal runs: short ones lane-parallel, long ones with the whole warp
+          if (ll <= 64) copy_lane(dst + my_out, lits + my_lit, ll);
+          unsigned big = __ballot_sync(0xffffffffu, ll > 64);
+          while (big) {
+            const int j = __ffs(big) - 1;
+            big &= big - 1;
+            const int64_t o = __shfl_sync(0xffffffffu, my_out, j), l0 = __shfl_sync(0xffffffffu, my_lit, j);
+            const uint32_t n = __shfl_sync(0xffffffffu, ll, j);
+            for (uint32_t i = lane; i < n; i += 32) dst[o + i] = lits[l0 + i];
+          }
+          __syncwarp();
+          // matches
+          const bool indep = lane < cnt && ml <= 64 && (my_match - (int64_t)offset + ml <= op);
+          if (indep) copy_lane(dst + my_match, dst + my_match - offset, ml);
+          __syncwarp();
+          unsigned serial = __ballot_sync(0xffffffffu, lane < cnt && !indep && ml > 0);
+          while (serial) {
+            const int j = __ffs(serial) - 1;
+            serial &= serial - 1;
+            const int64_t md = __shfl_sync(0xffffffffu, my_match, j);
+            const uint32_t off = __shfl_sync(0xffffffffu, offset, j), n = __shfl_sync(0xffffffffu, ml, j);
+            const uint8_t* m = dst + md - off;
+            if (off >= n) {
+              for (uint32_t i = lane; i < n; i += 32) dst[md + i] = m[i];
+            } else {  // overlapping match: only bytes that existed before this sequence are read
+              for (uint32_t i = lane; i < n; i += 32) dst[md + i] = m[i % off];
+            }
+            __syncwarp();
+          }
+          op += tot_out;
+          lpos += tot_lit;
         }
       }
       const int64_t rest = regen - lpos;
@@ -1001,11 +1076,12 @@ constexpr int kZstdWarpsPerBlock = 2;
 __global__ void __launch_bounds__(32 * kZstdWarpsPerBlock) zstd_pages_kernel(const PqZstdPage* pages, int npages, uint8_t* lit_scratch,
                                                                              int32_t* err) {
   __shared__ ZstdWork s_work[kZstdWarpsPerBlock];
+  __shared__ uint32_t s_seq[kZstdWarpsPerBlock][96];
   const int w = threadIdx.x >> 5;
   const int pi = blockIdx.x * kZstdWarpsPerBlock + w;
   if (pi >= npages) return;
   const PqZstdPage pg = pages[pi];
-  const int64_t r = zstd_frame_warp(s_work[w], reinterpret_cast<const uint8_t*>(pg.src_off), pg.comp_size,
+  const int64_t r = zstd_frame_warp(s_work[w], s_seq[w], reinterpret_cast<const uint8_t*>(pg.src_off), pg.comp_size,
                                     reinterpret_cast<uint8_t*>(pg.dst_off), pg.raw_size,
                                     lit_scratch + (int64_t)pi * kZstdBlockMax);
   if (r != pg.raw_size && (threadIdx.x & 31) == 0) atomicExch(err, kErrBadPage);
