@@ -2,7 +2,7 @@
 """One full-size bucket of configs 2..5 (all three encodings) through the C-ABI against the CPU oracle
 (development check; the pytest suite runs the same configs scaled down)."""
 import os, sys, tempfile, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this script lives in tests/: it uses the oracle)
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import mor_oracle as mo
 from conftest import assert_tables_equal
