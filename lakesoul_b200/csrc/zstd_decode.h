@@ -552,4 +552,327 @@ LSB_HD_NOINLINE int64_t zstd_decompress_frame(ZstdWork& W, const uint8_t* src, i
   return op;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Phased decoding: the same format logic cut into steps that a thread block can run side by side.
+//   scan    : block headers of the frame                                   (host, a few bytes per block)
+//   plan    : per compressed block, in order: section headers + entropy tables (tables may be inherited)
+//   entropy : per block, independent: the Huffman streams -> literals, the FSE bit stream -> sequences
+//   execute : in order: repeat offsets, literal runs and matches
+// zstd_decompress_frame_phased() runs them one after the other on the host (unit test); zstd_pages_kernel maps
+// "entropy" onto the threads of a block.
+// ---------------------------------------------------------------------------------------------------------
+struct ZstdBlockDesc {      // one block of a frame (scan)
+  int32_t src_off;          // first byte of the block content inside the frame
+  int32_t size;             // content bytes (RLE: 1)
+  int32_t type;             // 0 raw, 1 RLE, 2 compressed
+  int32_t out_size;         // raw / RLE: bytes produced; compressed: unknown (-1)
+};
+
+struct ZstdTables {
+  uint16_t huf[1 << kHufLogMax];
+  FseEntry ll[1 << kLLLogMax], ml[1 << kMLLogMax], of[1 << kOFLogMax];
+};
+
+struct ZstdBlockPlan {      // one compressed block (plan)
+  int32_t lit_type;         // 0 raw, 1 RLE, 2 Huffman (own or inherited table)
+  int32_t regen;            // literal bytes of the block
+  int32_t lit_src;          // block-relative: raw literals / the RLE byte / the first Huffman stream
+  int32_t streams;          // 1 or 4
+  int32_t stream_size[4];
+  int32_t huf_log;
+  int32_t nseq;
+  int32_t seq_src, seq_size;  // block-relative FSE bit stream
+  int32_t ll_log, ml_log, of_log;
+  int32_t lit_base;         // where the block's literals start inside the page's literal scratch
+  int32_t seq_base;         // where the block's sequences start inside the page's sequence scratch
+};
+
+struct ZstdPlanScratch {
+  int16_t norm[256];
+  uint16_t next[256];
+  uint8_t weights[256];
+  FseEntry wtab[64];
+};
+
+// sequence record: literal length (17 bits) | match length (17 bits) << 17 | raw offset value << 34
+LSB_HD uint64_t zstd_pack_seq(uint32_t ll, uint32_t ml, uint32_t ov) { return (uint64_t)ll | ((uint64_t)ml << 17) | ((uint64_t)ov << 34); }
+
+// Frame header + block headers. Returns the number of blocks or < 0; *end = bytes of the frame.
+LSB_HD int64_t zstd_scan_frame(const uint8_t* src, int64_t size, ZstdBlockDesc* out, int maxb, int64_t* end) {
+  if (size < 5) return ZSTD_E_TRUNCATED;
+  if (!(src[0] == 0x28 && src[1] == 0xB5 && src[2] == 0x2F && src[3] == 0xFD)) return ZSTD_E_MAGIC;
+  const int fhd = src[4];
+  const int fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, has_checksum = (fhd >> 2) & 1, did = fhd & 3;
+  if ((fhd & 0x08) || did != 0) return ZSTD_E_UNSUPPORTED;
+  int64_t ip = 5 + (single ? 0 : 1);
+  ip += fcs_flag == 0 ? (single ? 1 : 0) : (fcs_flag == 1 ? 2 : (fcs_flag == 2 ? 4 : 8));
+  int n = 0;
+  while (true) {
+    if (ip + 3 > size) return ZSTD_E_TRUNCATED;
+    const uint32_t bh = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8) | ((uint32_t)src[ip + 2] << 16);
+    ip += 3;
+    const int last = bh & 1, type = (bh >> 1) & 3;
+    const int64_t bsize = bh >> 3;
+    if (type == 3) return ZSTD_E_CORRUPT;
+    const int64_t content = type == 1 ? 1 : bsize;
+    if (bsize > kZstdBlockMax || ip + content > size) return ZSTD_E_TRUNCATED;
+    if (n >= maxb) return ZSTD_E_UNSUPPORTED;
+    out[n].src_off = (int32_t)ip;
+    out[n].size = (int32_t)content;
+    out[n].type = type;
+    out[n].out_size = type == 2 ? -1 : (int32_t)bsize;
+    ++n;
+    ip += content;
+    if (last) break;
+  }
+  if (has_checksum) ip += 4;
+  if (ip > size) return ZSTD_E_TRUNCATED;
+  *end = ip;
+  return n;
+}
+
+// Section headers and entropy tables of one compressed block. `prev`/`prevT` = the previous COMPRESSED block of the
+// frame (nullptr for the first): treeless literals and "repeat" sequence tables copy its tables.
+LSB_HD_NOINLINE int64_t zstd_plan_block(const uint8_t* b, int64_t bend, ZstdBlockPlan& P, ZstdTables& T, const ZstdBlockPlan* prev,
+                                        const ZstdTables* prevT, ZstdPlanScratch& S) {
+  using namespace zstd_detail;
+  if (bend < 1) return ZSTD_E_CORRUPT;
+  int64_t bp = 0;
+  const int ltype = b[0] & 3, lfmt = (b[0] >> 2) & 3;
+  int64_t regen = 0, lcomp = 0;
+  P.streams = 1;
+  P.huf_log = prev ? prev->huf_log : 0;
+  P.ll_log = prev ? prev->ll_log : -1;
+  P.ml_log = prev ? prev->ml_log : -1;
+  P.of_log = prev ? prev->of_log : -1;
+  if (ltype <= 1) {
+    int hs;
+    if (lfmt == 0 || lfmt == 2) { hs = 1; regen = b[0] >> 3; }
+    else if (lfmt == 1) { hs = 2; if (bend < 2) return ZSTD_E_TRUNCATED; regen = (b[0] >> 4) | ((int64_t)b[1] << 4); }
+    else { hs = 3; if (bend < 3) return ZSTD_E_TRUNCATED; regen = (b[0] >> 4) | ((int64_t)b[1] << 4) | ((int64_t)b[2] << 12); }
+    bp = hs;
+    if (regen > kZstdBlockMax) return ZSTD_E_CORRUPT;
+    P.lit_type = ltype;
+    P.lit_src = (int32_t)bp;
+    if (ltype == 0) { if (bp + regen > bend) return ZSTD_E_TRUNCATED; bp += regen; }
+    else { if (bp + 1 > bend) return ZSTD_E_TRUNCATED; bp += 1; }
+    // a later treeless block still inherits the last Huffman table: carry it along
+    if (prevT && P.huf_log > 0) for (int i = 0; i < (1 << P.huf_log); ++i) T.huf[i] = prevT->huf[i];
+  } else {
+    int hs;
+    if (lfmt == 0 || lfmt == 1) {
+      hs = 3; if (bend < 3) return ZSTD_E_TRUNCATED;
+      const uint32_t v = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16);
+      regen = (v >> 4) & 0x3ff; lcomp = (v >> 14) & 0x3ff;
+      P.streams = lfmt == 0 ? 1 : 4;
+    } else if (lfmt == 2) {
+      hs = 4; if (bend < 4) return ZSTD_E_TRUNCATED;
+      const uint32_t v = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+      regen = (v >> 4) & 0x3fff; lcomp = (v >> 18) & 0x3fff;
+      P.streams = 4;
+    } else {
+      hs = 5; if (bend < 5) return ZSTD_E_TRUNCATED;
+      const uint64_t v = (uint64_t)b[0] | ((uint64_t)b[1] << 8) | ((uint64_t)b[2] << 16) | ((uint64_t)b[3] << 24) | ((uint64_t)b[4] << 32);
+      regen = (v >> 4) & 0x3ffff; lcomp = (v >> 22) & 0x3ffff;
+      P.streams = 4;
+    }
+    bp = hs;
+    if (regen > kZstdBlockMax || bp + lcomp > bend) return ZSTD_E_CORRUPT;
+    const uint8_t* lp = b + bp;
+    int64_t lsize = lcomp;
+    P.lit_type = 2;
+    if (ltype == 2) {
+      // huf_read_table works on a ZstdWork: use a local view of its fields through a small adapter
+      int64_t t;
+      {
+        // inline copy of the table reader on T.huf (same logic as huf_read_table)
+        if (lsize < 1) return ZSTD_E_TRUNCATED;
+        const int hb = lp[0];
+        int nw = 0;
+        int64_t used;
+        if (hb >= 128) {
+          nw = hb - 127;
+          used = 1 + ((nw + 1) >> 1);
+          if (used > lsize) return ZSTD_E_TRUNCATED;
+          for (int i = 0; i < nw; ++i) {
+            const uint8_t x = lp[1 + (i >> 1)];
+            S.weights[i] = (i & 1) ? (x & 15) : (x >> 4);
+          }
+        } else {
+          used = 1 + hb;
+          if (hb == 0 || used > lsize) return ZSTD_E_TRUNCATED;
+          int nsym = 0, tlog = 0;
+          const int64_t hdr = fse_read_ncount(lp + 1, hb, 12, 6, S.norm, &nsym, &tlog);
+          if (hdr < 0) return hdr;
+          fse_build(S.wtab, tlog, S.norm, nsym, S.next);
+          BackBits bb;
+          if (!bb.init(lp + 1 + hdr, hb - hdr)) return ZSTD_E_CORRUPT;
+          uint32_t s1 = bb.read(tlog), s2 = bb.read(tlog);
+          while (true) {
+            if (nw > 253) return ZSTD_E_CORRUPT;
+            S.weights[nw++] = S.wtab[s1].symbol;
+            s1 = S.wtab[s1].baseline + bb.read(S.wtab[s1].nbits);
+            if (bb.bits_left < 0) { S.weights[nw++] = S.wtab[s2].symbol; break; }
+            S.weights[nw++] = S.wtab[s2].symbol;
+            s2 = S.wtab[s2].baseline + bb.read(S.wtab[s2].nbits);
+            if (bb.bits_left < 0) { S.weights[nw++] = S.wtab[s1].symbol; break; }
+          }
+        }
+        uint32_t total = 0;
+        for (int i = 0; i < nw; ++i) {
+          if (S.weights[i] > kHufLogMax) return ZSTD_E_CORRUPT;
+          if (S.weights[i]) total += 1u << (S.weights[i] - 1);
+        }
+        if (total == 0) return ZSTD_E_CORRUPT;
+        const int max_bits = highbit(total) + 1;
+        if (max_bits > kHufLogMax) return ZSTD_E_CORRUPT;
+        const uint32_t rest = (1u << max_bits) - total;
+        if (rest == 0 || (rest & (rest - 1))) return ZSTD_E_CORRUPT;
+        S.weights[nw++] = (uint8_t)(highbit(rest) + 1);
+        uint32_t pos = 0;
+        for (int w = 1; w <= max_bits; ++w) {
+          const uint32_t span = 1u << (w - 1);
+          const uint16_t nb = (uint16_t)(max_bits + 1 - w);
+          for (int sy = 0; sy < nw; ++sy) {
+            if (S.weights[sy] != w) continue;
+            for (uint32_t i = 0; i < span; ++i) T.huf[pos + i] = (uint16_t)(sy | (nb << 8));
+            pos += span;
+          }
+        }
+        if (pos != (1u << max_bits)) return ZSTD_E_CORRUPT;
+        P.huf_log = max_bits;
+        t = used;
+      }
+      lp += t; lsize -= t;
+    } else {
+      if (P.huf_log == 0 || !prevT) return ZSTD_E_CORRUPT;  // treeless without a previous table
+      for (int i = 0; i < (1 << P.huf_log); ++i) T.huf[i] = prevT->huf[i];
+    }
+    P.lit_src = (int32_t)(lp - b);
+    if (P.streams == 1) {
+      P.stream_size[0] = (int32_t)lsize; P.stream_size[1] = P.stream_size[2] = P.stream_size[3] = 0;
+    } else {
+      if (lsize < 6) return ZSTD_E_CORRUPT;
+      const int64_t s1 = lp[0] | (lp[1] << 8), s2 = lp[2] | (lp[3] << 8), s3 = lp[4] | (lp[5] << 8);
+      const int64_t s4 = lsize - 6 - s1 - s2 - s3;
+      if (s4 < 1 || regen - 3 * ((regen + 3) / 4) < 0) return ZSTD_E_CORRUPT;
+      P.lit_src += 6;
+      P.stream_size[0] = (int32_t)s1; P.stream_size[1] = (int32_t)s2; P.stream_size[2] = (int32_t)s3; P.stream_size[3] = (int32_t)s4;
+    }
+    bp += lcomp;
+  }
+  P.regen = (int32_t)regen;
+  // sequences header
+  if (bp + 1 > bend) return ZSTD_E_TRUNCATED;
+  int64_t nseq = b[bp++];
+  if (nseq >= 128) {
+    if (nseq == 255) {
+      if (bp + 2 > bend) return ZSTD_E_TRUNCATED;
+      nseq = (int64_t)b[bp] + ((int64_t)b[bp + 1] << 8) + 0x7F00;
+      bp += 2;
+    } else {
+      if (bp + 1 > bend) return ZSTD_E_TRUNCATED;
+      nseq = ((nseq - 128) << 8) + b[bp++];
+    }
+  }
+  P.nseq = (int32_t)nseq;
+  int modes = 0xFC;  // no sequences: every table is inherited as it is
+  if (nseq > 0) {
+    if (bp + 1 > bend) return ZSTD_E_TRUNCATED;
+    modes = b[bp++];
+    if (modes & 3) return ZSTD_E_CORRUPT;
+  }
+  const int mode[3] = {(modes >> 6) & 3, (modes >> 4) & 3, (modes >> 2) & 3};  // LL, OF, ML
+  for (int t = 0; t < 3; ++t) {
+    FseEntry* tab = t == 0 ? T.ll : (t == 1 ? T.of : T.ml);
+    const FseEntry* ptab = prevT ? (t == 0 ? prevT->ll : (t == 1 ? prevT->of : prevT->ml)) : nullptr;
+    int32_t* tlog = t == 0 ? &P.ll_log : (t == 1 ? &P.of_log : &P.ml_log);
+    const int max_sym = t == 0 ? 35 : (t == 1 ? 31 : 52);
+    const int max_log = t == 0 ? kLLLogMax : (t == 1 ? kOFLogMax : kMLLogMax);
+    if (mode[t] == 0) {
+      const int n = t == 0 ? 36 : (t == 1 ? 29 : 53);
+      for (int i = 0; i < n; ++i) S.norm[i] = t == 0 ? ll_default(i) : (t == 1 ? of_default(i) : ml_default(i));
+      *tlog = t == 1 ? 5 : 6;
+      fse_build(tab, *tlog, S.norm, n, S.next);
+    } else if (mode[t] == 1) {
+      if (bp + 1 > bend) return ZSTD_E_TRUNCATED;
+      if (b[bp] > max_sym) return ZSTD_E_CORRUPT;
+      fse_build_rle(tab, b[bp++]);
+      *tlog = 0;
+    } else if (mode[t] == 2) {
+      int nsym = 0, al = 0;
+      const int64_t u = fse_read_ncount(b + bp, bend - bp, max_sym, max_log, S.norm, &nsym, &al);
+      if (u < 0) return u;
+      bp += u;
+      fse_build(tab, al, S.norm, nsym, S.next);
+      *tlog = al;
+    } else {
+      if (*tlog < 0 || !ptab) { if (nseq > 0) return ZSTD_E_CORRUPT; }
+      else for (int i = 0; i < (1 << *tlog); ++i) tab[i] = ptab[i];
+    }
+  }
+  P.seq_src = (int32_t)bp;
+  P.seq_size = (int32_t)(bend - bp);
+  if (nseq == 0 && bp != bend) return ZSTD_E_CORRUPT;
+  return 0;
+}
+
+// one Huffman stream -> n literal bytes
+LSB_HD int64_t zstd_huf_stream(const uint16_t* huf, int log, const uint8_t* src, int64_t size, uint8_t* dst, int64_t n) {
+  zstd_detail::BackBits bb;
+  if (!bb.init(src, size)) return ZSTD_E_CORRUPT;
+  for (int64_t i = 0; i < n; ++i) {
+    const uint16_t e = huf[bb.peek(log)];
+    dst[i] = (uint8_t)e;
+    bb.bits_left -= e >> 8;
+  }
+  return bb.bits_left == 0 ? n : (int64_t)ZSTD_E_CORRUPT;
+}
+
+// FSE bit stream of one block -> packed sequence records (offsets still as coded: repeat codes unresolved)
+LSB_HD int64_t zstd_decode_sequences(const uint8_t* bits, int64_t size, const ZstdBlockPlan& P, const ZstdTables& T, uint64_t* out) {
+  using namespace zstd_detail;
+  BackBits bb;
+  if (!bb.init(bits, size)) return ZSTD_E_CORRUPT;
+  uint32_t sl = bb.read(P.ll_log), so = bb.read(P.of_log), sm = bb.read(P.ml_log);
+  for (int32_t q = 0; q < P.nseq; ++q) {
+    const int oc = T.of[so].symbol, mc = T.ml[sm].symbol, lc = T.ll[sl].symbol;
+    if (oc > 29 || mc > 52 || lc > 35) return ZSTD_E_CORRUPT;  // offsets beyond 1 GiB are not representable here
+    uint32_t ov;
+    if (oc > 24) {
+      const uint32_t hi = bb.read(oc - 16);
+      ov = (1u << oc) + (hi << 16) + bb.read(16);
+    } else {
+      ov = (1u << oc) + bb.read(oc);
+    }
+    const uint32_t ml = ml_base(mc) + bb.read(ml_bits(mc));
+    const uint32_t ll = ll_base(lc) + bb.read(ll_bits(lc));
+    if (q + 1 < P.nseq) {
+      sl = T.ll[sl].baseline + bb.read(T.ll[sl].nbits);
+      sm = T.ml[sm].baseline + bb.read(T.ml[sm].nbits);
+      so = T.of[so].baseline + bb.read(T.of[so].nbits);
+    }
+    if (bb.bits_left < 0) return ZSTD_E_CORRUPT;
+    out[q] = zstd_pack_seq(ll, ml, ov);
+  }
+  return bb.bits_left == 0 ? 0 : (int64_t)ZSTD_E_CORRUPT;
+}
+
+// coded offset value + repeat history -> actual offset (updates the history); 0 = corrupt
+LSB_HD uint32_t zstd_resolve_offset(uint32_t ov, uint32_t ll, uint32_t* rep) {
+  uint32_t offset;
+  if (ov > 3) {
+    offset = ov - 3;
+    rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = offset;
+  } else {
+    const uint32_t idx = ov - 1 + (ll == 0 ? 1 : 0);
+    if (idx == 0) return rep[0];
+    offset = idx == 3 ? rep[0] - 1 : rep[idx];
+    if (idx > 1) rep[2] = rep[1];
+    rep[1] = rep[0];
+    rep[0] = offset;
+  }
+  return offset;
+}
+
 }  // namespace lsb
