@@ -768,328 +768,240 @@ __device__ __forceinline__ void copy_lane(uint8_t* __restrict__ d, const uint8_t
   for (int k = 0; k < 8; ++k) if ((uint32_t)k < r) d[i + k] = t[k];
 }
 
-__device__ __forceinline__ int64_t huf_stream_device(const ZstdWork& W, const uint8_t* src, int64_t size, uint8_t* dst, int64_t n) {
+// FSE bit stream of one block -> packed sequence records (device twin of zstd_decode_sequences: register-window reader)
+__device__ int64_t sequences_device(const uint8_t* bits, int64_t size, const ZstdBlockPlan& P, const ZstdTables& T, uint64_t* out) {
+  using namespace zstd_detail;
+  FastBack bb;
+  bb.win = 0; bb.wlo = 0;
+  if (!bb.init(bits, size)) return ZSTD_E_CORRUPT;
+  uint32_t sl = bb.read(P.ll_log), so = bb.read(P.of_log), sm = bb.read(P.ml_log);
+  for (int32_t q = 0; q < P.nseq; ++q) {
+    const FseEntry eo = T.of[so], em = T.ml[sm], el = T.ll[sl];
+    const int oc = eo.symbol, mc = em.symbol, lc = el.symbol;
+    if (oc > 29 || mc > 52 || lc > 35) return ZSTD_E_CORRUPT;
+    uint32_t ov;
+    if (oc > 24) {
+      const uint32_t hi = bb.read(oc - 16);
+      ov = (1u << oc) + (hi << 16) + bb.read(16);
+    } else {
+      ov = (1u << oc) + bb.read(oc);
+    }
+    const uint32_t ml = ml_base(mc) + bb.read(ml_bits(mc));
+    const uint32_t ll = ll_base(lc) + bb.read(ll_bits(lc));
+    if (q + 1 < P.nseq) {
+      sl = el.baseline + bb.read(el.nbits);
+      sm = em.baseline + bb.read(em.nbits);
+      so = eo.baseline + bb.read(eo.nbits);
+    }
+    if (bb.bits_left < 0) return ZSTD_E_CORRUPT;
+    out[q] = zstd_pack_seq(ll, ml, ov);
+  }
+  return bb.bits_left == 0 ? 0 : (int64_t)ZSTD_E_CORRUPT;
+}
+
+__device__ __forceinline__ int64_t huf_stream_fast(const uint16_t* huf, int log, const uint8_t* src, int64_t size,
+                                                   uint8_t* dst, int64_t n) {
   FastBack bb;
   bb.win = 0; bb.wlo = 0;
   if (!bb.init(src, size)) return ZSTD_E_CORRUPT;
-  const int log = W.huf_log;
   for (int64_t i = 0; i < n; ++i) {
-    const uint16_t e = W.huf[bb.peek(log)];
+    const uint16_t e = huf[bb.peek(log)];
     dst[i] = (uint8_t)e;
     bb.bits_left -= e >> 8;
   }
   return bb.bits_left == 0 ? n : (int64_t)ZSTD_E_CORRUPT;
 }
 
-// Decodes one frame with the whole warp; every lane returns the same value (bytes written or < 0).
-__device__ int64_t zstd_frame_warp(ZstdWork& W, uint32_t* seq /* 96 words of shared memory */, const uint8_t* src, int64_t size,
-                                   uint8_t* dst, int64_t dst_cap, uint8_t* lit) {
-  using namespace zstd_detail;
-  const int lane = threadIdx.x & 31;
-  if (lane == 0) zstd_work_init(W);
-  __syncwarp();
-  if (size < 5) return ZSTD_E_TRUNCATED;
-  if (!(src[0] == 0x28 && src[1] == 0xB5 && src[2] == 0x2F && src[3] == 0xFD)) return ZSTD_E_MAGIC;
-  const int fhd = src[4];
-  const int fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, has_checksum = (fhd >> 2) & 1, did = fhd & 3;
-  if ((fhd & 0x08) || did != 0) return ZSTD_E_UNSUPPORTED;
-  int64_t ip = 5 + (single ? 0 : 1);
-  ip += fcs_flag == 0 ? (single ? 1 : 0) : (fcs_flag == 1 ? 2 : (fcs_flag == 2 ? 4 : 8));
-  if (ip > size) return ZSTD_E_TRUNCATED;
-  int64_t op = 0;
-  while (true) {
-    if (ip + 3 > size) return ZSTD_E_TRUNCATED;
-    const uint32_t bh = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8) | ((uint32_t)src[ip + 2] << 16);
-    ip += 3;
-    const int last = bh & 1, type = (bh >> 1) & 3;
-    const int64_t bsize = bh >> 3;
-    if (type == 0) {
-      if (ip + bsize > size) return ZSTD_E_TRUNCATED;
-      if (op + bsize > dst_cap) return ZSTD_E_DST_SMALL;
-      for (int64_t i = lane; i < bsize; i += 32) dst[op + i] = src[ip + i];
-      ip += bsize; op += bsize;
-    } else if (type == 1) {
-      if (ip + 1 > size) return ZSTD_E_TRUNCATED;
-      if (op + bsize > dst_cap) return ZSTD_E_DST_SMALL;
-      const uint8_t v = src[ip++];
-      for (int64_t i = lane; i < bsize; i += 32) dst[op + i] = v;
-      op += bsize;
-    } else if (type == 2) {
-      if (bsize > kZstdBlockMax || ip + bsize > size) return ZSTD_E_TRUNCATED;
-      const uint8_t* b = src + ip;
-      const int64_t bend = bsize;
-      int64_t bp = 0;
-      if (bend < 1) return ZSTD_E_CORRUPT;
-      // ---- literals ---------------------------------------------------------------------------
-      const int ltype = b[0] & 3, lfmt = (b[0] >> 2) & 3;
-      int64_t regen = 0, lcomp = 0;
-      int streams = 1;
-      const uint8_t* lits = lit;
-      if (ltype <= 1) {
-        int hs;
-        if (lfmt == 0 || lfmt == 2) { hs = 1; regen = b[0] >> 3; }
-        else if (lfmt == 1) { hs = 2; if (bend < 2) return ZSTD_E_TRUNCATED; regen = (b[0] >> 4) | ((int64_t)b[1] << 4); }
-        else { hs = 3; if (bend < 3) return ZSTD_E_TRUNCATED; regen = (b[0] >> 4) | ((int64_t)b[1] << 4) | ((int64_t)b[2] << 12); }
-        bp = hs;
-        if (regen > kZstdBlockMax) return ZSTD_E_CORRUPT;
-        if (ltype == 0) {
-          if (bp + regen > bend) return ZSTD_E_TRUNCATED;
-          lits = b + bp;
-          bp += regen;
-        } else {
-          if (bp + 1 > bend) return ZSTD_E_TRUNCATED;
-          const uint8_t v = b[bp++];
-          for (int64_t i = lane; i < regen; i += 32) lit[i] = v;
-        }
-      } else {
-        int hs;
-        if (lfmt == 0 || lfmt == 1) {
-          hs = 3; if (bend < 3) return ZSTD_E_TRUNCATED;
-          const uint32_t v = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16);
-          regen = (v >> 4) & 0x3ff; lcomp = (v >> 14) & 0x3ff;
-          streams = lfmt == 0 ? 1 : 4;
-        } else if (lfmt == 2) {
-          hs = 4; if (bend < 4) return ZSTD_E_TRUNCATED;
-          const uint32_t v = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
-          regen = (v >> 4) & 0x3fff; lcomp = (v >> 18) & 0x3fff;
-          streams = 4;
-        } else {
-          hs = 5; if (bend < 5) return ZSTD_E_TRUNCATED;
-          const uint64_t v = (uint64_t)b[0] | ((uint64_t)b[1] << 8) | ((uint64_t)b[2] << 16) | ((uint64_t)b[3] << 24) | ((uint64_t)b[4] << 32);
-          regen = (v >> 4) & 0x3ffff; lcomp = (v >> 22) & 0x3ffff;
-          streams = 4;
-        }
-        bp = hs;
-        if (regen > kZstdBlockMax || bp + lcomp > bend) return ZSTD_E_CORRUPT;
-        const uint8_t* lp = b + bp;
-        int64_t lsize = lcomp;
-        if (ltype == 2) {
-          int64_t t = 0;
-          if (lane == 0) t = huf_read_table(W, lp, lsize);
-          t = __shfl_sync(0xffffffffu, t, 0);
-          if (t < 0) return t;
-          lp += t; lsize -= t;
-        } else if (W.huf_log == 0) {
-          return ZSTD_E_CORRUPT;
-        }
-        __syncwarp();
-        int64_t r = 0;
-        if (streams == 1) {
-          if (lane == 0) r = huf_stream_device(W, lp, lsize, lit, regen);
-        } else {
-          if (lsize < 6) return ZSTD_E_CORRUPT;
-          const int64_t s1 = lp[0] | (lp[1] << 8), s2 = lp[2] | (lp[3] << 8), s3 = lp[4] | (lp[5] << 8);
-          const int64_t s4 = lsize - 6 - s1 - s2 - s3;
-          const int64_t per = (regen + 3) / 4;
-          const int64_t n4 = regen - 3 * per;
-          if (s4 < 1 || n4 < 0) return ZSTD_E_CORRUPT;
-          const uint8_t* sp = lp + 6;
-          if (lane == 0) r = huf_stream_device(W, sp, s1, lit, per);
-          else if (lane == 1) r = huf_stream_device(W, sp + s1, s2, lit + per, per);
-          else if (lane == 2) r = huf_stream_device(W, sp + s1 + s2, s3, lit + 2 * per, per);
-          else if (lane == 3) r = huf_stream_device(W, sp + s1 + s2 + s3, s4, lit + 3 * per, n4);
-        }
-        if (__any_sync(0xffffffffu, r < 0)) return ZSTD_E_CORRUPT;
-        bp += lcomp;
-      }
-      __syncwarp();
-      // ---- sequences --------------------------------------------------------------------------
-      if (bp + 1 > bend) return ZSTD_E_TRUNCATED;
-      int64_t nseq = b[bp++];
-      if (nseq >= 128) {
-        if (nseq == 255) {
-          if (bp + 2 > bend) return ZSTD_E_TRUNCATED;
-          nseq = (int64_t)b[bp] + ((int64_t)b[bp + 1] << 8) + 0x7F00;
-          bp += 2;
-        } else {
-          if (bp + 1 > bend) return ZSTD_E_TRUNCATED;
-          nseq = ((nseq - 128) << 8) + b[bp++];
-        }
-      }
-      int64_t lpos = 0;
-      if (nseq > 0) {
-        if (bp + 1 > bend) return ZSTD_E_TRUNCATED;
-        const int modes = b[bp++];
-        if (modes & 3) return ZSTD_E_CORRUPT;
-        // tables: built by lane 0 (short, serial), the new read position is broadcast
-        int64_t st = 0;
-        if (lane == 0) {
-          const int mode[3] = {(modes >> 6) & 3, (modes >> 4) & 3, (modes >> 2) & 3};
-          for (int t = 0; t < 3 && st >= 0; ++t) {
-            FseEntry* tab = t == 0 ? W.ll : (t == 1 ? W.of : W.ml);
-            int* tlog = t == 0 ? &W.ll_log : (t == 1 ? &W.of_log : &W.ml_log);
-            const int max_sym = t == 0 ? 35 : (t == 1 ? 31 : 52);
-            const int max_log = t == 0 ? kLLLogMax : (t == 1 ? kOFLogMax : kMLLogMax);
-            if (mode[t] == 0) {
-              const int n = t == 0 ? 36 : (t == 1 ? 29 : 53);
-              for (int i = 0; i < n; ++i) W.norm[i] = t == 0 ? ll_default(i) : (t == 1 ? of_default(i) : ml_default(i));
-              *tlog = t == 1 ? 5 : 6;
-              fse_build(tab, *tlog, W.norm, n, W.next);
-            } else if (mode[t] == 1) {
-              if (bp + 1 > bend) { st = ZSTD_E_TRUNCATED; break; }
-              if (b[bp] > max_sym) { st = ZSTD_E_CORRUPT; break; }
-              fse_build_rle(tab, b[bp++]);
-              *tlog = 0;
-            } else if (mode[t] == 2) {
-              int nsym = 0, al = 0;
-              const int64_t u = fse_read_ncount(b + bp, bend - bp, max_sym, max_log, W.norm, &nsym, &al);
-              if (u < 0) { st = u; break; }
-              bp += u;
-              fse_build(tab, al, W.norm, nsym, W.next);
-              *tlog = al;
-            } else if (*tlog < 0) {
-              st = ZSTD_E_CORRUPT;
-            }
-          }
-          if (st >= 0) st = bp;
-        }
-        st = __shfl_sync(0xffffffffu, st, 0);
-        if (st < 0) return st;
-        bp = st;
-        __syncwarp();
-        FastBack bb;
-        bb.p = nullptr; bb.bits_left = 0; bb.win = 0; bb.wlo = 0;
-        uint32_t sl = 0, so = 0, sm = 0;
-        int ok = 1;
-        if (lane == 0) {
-          ok = bb.init(b + bp, bend - bp) ? 1 : 0;
-          if (ok) { sl = bb.read(W.ll_log); so = bb.read(W.of_log); sm = bb.read(W.ml_log); }
-        }
-        if (!__shfl_sync(0xffffffffu, ok, 0)) return ZSTD_E_CORRUPT;
-        // 32 sequences at a time: lane 0 decodes them (the bit stream and the FSE states are serial), then the
-        // warp executes them: output positions by a scan, literal runs in parallel, matches whose source lies
-        // entirely before the chunk's output in parallel, the rest (and the long ones) one by one with 32 lanes
-        for (int64_t q0 = 0; q0 < nseq; q0 += 32) {
-          const int cnt = (int)min((int64_t)32, nseq - q0);
-          int bad = 0;
-          if (lane == 0) {
-            for (int i = 0; i < cnt && !bad; ++i) {
-              const int oc = W.of[so].symbol, mc = W.ml[sm].symbol, lc = W.ll[sl].symbol;
-              if (oc > 31 || mc > 52 || lc > 35) { bad = 1; break; }
-              uint32_t ov;
-              if (oc > 24) {
-                const uint32_t hi = bb.read(oc - 16);
-                ov = (1u << oc) + (hi << 16) + bb.read(16);
-              } else {
-                ov = (1u << oc) + bb.read(oc);
-              }
-              const uint32_t ml = ml_base(mc) + bb.read(ml_bits(mc));
-              const uint32_t ll = ll_base(lc) + bb.read(ll_bits(lc));
-              if (q0 + i + 1 < nseq) {
-                sl = W.ll[sl].baseline + bb.read(W.ll[sl].nbits);
-                sm = W.ml[sm].baseline + bb.read(W.ml[sm].nbits);
-                so = W.of[so].baseline + bb.read(W.of[so].nbits);
-              }
-              if (bb.bits_left < 0) bad = 1;
-              uint32_t offset;
-              if (ov > 3) {
-                offset = ov - 3;
-                W.rep[2] = W.rep[1]; W.rep[1] = W.rep[0]; W.rep[0] = offset;
-              } else {
-                const uint32_t idx = ov - 1 + (ll == 0 ? 1 : 0);
-                if (idx == 0) {
-                  offset = W.rep[0];
-                } else {
-                  offset = idx == 3 ? W.rep[0] - 1 : W.rep[idx];
-                  if (idx > 1) W.rep[2] = W.rep[1];
-                  W.rep[1] = W.rep[0];
-                  W.rep[0] = offset;
-                }
-              }
-              if (offset == 0) bad = 1;
-              if (q0 + i + 1 == nseq && bb.bits_left != 0) bad = 1;
-              seq[i] = ll; seq[32 + i] = ml; seq[64 + i] = offset;
-            }
-          }
-          if (__shfl_sync(0xffffffffu, bad, 0)) return ZSTD_E_CORRUPT;
-          __syncwarp();
-          const uint32_t ll = lane < cnt ? seq[lane] : 0u, ml = lane < cnt ? seq[32 + lane] : 0u;
-          const uint32_t offset = lane < cnt ? seq[64 + lane] : 1u;
-          __syncwarp();  // seq[] may be rewritten by lane 0 in the next round
-          // positions
-          uint32_t io = ll + ml, il = ll;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t yo = __shfl_up_sync(0xffffffffu, io, d), yl = __shfl_up_sync(0xffffffffu, il, d);
-            if (lane >= d) { io += yo; il += yl; }
-          }
-          const uint32_t tot_out = __shfl_sync(0xffffffffu, io, 31), tot_lit = __shfl_sync(0xffffffffu, il, 31);
-          if (lpos + tot_lit > regen) return ZSTD_E_CORRUPT;
-          if (op + tot_out > dst_cap) return ZSTD_E_DST_SMALL;
-          const int64_t my_out = op + (io - ll - ml);   // where this sequence's literals go
-          const int64_t my_lit = lpos + (il - ll);
-          const int64_t my_match = my_out + ll;
-          if (__any_sync(0xffffffffu, lane < cnt && (int64_t)offset > my_match)) return ZSTD_E_CORRUPT;
-          // literal runs: short ones lane-parallel, long ones with the whole warp
-          if (ll <= 64) copy_lane(dst + my_out, lits + my_lit, ll);
-          unsigned big = __ballot_sync(0xffffffffu, ll > 64);
-          while (big) {
-            const int j = __ffs(big) - 1;
-            big &= big - 1;
-            const int64_t o = __shfl_sync(0xffffffffu, my_out, j), l0 = __shfl_sync(0xffffffffu, my_lit, j);
-            const uint32_t n = __shfl_sync(0xffffffffu, ll, j);
-            for (uint32_t i = lane; i < n; i += 32) dst[o + i] = lits[l0 + i];
-          }
-          __syncwarp();
-          // matches
-          const bool indep = lane < cnt && ml <= 64 && (my_match - (int64_t)offset + ml <= op);
-          if (indep) copy_lane(dst + my_match, dst + my_match - offset, ml);
-          __syncwarp();
-          unsigned serial = __ballot_sync(0xffffffffu, lane < cnt && !indep && ml > 0);
-          while (serial) {
-            const int j = __ffs(serial) - 1;
-            serial &= serial - 1;
-            const int64_t md = __shfl_sync(0xffffffffu, my_match, j);
-            const uint32_t off = __shfl_sync(0xffffffffu, offset, j), n = __shfl_sync(0xffffffffu, ml, j);
-            const uint8_t* m = dst + md - off;
-            if (off >= n) {
-              for (uint32_t i = lane; i < n; i += 32) dst[md + i] = m[i];
-            } else {  // overlapping match: only bytes that existed before this sequence are read
-              for (uint32_t i = lane; i < n; i += 32) dst[md + i] = m[i % off];
-            }
-            __syncwarp();
-          }
-          op += tot_out;
-          lpos += tot_lit;
-        }
-      }
-      const int64_t rest = regen - lpos;
-      if (rest < 0) return ZSTD_E_CORRUPT;
-      if (op + rest > dst_cap) return ZSTD_E_DST_SMALL;
-      for (int64_t i = lane; i < rest; i += 32) dst[op + i] = lits[lpos + i];
-      op += rest;
-      ip += bsize;
-      __syncwarp();
-    } else {
-      return ZSTD_E_CORRUPT;
-    }
-    if (last) break;
-  }
-  if (has_checksum) ip += 4;
-  if (ip > size) return ZSTD_E_TRUNCATED;
-  return op;
-}
-
 }  // namespace
 
-constexpr int kZstdWarpsPerBlock = 2;
-__global__ void __launch_bounds__(32 * kZstdWarpsPerBlock) zstd_pages_kernel(const PqZstdPage* pages, int npages, uint8_t* lit_scratch,
-                                                                             int32_t* err) {
-  __shared__ ZstdWork s_work[kZstdWarpsPerBlock];
-  __shared__ uint32_t s_seq[kZstdWarpsPerBlock][96];
-  const int w = threadIdx.x >> 5;
-  const int pi = blockIdx.x * kZstdWarpsPerBlock + w;
-  if (pi >= npages) return;
-  const PqZstdPage pg = pages[pi];
-  const int64_t r = zstd_frame_warp(s_work[w], s_seq[w], reinterpret_cast<const uint8_t*>(pg.src_off), pg.comp_size,
-                                    reinterpret_cast<uint8_t*>(pg.dst_off), pg.raw_size,
-                                    lit_scratch + (int64_t)pi * kZstdBlockMax);
-  if (r != pg.raw_size && (threadIdx.x & 31) == 0) atomicExch(err, kErrBadPage);
+// One thread block per page, three steps separated by block barriers (the phased pipeline of zstd_decode.h):
+//   plan    thread 0: section headers and entropy tables of the page's blocks, in order (tables can be inherited)
+//   entropy 8 threads per block, all blocks side by side: 4 Huffman streams, the FSE sequence stream, raw / RLE literals
+//   execute warp 0, in order, 32 sequences per round: repeat offsets (lane 0), output positions (scan), literal runs
+//           in parallel, matches whose source lies before the round's output in parallel, the rest one by one
+constexpr int kZstdThreads = 64;
+__global__ void __launch_bounds__(kZstdThreads) zstd_pages_kernel(const PqZstdPage* pages, const ZstdBlockDesc* blocks_all,
+                                                                  ZstdBlockPlan* plans_all, ZstdTables* tables_all, uint8_t* lit_all,
+                                                                  uint64_t* seq_all, int32_t* err) {
+  __shared__ ZstdPlanScratch s_plan;
+  __shared__ int s_fail;
+  __shared__ uint32_t s_round[96];  // ll | ml | resolved offset of the 32 sequences of a round
+  const PqZstdPage pg = pages[blockIdx.x];
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(pg.src_off);
+  uint8_t* dst = reinterpret_cast<uint8_t*>(pg.dst_off);
+  const ZstdBlockDesc* blocks = blocks_all + pg.first_block;
+  ZstdBlockPlan* plans = plans_all + pg.first_block;
+  ZstdTables* tables = tables_all + pg.first_block;
+  uint8_t* lit = lit_all + pg.lit_off;
+  uint64_t* seq = seq_all + pg.seq_off;
+  const int nb = pg.nblocks;
+  const int tid = threadIdx.x;
+  // plan: the tables of a block are built in shared memory (thread 0, serial: a block may inherit the tables of the
+  // one before it) and copied to the page's table scratch by the whole thread block
+  __shared__ ZstdTables s_tab;
+  __shared__ ZstdBlockPlan s_prev_plan, s_cur_plan;
+  __shared__ int s_have_prev;
+  if (tid == 0) { s_fail = 0; s_have_prev = 0; }
+  __syncthreads();
+  {
+    int64_t lit_total = 0, seq_total = 0;  // meaningful in thread 0
+    for (int k = 0; k < nb; ++k) {
+      if (blocks[k].type != 2) continue;  // uniform: block descriptors are the same for every thread
+      if (tid == 0 && !s_fail) {
+        // s_tab still holds the previous compressed block's tables: inherited entries stay where they are
+        const int64_t r = zstd_plan_block(src + blocks[k].src_off, blocks[k].size, s_cur_plan, s_tab, s_have_prev ? &s_prev_plan : nullptr,
+                                          s_have_prev ? &s_tab : nullptr, s_plan);
+        if (r < 0) s_fail = 1;
+        s_cur_plan.lit_base = (int32_t)lit_total;
+        s_cur_plan.seq_base = (int32_t)seq_total;
+        lit_total += s_cur_plan.regen;
+        seq_total += s_cur_plan.nseq;
+        if (lit_total > pg.raw_size || seq_total > pg.raw_size / 3 + 1) s_fail = 1;
+        s_prev_plan = s_cur_plan;
+        s_have_prev = 1;
+        plans[k] = s_cur_plan;
+      }
+      __syncthreads();
+      if (!s_fail) {
+        const uint32_t* from = reinterpret_cast<const uint32_t*>(&s_tab);
+        uint32_t* to = reinterpret_cast<uint32_t*>(&tables[k]);
+        for (int i = tid; i < (int)(sizeof(ZstdTables) / 4); i += kZstdThreads) to[i] = from[i];
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (s_fail) {
+    if (tid == 0) atomicExch(err, kErrBadPage);
+    return;
+  }
+  // ---- entropy: 8 roles per block --------------------------------------------------------------
+  for (int k = tid >> 3; k < nb; k += kZstdThreads >> 3) {
+    if (blocks[k].type != 2) continue;
+    const ZstdBlockPlan& P = plans[k];
+    const uint8_t* b = src + blocks[k].src_off;
+    uint8_t* L = lit + P.lit_base;
+    const int role = tid & 7;
+    int64_t r = 0;
+    if (role < 4) {
+      if (P.lit_type == 2 && role < P.streams) {
+        const int64_t per = P.streams == 4 ? (P.regen + 3) / 4 : P.regen;
+        int64_t so = 0;
+        for (int st = 0; st < role; ++st) so += P.stream_size[st];
+        const int64_t n = role < 3 ? per : P.regen - 3 * per;
+        r = huf_stream_fast(tables[k].huf, P.huf_log, b + P.lit_src + so, P.stream_size[role], L + role * per, P.streams == 4 ? n : P.regen);
+      }
+    } else if (role == 4) {
+      if (P.nseq > 0) r = sequences_device(b + P.seq_src, P.seq_size, P, tables[k], seq + P.seq_base);
+    } else if (role == 5) {
+      if (P.lit_type == 0) for (int i = 0; i < P.regen; ++i) L[i] = b[P.lit_src + i];
+      else if (P.lit_type == 1) { const uint8_t v = b[P.lit_src]; for (int i = 0; i < P.regen; ++i) L[i] = v; }
+    }
+    if (r < 0) s_fail = 1;
+  }
+  __syncthreads();
+  if (s_fail) {
+    if (tid == 0) atomicExch(err, kErrBadPage);
+    return;
+  }
+  if (tid >= 32) return;
+  // ---- execute: warp 0 ----------------------------------------------------------------------------
+  const int lane = tid;
+  uint32_t rep0 = 1, rep1 = 4, rep2 = 8;  // kept by lane 0
+  int64_t op = 0;
+  const int64_t cap = pg.raw_size;
+  for (int k = 0; k < nb; ++k) {
+    const uint8_t* b = src + blocks[k].src_off;
+    if (blocks[k].type != 2) {
+      const int64_t n = blocks[k].out_size;
+      if (op + n > cap) { if (lane == 0) atomicExch(err, kErrBadPage); return; }
+      if (blocks[k].type == 0) for (int64_t i = lane; i < n; i += 32) dst[op + i] = b[i];
+      else { const uint8_t v = b[0]; for (int64_t i = lane; i < n; i += 32) dst[op + i] = v; }
+      op += n;
+      __syncwarp();
+      continue;
+    }
+    const ZstdBlockPlan P = plans[k];
+    const uint8_t* lits = lit + P.lit_base;
+    const uint64_t* sq = seq + P.seq_base;
+    int64_t lpos = 0;
+    for (int q0 = 0; q0 < P.nseq; q0 += 32) {
+      const int cnt = min(32, P.nseq - q0);
+      const uint64_t v = lane < cnt ? sq[q0 + lane] : 0ull;
+      const uint32_t ll = (uint32_t)(v & 0x1ffff), ml = (uint32_t)((v >> 17) & 0x1ffff);
+      s_round[lane] = ll;
+      s_round[64 + lane] = (uint32_t)(v >> 34);
+      __syncwarp();
+      int bad = 0;
+      if (lane == 0) {  // repeat-offset history is a chain through the sequences
+        uint32_t rep[3] = {rep0, rep1, rep2};
+        for (int i = 0; i < cnt; ++i) {
+          const uint32_t o = zstd_resolve_offset(s_round[64 + i], s_round[i], rep);
+          if (o == 0) bad = 1;
+          s_round[64 + i] = o;
+        }
+        rep0 = rep[0]; rep1 = rep[1]; rep2 = rep[2];
+      }
+      __syncwarp();
+      const uint32_t offset = lane < cnt ? s_round[64 + lane] : 1u;
+      __syncwarp();
+      uint32_t io = ll + ml, il = ll;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t yo = __shfl_up_sync(0xffffffffu, io, d), yl = __shfl_up_sync(0xffffffffu, il, d);
+        if (lane >= d) { io += yo; il += yl; }
+      }
+      const uint32_t tot_out = __shfl_sync(0xffffffffu, io, 31), tot_lit = __shfl_sync(0xffffffffu, il, 31);
+      const int64_t my_out = op + (io - ll - ml);
+      const int64_t my_lit = lpos + (il - ll);
+      const int64_t my_match = my_out + ll;
+      bad = __shfl_sync(0xffffffffu, bad, 0) || lpos + tot_lit > P.regen || op + tot_out > cap;
+      if (__any_sync(0xffffffffu, bad || (lane < cnt && (int64_t)offset > my_match))) {
+        if (lane == 0) atomicExch(err, kErrBadPage);
+        return;
+      }
+      if (ll <= 64) copy_lane(dst + my_out, lits + my_lit, ll);
+      unsigned big = __ballot_sync(0xffffffffu, ll > 64);
+      while (big) {
+        const int j = __ffs(big) - 1;
+        big &= big - 1;
+        const int64_t o = __shfl_sync(0xffffffffu, my_out, j), l0 = __shfl_sync(0xffffffffu, my_lit, j);
+        const uint32_t n = __shfl_sync(0xffffffffu, ll, j);
+        for (uint32_t i = lane; i < n; i += 32) dst[o + i] = lits[l0 + i];
+      }
+      __syncwarp();
+      const bool indep = lane < cnt && ml <= 64 && (my_match - (int64_t)offset + ml <= op);
+      if (indep) copy_lane(dst + my_match, dst + my_match - offset, ml);
+      __syncwarp();
+      unsigned serial = __ballot_sync(0xffffffffu, lane < cnt && !indep && ml > 0);
+      while (serial) {
+        const int j = __ffs(serial) - 1;
+        serial &= serial - 1;
+        const int64_t md = __shfl_sync(0xffffffffu, my_match, j);
+        const uint32_t off = __shfl_sync(0xffffffffu, offset, j), n = __shfl_sync(0xffffffffu, ml, j);
+        const uint8_t* m = dst + md - off;
+        if (off >= n) {
+          for (uint32_t i = lane; i < n; i += 32) dst[md + i] = m[i];
+        } else {  // overlapping match: only bytes that existed before this sequence are read
+          for (uint32_t i = lane; i < n; i += 32) dst[md + i] = m[i % off];
+        }
+        __syncwarp();
+      }
+      op += tot_out;
+      lpos += tot_lit;
+    }
+    const int64_t rest = P.regen - lpos;
+    if (rest < 0 || op + rest > cap) { if (lane == 0) atomicExch(err, kErrBadPage); return; }
+    for (int64_t i = lane; i < rest; i += 32) dst[op + i] = lits[lpos + i];
+    op += rest;
+    __syncwarp();
+  }
+  if (op != cap && lane == 0) atomicExch(err, kErrBadPage);
 }
 
-void launch_zstd_pages(const PqZstdPage* pages, int npages, uint8_t* lit_scratch, int32_t* err, cudaStream_t s) {
-  if (npages > 0)
-    zstd_pages_kernel<<<(npages + kZstdWarpsPerBlock - 1) / kZstdWarpsPerBlock, 32 * kZstdWarpsPerBlock, 0, s>>>(pages, npages, lit_scratch, err);
+void launch_zstd_pages(const PqZstdPage* pages, int npages, const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, ZstdTables* tables,
+                       uint8_t* lit, uint64_t* seq, int32_t* err, cudaStream_t s) {
+  if (npages > 0) zstd_pages_kernel<<<npages, kZstdThreads, 0, s>>>(pages, blocks, plans, tables, lit, seq, err);
 }
 
 // ---- launchers (called from device_scan.cc) -----------------------------------------------------

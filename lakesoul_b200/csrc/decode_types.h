@@ -94,6 +94,10 @@ struct PqZstdPage {
   int64_t dst_off;       // where the decompressed payload goes (absolute device address)
   int32_t comp_size;
   int32_t raw_size;      // uncompressed_page_size of the page header
+  int32_t first_block;   // the frame's blocks in the block list (scanned by the host: three header bytes per block)
+  int32_t nblocks;
+  int64_t lit_off;       // the page's slice of the literal scratch (bytes)
+  int64_t seq_off;       // the page's slice of the sequence scratch (records)
 };
 
 struct DecodeArgs {

@@ -193,7 +193,8 @@ void launch_block_count(const DecodeArgs& A, cudaStream_t s);
 void launch_block_scan(const DecodeArgs& A, const int32_t* seg_bounds, const int64_t* seg_base, int nseg,
                        int64_t* seg_total, cudaStream_t s);
 void launch_block_decode(const DecodeArgs& A, cudaStream_t s);
-void launch_zstd_pages(const PqZstdPage* pages, int npages, uint8_t* lit_scratch, int32_t* err, cudaStream_t s);
+void launch_zstd_pages(const PqZstdPage* pages, int npages, const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, ZstdTables* tables,
+                       uint8_t* lit, uint64_t* seq, int32_t* err, cudaStream_t s);
 
 namespace {
 
@@ -526,6 +527,8 @@ void DeviceScan::Impl::upload() {
     bool any_dict_var = false;
     std::vector<PqZstdPage> zpages;
     std::vector<int32_t> zstd_page_of;
+    std::vector<ZstdBlockDesc> zblocks;
+    int64_t zlit_bytes = 0, zseq_recs = 0;
     for (int c = 0; c < C; ++c) {
       if (!cols[c].has_raw) continue;
       for (int b = 0; b < nb; ++b) {
@@ -572,6 +575,19 @@ void DeviceScan::Impl::upload() {
               zp.raw_size = rp.size;
               zp.dst_off = zstd_bytes;  // relative for now; the buffer is allocated once the total is known
               zstd_bytes = (zstd_bytes + rp.size + 64 + 63) & ~63ll;
+              // block headers of the frame (three bytes each), read from the pinned image
+              zblocks.resize(zblocks.size() + 4096);
+              int64_t frame_end = 0;
+              const size_t b0 = zblocks.size() - 4096;
+              const int64_t nblk = zstd_scan_frame(fi.raw->image() + rp.src_off, rp.comp_size, zblocks.data() + b0, 4096, &frame_end);
+              if (nblk < 0) fail("malformed ZSTD page in " + spec.physical_schema->field(c)->name());
+              zblocks.resize(b0 + (size_t)nblk);
+              zp.first_block = (int32_t)b0;
+              zp.nblocks = (int32_t)nblk;
+              zp.lit_off = zlit_bytes;
+              zp.seq_off = zseq_recs;
+              zlit_bytes += ((int64_t)rp.size + 63) & ~63ll;
+              zseq_recs += rp.size / 3 + 8;
               zstd_page_of.push_back((int32_t)pages.size());
               zpages.push_back(zp);
             }
@@ -627,16 +643,21 @@ void DeviceScan::Impl::upload() {
     int32_t* d_vpos = static_cast<int32_t*>(dalloc(sizeof(int32_t) * (size_t)(vpos_entries + 1)));
     SCAN_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int32_t), stream));
     if (!zpages.empty()) {
-      // ZSTD frames -> plain page payloads, one warp per page, before anything reads the pages
+      // ZSTD frames -> plain page payloads, one thread block per page, before anything reads the pages
       uint8_t* d_zout = static_cast<uint8_t*>(dalloc((size_t)zstd_bytes + 64));
-      uint8_t* d_zlit = static_cast<uint8_t*>(dalloc((size_t)zpages.size() * kZstdBlockMax));
       for (size_t z = 0; z < zpages.size(); ++z) {
         zpages[z].dst_off += (int64_t)reinterpret_cast<uintptr_t>(d_zout);
         pages[(size_t)zstd_page_of[z]].src_off = zpages[z].dst_off;
       }
       PqZstdPage* d_zpages = static_cast<PqZstdPage*>(dalloc(sizeof(PqZstdPage) * zpages.size()));
+      ZstdBlockDesc* d_zblocks = static_cast<ZstdBlockDesc*>(dalloc(sizeof(ZstdBlockDesc) * zblocks.size()));
+      ZstdBlockPlan* d_zplans = static_cast<ZstdBlockPlan*>(dalloc(sizeof(ZstdBlockPlan) * zblocks.size()));
+      ZstdTables* d_ztables = static_cast<ZstdTables*>(dalloc(sizeof(ZstdTables) * zblocks.size()));
+      uint8_t* d_zlit = static_cast<uint8_t*>(dalloc((size_t)zlit_bytes + 64));
+      uint64_t* d_zseq = static_cast<uint64_t*>(dalloc(sizeof(uint64_t) * (size_t)(zseq_recs + 8)));
       h2d(d_zpages, zpages.data(), sizeof(PqZstdPage) * zpages.size());
-      launch_zstd_pages(d_zpages, (int)zpages.size(), d_zlit, d_err, stream);
+      h2d(d_zblocks, zblocks.data(), sizeof(ZstdBlockDesc) * zblocks.size());
+      launch_zstd_pages(d_zpages, (int)zpages.size(), d_zblocks, d_zplans, d_ztables, d_zlit, d_zseq, d_err, stream);
       ctr.kernel_launches += 1;
       ctr.device_decompressed_pages += (int64_t)zpages.size();
     }
