@@ -12,6 +12,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -22,15 +23,21 @@ namespace lsb {
 namespace {
 [[noreturn]] void fail(const std::string& m) { throw std::runtime_error(m); }
 
-// ZSTD page payloads: expanded by the GPU (zstd_pages_kernel) or by Arrow's codec on the host.
-// LAKESOUL_B200_DEVICE_ZSTD=1|0 selects; see kDeviceZstdDefault.
-constexpr bool kDeviceZstdDefault = false;
-bool device_zstd() {
-  static const bool on = [] {
-    const char* v = getenv("LAKESOUL_B200_DEVICE_ZSTD");
-    return v ? (*v == '1') : kDeviceZstdDefault;
+// ZSTD page payloads are expanded by Arrow's codec on the host or by the GPU (zstd_pages_kernel). Measured on config-2
+// PLAIN+ZSTD buckets: all-host 73-83 M rows/s (13-15 cores busy), all-device 51-54 M rows/s (1.4 cores busy), and
+// splits that send the 30-50 % smallest column chunks to the device stay at 46-54 M rows/s -- the device decoder's
+// per-page latency, not its share of the bytes, is what holds a reader back. Until the execute step of the kernel is
+// parallel the default is the host codec; LAKESOUL_B200_DEVICE_ZSTD_SHARE=<0..1> sends that share of a file's
+// compressed-chunk bytes (smallest chunks first) to the GPU, 1 = everything.
+double device_zstd_share() {
+  static const double share = [] {
+    const char* v = getenv("LAKESOUL_B200_DEVICE_ZSTD_SHARE");
+    if (!v) v = getenv("LAKESOUL_B200_DEVICE_ZSTD");  // 0 / 1
+    if (!v || !*v) return 0.0;
+    const double x = atof(v);
+    return x < 0 ? 0.0 : (x > 1 ? 1.0 : x);
   }();
-  return on;
+  return share;
 }
 
 int32_t map_encoding(parquet::Encoding::type e) {
@@ -269,6 +276,32 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
   cols_.resize(want.size());
   // flat schemas only: leaf index == field index
   if (sd->num_columns() != schema_->num_fields()) { *why = "nested schema"; return false; }
+  // which ZSTD column chunks the GPU expands: smallest payloads first, up to the configured share of the bytes
+  std::set<std::pair<int, int>> device_chunks;  // (row group, column)
+  if (device_zstd_share() > 0) {
+    std::vector<std::pair<int64_t, std::pair<int, int>>> cand;
+    int64_t total = 0;
+    for (size_t w = 0; w < want.size(); ++w) {
+      const int ci = schema_->GetFieldIndex(want[w]->name());
+      if (ci < 0) continue;
+      for (int rg : kept_rg_) {
+        auto ccm = md->RowGroup(rg)->ColumnChunk(ci);
+        if (ccm->compression() != parquet::Compression::ZSTD || ccm->has_dictionary_page() || ccm->data_page_offset() <= 0 ||
+            ccm->data_page_offset() + ccm->total_compressed_size() > image_bytes_)
+          continue;
+        cand.push_back({ccm->total_uncompressed_size(), {rg, ci}});
+        total += ccm->total_uncompressed_size();
+      }
+    }
+    std::sort(cand.begin(), cand.end());
+    const double budget = device_zstd_share() * (double)total;
+    int64_t acc = 0;
+    for (const auto& c : cand) {
+      if (device_zstd_share() < 1.0 && (double)(acc + c.first) > budget) break;
+      device_chunks.insert(c.second);
+      acc += c.first;
+    }
+  }
   for (size_t w = 0; w < want.size(); ++w) {
     RawColumn& rc = cols_[w];
     rc.name = want[w]->name();
@@ -343,9 +376,7 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
       std::unique_ptr<parquet::PageReader> pr;
       // ZSTD chunks without a dictionary page (what the LakeSoul writer emits): the pages stay compressed in the
       // file image and are expanded by the GPU (zstd_pages_kernel); everything else is decompressed here
-      bool raw_zstd = device_zstd() && ccm->compression() == parquet::Compression::ZSTD && !ccm->has_dictionary_page() &&
-                            ccm->data_page_offset() > 0 &&
-                            ccm->data_page_offset() + ccm->total_compressed_size() <= image_bytes_;
+      bool raw_zstd = device_chunks.count({rg, ci}) > 0;
       try {
         if (raw_zstd) {
           auto whole = std::make_shared<arrow::Buffer>(image_.get(), image_bytes_);

@@ -333,16 +333,16 @@ def test_key_filters_prune_row_groups(tmp_path, key_type):
 
 def test_zstd_pages_are_expanded_on_the_device(tmp_path):
     """PLAIN + ZSTD without dictionaries is what the LakeSoul writer emits (multipart_writer.rs:128-129): with
-    LAKESOUL_B200_DEVICE_ZSTD=1 the page payloads stay compressed on the host and are expanded by
+    LAKESOUL_B200_DEVICE_ZSTD_SHARE=1 every page payload stays compressed on the host and are expanded by
     zstd_pages_kernel; same table as the host codec path. (The variable is read once per process: the test runs
     the reader in a child process.)"""
     import subprocess
     import sys
     import textwrap
-    if os.environ.get("LAKESOUL_B200_DEVICE_ZSTD") != "1":
+    if os.environ.get("LAKESOUL_B200_DEVICE_ZSTD_SHARE") != "1":
         here = os.path.dirname(os.path.abspath(__file__))
         root = os.path.dirname(here)
-        env = dict(os.environ, LAKESOUL_B200_DEVICE_ZSTD="1")
+        env = dict(os.environ, LAKESOUL_B200_DEVICE_ZSTD_SHARE="1")
         code = textwrap.dedent(f"""
             import sys, pathlib
             sys.path[:0] = [{here!r}, {os.path.join(root, "oracle")!r}, {root!r}]
