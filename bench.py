@@ -490,6 +490,13 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": "rows/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(line))
     if world > 1:
+        # rank 0 is still measuring the end-to-end and CPU legs on the host cores: the other ranks wait on the
+        # rendezvous store (a blocking socket read) instead of spinning in an NCCL barrier
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("lsb_bench_done", "1")
+        else:
+            store.wait(["lsb_bench_done"])
         dist.barrier()
         dist.destroy_process_group()
 
