@@ -490,6 +490,10 @@ void DeviceScan::Impl::upload() {
         }
       }
     }
+    // rows of a file that lacks the column must come out null on every path (the concat path and the
+    // full merge never look at present[]): the zero-initialised validity bitmap marks them, and a null
+    // row's values / offsets are never dereferenced (DefaultColumnStream null-fills, default_column.rs:62-108)
+    if (!dc.all_present) dc.any_nulls = true;
   }
 
   // ---- raw files: image upload, page descriptors, string sizing -----------------------------

@@ -137,6 +137,25 @@ Bound chunk_bound(const parquet::ColumnChunkMetaData& ccm, const parquet::Column
       if (!arrow::is_integer(type.id()) && type.id() != AT::TIMESTAMP && type.id() != AT::TIME64) return b;
       auto ts = std::static_pointer_cast<parquet::Int64Statistics>(st);
       b.imin = ts->min(); b.imax = ts->max(); b.fam = Bound::kInt;
+      if (type.id() == AT::TIMESTAMP) {
+        // filter literals are microseconds (filter.cc parse_literal); the statistics are in the column's own
+        // unit. Bring the bounds to microseconds, widening (never narrowing) the interval; no bound on overflow.
+        const auto unit = static_cast<const arrow::TimestampType&>(type).unit();
+        auto mul = [&](int64_t f) {
+          if (b.imin > INT64_MAX / f || b.imin < INT64_MIN / f || b.imax > INT64_MAX / f || b.imax < INT64_MIN / f) {
+            b.fam = Bound::kNone;
+            return;
+          }
+          b.imin *= f; b.imax *= f;
+        };
+        auto floor_div = [](int64_t v, int64_t d) { return v / d - ((v % d != 0 && v < 0) ? 1 : 0); };
+        if (unit == arrow::TimeUnit::SECOND) mul(1000000);
+        else if (unit == arrow::TimeUnit::MILLI) mul(1000);
+        else if (unit == arrow::TimeUnit::NANO) {
+          b.imin = floor_div(b.imin, 1000);
+          b.imax = floor_div(b.imax, 1000) + (b.imax % 1000 != 0 ? 1 : 0);
+        }
+      }
     } break;
     case parquet::Type::FLOAT: {
       auto ts = std::static_pointer_cast<parquet::FloatStatistics>(st);

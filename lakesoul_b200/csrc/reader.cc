@@ -168,32 +168,33 @@ bool IOConfig::skip_merge_on_read() const {
 }
 
 int ensure_device() {
-  static int dev = -2;
-  static std::string err;
-  if (dev == -2) {
+  // JVM task threads start readers concurrently: the device is chosen exactly once
+  struct Choice { int dev = -1; std::string err; };
+  static const Choice choice = [] {
+    Choice c;
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
-      dev = -1;
-      err = std::string("lakesoul_b200: no CUDA device available (") +
-            (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") +
-            "); the merge-on-read engine has no CPU fallback";
-    } else {
-      int want = 0;
-      if (const char* v = getenv("LAKESOUL_B200_DEVICE")) want = atoi(v);
-      else if (const char* v2 = getenv("LOCAL_RANK")) want = atoi(v2) % n;
-      dev = want < n ? want : 0;
-      // keep freed blocks in the stream-ordered pool: readers are created per bucket
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-      }
+      c.err = std::string("lakesoul_b200: no CUDA device available (") +
+              (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") +
+              "); the merge-on-read engine has no CPU fallback";
+      return c;
     }
-  }
-  if (dev < 0) fail(err);
-  cudaSetDevice(dev);
-  return dev;
+    int want = 0;
+    if (const char* v = getenv("LAKESOUL_B200_DEVICE")) want = atoi(v);
+    else if (const char* v2 = getenv("LOCAL_RANK")) want = atoi(v2) % n;
+    c.dev = (want >= 0 && want < n) ? want : 0;
+    // keep freed blocks in the stream-ordered pool: readers are created per bucket
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c.dev) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    return c;
+  }();
+  if (choice.dev < 0) fail(choice.err);
+  cudaSetDevice(choice.dev);
+  return choice.dev;
 }
 
 // ---------------------------------------------------------------------------------------

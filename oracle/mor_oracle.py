@@ -329,10 +329,25 @@ def merge_tables(files: Sequence[pa.Table], primary_keys: Sequence[str], schema:
     n = allt.num_rows
     if n == 0:
         return schema.empty_table()
-    keys = [(p, "ascending") for p in primary_keys] + [("__file", "ascending"), ("__row", "ascending")]
+    # floating-point keys compare by IEEE total order and are equal only bit for bit (cursor.rs:265-276:
+    # ArrowNativeTypeOp::compare = total_cmp, is_eq = to_bits equality): order and group them by the integer
+    # image total_cmp itself uses (bits ^ ((bits >> 63) as unsigned >> 1), compared as signed integers)
+    key_names = []
+    for p in primary_keys:
+        t = allt.schema.field(p).type
+        if pa.types.is_floating(t):
+            col = allt.column(p).combine_chunks()
+            it, ut, sh = (np.int64, np.uint64, 63) if t == pa.float64() else (np.int32, np.uint32, 31)
+            bits = np.asarray(col.fill_null(0.0)).view(it)
+            img = bits ^ ((bits >> sh).view(ut) >> ut(1)).view(it)
+            allt = allt.append_column("__k_" + p, pa.array(img, mask=~np.asarray(col.is_valid())))
+            key_names.append("__k_" + p)
+        else:
+            key_names.append(p)
+    keys = [(p, "ascending") for p in key_names] + [("__file", "ascending"), ("__row", "ascending")]
     order = pc.sort_indices(allt, sort_keys=keys, null_placement="at_start")
     st = allt.take(order)
-    new = _group_boundaries(st, primary_keys)
+    new = _group_boundaries(st, key_names)
     starts = np.flatnonzero(new)
     ends = np.append(starts[1:], n) - 1
     gid = np.cumsum(new) - 1

@@ -22,8 +22,11 @@
 //   line 2: primary keys, tab separated      line 3: columns, tab separated
 //   then one line per bucket: file paths, tab separated
 // Output: one JSON line {"seconds":..,"threads":..,"rows_in":..,"rows_out":..,"checksum":..}
+// verify = 1: every bucket's merged batches are also written as an Arrow IPC file
+//   $REF_CPU_VERIFY_DIR/bucket_<index>.arrow (tests/test_ref_cpu.py compares them with mor_oracle.py)
 #include <arrow/api.h>
 #include <arrow/io/file.h>
+#include <arrow/ipc/writer.h>
 #include <parquet/arrow/reader.h>
 #include <parquet/file_reader.h>
 
@@ -112,6 +115,9 @@ struct Reader {
   std::vector<int> tree;
   int64_t rows_in = 0, rows_out = 0;
   uint64_t checksum = 0;
+  bool keep_output = false;  // verify mode: the merged batches are kept as Arrow arrays
+  std::shared_ptr<arrow::Schema> out_schema;
+  std::vector<std::shared_ptr<arrow::RecordBatch>> out_batches;
   bool have_pending = false;
   int pend_stream = -1;
   int64_t pend_row = 0;
@@ -186,6 +192,7 @@ struct Reader {
   void build_batch() {  // build_record_batch_full_merge + interleave
     const int64_t n = (int64_t)in_progress.size();
     if (n == 0) return;
+    std::vector<std::shared_ptr<arrow::Array>> kept;
     for (int c = 0; c < ncols; ++c) {
       OutColumn oc;
       const auto& type = live[in_progress[0].first]->column(c)->type();
@@ -223,7 +230,22 @@ struct Reader {
         }
         checksum += oc.values[oc.values.size() / 2];
       }
+      if (keep_output) {
+        auto buf = [](const void* p, size_t bytes) -> std::shared_ptr<arrow::Buffer> {
+          auto b = arrow::AllocateBuffer((int64_t)bytes).ValueOrDie();
+          if (bytes) memcpy(b->mutable_data(), p, bytes);
+          return std::shared_ptr<arrow::Buffer>(std::move(b));
+        };
+        std::shared_ptr<arrow::Buffer> valid = any_null ? buf(oc.validity.data(), oc.validity.size()) : nullptr;
+        std::shared_ptr<arrow::ArrayData> ad;
+        if (!oc.offsets.empty())
+          ad = arrow::ArrayData::Make(type, n, {valid, buf(oc.offsets.data(), oc.offsets.size() * 4), buf(oc.data.data(), oc.data.size())});
+        else
+          ad = arrow::ArrayData::Make(type, n, {valid, buf(oc.values.data(), oc.values.size())});
+        kept.push_back(arrow::MakeArray(ad));
+      }
     }
+    if (keep_output) out_batches.push_back(arrow::RecordBatch::Make(out_schema, n, kept));
     rows_out += n;
     in_progress.clear();
     // drop batches nobody references any more (streams keep their current one)
@@ -330,7 +352,20 @@ int main() {
           if (i < 0) throw std::runtime_error("primary key not in the column list: " + p);
           rd.pk_idx.push_back(i);
         }
+        rd.keep_output = verify != 0;
+        rd.out_schema = out_schema;
         rd.run();
+        if (verify) {
+          const char* dir = getenv("REF_CPU_VERIFY_DIR");
+          if (!dir) throw std::runtime_error("verify mode needs REF_CPU_VERIFY_DIR");
+          auto sink = arrow::io::FileOutputStream::Open(std::string(dir) + "/bucket_" + std::to_string(b) + ".arrow").ValueOrDie();
+          auto wr = arrow::ipc::MakeFileWriter(sink, out_schema).ValueOrDie();
+          for (const auto& rb : rd.out_batches) {
+            auto st2 = wr->WriteRecordBatch(*rb);
+            if (!st2.ok()) throw std::runtime_error(st2.ToString());
+          }
+          if (!wr->Close().ok() || !sink->Close().ok()) throw std::runtime_error("cannot write the verify output");
+        }
         rows_in += rd.rows_in;
         rows_out += rd.rows_out;
         checksum += rd.checksum;

@@ -17,13 +17,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_CPU = os.path.join(HERE, "_build", "ref_cpu")
 
 
-def run(paths, schema, primary_keys, batch_size=8192, threads=None):
+def run(paths, schema, primary_keys, batch_size=8192, threads=None, verify_dir=None):
+    """verify_dir: the C++ port also writes every bucket's merged output as <verify_dir>/bucket_<i>.arrow (IPC file)."""
     threads = threads or (os.cpu_count() or 1)
     if os.path.exists(REF_CPU):
-        spec = (f"{threads} {batch_size} 0\n" + "\t".join(primary_keys) + "\n" + "\t".join(schema.names) + "\n" +
+        spec = (f"{threads} {batch_size} {1 if verify_dir else 0}\n" + "\t".join(primary_keys) + "\n" + "\t".join(schema.names) + "\n" +
                 "\n".join("\t".join(p) for p in paths) + "\n")
         t0 = time.perf_counter()
-        out = subprocess.run([REF_CPU], input=spec, capture_output=True, text=True, check=True)
+        env = dict(os.environ)
+        if verify_dir:
+            env["REF_CPU_VERIFY_DIR"] = verify_dir
+        out = subprocess.run([REF_CPU], input=spec, capture_output=True, text=True, check=True, env=env)
         res = json.loads(out.stdout.strip().splitlines()[-1])
         res.setdefault("seconds", time.perf_counter() - t0)
         res.update(kind="port", impl="C++ port of rust/lakesoul-io SortedStreamMerger/UseLastRangeCombiner (oracle/ref_cpu.cc)")

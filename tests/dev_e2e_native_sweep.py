@@ -2,7 +2,7 @@
 """End-to-end rows/s of the native C-ABI task executor (tools/cabi_driver.cc) over task-slot counts."""
 import os, sys, tempfile, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
 import bench
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 threads = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [8, 16, 24, 32, 48]

@@ -70,3 +70,13 @@ def test_writer_entry_points_report_errors(lib):
     assert st.contents.status == -1
     lib.free_c_status(st)
     lib.free_lakesoul_writer(w)
+
+
+def test_library_exports_nothing_but_the_declared_symbols():
+    """Link hygiene (csrc/exports.map): no libstdc++ / Arrow / CUDA-runtime symbols leak into the host JVM."""
+    import subprocess
+    so = os.path.join(ROOT, "lakesoul_b200", "lib", "liblakesoul_io_c.so")
+    out = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout
+    exported = {ln.split()[-1].split("@")[0] for ln in out.splitlines() if ln.strip()}
+    declared = _declared("lakesoul_c_bindings.h") | _declared("lakesoul_b200_ext.h")
+    assert exported == declared, (sorted(exported - declared)[:10], sorted(declared - exported)[:10])
