@@ -20,6 +20,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
 import tempfile
@@ -37,6 +38,7 @@ K = 8
 BASE_ROWS = 117_188
 DELTA_ROWS = 16_741
 BATCH_SIZE = 8192
+TRAFFIC_FILE = "r02_traffic.json"  # ncu dram bytes of the step kernels (profiles/make_traffic.py)
 
 
 def parse_args():
@@ -46,9 +48,15 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--buckets", type=int, default=BUCKETS, help="hash buckets per GPU")
-    ap.add_argument("--e2e-buckets", type=int, default=64, help="buckets written as Parquet for the e2e leg")
+    ap.add_argument("--e2e-buckets", type=int, default=4096, help="hash buckets of the end-to-end table (config 5: 4096)")
+    ap.add_argument("--e2e-distinct", type=int, default=256,
+                    help="distinct bucket contents generated; the remaining bucket ids are hard links to them")
+    ap.add_argument("--e2e-passes", type=int, default=5, help="timed passes over the whole table (median reported)")
     ap.add_argument("--e2e-threads", type=int, default=0,
-                    help="concurrent per-bucket readers (task slots); 0 = usable host cores")
+                    help="concurrent per-bucket readers (task slots) per rank; 0 = min(cores/ranks, --e2e-slot-cap)")
+    ap.add_argument("--e2e-slot-cap", type=int, default=24)
+    ap.add_argument("--side-buckets", type=int, default=64, help="buckets of the E1/E2/E3 side comparison (1 GPU only)")
+    ap.add_argument("--keep-data", action="store_true")
     ap.add_argument("--cpu-buckets", type=int, default=32, help="distinct buckets in the bounded CPU baseline sample")
     ap.add_argument("--cpu-threads", type=int, default=0, help="CPU baseline reader threads (0 = usable host cores)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -231,70 +239,7 @@ class Shard:
 
 
 # ------------------------------------------------------------------------------------------------
-# e2e leg: Parquet files -> C-ABI readers -> host Arrow batches
-# ------------------------------------------------------------------------------------------------
-def make_e2e_files(nb: int, root: str, encoding: str = "E1"):
-    from lakesoul_b200 import datagen
-    spec = datagen.config_spec(2, 1.0)
-    spec.buckets = nb
-    tables = datagen.generate_table(spec)
-    paths = datagen.write_table(root, spec, tables, encoding=encoding)
-    rows = [sum(t.num_rows for t in b) for b in tables]
-    return spec, paths, rows
-
-
-def run_e2e(spec, paths, threads: int):
-    from concurrent.futures import ThreadPoolExecutor
-    from lakesoul_b200 import LakeSoulArrowReader, NativeIOReader
-
-    def read_one(files):
-        r = NativeIOReader()
-        for f in files:
-            r.addFile(f)
-        r.setPrimaryKeys(spec.primary_keys)
-        r.setSchema(spec.schema)
-        r.setBatchSize(BATCH_SIZE)
-        r.initializeReader()
-        rows = 0
-        for batch in LakeSoulArrowReader(r):
-            rows += batch.num_rows
-        st = r.stats()
-        r.close()
-        return rows, st
-
-    from lakesoul_b200 import load_library
-    load_library()
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        res = list(ex.map(read_one, paths))
-    dt = time.perf_counter() - t0
-    out_rows = sum(r for r, _ in res)
-    h2d = sum(s["h2d_bytes"] for _, s in res)
-    d2h = sum(s["d2h_bytes"] for _, s in res)
-    launches = sum(s["kernel_launches"] for _, s in res)
-    run_e2e.last_decode = (sum(s["device_decoded_pages"] for _, s in res), sum(s["host_decoded_files"] for _, s in res))
-    return dt, out_rows, h2d, d2h, launches
-
-
-def run_e2e_native(spec, paths, threads: int, repeat: int = 3):
-    """Same call sequence from a native task executor (tools/cabi_driver.cc): T threads, one reader per
-    bucket through the C-ABI, every batch released by the consumer. No Python in the timed path."""
-    drv = os.path.join(ROOT, "lakesoul_b200", "lib", "cabi_driver")
-    if not os.path.exists(drv):
-        return None
-    inp = (f"{threads} {BATCH_SIZE} {repeat}\n" + "\t".join(spec.primary_keys) + "\n\n\n" +
-           "\n".join("\t".join(p) for p in paths) + "\n")
-    env = dict(os.environ)
-    out = subprocess.run([drv], input=inp, capture_output=True, text=True, env=env)
-    if out.returncode != 0:
-        raise RuntimeError("cabi_driver failed: " + out.stderr[-500:])
-    if os.environ.get("LAKESOUL_B200_TRACE") == "1":
-        sys.stderr.write(out.stderr)
-    return json.loads(out.stdout.strip().splitlines()[-1])
-
-
-# ------------------------------------------------------------------------------------------------
-# CPU baseline: the reference-structured CPU reader (oracle/) on a bounded sample
+# host topology: cores this rank's readers may use
 # ------------------------------------------------------------------------------------------------
 def usable_cores() -> int:
     """Cores this process may run on (affinity mask, then the cgroup CPU quota)."""
@@ -308,20 +253,224 @@ def usable_cores() -> int:
     return n
 
 
-def run_cpu_baseline(spec, paths, rows, nb: int, threads: int = 0):
+def _parse_cpulist(text: str):
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        out.extend(range(int(a), int(b or a) + 1))
+    return out
+
+
+def gpu_numa_nodes(n_gpus: int):
+    """NUMA node of every GPU 0..n_gpus-1 (sysfs, via the PCI bus id nvidia-smi reports); -1 when unknown."""
+    nodes = [-1] * n_gpus
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout
+        for ln in out.splitlines():
+            idx, bus = [x.strip() for x in ln.split(",")]
+            if int(idx) >= n_gpus:
+                continue
+            bus = bus.lower()
+            if len(bus.split(":")[0]) == 8:  # 00000000:1B:00.0 -> 0000:1b:00.0
+                bus = bus[4:]
+            try:
+                nodes[int(idx)] = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+            except Exception:
+                pass
+    except Exception:
+        pass
+    return nodes
+
+
+def rank_cpus(local_rank: int, world: int):
+    """CPUs for this rank's reader threads: whole physical cores of its GPU's NUMA node, shared evenly with the
+    other ranks whose GPU sits on the same node (SCALE_r01: GPU0-3 on node 0, GPU4-7 on node 1)."""
+    allowed = sorted(os.sched_getaffinity(0))
+    nodes = gpu_numa_nodes(world)
+    my = nodes[local_rank] if local_rank < len(nodes) else -1
+    node_cpus = allowed
+    if my >= 0:
+        try:
+            lst = set(_parse_cpulist(open(f"/sys/devices/system/node/node{my}/cpulist").read()))
+            inter = [c for c in allowed if c in lst]
+            if inter:
+                node_cpus = inter
+        except Exception:
+            pass
+    peers = [r for r in range(world) if (nodes[r] if r < len(nodes) else -1) == my] or [local_rank]
+    cores = {}
+    for c in node_cpus:
+        try:
+            key = (open(f"/sys/devices/system/cpu/cpu{c}/topology/physical_package_id").read().strip(),
+                   open(f"/sys/devices/system/cpu/cpu{c}/topology/core_id").read().strip())
+        except Exception:
+            key = ("0", str(c))
+        cores.setdefault(key, []).append(c)
+    core_list = [cores[k] for k in sorted(cores, key=lambda k: (int(k[0]), int(k[1])))]
+    i = peers.index(local_rank)
+    per = max(1, len(core_list) // len(peers))  # a contiguous block of whole cores per rank
+    mine = core_list[i * per:(i + 1) * per] if i < len(peers) - 1 else core_list[i * per:]
+    cpus = sorted(c for grp in (mine or core_list) for c in grp)
+    return cpus, my
+
+
+# ------------------------------------------------------------------------------------------------
+# e2e leg: the config-5-shaped table as Parquet files -> C-ABI readers -> host Arrow batches
+# ------------------------------------------------------------------------------------------------
+E2E_CONFIG = 5
+E2E_COMMITS = 64
+E2E_ROWS_PER_BUCKET = 146_484
+E2E_PKS = ["l_orderkey", "l_linenumber"]
+
+
+def table_root(args) -> str:
+    if args.data_dir:
+        return args.data_dir
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    tag = os.environ.get("MASTER_PORT", "0") + "_" + os.environ.get("TORCHELASTIC_RUN_ID", str(os.getppid()))
+    return os.path.join(base, f"lsb_bench_{tag}")
+
+
+def make_table(root: str, buckets: int, distinct: int, encodings: str, part: int, parts: int, procs: int, links: bool):
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "make_table.py"), "--root", root, "--config", str(E2E_CONFIG),
+           "--buckets", str(buckets), "--distinct", str(distinct), "--encodings", encodings, "--part", str(part),
+           "--parts", str(parts), "--procs", str(max(1, procs))]
+    if links:
+        cmd.append("--links-only")
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("make_table failed: " + out.stderr[-800:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def bucket_paths(root: str, encoding: str, bucket: int):
+    from lakesoul_b200 import datagen
+    spec_seed = datagen.BASE_SEED + 1000 * E2E_CONFIG
+    return datagen.bucket_file_paths(root, encoding, bucket, E2E_COMMITS, spec_seed)
+
+
+class NativeReaders:
+    """tools/cabi_driver.cc in --serve mode: T task slots, one C-ABI reader per bucket, pinned to `cpus`."""
+
+    def __init__(self, paths, threads: int, cpus, env=None):
+        self.drv = os.path.join(ROOT, "lakesoul_b200", "lib", "cabi_driver")
+        if not os.path.exists(self.drv):
+            raise RuntimeError("lakesoul_b200/lib/cabi_driver is not built (run __graft_entry__.build())")
+        fd, self.job = tempfile.mkstemp(prefix="lsb_job_", suffix=".txt")
+        with os.fdopen(fd, "w") as f:
+            f.write(f"{threads} {BATCH_SIZE} 1\n" + "\t".join(E2E_PKS) + "\n\n\n")
+            f.write("\n".join("\t".join(p) for p in paths) + "\n")
+        e = dict(os.environ)
+        e.update(env or {})
+
+        def pin():
+            if cpus:
+                try:
+                    os.sched_setaffinity(0, cpus)
+                except Exception:
+                    pass
+        self.errf = tempfile.TemporaryFile(mode="w+")  # a pipe nobody drains could block the driver
+        self.p = subprocess.Popen([self.drv, self.job, "--serve"], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                  stderr=self.errf, text=True, env=e, preexec_fn=pin)
+        line = self.p.stdout.readline().strip()
+        if line != "READY":
+            raise RuntimeError("cabi_driver did not start: " + line + self._stderr())
+
+    def _stderr(self) -> str:
+        self.errf.seek(0)
+        return self.errf.read()[-1500:]
+
+    def run_pass(self, n: int = 0) -> dict:
+        self.p.stdin.write(f"GO {n}\n" if n else "GO\n")
+        self.p.stdin.flush()
+        line = self.p.stdout.readline()
+        if not line or "error" in line:
+            raise RuntimeError("cabi_driver pass failed: " + self._stderr())
+        return json.loads(line)
+
+    def close(self):
+        try:
+            self.p.stdin.write("QUIT\n")
+            self.p.stdin.flush()
+            self.p.wait(timeout=30)
+        except Exception:
+            self.p.kill()
+        if os.environ.get("LAKESOUL_B200_TRACE") == "1":
+            sys.stderr.write(self._stderr())
+        try:
+            os.unlink(self.job)
+        except OSError:
+            pass
+
+
+def e2e_env(encoding: str):
+    """Reader knobs per file layout."""
+    env = {}
+    if "LAKESOUL_B200_DEVICE_ZSTD_SHARE" in os.environ:
+        env["LAKESOUL_B200_DEVICE_ZSTD_SHARE"] = os.environ["LAKESOUL_B200_DEVICE_ZSTD_SHARE"]
+    return env
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the reference-structured CPU reader (oracle/) on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def run_cpu_baseline(paths, rows, threads: int = 0):
     """The reference-structured CPU reader (oracle/ref_cpu) with one reader per usable host core.
-    The bounded sample = `nb` distinct buckets, replicated so that every thread owns at least one."""
+    The bounded sample = the given buckets, replicated so that every thread owns at least one."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref_cpu_driver
+    from lakesoul_b200 import datagen
     threads = threads or usable_cores()
-    paths, rows = paths[:nb], rows[:nb]
     reps = max(1, -(-threads // len(paths)))
-    res = ref_cpu_driver.run(paths * reps, spec.schema, spec.primary_keys, batch_size=BATCH_SIZE, threads=threads)
+    res = ref_cpu_driver.run(paths * reps, datagen.LINEITEM_SCHEMA, E2E_PKS, batch_size=BATCH_SIZE, threads=threads)
     total = sum(rows) * reps
     return {"value": total / res["seconds"], "unit": "rows/s", "cores": res["threads"], "kind": res["kind"],
-            "sample": f"{len(paths)} distinct config-2 buckets x {K} files read {reps}x ({total} input rows, "
+            "sample": f"{len(paths)} distinct config-5 buckets x {E2E_COMMITS} ZSTD files read {reps}x ({total} input rows, "
                       f"{res['seconds']:.2f} s), {res['impl']}, one reader per host thread "
                       f"({res['threads']} threads on {os.cpu_count()} logical CPUs)"}, res
+
+
+def workload_config(args, world: int):
+    return {"workload": f"HBM-resident leg (value, roofline): config2, {args.buckets} hash buckets x {K} delta files per GPU, "
+                        f"TPC-H lineitem schema, PK (l_orderkey,l_linenumber), last-write-wins, batch_size {BATCH_SIZE}; "
+                        f"end-to-end leg (e2e): config5-shaped full scan, {args.e2e_buckets} hash buckets x {E2E_COMMITS} delta files "
+                        f"x {E2E_ROWS_PER_BUCKET} rows per bucket ({args.e2e_buckets * E2E_ROWS_PER_BUCKET} input rows), PLAIN+ZSTD "
+                        f"Parquet as the LakeSoul writer emits it, the SAME table at every N (strong scaling), buckets sharded by "
+                        f"contiguous byte-balanced ranges; {min(args.e2e_distinct, args.e2e_buckets)} distinct bucket contents, the other "
+                        f"bucket ids are hard links to them (bounds the generation time; every bucket is opened, read, decoded and merged on its own)",
+            "rows_in_per_gpu": args.buckets * (BASE_ROWS + (K - 1) * DELTA_ROWS),
+            "e2e_rows_in": args.e2e_buckets * E2E_ROWS_PER_BUCKET,
+            "l2_policy": "inputs (~10 GB per GPU) are far larger than the 126 MB L2; no explicit flush",
+            "parallelism": f"bucket-sharded x{world}"}
+
+
+def reference_arm(args, rank: int, config):
+    """The reference's own CPU path (C++ port of the loser-tree reader; the Rust crate cannot be built here) on a
+    bounded sample of the same table: `cpu_buckets` config-5 buckets in the writer's layout, all host threads."""
+    if rank != 0:
+        return
+    root = table_root(args) + "_ref"
+    info = make_table(root, args.cpu_buckets, args.cpu_buckets, "E3", 0, 1, usable_cores(), links=False)
+    paths = [bucket_paths(root, "E3", b) for b in range(args.cpu_buckets)]
+    rows = [info["rows"][str(b)] for b in range(args.cpu_buckets)]
+    vals = []
+    for i in range(args.warmup + args.steps):
+        cb, res = run_cpu_baseline(paths, rows, args.cpu_threads)
+        if i >= args.warmup:
+            vals.append((cb, res))
+    cb = vals[-1][0]
+    v = float(np.median([c["value"] for c, _ in vals]))
+    cb["value"] = v
+    line = {"metric": "merge-on-read rows/sec", "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.median([r["seconds"] for _, r in vals]) * 1e3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "impl": "reference", "config": config, "cpu_baseline": cb, "statistic": "median over the timed steps",
+            "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    shutil.rmtree(root, ignore_errors=True)
 
 
 def main():
@@ -329,32 +478,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": f"config2: {args.buckets} hash buckets x {K} delta files per GPU, TPC-H lineitem schema, "
-                          f"PK (l_orderkey,l_linenumber), last-write-wins, batch_size {BATCH_SIZE}",
-              "rows_in_per_gpu": args.buckets * (BASE_ROWS + (K - 1) * DELTA_ROWS),
-              "l2_policy": "inputs (~10 GB per GPU) are far larger than the 126 MB L2; no explicit flush",
-              "parallelism": f"bucket-sharded x{world}"}
-
+    config = workload_config(args, world)
     if args.impl == "reference":
-        # the reference's own CPU path (C++ port of the loser-tree reader; the Rust crate cannot be built here)
-        if rank != 0:
-            return
-        tmp = args.data_dir or tempfile.mkdtemp(prefix="lsb_bench_")
-        spec, paths, rows = make_e2e_files(args.cpu_buckets, tmp)
-        vals = []
-        for i in range(args.warmup + args.steps):
-            cb, res = run_cpu_baseline(spec, paths, rows, args.cpu_buckets, args.cpu_threads)
-            if i >= args.warmup:
-                vals.append((cb, res))
-        cb = vals[-1][0]
-        v = float(np.mean([c["value"] for c, _ in vals]))
-        cb["value"] = v
-        line = {"metric": "merge-on-read rows/sec", "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": float(np.mean([r["seconds"] for _, r in vals]) * 1e3),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-                "impl": "reference", "config": config, "cpu_baseline": cb,
-                "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        reference_arm(args, rank, config)
         return
 
     import torch
@@ -367,20 +493,7 @@ def main():
     lib = load_library()
     if lib.lsb_init_device() < 0:
         raise RuntimeError(lib.lsb_last_error().decode())
-
-    # ---- bucket ranges balanced by bytes (NCCL all-gather of per-bucket sizes) ------------------
-    nb_total = args.buckets * world
-    my_sizes = torch.full((args.buckets,), float(BASE_ROWS + (K - 1) * DELTA_ROWS) * 169.0, device="cuda")
-    if world > 1:
-        gathered = [torch.empty_like(my_sizes) for _ in range(world)]
-        dist.all_gather(gathered, my_sizes)
-        sizes = torch.cat(gathered).cpu().numpy()
-    else:
-        sizes = my_sizes.cpu().numpy()
     from lakesoul_b200.sharding import balanced_ranges
-    ranges = balanced_ranges(sizes, world)
-    lo, hi = ranges[rank]
-    shard = Shard(hi - lo, seed=20260921 + 2000 + rank)
 
     def barrier():
         torch.cuda.synchronize()
@@ -388,6 +501,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ============ HBM-resident leg: `value`, `roofline` ===============================================
+    # bucket ranges balanced by bytes (NCCL all-gather of per-bucket sizes)
+    my_sizes = torch.full((args.buckets,), float(BASE_ROWS + (K - 1) * DELTA_ROWS) * 169.0, device="cuda")
+    if world > 1:
+        gathered = [torch.empty_like(my_sizes) for _ in range(world)]
+        dist.all_gather(gathered, my_sizes)
+        sizes = torch.cat(gathered).cpu().numpy()
+    else:
+        sizes = my_sizes.cpu().numpy()
+    lo, hi = balanced_ranges(sizes, world)[rank]
+    shard = Shard(hi - lo, seed=20260921 + 2000 + rank)
     for _ in range(args.warmup):
         shard.step()
     rec = {"merge_ms": [], "gather_ms": []}
@@ -416,12 +540,15 @@ def main():
     ms_total = float(ms.item())
     rows_in_all, rows_out_all = int(tot[0].item()), int(tot[1].item())
     value = rows_in_all / (ms_total / 1e3)
+    U = rows_out // args.steps
+    mb, gb = shard.algorithmic_bytes(U)
+    merge_ms = float(np.mean(rec["merge_ms"]))
+    gather_ms = float(np.mean(rec["gather_ms"]))
+    del shard
+    torch.cuda.empty_cache()
 
+    line = None
     if rank == 0:
-        U = rows_out // args.steps
-        mb, gb = shard.algorithmic_bytes(U)
-        merge_ms = float(np.mean(rec["merge_ms"]))
-        gather_ms = float(np.mean(rec["gather_ms"]))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -431,7 +558,7 @@ def main():
         ach = (mb + gb) / ((merge_ms + gather_ms) / 1e3) / 1e9
         traffic = None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)))
             traffic = tj["dram_bytes_per_step"]
         except Exception:
             pass
@@ -445,58 +572,101 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
                 "config": config, "rows_out_per_step": rows_out_all // args.steps, "gpu_launches": launches,
-                "clocks": clocks, "roofline": roofline, "wall_s": wall}
-        e2e_ctx = None
-        if not args.no_e2e or not args.no_cpu:
-            tmp = args.data_dir or tempfile.mkdtemp(prefix="lsb_bench_")
-            e2e_ctx = make_e2e_files(max(args.e2e_buckets, args.cpu_buckets), tmp)
-        if not args.no_e2e:
-            spec, paths, rows = e2e_ctx
-            args.e2e_threads = args.e2e_threads or usable_cores()
-            paths_e, rows_e = paths[:args.e2e_buckets], rows[:args.e2e_buckets]
-            run_e2e(spec, paths_e[:min(4, len(paths_e))], args.e2e_threads)  # warm-up (pinned pool, page cache)
-            best = None
-            for _ in range(3):
-                r = run_e2e(spec, paths_e, args.e2e_threads)
-                if best is None or r[0] < best[0]:
-                    best = r
-            dt, out_rows, h2d, d2h, e_launch = best
-            py_val = sum(rows_e) / dt
-            dec = run_e2e.last_decode
-            harness = "python ctypes harness (lakesoul_b200.NativeIOReader)"
-            host_busy = None
-            nat = run_e2e_native(spec, paths_e, args.e2e_threads)
-            if nat is not None and nat["rows_out"] == out_rows:
-                dt, h2d, d2h, e_launch = nat["seconds"], nat["h2d_bytes"], nat["d2h_bytes"], nat["kernel_launches"]
-                dec = (nat["device_decoded_pages"], nat["host_decoded_files"])
-                harness = "native task executor tools/cabi_driver.cc (C-ABI calls only)"
-                host_busy = nat.get("cpu_seconds", 0.0) / nat["seconds"]
-            line["e2e"] = {"value": sum(rows_e) / dt, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                           "rows_in": sum(rows_e), "rows_out": out_rows, "seconds": dt, "gpu_launches": e_launch,
-                           "device_decoded_pages": dec[0], "host_decoded_files": dec[1],
-                           "consumer": harness, "python_harness_value": py_val, "task_slots": args.e2e_threads,
-                           "host_cores_busy": host_busy,
-                           "how": f"{len(paths_e)} config-2 buckets (Parquet PLAIN, uncompressed) read through the "
-                                  f"lakesoul-io-c C-ABI by {args.e2e_threads} concurrent per-bucket readers (one per task slot); "
-                                  "pread into pinned memory, every file image sent to the GPU while the next one is read, "
-                                  "device page decode + merge/gather kernels, one D2H of the Arrow buffers consumed by "
-                                  "the caller; best of 3"}
-        if not args.no_cpu:
-            spec, paths, rows = e2e_ctx
-            try:
-                cb, _ = run_cpu_baseline(spec, paths, rows, args.cpu_buckets, args.cpu_threads)
-                line["cpu_baseline"] = cb
-            except Exception as e:  # the baseline is reporting only
-                line["cpu_baseline"] = {"value": None, "unit": "rows/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+                "clocks": clocks, "roofline": roofline, "wall_s": wall,
+                "scaling_note": "value = HBM-resident kernels on one config-2 shard per GPU (weak: nothing is exchanged); "
+                                "e2e = one fixed table read from files by all ranks (strong, e2e.scaling)"}
+
+    # ============ end-to-end leg: files -> C-ABI -> host Arrow batches, every rank =====================
+    if not args.no_e2e:
+        root = table_root(args)
+        B = args.e2e_buckets
+        D = min(args.e2e_distinct, B)
+        cores_total = usable_cores()
+        procs = max(1, cores_total // world)
+        t_gen0 = time.perf_counter()
+        info = make_table(root, B, D, "E3", rank, world, procs, links=False)
+        barrier()
+        make_table(root, B, D, "E3", rank, world, procs, links=True)
+        barrier()
+        gen_s = time.perf_counter() - t_gen0
+        # real per-bucket byte sizes: every rank stats a slice, NCCL all-reduce, same split everywhere
+        mine = torch.zeros(B, dtype=torch.float64, device="cuda")
+        for b in range(rank, B, world):
+            mine[b] = float(sum(os.path.getsize(p) for p in bucket_paths(root, "E3", b)))
+        if world > 1:
+            dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+        bsizes = mine.cpu().numpy()
+        lo, hi = balanced_ranges(bsizes, world)[rank]
+        paths = [bucket_paths(root, "E3", b) for b in range(lo, hi)]
+        cpus, numa = rank_cpus(local_rank, world)
+        slots = args.e2e_threads or max(2, min(cores_total // world, len(cpus), args.e2e_slot_cap))
+        readers = NativeReaders(paths, slots, cpus, e2e_env("E3"))
+        readers.run_pass(min(len(paths), 2 * slots))  # warm-up: pinned pool, arenas, page cache
+        passes = []
+        for _ in range(args.e2e_passes):
+            barrier()
+            r = readers.run_pass()
+            t = torch.tensor([r["seconds"]], dtype=torch.float64, device="cuda")
+            c = torch.tensor([r["rows_in"], r["rows_out"], r["h2d_bytes"], r["d2h_bytes"], r["kernel_launches"],
+                              r["device_decoded_pages"], r["device_decompressed_pages"], r["host_decoded_files"],
+                              int(r["cpu_seconds"] * 1e6)], dtype=torch.int64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            passes.append((float(t.item()), [int(x) for x in c.tolist()], r["seconds"]))
+        readers.close()
+        if rank == 0:
+            secs = sorted(p[0] for p in passes)
+            med = secs[len(secs) // 2]
+            cnt = passes[0][1]
+            line["e2e"] = {"value": cnt[0] / med, "unit": "rows/s", "h2d_bytes_per_step": cnt[2], "d2h_bytes_per_step": cnt[3],
+                           "scaling": "strong", "encoding": "E3 (PLAIN + ZSTD, dictionary off: multipart_writer.rs:121-133)",
+                           "rows_in": cnt[0], "rows_out": cnt[1], "seconds": med, "pass_seconds": [p[0] for p in passes],
+                           "statistic": f"median of {len(passes)} passes over all {B} buckets, each pass = max over ranks",
+                           "gpu_launches": cnt[4], "launches_per_bucket": cnt[4] / B, "device_decoded_pages": cnt[5],
+                           "device_decompressed_pages": cnt[6], "host_decoded_files": cnt[7],
+                           "host_cores_busy": cnt[8] / 1e6 / med, "task_slots_per_rank": slots, "ranks": world,
+                           "rank0_cpus": f"{len(cpus)} CPUs of NUMA node {numa}", "buckets": B, "distinct_buckets": D,
+                           "table_bytes": float(bsizes.sum()), "generation_s": gen_s,
+                           "consumer": "native task executor tools/cabi_driver.cc (C-ABI calls only), one process per GPU",
+                           "how": "every rank reads its byte-balanced contiguous bucket range through the lakesoul-io-c C-ABI, one reader "
+                                  "per bucket on a pool of task slots pinned to the GPU's NUMA node; pread into pinned memory, file images "
+                                  "sent to the GPU while the next file is read, device page decompression + decode + merge + gather, "
+                                  "D2H of the Arrow buffers consumed by the caller; barrier in front of every pass, time = max over ranks"}
+        # other file layouts beside the headline (1 GPU only: the same first buckets in E1 / E2 / E3)
+        if world == 1 and args.side_buckets > 0:
+            nb_side = min(args.side_buckets, B)
+            side = {}
+            make_table(root, nb_side, nb_side, "E1,E2", 0, 1, procs, links=False)
+            for enc in ("E3", "E1", "E2"):
+                sp = [bucket_paths(root, enc, b) for b in range(nb_side)]
+                rd = NativeReaders(sp, slots, cpus, e2e_env(enc))
+                rd.run_pass(min(nb_side, 2 * slots))
+                rs = [rd.run_pass() for _ in range(args.e2e_passes)]
+                rd.close()
+                rs.sort(key=lambda x: x["seconds"])
+                m = rs[len(rs) // 2]
+                side[enc] = {"value": m["rows_in"] / m["seconds"], "seconds": m["seconds"], "rows_in": m["rows_in"],
+                             "device_decompressed_pages": m["device_decompressed_pages"],
+                             "host_decoded_files": m["host_decoded_files"], "host_cores_busy": m["cpu_seconds"] / m["seconds"]}
+            line["e2e"]["layouts"] = {"buckets": nb_side, "statistic": f"median of {args.e2e_passes}",
+                                      "E1 = PLAIN uncompressed, E2 = dictionary + SNAPPY (pyarrow/Spark default), E3 = PLAIN + ZSTD": side}
+        barrier()
+        if rank == 0:
+            if not args.no_cpu and world == 1:
+                try:
+                    nb_cpu = min(args.cpu_buckets, D)
+                    cp = [bucket_paths(root, "E3", b) for b in range(nb_cpu)]
+                    cb, _ = run_cpu_baseline(cp, [info["rows"].get(str(b), E2E_ROWS_PER_BUCKET) for b in range(nb_cpu)],
+                                             args.cpu_threads)
+                    line["cpu_baseline"] = cb
+                except Exception as e:  # the baseline is reporting only
+                    line["cpu_baseline"] = {"value": None, "unit": "rows/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+            if not args.keep_data:
+                shutil.rmtree(root, ignore_errors=True)
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
-        # rank 0 is still measuring the end-to-end and CPU legs on the host cores: the other ranks wait on the
-        # rendezvous store (a blocking socket read) instead of spinning in an NCCL barrier
-        store = dist.distributed_c10d._get_default_store()
-        if rank == 0:
-            store.set("lsb_bench_done", "1")
-        else:
-            store.wait(["lsb_bench_done"])
         dist.barrier()
         dist.destroy_process_group()
 

@@ -20,6 +20,9 @@
 // loads), values inside a run are addressed directly by lane.
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "decode_types.h"
 #include "zstd_decode.h"
 
@@ -820,6 +823,8 @@ __device__ __forceinline__ int64_t huf_stream_fast(const uint16_t* huf, int log,
 //   execute warp 0, in order, 32 sequences per round: repeat offsets (lane 0), output positions (scan), literal runs
 //           in parallel, matches whose source lies before the round's output in parallel, the rest one by one
 constexpr int kZstdThreads = 64;
+// development profile (LAKESOUL_B200_ZSTD_PROFILE=1): cycles of the three phases summed over the pages >= 256 KiB
+__device__ unsigned long long g_zstd_prof[8];
 __global__ void __launch_bounds__(kZstdThreads) zstd_pages_kernel(const PqZstdPage* pages, const ZstdBlockDesc* blocks_all,
                                                                   ZstdBlockPlan* plans_all, ZstdTables* tables_all, uint8_t* lit_all,
                                                                   uint64_t* seq_all, int32_t* err) {
@@ -843,6 +848,8 @@ __global__ void __launch_bounds__(kZstdThreads) zstd_pages_kernel(const PqZstdPa
   __shared__ int s_have_prev;
   if (tid == 0) { s_fail = 0; s_have_prev = 0; }
   __syncthreads();
+  const bool prof = pg.raw_size >= (256 << 10);
+  const long long t_start = clock64();
   {
     int64_t lit_total = 0, seq_total = 0;  // meaningful in thread 0
     for (int k = 0; k < nb; ++k) {
@@ -875,6 +882,7 @@ __global__ void __launch_bounds__(kZstdThreads) zstd_pages_kernel(const PqZstdPa
     if (tid == 0) atomicExch(err, kErrBadPage);
     return;
   }
+  const long long t_plan = clock64();
   // ---- entropy: 8 roles per block --------------------------------------------------------------
   for (int k = tid >> 3; k < nb; k += kZstdThreads >> 3) {
     if (blocks[k].type != 2) continue;
@@ -904,6 +912,7 @@ __global__ void __launch_bounds__(kZstdThreads) zstd_pages_kernel(const PqZstdPa
     if (tid == 0) atomicExch(err, kErrBadPage);
     return;
   }
+  const long long t_entropy = clock64();
   if (tid >= 32) return;
   // ---- execute: warp 0 ----------------------------------------------------------------------------
   const int lane = tid;
@@ -997,11 +1006,30 @@ __global__ void __launch_bounds__(kZstdThreads) zstd_pages_kernel(const PqZstdPa
     __syncwarp();
   }
   if (op != cap && lane == 0) atomicExch(err, kErrBadPage);
+  if (prof && lane == 0) {
+    const long long t_end = clock64();
+    atomicAdd(&g_zstd_prof[0], (unsigned long long)(t_plan - t_start));
+    atomicAdd(&g_zstd_prof[1], (unsigned long long)(t_entropy - t_plan));
+    atomicAdd(&g_zstd_prof[2], (unsigned long long)(t_end - t_entropy));
+    atomicAdd(&g_zstd_prof[3], 1ull);
+    atomicMax(&g_zstd_prof[4], (unsigned long long)(t_plan - t_start));
+    atomicMax(&g_zstd_prof[5], (unsigned long long)(t_entropy - t_plan));
+    atomicMax(&g_zstd_prof[6], (unsigned long long)(t_end - t_entropy));
+  }
 }
 
 void launch_zstd_pages(const PqZstdPage* pages, int npages, const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, ZstdTables* tables,
                        uint8_t* lit, uint64_t* seq, int32_t* err, cudaStream_t s) {
   if (npages > 0) zstd_pages_kernel<<<npages, kZstdThreads, 0, s>>>(pages, blocks, plans, tables, lit, seq, err);
+  static const bool prof = [] { const char* v = getenv("LAKESOUL_B200_ZSTD_PROFILE"); return v && *v == '1'; }();
+  if (prof && npages > 0) {
+    unsigned long long h[8] = {0}, z[8] = {0};
+    cudaStreamSynchronize(s);
+    cudaMemcpyFromSymbol(h, g_zstd_prof, sizeof(h));
+    cudaMemcpyToSymbol(g_zstd_prof, z, sizeof(z));
+    if (h[3]) fprintf(stderr, "ZSTDPROF pages>=256K %llu  mean kcycles plan %.0f entropy %.0f execute %.0f  max plan %.0f entropy %.0f execute %.0f\n",
+                      h[3], h[0] / 1e3 / h[3], h[1] / 1e3 / h[3], h[2] / 1e3 / h[3], h[4] / 1e3, h[5] / 1e3, h[6] / 1e3);
+  }
 }
 
 // ---- launchers (called from device_scan.cc) -----------------------------------------------------

@@ -962,6 +962,8 @@ void DeviceScan::Impl::merge_and_gather() {
       vc.dst_data = static_cast<uint8_t*>(d_data[c]);
       vc.dst_valid = d_valid;
       vc.batch_data_start = reinterpret_cast<int64_t*>(d_region + sg.bstart);
+      // Joined* operators gather from a computed scratch column addressed by output row, not by file row
+      vc.direct = (general && general_data(general, c, nullptr) != nullptr) ? 1 : 0;
       vars.push_back(vc);
     } else {
       FixedCol fc{};
@@ -997,9 +999,15 @@ void DeviceScan::Impl::merge_and_gather() {
       }
     }
   }
+  // error flag of the gather kernels (a look-back scan that never saw its predecessor publish), same wait
+  std::shared_ptr<uint8_t> h_gerr = pinned_alloc(64);
+  *reinterpret_cast<int32_t*>(h_gerr.get()) = 0;
+  SCAN_CUDA(cudaMemcpyAsync(h_gerr.get(), plan_error_flag_dev(plan), sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   trace_mark("gather_enqueue");
   SCAN_CUDA(stream_wait(stream));
   trace_mark("wait_gather");
+  if (*reinterpret_cast<const int32_t*>(h_gerr.get()) != 0)
+    fail("gather kernel reported error code " + std::to_string(*reinterpret_cast<const int32_t*>(h_gerr.get())));
   ctr.gather_ms += now_ms() - t1;
   const double t2 = now_ms();
   // string bytes: exact sizes are known now; one pinned block for all columns

@@ -19,9 +19,11 @@
 #include "general_merge.h"
 
 #include <algorithm>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <stdexcept>
 
 namespace lsb {
@@ -242,6 +244,8 @@ struct PlanDev {
   int64_t* tile_out;              // level-0 tiles + 1
   uint32_t* win_tmp;              // N
   uint32_t* win;                  // N
+  uint8_t* wfile_tmp;             // N: file (inside its bucket) of every winner, written next to win_tmp
+  uint8_t* wfile;                 // N: dense, parallel to win
   int64_t* out_base;              // nb+1
   int64_t* batch_base;            // nb+1
   const int64_t* dense_base;      // F+1: prefix of file_rows (rows packed without padding)
@@ -601,6 +605,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) tile_kernel(PlanDev P, PkDesc
   }
   const int64_t gstart = B.row_base + s_tile_start;
   uint32_t* wt = P.win_tmp + gstart;
+  uint8_t* wf = P.wfile_tmp + gstart;
   for (int q = q0; q < q1; ++q) {
     const int e = in[q];
     const KeyT kq = K[e];
@@ -609,7 +614,9 @@ __global__ void __launch_bounds__(kTileThreads, 3) tile_kernel(PlanDev P, PkDesc
     else end = has_next ? ops.ne(kq, next_key) : true;
     if (end) {
       const int j = upper_idx(seg_start, k, e);
-      wt[off++] = (uint32_t)(frb[j] + seg_lo[j] + (e - seg_start[j]));
+      wt[off] = (uint32_t)(frb[j] + seg_lo[j] + (e - seg_start[j]));
+      wf[off] = (uint8_t)j;  // the string gather stages per-file source windows: no search per column there
+      ++off;
     }
   }
   if (tid == 0) {
@@ -726,7 +733,9 @@ __global__ void __launch_bounds__(256) compact_kernel(PlanDev P) {
   const int cnt = P.tile_cnt[t];
   const uint32_t* src = P.win_tmp + P.tile_gstart[t];
   uint32_t* dst = P.win + P.tile_out[t];
-  for (int x = threadIdx.x; x < cnt; x += blockDim.x) dst[x] = src[x];
+  const uint8_t* fsrc = P.wfile_tmp + P.tile_gstart[t];
+  uint8_t* fdst = P.wfile + P.tile_out[t];
+  for (int x = threadIdx.x; x < cnt; x += blockDim.x) { dst[x] = src[x]; fdst[x] = fsrc[x]; }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -739,6 +748,9 @@ struct GatherGeom {
   const uint32_t* win;
   const int64_t* out_base;
   const int64_t* batch_base;
+  const uint8_t* win_file;        // file (inside its bucket) of every plan winner, or nullptr
+  const BucketDesc* buckets;      // file range of every bucket (windowed string gather)
+  const int64_t* file_row_base;   // first global row of every file
   int32_t nb;
   int32_t batch_size;
   int32_t chunks_per_batch;
@@ -984,8 +996,11 @@ struct VarScan {
   unsigned long long* incl;   // [col][chunk]: bytes up to and including the chunk
   int64_t stride;             // chunks per column
   int32_t ncols;
+  int32_t* err;               // plan error flag (kErrScanStall when a predecessor never publishes)
 };
 constexpr unsigned long long kScanFlag = 1ull << 63;
+constexpr int kErrScanStall = 2;
+constexpr int kScanSpinLimit = 1 << 22;  // x 40+ ns: seconds, far beyond any healthy wait
 __device__ __forceinline__ unsigned long long ld_scan(const unsigned long long* p) {
   return *reinterpret_cast<const volatile unsigned long long*>(p);
 }
@@ -996,13 +1011,14 @@ __device__ __forceinline__ void st_scan(unsigned long long* p, unsigned long lon
 // Executed by one warp: publishes `tot` for `chunk`, returns the bytes before the chunk (*c0) and the bytes
 // of the chunk's batch before it (*rel; the c_in preceding chunks belong to the same batch).
 __device__ __forceinline__ void scan_lookback(unsigned long long* agg, unsigned long long* incl, int64_t chunk, int c_in,
-                                              int tot, long long* c0, long long* rel) {
+                                              int tot, long long* c0, long long* rel, int32_t* err) {
   const int lane = threadIdx.x & 31;
   if (lane == 0) st_scan(agg + chunk, kScanFlag | (unsigned long long)tot);
   unsigned long long excl = 0, relv = 0;
   int64_t idx = chunk - 1;
   int rel_left = c_in;  // totals still to be added to relv, nearest chunk first
   bool have_excl = chunk == 0;
+  int spins = 0;
   while (!have_excl || rel_left > 0) {
     // 32 predecessors per round trip: both status words of each, so that one trip usually settles everything
     const int64_t my = idx - lane;
@@ -1015,7 +1031,16 @@ __device__ __forceinline__ void scan_lookback(unsigned long long* agg, unsigned 
     const int n_excl = have_excl ? 0 : first_incl;
     const int n_need = max(n_excl, min(rel_left, 32));
     const unsigned need = n_need >= 32 ? 0xffffffffu : ((1u << n_need) - 1);
-    if ((m_agg & need) != need) { __nanosleep(40); continue; }  // a predecessor has not published yet
+    if ((m_agg & need) != need) {  // a predecessor has not published yet
+      // blocks are dispatched in index order, so the wait is short; should that ever not hold (preemption, MPS
+      // time slicing), give up with an error flag instead of spinning forever
+      if (++spins > kScanSpinLimit) {
+        if (lane == 0) atomicExch(err, kErrScanStall);
+        break;
+      }
+      __nanosleep(40);
+      continue;
+    }
     unsigned long long c = 0, r = 0;
     if (my >= 0) {
       if (!have_excl) {
@@ -1093,7 +1118,7 @@ __global__ void __launch_bounds__(kGatherThreads) var_write_kernel(GatherGeom G,
   }
   if (threadIdx.x == 0) s_off[nloc] = tot;
   // publish the chunk total, then resolve the chunk's position by looking back
-  if (threadIdx.x < 32) scan_lookback(agg, incl, chunk, c_in, tot, &s_c0, &s_rel);
+  if (threadIdx.x < 32) scan_lookback(agg, incl, chunk, c_in, tot, &s_c0, &s_rel, S.err);
   __syncthreads();
   if (!live) return;
   const int64_t c0 = s_c0;
@@ -1152,6 +1177,319 @@ __global__ void __launch_bounds__(kGatherThreads) var_write_kernel(GatherGeom G,
     __syncthreads();
     w0 = w1;
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// Windowed string gather (TMA bulk copies).
+// The winners of ONE file are monotone in row order, so the bytes a chunk needs from file j are one
+// contiguous window [offs[first winner], offs[last winner + 1]) of the column's byte buffer -- losers in
+// between included (about 1/density - 1 extra bytes). Per piece of output (<= kWinOutBytes):
+//   1. every row of the piece folds its source range into its file's window (shared-memory atomics);
+//   2. warp 0 lays the windows out in shared memory (16-byte congruent with their global address) and
+//      issues one cp.async.bulk (global -> shared, mbarrier-completed) per window: fully coalesced DRAM
+//      reads and no thread is busy with the load; windows that do not fit are read directly as before;
+//   3. rows are moved shared -> shared into the output stage (address-congruent with the destination);
+//   4. the stage leaves with one cp.async.bulk shared -> global (+ <= 15 head / tail bytes by hand).
+// Replaces the sector-granular random DRAM reads of var_write_kernel (r01: 38 % long-scoreboard stalls).
+// ---------------------------------------------------------------------------------------
+constexpr int kWinDirect = INT32_MIN;    // s_wbase marker: this file's rows are read straight from HBM
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(smem_src)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int kWinMaxPieces = 64;
+constexpr bool kWindowGatherDefault = false;  // flipped once the windowed kernel beats the direct one
+
+template <int kOutLog2, int kInBytes>
+struct WinSmem {
+  static constexpr int kOutBytes = 1 << kOutLog2;
+  int32_t off[kRowsPerChunk + 1];     // chunk-relative destination offset of every row
+  int32_t src[kRowsPerChunk];         // bucket-relative source offset of every row
+  uint8_t file[kRowsPerChunk];        // file (inside the bucket) of every row
+  uint32_t frb[kMaxFilesPerBucket];   // first global row of the bucket's files
+  int32_t wlo[kMaxFilesPerBucket];    // piece: lowest source offset per file
+  int32_t whi[kMaxFilesPerBucket];    // piece: highest source end per file
+  int32_t wbase[kMaxFilesPerBucket];  // source offset o of file j lives at in[wbase[j] + o]; kWinDirect = not staged
+  int32_t pstart[kWinMaxPieces + 1];  // first row of every output piece
+  alignas(16) uint8_t in[kInBytes];
+  alignas(16) uint8_t out[kOutBytes + 16];
+  alignas(8) uint64_t bar;
+  int scan[kGatherThreads / 32 + 2];
+  long long c0, rel;
+  // chunk geometry, computed once by thread 0
+  int g_b, g_r_begin, g_rows, g_live;
+  long long g_gb, g_u0;
+};
+
+// n bytes src (shared window or HBM) -> dst (shared stage): byte head until dst is word aligned, words fed by
+// aligned source words through a funnel shift, byte tail. Loops, not predication: most rows are a few bytes.
+__device__ __forceinline__ void copy_row(uint8_t* dst, const uint8_t* src, int n) {
+  int head = (int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);
+  head = min(head, n);
+  for (int i = 0; i < head; ++i) dst[i] = src[i];
+  dst += head;
+  src += head;
+  n -= head;
+  const int nw = n >> 2;
+  if (nw > 0) {
+    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
+    if (sh == 0) {
+      for (int i = 0; i < nw; ++i) dw[i] = sw[i];
+    } else {
+      uint32_t lo = sw[0];
+      for (int i = 0; i < nw; ++i) {
+        const uint32_t hi = sw[i + 1];  // holds source bytes of this row (sh != 0): always readable
+        dw[i] = __funnelshift_r(lo, hi, sh);
+        lo = hi;
+      }
+    }
+  }
+  for (int i = nw * 4; i < n; ++i) dst[i] = src[i];
+}
+
+template <int kOutLog2, int kInBytes>
+__global__ void __launch_bounds__(kGatherThreads) var_window_kernel(GatherGeom G, const VarColSet* __restrict__ set,
+                                                                    VarScan S, int64_t total_batches) {
+  using Smem = WinSmem<kOutLog2, kInBytes>;
+  constexpr int kOutBytes = Smem::kOutBytes;
+  extern __shared__ __align__(16) unsigned char win_smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(win_smem_raw);
+  const int tid = threadIdx.x;
+  const int ci = (int)(blockIdx.x % (unsigned)S.ncols);
+  const int64_t chunk = blockIdx.x / (unsigned)S.ncols;
+  if (tid == 0) {
+    int b, r_begin, r_end, rows;
+    int64_t gb, u0;
+    sm.g_live = chunk_geometry(G, chunk, b, gb, u0, r_begin, r_end, rows) ? 1 : 0;
+    sm.g_b = b; sm.g_r_begin = r_begin; sm.g_rows = rows; sm.g_gb = gb; sm.g_u0 = u0;
+    mbar_init(&sm.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const bool live = sm.g_live != 0;
+  const int b = sm.g_b, r_begin = sm.g_r_begin, rows = sm.g_rows;
+  const int64_t gb = sm.g_gb, u0 = sm.g_u0;
+  const VarCol col = set->col[ci];
+  unsigned long long* agg = S.agg + (int64_t)ci * S.stride;
+  unsigned long long* incl = S.incl + (int64_t)ci * S.stride;
+  const uint32_t* win = col.win ? col.win : G.win;
+  const uint8_t* win_file = (col.win == nullptr) ? G.win_file : nullptr;
+  const int c_in = (int)(chunk % G.chunks_per_batch);
+  const BucketDesc& B = G.buckets[b];
+  const int k = B.k;
+  const uint8_t* src_base = col.src_data + col.src_data_base[b];
+  const int nloc = live ? min(rows - r_begin, kRowsPerChunk) : 0;  // rows of this chunk
+  if (!win_file) {
+    for (int j = tid; j < k; j += kGatherThreads) sm.frb[j] = (uint32_t)G.file_row_base[B.file_begin + j];
+    __syncthreads();
+  }
+  const int rl0 = tid * kRowsPerThread;
+  int len[kRowsPerThread];
+  int mine = 0;
+  unsigned vbits = 0;
+#pragma unroll
+  for (int x = 0; x < kRowsPerThread; ++x) {
+    len[x] = 0;
+    if (rl0 + x < nloc) {
+      const int64_t u = u0 + r_begin + rl0 + x;
+      const uint32_t g = win[u];
+      bool valid;
+      len[x] = var_row_len(col, g, valid);
+      sm.src[rl0 + x] = valid ? col.src_offsets[g] : 0;
+      sm.file[rl0 + x] = win_file ? win_file[u] : (valid ? (uint8_t)upper_idx(sm.frb, k, g) : (uint8_t)0);
+      vbits |= valid ? (1u << x) : 0u;
+    }
+    mine += len[x];
+  }
+  if (col.dst_valid && rl0 < ((nloc + 31) & ~31))
+    (col.dst_valid + gb * G.valid_stride)[(r_begin + rl0) >> 3] = (uint8_t)vbits;
+  int tot;
+  const int run0 = block_exclusive_scan<kGatherThreads>(mine, sm.scan, tot);
+  {
+    int run = run0;
+#pragma unroll
+    for (int x = 0; x < kRowsPerThread; ++x) {
+      if (rl0 + x < nloc) {
+        sm.off[rl0 + x] = run;
+        run += len[x];
+      }
+    }
+  }
+  if (tid == 0) sm.off[nloc] = tot;
+  if (tid < 32) scan_lookback(agg, incl, chunk, c_in, tot, &sm.c0, &sm.rel, S.err);
+  __syncthreads();
+  if (!live) return;
+  const int64_t c0 = sm.c0;
+  const int32_t rel = (int32_t)sm.rel;
+  int32_t* dst_off = col.dst_offsets + u0 + gb + r_begin;
+  for (int r = tid; r < nloc; r += kGatherThreads) dst_off[r] = rel + sm.off[r];
+  const bool last_chunk = r_begin + nloc == rows;
+  if (tid == 0) {
+    if (last_chunk) dst_off[nloc] = rel + tot;
+    if (c_in == 0) col.batch_data_start[gb] = c0 - rel;
+    if (last_chunk && gb == total_batches - 1) col.batch_data_start[total_batches] = c0 + tot;
+  }
+  // ---- output pieces: piece p covers stage-aligned bytes [p << kOutLog2, (p + 1) << kOutLog2) of mis + offset ----
+  uint8_t* dst_bytes = col.dst_data + c0;  // chunk-relative byte q lives at dst_bytes[q]
+  const int mis = (int)((reinterpret_cast<uintptr_t>(dst_bytes)) & 15);  // out[(mis + q) & (kOutBytes - 1)] <-> q
+  const int npieces = tot > 0 ? ((mis + tot - 1) >> kOutLog2) + 1 : 0;
+  const bool have_table = npieces <= kWinMaxPieces;
+  if (have_table) {
+    // first row of every piece: the row that owns the piece's first byte (rows are blocked per thread)
+    if (tid == 0) sm.pstart[0] = 0;
+    int run = run0;
+#pragma unroll
+    for (int x = 0; x < kRowsPerThread; ++x) {
+      if (len[x] > 0) {
+        const int p0 = (mis + run) >> kOutLog2, p1 = (mis + run + len[x] - 1) >> kOutLog2;
+        for (int pp = p0 + 1; pp <= p1; ++pp) sm.pstart[pp] = rl0 + x;
+        if (((mis + run) & (kOutBytes - 1)) == 0 && p0 > 0) sm.pstart[p0] = rl0 + x;
+      }
+      run += len[x];
+    }
+  }
+  uint32_t parity = 0;
+  for (int p = 0; p < npieces; ++p) {
+    const int w0 = p == 0 ? 0 : (p << kOutLog2) - mis;
+    const int w1 = min(tot, ((p + 1) << kOutLog2) - mis);
+    const int first_pad = (p == 0) ? mis : 0;  // later pieces start on a 16-byte boundary
+    // 1. per-file source windows of the piece
+    for (int j = tid; j < k; j += kGatherThreads) { sm.wlo[j] = INT32_MAX; sm.whi[j] = 0; }
+    __syncthreads();  // (also orders pstart / the previous piece's reads of `in`)
+    int r_lo, r_hi;
+    if (have_table) {
+      r_lo = sm.pstart[p];
+      r_hi = (p + 1 < npieces) ? sm.pstart[p + 1] : nloc - 1;
+    } else {
+      r_lo = upper_idx(sm.off, nloc + 1, w0);
+      r_hi = upper_idx(sm.off, nloc + 1, w1 - 1);
+    }
+    for (int r = r_lo + tid; r <= r_hi; r += kGatherThreads) {
+      const int a = max(sm.off[r], w0), e = min(sm.off[r + 1], w1);
+      if (e > a) {
+        const int so = sm.src[r] + (a - sm.off[r]);
+        const int j = sm.file[r];
+        atomicMin(&sm.wlo[j], so);
+        atomicMax(&sm.whi[j], so + (e - a));
+      }
+    }
+    __syncthreads();
+    // 2. layout + bulk loads (warp 0)
+    if (tid < 32) {
+      const int lane = tid;
+      const int per = (k + 31) >> 5;
+      int sizes[kMaxFilesPerBucket / 32];
+      int sum = 0;
+#pragma unroll
+      for (int x = 0; x < kMaxFilesPerBucket / 32; ++x) {
+        sizes[x] = 0;
+        const int j = lane * per + x;
+        if (x < per && j < k && sm.whi[j] > sm.wlo[j]) {
+          const uintptr_t a0 = reinterpret_cast<uintptr_t>(src_base + sm.wlo[j]);
+          const uintptr_t a1 = reinterpret_cast<uintptr_t>(src_base + sm.whi[j]);
+          sizes[x] = (int)(((a1 + 15) & ~(uintptr_t)15) - (a0 & ~(uintptr_t)15));
+          if (sizes[x] > kInBytes / 2) sizes[x] = -1;  // sparse winners of a big file: read its rows directly
+        }
+        sum += max(sizes[x], 0);
+      }
+      int inclv = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, inclv, d);
+        if (lane >= d) inclv += y;
+      }
+      int pos = inclv - sum;
+      uint32_t my_bytes = 0;
+#pragma unroll
+      for (int x = 0; x < kMaxFilesPerBucket / 32; ++x) {
+        const int j = lane * per + x;
+        if (x < per && j < k) {
+          if (sizes[x] > 0 && pos + sizes[x] <= kInBytes) {
+            const int lo_al = sm.wlo[j] - (int)(reinterpret_cast<uintptr_t>(src_base + sm.wlo[j]) & 15);
+            sm.wbase[j] = pos - lo_al;
+            my_bytes += (uint32_t)sizes[x];
+          } else {
+            sm.wbase[j] = kWinDirect;
+          }
+          pos += max(sizes[x], 0);
+        }
+      }
+      uint32_t total = my_bytes;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+      if (lane == 0) {
+        bulk_store_wait_read();  // the previous piece's bulk store has finished reading `out`
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&sm.bar, total);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int x = 0; x < kMaxFilesPerBucket / 32; ++x) {
+        const int j = lane * per + x;
+        if (x < per && j < k && sizes[x] > 0 && sm.wbase[j] != kWinDirect) {
+          const int lo_al = sm.wlo[j] - (int)(reinterpret_cast<uintptr_t>(src_base + sm.wlo[j]) & 15);
+          bulk_load(sm.in + sm.wbase[j] + lo_al, src_base + lo_al, (uint32_t)sizes[x], &sm.bar);
+        }
+      }
+    }
+    __syncthreads();
+    while (!mbar_try_wait(&sm.bar, parity)) {}
+    parity ^= 1;
+    // 3. rows: staged window (shared) or HBM -> output stage
+    for (int r = r_lo + tid; r <= r_hi; r += kGatherThreads) {
+      const int a = max(sm.off[r], w0), e = min(sm.off[r + 1], w1);
+      if (e > a) {
+        const int so = sm.src[r] + (a - sm.off[r]);
+        const int wb = sm.wbase[sm.file[r]];
+        const uint8_t* sp = (wb != kWinDirect) ? (sm.in + wb + so) : (src_base + so);
+        copy_row(sm.out + first_pad + (a - w0), sp, e - a);
+      }
+    }
+    fence_proxy_async();  // the stage was written through the generic proxy, the bulk store reads it asynchronously
+    __syncthreads();
+    // 4. flush: global address of out[first_pad] is dst_bytes + w0
+    uint8_t* gdst = dst_bytes + w0 - first_pad;  // 16-byte aligned
+    const int nbytes = first_pad + (w1 - w0);
+    const int v_lo = first_pad ? 16 : 0;  // bytes [0, first_pad) belong to the chunk before
+    const int v_hi = nbytes & ~15;
+    if (tid == 0 && v_hi > v_lo) bulk_store(gdst + v_lo, sm.out + v_lo, (uint32_t)(v_hi - v_lo));
+    if (first_pad) {
+      for (int t = first_pad + tid; t < min(16, nbytes); t += kGatherThreads) gdst[t] = sm.out[t];
+    }
+    for (int t = max(v_hi, v_lo) + tid; t < nbytes; t += kGatherThreads)
+      if (t >= first_pad) gdst[t] = sm.out[t];
+  }
+  if (tid == 0) bulk_store_wait_read();  // shared memory must outlive the last bulk store's reads
 }
 
 // device-wide exclusive scan int32 -> int64 (used by the winner compaction), chunk of 4096 per block
@@ -1231,6 +1569,8 @@ struct MergePlan {
   int32_t *d_tile_bucket = nullptr, *d_tile_idx = nullptr, *d_tile_cnt = nullptr;
   int64_t *d_tile_gstart = nullptr, *d_tile_out = nullptr;
   uint32_t *d_win_tmp = nullptr, *d_win = nullptr;
+  uint8_t *d_wfile_tmp = nullptr, *d_wfile = nullptr;
+  bool has_wfile = false;  // d_wfile matches d_win (merge path; the concat path leaves it unset)
   int64_t *d_out_base = nullptr, *d_batch_base = nullptr;
   int64_t* d_dense_base = nullptr;
   uint32_t* d_R = nullptr;     // general path (owned by GeneralMerge, borrowed here while it runs)
@@ -1252,10 +1592,8 @@ struct MergePlan {
   int64_t* d_sums = nullptr;
   FixedCol* d_cols = nullptr;
   int d_cols_cap = 0;
-  int64_t* d_chunk_sums = nullptr;
-  int64_t d_chunk_cap = 0;
-  struct VarColSet* d_varset = nullptr;
-  VarColSet h_varset;
+  std::vector<void*> var_scratch;        // look-back state + descriptor blocks of the string gathers
+  std::deque<VarColSet> h_varsets;       // host copies outlive the asynchronous descriptor uploads
   size_t smem_bytes = 0;
 };
 
@@ -1510,6 +1848,8 @@ MergePlan* plan_create(int nb, const int32_t* bucket_file_begin, const int64_t* 
     P->d_tile_out = dev_alloc<int64_t>(T0 + 1, stream);
     P->d_win_tmp = dev_alloc<uint32_t>(P->n_total, stream);
     P->d_win = dev_alloc<uint32_t>(P->n_total, stream);
+    P->d_wfile_tmp = dev_alloc<uint8_t>(P->n_total, stream);
+    P->d_wfile = dev_alloc<uint8_t>(P->n_total, stream);
     P->d_out_base = dev_alloc<int64_t>(nb + 1, stream);
     P->d_batch_base = dev_alloc<int64_t>(nb + 1, stream);
     P->d_err = dev_alloc<int32_t>(1, stream);
@@ -1567,10 +1907,11 @@ void plan_destroy(MergePlan* P) {
   if (!P) return;
   cudaStream_t st = P->alloc_stream;
   void* ptrs[] = {P->d_buckets, P->d_file_rows, P->d_file_row_base, P->d_splits, P->d_mlist, P->d_tile_bucket,
-                  P->d_tile_idx, P->d_tile_cnt, P->d_tile_gstart, P->d_tile_out, P->d_win_tmp, P->d_win,
+                  P->d_tile_idx, P->d_tile_cnt, P->d_tile_gstart, P->d_tile_out, P->d_win_tmp, P->d_win, P->d_wfile_tmp, P->d_wfile,
                   P->d_out_base, P->d_batch_base, P->d_dense_base, P->d_ctmp, P->d_err, P->d_len, P->d_doff,
-                  P->d_sums, P->d_cols, P->d_chunk_sums, P->d_varset};
+                  P->d_sums, P->d_cols};
   for (void* p : ptrs) dev_free(p, st);
+  for (void* p : P->var_scratch) dev_free(p, st);
   delete P;
 }
 
@@ -1588,6 +1929,8 @@ static PlanDev plan_dev(const MergePlan* P) {
   D.tile_out = P->d_tile_out;
   D.win_tmp = P->d_win_tmp;
   D.win = P->d_win;
+  D.wfile_tmp = P->d_wfile_tmp;
+  D.wfile = P->d_wfile;
   D.out_base = P->d_out_base;
   D.batch_base = P->d_batch_base;
   D.dense_base = P->d_dense_base;
@@ -1643,6 +1986,7 @@ void plan_merge(MergePlan* P, const PkDesc& pk, cudaStream_t stream) {
   P->last_pk = pk;
   P->merged = true;
   P->synced = false;
+  P->has_wfile = true;
 }
 
 void plan_identity(MergePlan* P, cudaStream_t stream) {
@@ -1659,6 +2003,7 @@ void plan_identity(MergePlan* P, cudaStream_t stream) {
   P->stats.launches = launches;
   P->merged = true;
   P->synced = false;
+  P->has_wfile = false;
 }
 
 const std::vector<int64_t>& plan_sync_counts(MergePlan* P, cudaStream_t stream) {
@@ -1697,6 +2042,7 @@ int plan_num_buckets(const MergePlan* P) { return P->nb; }
 int plan_batch_size(const MergePlan* P) { return P->batch_size; }
 const uint32_t* plan_winners(const MergePlan* P) { return P->d_win; }
 const int64_t* plan_out_base_dev(const MergePlan* P) { return P->d_out_base; }
+const int32_t* plan_error_flag_dev(const MergePlan* P) { return P->d_err; }
 int64_t plan_valid_stride_bytes(const MergePlan* P) {
   return (((int64_t)P->batch_size + 7) / 8 + 63) / 64 * 64;
 }
@@ -1708,6 +2054,9 @@ static GatherGeom make_geom(const MergePlan* P) {
   G.win = P->d_win;
   G.out_base = P->d_out_base;
   G.batch_base = P->d_batch_base;
+  G.win_file = P->has_wfile ? P->d_wfile : nullptr;
+  G.buckets = P->d_buckets;
+  G.file_row_base = P->d_file_row_base;
   G.nb = P->nb;
   G.batch_size = P->batch_size;
   G.chunks_per_batch = (P->batch_size + kRowsPerChunk - 1) / kRowsPerChunk;
@@ -1742,15 +2091,6 @@ void gather_fixed(MergePlan* P, const FixedCol* cols, int ncols, cudaStream_t st
 
 void gather_var_multi(MergePlan* P, const VarCol* cols, int ncols, cudaStream_t stream);
 
-static void ensure_var_scratch(MergePlan* P, int64_t words, cudaStream_t stream) {
-  if (P->d_chunk_cap < words) {
-    dev_free(P->d_chunk_sums, stream);
-    P->d_chunk_sums = dev_alloc<int64_t>(words, stream);
-    P->d_chunk_cap = words;
-  }
-  if (!P->d_varset) P->d_varset = dev_alloc<VarColSet>(1, stream);
-}
-
 // Fixed-width and variable-width columns of one scan: 2 launches.
 void gather_all(MergePlan* P, const FixedCol* fixed, int nfixed, const VarCol* vars, int nvars, cudaStream_t stream) {
   if (nfixed > 0) gather_fixed(P, fixed, nfixed, stream);
@@ -1773,26 +2113,59 @@ void gather_var_multi(MergePlan* P, const VarCol* cols, int ncols, cudaStream_t 
   if (total_batches == 0 || ncols <= 0) return;
   GatherGeom G = make_geom(P);
   const int64_t chunks = total_batches * G.chunks_per_batch;
-  for (int c0 = 0; c0 < ncols; c0 += kMaxVarCols) {
-    const int n = std::min(kMaxVarCols, ncols - c0);
-    if (chunks * n > 0x7fffffffll) {
-      g_last_error = "too many string chunks in one scan";
-      throw std::runtime_error(g_last_error);
+  // LAKESOUL_B200_WINDOW_GATHER=0/1 overrides the default
+  static const bool no_windows = [] { const char* v = getenv("LAKESOUL_B200_WINDOW_GATHER"); return v ? *v != '1' : !kWindowGatherDefault; }();
+  static thread_local int attr_device = -1;
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  if (attr_device != cur_dev) {
+    attr_device = cur_dev;
+    LSB_CUDA(cudaFuncSetAttribute(var_window_kernel<14, 24576>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(WinSmem<14, 24576>)));
+    LSB_CUDA(cudaFuncSetAttribute(var_window_kernel<13, 16384>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(WinSmem<13, 16384>)));
+  }
+  // columns whose rows are file rows of the plan take the windowed kernel; computed columns (merge operators:
+  // rows of a scan-wide scratch column) keep the direct one. Each group: one launch per 16 columns.
+  for (int pass = 0; pass < 2; ++pass) {
+    std::vector<VarCol> group;
+    for (int i = 0; i < ncols; ++i) {
+      const bool windowed = !cols[i].direct && !no_windows;
+      if (windowed == (pass == 0)) group.push_back(cols[i]);
     }
-    // look-back scan state: two status words per (column, chunk), zeroed = "not published"
-    const int64_t words = 2 * chunks * n;
-    ensure_var_scratch(P, words, stream);
-    LSB_CUDA(cudaMemsetAsync(P->d_chunk_sums, 0, sizeof(int64_t) * words, stream));
-    VarScan S{};
-    S.agg = reinterpret_cast<unsigned long long*>(P->d_chunk_sums);
-    S.incl = S.agg + chunks * n;
-    S.stride = chunks;
-    S.ncols = n;
-    VarColSet& set = P->h_varset;
-    set.n = n;
-    for (int i = 0; i < n; ++i) set.col[i] = cols[c0 + i];
-    LSB_CUDA(cudaMemcpyAsync(P->d_varset, &set, sizeof(VarColSet), cudaMemcpyHostToDevice, stream));
-    var_write_kernel<<<(unsigned)(chunks * n), kGatherThreads, 0, stream>>>(G, P->d_varset, S, total_batches);
+    for (size_t c0 = 0; c0 < group.size(); c0 += kMaxVarCols) {
+      const int n = (int)std::min<size_t>(kMaxVarCols, group.size() - c0);
+      if (chunks * n > 0x7fffffffll) {
+        g_last_error = "too many string chunks in one scan";
+        throw std::runtime_error(g_last_error);
+      }
+      // look-back scan state: two status words per (column, chunk), zeroed = "not published"; every launch of a
+      // gather has its own state and descriptor block (the launches are asynchronous)
+      const int64_t words = 2 * chunks * n;
+      int64_t* state = dev_alloc<int64_t>(words, stream);
+      VarColSet* d_set = dev_alloc<VarColSet>(1, stream);
+      P->var_scratch.push_back(state);
+      P->var_scratch.push_back(d_set);
+      LSB_CUDA(cudaMemsetAsync(state, 0, sizeof(int64_t) * words, stream));
+      VarScan S{};
+      S.agg = reinterpret_cast<unsigned long long*>(state);
+      S.incl = S.agg + chunks * n;
+      S.stride = chunks;
+      S.ncols = n;
+      S.err = P->d_err;
+      P->h_varsets.emplace_back();
+      VarColSet& set = P->h_varsets.back();
+      set.n = n;
+      for (int i = 0; i < n; ++i) set.col[i] = group[c0 + i];
+      LSB_CUDA(cudaMemcpyAsync(d_set, &set, sizeof(VarColSet), cudaMemcpyHostToDevice, stream));
+      static const int win_variant = [] { const char* v = getenv("LAKESOUL_B200_WINDOW_VARIANT"); return v ? atoi(v) : 0; }();
+      if (pass == 0 && win_variant == 1)
+        var_window_kernel<14, 24576><<<(unsigned)(chunks * n), kGatherThreads, sizeof(WinSmem<14, 24576>), stream>>>(G, d_set, S, total_batches);
+      else if (pass == 0)
+        var_window_kernel<13, 16384><<<(unsigned)(chunks * n), kGatherThreads, sizeof(WinSmem<13, 16384>), stream>>>(G, d_set, S, total_batches);
+      else
+        var_write_kernel<<<(unsigned)(chunks * n), kGatherThreads, 0, stream>>>(G, d_set, S, total_batches);
+    }
   }
   LSB_CUDA(cudaGetLastError());
 }
@@ -1808,6 +2181,11 @@ __global__ void __launch_bounds__(256) keep_to_i32(const uint8_t* keep, int64_t 
 }
 __global__ void __launch_bounds__(256) scatter_kept(const uint8_t* keep, const int64_t* pos, int64_t n,
                                                    const uint32_t* src, uint32_t* dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && keep[i]) dst[pos[i]] = src[i];
+}
+__global__ void __launch_bounds__(256) scatter_kept_u8(const uint8_t* keep, const int64_t* pos, int64_t n,
+                                                      const uint8_t* src, uint8_t* dst) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && keep[i]) dst[pos[i]] = src[i];
 }
@@ -1836,6 +2214,10 @@ void plan_compact(MergePlan* P, const uint8_t* keep, const std::vector<uint32_t*
   // plan winners: scatter into win_tmp, then swap roles
   scatter_kept<<<g, 256, 0, stream>>>(keep, P->d_doff, U, P->d_win, P->d_win_tmp);
   std::swap(P->d_win, P->d_win_tmp);
+  if (P->has_wfile) {
+    scatter_kept_u8<<<g, 256, 0, stream>>>(keep, P->d_doff, U, P->d_wfile, P->d_wfile_tmp);
+    std::swap(P->d_wfile, P->d_wfile_tmp);
+  }
   for (uint32_t* list : extra_lists) {
     scatter_kept<<<g, 256, 0, stream>>>(keep, P->d_doff, U, list, P->d_ctmp);
     LSB_CUDA(cudaMemcpyAsync(list, P->d_ctmp, sizeof(uint32_t) * U, cudaMemcpyDeviceToDevice, stream));

@@ -120,6 +120,7 @@ int plan_batch_size(const MergePlan*);
 // Device views (valid after plan_merge on the same stream).
 const uint32_t* plan_winners(const MergePlan*);      // dense winners, bucket b at [out_base[b], out_base[b+1])
 const int64_t* plan_out_base_dev(const MergePlan*);  // nb+1 entries (device)
+const int32_t* plan_error_flag_dev(const MergePlan*);  // device int32: 0 = no kernel of the plan reported an error
 
 // Layout helpers for batch-segmented outputs, valid after plan_sync_counts():
 //   validity: every batch owns valid_stride_bytes() bytes; batch (b,i) is batch number
@@ -135,6 +136,8 @@ void gather_fixed(MergePlan*, const FixedCol* cols, int ncols, cudaStream_t stre
 // g+1 delimit row g, so a file needs one spare global row after its last row, or the next file
 // must continue the same data run), relative to the bucket's data base `src_data_base[b]`
 // (int64, device array of nb).
+// src_data must be readable up to the next 16-byte boundary after its last byte and start 16-byte aligned (true
+// for any cudaMalloc'd buffer): the windowed gather moves whole 16-byte aligned windows with TMA bulk copies.
 // Produces: dst_offsets (int32, batch-rebased, (rows+1) per batch), dst_data (dense bytes),
 // batch_data_start (int64 per batch + 1, device) = byte offset of each batch inside dst_data.
 struct VarCol {
@@ -147,6 +150,8 @@ struct VarCol {
   uint8_t* dst_data;             // capacity must be >= total source bytes of the column
   uint8_t* dst_valid;            // or nullptr
   int64_t* batch_data_start;     // device, (total_batches + 1)
+  int32_t direct;                // 1: src rows are NOT file rows of the plan (computed columns) -> no source windows
+  int32_t pad;
 };
 void gather_var(MergePlan*, const VarCol& col, cudaStream_t stream);
 // same for several columns: one launch per 16 columns (chunk positions by a look-back scan inside the kernel)

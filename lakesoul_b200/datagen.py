@@ -270,3 +270,33 @@ def write_table(root: str, spec: TableSpec, tables: Optional[List[List[pa.Table]
             row.append(p)
         paths.append(row)
     return paths
+
+
+# ---- bench-scale tables: full-size buckets generated independently ----------------------------------
+def bucket_file_paths(root: str, encoding: str, bucket: int, commits: int, seed: int) -> List[str]:
+    """Deterministic paths of the delta files of one hash bucket (every rank computes the same list)."""
+    return [os.path.join(root, encoding, file_name(bucket, j, seed)) for j in range(commits)]
+
+
+def write_full_bucket(root: str, config: int, bucket: int, encodings: Sequence[str] = ("E3",)) -> int:
+    """One hash bucket of BASELINE config `config` at its full per-bucket size, generated on its own
+    (seed = the config's seed + bucket; every key lands in this bucket) and written once per encoding under
+    <root>/<encoding>/. Returns the bucket's input rows. Independent per bucket, so a pool of processes can build a
+    table of thousands of buckets in parallel (tools/make_table.py)."""
+    spec = config_spec(config, 1.0)
+    spec.buckets = 1
+    base_seed = spec.seed
+    spec.seed = base_seed + 104729 * (bucket + 1)
+    tables = generate_table(spec)[0]
+    rows = 0
+    for enc in encodings:
+        os.makedirs(os.path.join(root, enc), exist_ok=True)
+        opts = ENCODINGS[enc]
+        for t, p in zip(tables, bucket_file_paths(root, enc, bucket, spec.commits, base_seed)):
+            tmp = p + ".tmp"
+            pq.write_table(t, tmp, data_page_version="1.0", data_page_size=1 << 20, row_group_size=250_000,
+                           write_statistics=True, **opts)
+            os.replace(tmp, p)
+    for t in tables:
+        rows += t.num_rows
+    return rows
