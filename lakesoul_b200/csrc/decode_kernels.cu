@@ -824,7 +824,7 @@ __device__ __forceinline__ int64_t huf_stream_fast(const uint16_t* huf, int log,
 //           in parallel, matches whose source lies before the round's output in parallel, the rest one by one
 constexpr int kZstdThreads = 64;
 // development profile (LAKESOUL_B200_ZSTD_PROFILE=1): cycles of the three phases summed over the pages >= 256 KiB
-__device__ unsigned long long g_zstd_prof[8];
+__device__ unsigned long long g_zstd_prof[16];
 __global__ void __launch_bounds__(kZstdThreads) zstd_pages_kernel(const PqZstdPage* pages, const ZstdBlockDesc* blocks_all,
                                                                   ZstdBlockPlan* plans_all, ZstdTables* tables_all, uint8_t* lit_all,
                                                                   uint64_t* seq_all, int32_t* err) {
@@ -1016,6 +1016,531 @@ __global__ void __launch_bounds__(kZstdThreads) zstd_pages_kernel(const PqZstdPa
     atomicMax(&g_zstd_prof[5], (unsigned long long)(t_entropy - t_plan));
     atomicMax(&g_zstd_prof[6], (unsigned long long)(t_end - t_entropy));
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ZSTD pages, second generation (the default): the same three phases, but
+//   * entropy tables live in shared memory (one slot per block of a group), the bit readers keep a 64-bit
+//     container in registers and refill it with two aligned 8-byte loads (zstd's BIT_DStream scheme): a symbol
+//     costs one shared-memory lookup instead of a chain of global loads (r1 profile: ~470 cycles per symbol);
+//   * Huffman streams emit 4 symbols per refill and store them as one word;
+//   * the sequence decoder resolves repeat offsets on the fly, relative to the block's INITIAL history
+//     (symbolically): the only state that crosses blocks becomes three words per block, chained by one thread;
+//   * every block is executed by its own warp; a match that reaches into an earlier block waits for that block's
+//     progress counter. Within a round (32 sequences) the positions come from a scan, literal runs and matches
+//     whose source lies before the round are copied in parallel, the rest in order.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+// backward bit stream (zstd's BIT_DStream scheme): `c` = the 8 bytes at `ptr`, `consumed` bits of it already used
+// from the top. The stream is walked from its end to its start; the aligned 8-byte words it will need next sit in a
+// register queue that is filled three words ahead, so a refill is a funnel shift, not a memory round trip (with the
+// entropy tables in shared memory the L1 is small: r2 profile, ~800 cycles per sequence on un-queued refills).
+struct BitD {
+  const uint8_t* start;
+  const uint8_t* ptr;
+  uint64_t c;
+  uint32_t consumed;
+  uint64_t q0, q1, q2, q3, q4;  // words at base - 24, base - 16, base - 8, base, base + 8 with base = ptr & ~7
+  uintptr_t floor_word;         // lowest word address worth loading
+  static __device__ __forceinline__ uint64_t word(uintptr_t a) { return __ldg(reinterpret_cast<const uint64_t*>(a)); }
+  __device__ __forceinline__ uint64_t word_clamped(uintptr_t a) const { return word(a < floor_word ? floor_word : a); }
+  __device__ __forceinline__ void compose() {
+    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(ptr) & 7) * 8;
+    c = sh == 0 ? q3 : ((q3 >> sh) | (q4 << (64 - sh)));
+  }
+  __device__ __forceinline__ void fill() {
+    const uintptr_t base = reinterpret_cast<uintptr_t>(ptr) & ~(uintptr_t)7;
+    q4 = word(base + 8);  // <= 15 bytes past the stream: inside the padded image
+    q3 = word(base);
+    q2 = word_clamped(base - 8);
+    q1 = word_clamped(base - 16);
+    q0 = word_clamped(base - 24);
+    compose();
+  }
+  __device__ __forceinline__ bool init(const uint8_t* src, int64_t size) {
+    start = src;
+    floor_word = reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)7;
+    if (size <= 0) return false;
+    const uint32_t last = src[size - 1];
+    if (last == 0) return false;
+    const uint32_t hb = 31 - __clz(last);
+    if (size >= 8) {
+      ptr = src + size - 8;
+      fill();
+      consumed = 8 - hb;
+    } else {
+      ptr = src;
+      fill();
+      uint64_t v = 0;
+      for (int i = 0; i < (int)size; ++i) v |= (uint64_t)src[i] << (8 * i);
+      c = v;
+      consumed = 8 - hb + (uint32_t)(8 - size) * 8;
+    }
+    return true;
+  }
+  __device__ __forceinline__ uint32_t peek(int n) const {  // 1 <= n <= 32
+    return (uint32_t)((c << (consumed & 63)) >> (64 - n));
+  }
+  __device__ __forceinline__ uint32_t read(int n) {
+    if (n == 0) return 0u;
+    const uint32_t v = peek(n);
+    consumed += n;
+    return v;
+  }
+  __device__ __forceinline__ void move_to(const uint8_t* np) {  // np <= ptr, at most 8 bytes lower
+    const uintptr_t ob = reinterpret_cast<uintptr_t>(ptr) & ~(uintptr_t)7, nbase = reinterpret_cast<uintptr_t>(np) & ~(uintptr_t)7;
+    ptr = np;
+    if (nbase != ob) {  // one word down: shift the queue, fetch the word three below
+      q4 = q3; q3 = q2; q2 = q1; q1 = q0;
+      q0 = word_clamped(nbase - 24);
+    }
+    compose();
+  }
+  __device__ __forceinline__ void reload() {
+    if (ptr >= start + 8) {
+      const uint32_t nb = consumed >> 3;
+      consumed &= 7;
+      move_to(ptr - nb);
+    } else if (ptr != start) {
+      uint32_t nb = consumed >> 3;
+      if (ptr - nb < start) nb = (uint32_t)(ptr - start);
+      consumed -= nb * 8;
+      move_to(ptr - nb);
+    }
+  }
+  __device__ __forceinline__ bool finished_exactly() const { return ptr == start && consumed == 64; }
+  __device__ __forceinline__ bool overrun() const { return consumed > 64; }
+};
+
+// one Huffman stream -> n literal bytes; `huf` in shared memory
+__device__ int64_t huf_stream_v2(const uint16_t* huf, int log, const uint8_t* src, int64_t size, uint8_t* dst, int64_t n) {
+  BitD d;
+  if (!d.init(src, size)) return ZSTD_E_CORRUPT;
+  int64_t i = 0;
+  while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 3)) {
+    d.reload();
+    const uint16_t e = huf[d.peek(log)];
+    dst[i++] = (uint8_t)e;
+    d.consumed += e >> 8;
+  }
+  for (; i + 4 <= n; i += 4) {  // 4 x <= 11 bits after a refill that leaves >= 57
+    d.reload();
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint16_t e = huf[d.peek(log)];
+      w |= (uint32_t)(e & 0xff) << (8 * k);
+      d.consumed += e >> 8;
+    }
+    *reinterpret_cast<uint32_t*>(dst + i) = w;
+  }
+  for (; i < n; ++i) {
+    d.reload();
+    const uint16_t e = huf[d.peek(log)];
+    dst[i] = (uint8_t)e;
+    d.consumed += e >> 8;
+  }
+  d.reload();
+  return (!d.overrun() && d.finished_exactly()) ? n : (int64_t)ZSTD_E_CORRUPT;
+}
+
+// sequence record of the v2 path: ll (17) | ml (17) << 17 | tag (2) << 34 | value (28) << 36
+//   tag 0: value = the offset;  tag t > 0: offset = rep_init[t - 1] + sign-extended value
+constexpr uint32_t kSeqValMask = (1u << 28) - 1;
+struct RepSym { int32_t src; int32_t val; };  // src 3 = constant
+__device__ __forceinline__ uint64_t pack_seq_v2(uint32_t ll, uint32_t ml, const RepSym& o) {
+  const uint64_t tag = o.src == 3 ? 0ull : (uint64_t)(o.src + 1);
+  return (uint64_t)ll | ((uint64_t)ml << 17) | (tag << 34) | ((uint64_t)((uint32_t)o.val & kSeqValMask) << 36);
+}
+
+// FSE bit stream of one block -> records with offsets resolved against the block's initial repeat history.
+// Returns 0 or < 0; *ml_total = sum of the match lengths; fin[3] = the final history (symbolic).
+__device__ int64_t sequences_v2(const uint8_t* bits, int64_t size, const ZstdBlockPlan& P, const FseEntry* tll, const FseEntry* tml,
+                                const FseEntry* tof, uint64_t* out, int64_t* ml_total, RepSym* fin) {
+  using namespace zstd_detail;
+  BitD d;
+  if (!d.init(bits, size)) return ZSTD_E_CORRUPT;
+  uint32_t sl = d.read(P.ll_log), so = d.read(P.of_log), sm = d.read(P.ml_log);
+  RepSym r0{0, 0}, r1{1, 0}, r2{2, 0};
+  int64_t mls = 0;
+  for (int32_t q = 0; q < P.nseq; ++q) {
+    d.reload();
+    const FseEntry eo = tof[so], em = tml[sm], el = tll[sl];
+    const int oc = eo.symbol, mc = em.symbol, lc = el.symbol;
+    if (oc > 27 || mc > 52 || lc > 35) return ZSTD_E_CORRUPT;  // offsets >= 256 MiB cannot occur inside a page
+    const uint32_t ov = (1u << oc) + d.read(oc);              // <= 27 bits
+    const uint32_t ml = ml_base(mc) + d.read(ml_bits(mc));    // <= 16 bits
+    d.reload();
+    const uint32_t ll = ll_base(lc) + d.read(ll_bits(lc));    // <= 16 bits
+    if (q + 1 < P.nseq) {                                      // <= 9 + 9 + 8 bits
+      sl = el.baseline + d.read(el.nbits);
+      sm = em.baseline + d.read(em.nbits);
+      so = eo.baseline + d.read(eo.nbits);
+    }
+    if (d.overrun()) return ZSTD_E_CORRUPT;
+    RepSym o;
+    if (ov > 3) {
+      o = RepSym{3, (int32_t)(ov - 3)};
+      r2 = r1; r1 = r0; r0 = o;
+    } else {
+      const uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);
+      if (idx == 0) {
+        o = r0;
+      } else {
+        o = idx == 1 ? r1 : (idx == 2 ? r2 : RepSym{r0.src, r0.val - 1});
+        if (idx > 1) r2 = r1;
+        r1 = r0;
+        r0 = o;
+      }
+    }
+    if (o.src != 3 && (o.val < -(1 << 20) || o.val > 0)) return ZSTD_E_UNSUPPORTED;  // a chain of 2^20 "rep0 - 1": not a page
+    mls += ml;
+    out[q] = pack_seq_v2(ll, ml, o);
+  }
+  d.reload();
+  if (d.overrun() || !d.finished_exactly()) return ZSTD_E_CORRUPT;
+  *ml_total = mls;
+  fin[0] = r0; fin[1] = r1; fin[2] = r2;
+  return 0;
+}
+
+constexpr int kZstdMaxTracked = 64;  // blocks per page with a progress counter; larger pages run on one warp
+
+// n bytes, one lane: loads of 8 bytes are in flight before the first store (ranges do not overlap)
+__device__ __forceinline__ void copy_lane_cg(uint8_t* d, const uint8_t* s, uint32_t n) {
+  uint32_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint8_t t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = s[i + k];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[i + k] = t[k];
+  }
+  const uint32_t r = n - i;
+  uint8_t t[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) if ((uint32_t)k < r) t[k] = s[i + k];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) if ((uint32_t)k < r) d[i + k] = t[k];
+}
+// n bytes, the whole warp, 4 x 32 bytes in flight
+__device__ __forceinline__ void copy_warp_cg(uint8_t* d, const uint8_t* s, uint32_t n, int lane) {
+  uint32_t i = lane;
+  for (; i + 96 < n; i += 128) {
+    const uint8_t a = s[i], b = s[i + 32], c = s[i + 64], e = s[i + 96];
+    d[i] = a; d[i + 32] = b; d[i + 64] = c; d[i + 96] = e;
+  }
+  for (; i < n; i += 32) d[i] = s[i];
+}
+
+}  // namespace
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) zstd_pages_kernel_v2(const PqZstdPage* pages, const int32_t* order,
+                                                                    const ZstdBlockDesc* blocks_all, ZstdBlockPlan* plans_all,
+                                                                    uint8_t* lit_all, uint64_t* seq_all, int32_t* err) {
+  constexpr int kThreads = kWarps * 32;
+  constexpr int kGroup = kWarps;  // blocks whose tables are resident at a time
+  extern __shared__ __align__(16) unsigned char zsm_raw[];
+  ZstdTables* s_tabs = reinterpret_cast<ZstdTables*>(zsm_raw);  // kGroup slots
+  __shared__ ZstdPlanScratch s_plan;
+  __shared__ ZstdBlockPlan s_cur_plan, s_prev_plan;
+  __shared__ int s_fail, s_have_prev, s_prev_slot;
+  __shared__ int s_done[kZstdMaxTracked];  // absolute output position every block has completed
+  __shared__ int s_abort;                  // a block met corrupt data: nobody waits for anybody any more
+  const PqZstdPage pg = pages[order[blockIdx.x]];
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(pg.src_off);
+  uint8_t* dst = reinterpret_cast<uint8_t*>(pg.dst_off);
+  const ZstdBlockDesc* blocks = blocks_all + pg.first_block;
+  ZstdBlockPlan* plans = plans_all + pg.first_block;
+  uint8_t* lit = lit_all + pg.lit_off;
+  uint64_t* seq = seq_all + pg.seq_off;
+  const int nb = pg.nblocks;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { s_fail = 0; s_have_prev = 0; s_prev_slot = 0; s_abort = 0; }
+  __syncthreads();
+  int64_t lit_total = 0, seq_total = 0;  // meaningful in thread 0
+  const bool prof = pg.raw_size >= (64 << 10);
+  long long c_plan = 0, c_entropy = 0;
+  for (int g0 = 0; g0 < nb; g0 += kGroup) {
+    const int g1 = min(nb, g0 + kGroup);
+    const long long tp0 = clock64();
+    // ---- plan (thread 0, in order: tables may be inherited from the previous compressed block) ----
+    if (tid == 0) {
+      for (int k = g0; k < g1 && !s_fail; ++k) {
+        if (blocks[k].type != 2) continue;
+        const int slot = k - g0;
+        const int64_t r = zstd_plan_block(src + blocks[k].src_off, blocks[k].size, s_cur_plan, s_tabs[slot],
+                                          s_have_prev ? &s_prev_plan : nullptr, s_have_prev ? &s_tabs[s_prev_slot] : nullptr, s_plan);
+        if (r < 0) { s_fail = 1; break; }
+        s_cur_plan.lit_base = (int32_t)lit_total;
+        s_cur_plan.seq_base = (int32_t)seq_total;
+        lit_total += s_cur_plan.regen;
+        seq_total += s_cur_plan.nseq;
+        if (lit_total > pg.raw_size || seq_total > pg.raw_size / 3 + 1) { s_fail = 1; break; }
+        s_prev_plan = s_cur_plan;
+        s_have_prev = 1;
+        s_prev_slot = slot;
+        plans[k] = s_cur_plan;
+      }
+    }
+    __syncthreads();
+    if (s_fail) break;
+    const long long tp1 = clock64();
+    c_plan += tp1 - tp0;
+    // ---- entropy, all blocks of the group side by side. Roles are split by WARP so that lanes of a warp run the
+    // same loop: warp 0 = the Huffman streams (lane = block * 4 + stream), warp 1 = the FSE sequence streams and the
+    // RLE literal fills (lane = block). (Mixed roles inside one warp serialise: r2 profile, entropy = sum of both.)
+    if (warp == 0 && lane < 4 * (g1 - g0)) {
+      const int k = g0 + (lane >> 2), role = lane & 3;
+      if (blocks[k].type == 2) {
+        const ZstdBlockPlan& P = plans[k];
+        if (P.lit_type == 2 && role < P.streams) {
+          const uint8_t* b = src + blocks[k].src_off;
+          uint8_t* L = lit + P.lit_base;
+          const int64_t per = P.streams == 4 ? (P.regen + 3) / 4 : P.regen;
+          int64_t so = 0;
+          for (int st = 0; st < role; ++st) so += P.stream_size[st];
+          const int64_t n = P.streams == 4 ? (role < 3 ? per : P.regen - 3 * per) : P.regen;
+          const long long th0 = clock64();
+          if (huf_stream_v2(s_tabs[k - g0].huf, P.huf_log, b + P.lit_src + so, P.stream_size[role], L + role * per, n) < 0) s_fail = 1;
+          if (prof) {
+            const unsigned long long c = (unsigned long long)(clock64() - th0);
+            if (atomicMax(&g_zstd_prof[10], c) < c) g_zstd_prof[11] = (unsigned long long)n;
+          }
+        }
+      }
+    } else if (warp == 1 && lane < (g1 - g0)) {
+      const int k = g0 + lane;
+      if (blocks[k].type == 2) {
+        const ZstdBlockPlan P = plans[k];
+        const ZstdTables& T = s_tabs[k - g0];
+        const uint8_t* b = src + blocks[k].src_off;
+        int64_t mls = 0;
+        RepSym fin[3] = {{0, 0}, {1, 0}, {2, 0}};
+        int64_t r = 0;
+        const long long ts0 = clock64();
+        if (P.nseq > 0) r = sequences_v2(b + P.seq_src, P.seq_size, P, T.ll, T.ml, T.of, seq + P.seq_base, &mls, fin);
+        if (prof) {
+          const unsigned long long c = (unsigned long long)(clock64() - ts0);
+          if (atomicMax(&g_zstd_prof[8], c) < c) g_zstd_prof[9] = (unsigned long long)P.nseq;
+        }
+        if (r < 0) s_fail = 1;
+        plans[k].out_size = (int32_t)min((int64_t)INT32_MAX, (int64_t)P.regen + mls);
+        for (int j = 0; j < 3; ++j) { plans[k].rep_src[j] = fin[j].src; plans[k].rep_val[j] = fin[j].val; }
+        if (P.lit_type == 1) {  // RLE literals (raw literals are read in place by the execute phase)
+          uint8_t* L = lit + P.lit_base;
+          const uint8_t v = b[P.lit_src];
+          for (int i = 0; i < P.regen; ++i) L[i] = v;
+        }
+      }
+    }
+    __syncthreads();
+    if (s_fail) break;
+    c_entropy += clock64() - tp1;
+    // tables of the group's last compressed block must survive in a slot the next group's first plan does not
+    // overwrite before reading: move them to the last slot and plan the next group from slot 0 upwards
+    if (g1 < nb && s_have_prev && s_prev_slot != kGroup - 1) {
+      const uint32_t* from = reinterpret_cast<const uint32_t*>(&s_tabs[s_prev_slot]);
+      uint32_t* to = reinterpret_cast<uint32_t*>(&s_tabs[kGroup - 1]);
+      for (int i = tid; i < (int)(sizeof(ZstdTables) / 4); i += kThreads) to[i] = from[i];
+      __syncthreads();
+      if (tid == 0) s_prev_slot = kGroup - 1;
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (s_fail) {
+    if (tid == 0) atomicExch(err, kErrBadPage);
+    return;
+  }
+  // ---- chain: output bases and repeat histories of the blocks (thread 0) ----
+  if (tid == 0) {
+    int64_t op = 0;
+    uint32_t rep[3] = {1, 4, 8};
+    for (int k = 0; k < nb; ++k) {
+      if (blocks[k].type != 2) {
+        op += blocks[k].out_size;
+        if (k < kZstdMaxTracked) s_done[k] = 0;
+        continue;
+      }
+      ZstdBlockPlan& P = plans[k];
+      P.out_base = (int32_t)op;
+      for (int j = 0; j < 3; ++j) P.rep_init[j] = rep[j];
+      uint32_t nx[3];
+      for (int j = 0; j < 3; ++j) nx[j] = P.rep_src[j] == 3 ? (uint32_t)P.rep_val[j] : rep[P.rep_src[j]] + (uint32_t)P.rep_val[j];
+      for (int j = 0; j < 3; ++j) rep[j] = nx[j];
+      op += P.out_size;
+      if (k < kZstdMaxTracked) s_done[k] = 0;
+      if (op > pg.raw_size) { s_fail = 1; break; }
+    }
+    if (op != pg.raw_size) s_fail = 1;
+  }
+  __syncthreads();
+  if (s_fail) {
+    if (tid == 0) atomicExch(err, kErrBadPage);
+    return;
+  }
+  // ---- execute: one warp per block (all blocks on warp 0 when the page has more blocks than counters) ----
+  const bool tracked = nb <= kZstdMaxTracked;
+  if (!tracked && warp != 0) return;
+  const long long t_exec0 = clock64();
+  long long c_wait = 0;
+  if (prof && tid == 0) {
+    atomicAdd(&g_zstd_prof[0], (unsigned long long)c_plan);
+    atomicAdd(&g_zstd_prof[1], (unsigned long long)c_entropy);
+    atomicAdd(&g_zstd_prof[3], 1ull);
+    atomicMax(&g_zstd_prof[4], (unsigned long long)c_plan);
+    atomicMax(&g_zstd_prof[5], (unsigned long long)c_entropy);
+  }
+  const int64_t cap = pg.raw_size;
+  volatile int* done = s_done;
+  volatile int* abort_flag = &s_abort;
+  int64_t base_k = 0;  // output base of block k (raw / RLE blocks carry no plan: recomputed while walking)
+  for (int k = 0; k < nb; ++k) {
+    const int64_t out_k = blocks[k].type == 2 ? plans[k].out_size : blocks[k].out_size;
+    const int64_t my_base = base_k;
+    base_k += out_k;
+    if (tracked && (k % kWarps) != warp) continue;
+    const uint8_t* b = src + blocks[k].src_off;
+    if (blocks[k].type != 2) {
+      if (blocks[k].type == 0) for (int64_t i = lane; i < out_k; i += 32) dst[my_base + i] = b[i];
+      else { const uint8_t v = b[0]; for (int64_t i = lane; i < out_k; i += 32) dst[my_base + i] = v; }
+      __syncwarp();
+      __threadfence_block();
+      if (lane == 0 && tracked) done[k] = (int)(my_base + out_k);
+      continue;
+    }
+    const ZstdBlockPlan P = plans[k];
+    const uint8_t* lits = P.lit_type == 0 ? b + P.lit_src : lit + P.lit_base;  // raw literals stay where they are
+    const uint64_t* sq = seq + P.seq_base;
+    const uint32_t rep_i0 = P.rep_init[0], rep_i1 = P.rep_init[1], rep_i2 = P.rep_init[2];
+    int64_t op = my_base, lpos = 0;
+    uint64_t v_next = (lane < P.nseq) ? sq[lane] : 0ull;
+    for (int q0 = 0; q0 < P.nseq; q0 += 32) {
+      const int cnt = min(32, P.nseq - q0);
+      const uint64_t v = v_next;
+      v_next = (q0 + 32 + lane < P.nseq) ? sq[q0 + 32 + lane] : 0ull;  // the next round's records travel meanwhile
+      const uint32_t ll = (uint32_t)(v & 0x1ffff), ml = (uint32_t)((v >> 17) & 0x1ffff);
+      const uint32_t tag = (uint32_t)(v >> 34) & 3u;
+      const int32_t val = (int32_t)((uint32_t)(v >> 36) << 4) >> 4;  // sign-extend 28 bits
+      const uint32_t rep_t = tag == 1 ? rep_i0 : (tag == 2 ? rep_i1 : rep_i2);
+      const uint32_t offset = lane < cnt ? (tag == 0 ? (uint32_t)val : rep_t + (uint32_t)val) : 1u;
+      uint32_t io = ll + ml, il = ll;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t yo = __shfl_up_sync(0xffffffffu, io, d), yl = __shfl_up_sync(0xffffffffu, il, d);
+        if (lane >= d) { io += yo; il += yl; }
+      }
+      const uint32_t tot_out = __shfl_sync(0xffffffffu, io, 31), tot_lit = __shfl_sync(0xffffffffu, il, 31);
+      const int64_t my_out = op + (io - ll - ml);
+      const int64_t my_lit = lpos + (il - ll);
+      const int64_t my_match = my_out + ll;
+      const bool bad = lpos + tot_lit > P.regen || op + tot_out > my_base + out_k ||
+                       (lane < cnt && (offset == 0 || (int64_t)offset > my_match));
+      if (__any_sync(0xffffffffu, bad)) {
+        if (lane == 0) { atomicExch(err, kErrBadPage); *abort_flag = 1; }
+        return;
+      }
+      // matches that reach below this block wait for the blocks that own those bytes
+      if (tracked && k > 0) {
+        const int64_t s0 = (lane < cnt && ml > 0) ? my_match - (int64_t)offset : INT64_MAX;
+        int64_t lo = s0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        if (lo < my_base) {
+          const long long tw0 = clock64();
+          int64_t bb = my_base;  // walk down the blocks that end above `lo`
+          for (int kk = k - 1; kk >= 0 && bb > lo; --kk) {
+            const int64_t need = bb;  // the whole block below us up to its end (conservative, rarely more than one)
+            while (done[kk] < (int)need && !*abort_flag) __nanosleep(64);
+            bb -= blocks[kk].type == 2 ? plans[kk].out_size : blocks[kk].out_size;
+          }
+          if (*abort_flag) return;
+          __threadfence_block();
+          c_wait += clock64() - tw0;
+        }
+      }
+      if (ll <= 64) copy_lane_cg(dst + my_out, lits + my_lit, ll);
+      unsigned big = __ballot_sync(0xffffffffu, ll > 64);
+      while (big) {
+        const int j = __ffs(big) - 1;
+        big &= big - 1;
+        const int64_t o = __shfl_sync(0xffffffffu, my_out, j), l0 = __shfl_sync(0xffffffffu, my_lit, j);
+        const uint32_t n = __shfl_sync(0xffffffffu, ll, j);
+        copy_warp_cg(dst + o, lits + l0, n, lane);
+      }
+      __syncwarp();
+      const bool indep = lane < cnt && ml <= 64 && (my_match - (int64_t)offset + ml <= op);
+      if (indep) copy_lane_cg(dst + my_match, dst + my_match - offset, ml);
+      __syncwarp();
+      unsigned serial = __ballot_sync(0xffffffffu, lane < cnt && !indep && ml > 0);
+      while (serial) {
+        const int j = __ffs(serial) - 1;
+        serial &= serial - 1;
+        const int64_t md = __shfl_sync(0xffffffffu, my_match, j);
+        const uint32_t off = __shfl_sync(0xffffffffu, offset, j), n = __shfl_sync(0xffffffffu, ml, j);
+        const uint8_t* m = dst + md - off;
+        if (off >= n) {
+          copy_warp_cg(dst + md, m, n, lane);
+        } else {  // overlapping match: only bytes that existed before this sequence are read
+          for (uint32_t i = lane; i < n; i += 32) dst[md + i] = m[i % off];
+        }
+        __syncwarp();
+      }
+      op += tot_out;
+      lpos += tot_lit;
+      __threadfence_block();
+      if (lane == 0 && tracked) done[k] = (int)op;
+    }
+    const int64_t rest = P.regen - lpos;
+    if (rest < 0 || op + rest != my_base + out_k) {
+      if (lane == 0) { atomicExch(err, kErrBadPage); *abort_flag = 1; }
+      return;
+    }
+    copy_warp_cg(dst + op, lits + lpos, (uint32_t)rest, lane);
+    op += rest;
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0 && tracked) done[k] = (int)op;
+  }
+  (void)cap;
+  if (prof && lane == 0) {
+    const unsigned long long c = (unsigned long long)(clock64() - t_exec0);
+    atomicAdd(&g_zstd_prof[2], c);
+    atomicMax(&g_zstd_prof[6], c);
+    atomicMax(&g_zstd_prof[7], (unsigned long long)c_wait);
+  }
+}
+
+void launch_zstd_pages_v2(const PqZstdPage* pages, const int32_t* order_small, int nsmall, const int32_t* order_big, int nbig,
+                          const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, uint8_t* lit, uint64_t* seq, int32_t* err, cudaStream_t s) {
+  static thread_local int attr_device = -1;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (attr_device != cur) {
+    attr_device = cur;
+    cudaFuncSetAttribute(zstd_pages_kernel_v2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(ZstdTables)));
+    cudaFuncSetAttribute(zstd_pages_kernel_v2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(ZstdTables)));
+  }
+  if (nbig > 0)
+    zstd_pages_kernel_v2<8><<<nbig, 8 * 32, 8 * sizeof(ZstdTables), s>>>(pages, order_big, blocks, plans, lit, seq, err);
+  static const bool prof = [] { const char* v = getenv("LAKESOUL_B200_ZSTD_PROFILE"); return v && *v == '1'; }();
+  auto dump = [&](const char* what) {
+    unsigned long long h[16] = {0}, z[16] = {0};
+    cudaStreamSynchronize(s);
+    cudaMemcpyFromSymbol(h, g_zstd_prof, sizeof(h));
+    cudaMemcpyToSymbol(g_zstd_prof, z, sizeof(z));
+    if (h[3]) fprintf(stderr, "ZSTDPROF2b %s slowest sequence stream %.0f kcycles for %llu sequences; slowest huffman stream %.0f kcycles for %llu symbols\n",
+                      what, h[8] / 1e3, h[9], h[10] / 1e3, h[11]);
+    if (h[3]) fprintf(stderr, "ZSTDPROF2 %s pages>=64K %llu  mean kcycles plan %.0f entropy %.0f execute(per warp) %.0f  max plan %.0f entropy %.0f execute %.0f (max waiting %.0f)\n",
+                      what, h[3], h[0] / 1e3 / h[3], h[1] / 1e3 / h[3], h[2] / 1e3 / h[3], h[4] / 1e3, h[5] / 1e3, h[6] / 1e3, h[7] / 1e3);
+  };
+  if (prof) dump("big");
+  if (nsmall > 0)
+    zstd_pages_kernel_v2<2><<<nsmall, 2 * 32, 2 * sizeof(ZstdTables), s>>>(pages, order_small, blocks, plans, lit, seq, err);
+  if (prof) dump("small");
 }
 
 void launch_zstd_pages(const PqZstdPage* pages, int npages, const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, ZstdTables* tables,

@@ -195,6 +195,8 @@ void launch_block_scan(const DecodeArgs& A, const int32_t* seg_bounds, const int
 void launch_block_decode(const DecodeArgs& A, cudaStream_t s);
 void launch_zstd_pages(const PqZstdPage* pages, int npages, const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, ZstdTables* tables,
                        uint8_t* lit, uint64_t* seq, int32_t* err, cudaStream_t s);
+void launch_zstd_pages_v2(const PqZstdPage* pages, const int32_t* order_small, int nsmall, const int32_t* order_big, int nbig,
+                          const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, uint8_t* lit, uint64_t* seq, int32_t* err, cudaStream_t s);
 
 namespace {
 
@@ -352,6 +354,7 @@ struct DeviceScan::Impl : std::enable_shared_from_this<DeviceScan::Impl> {
     ctr.d2h_bytes += (int64_t)n;
   }
 
+  std::vector<int32_t> scratch_order;  // page order of the ZSTD launches (outlives the asynchronous upload)
   std::shared_ptr<uint8_t> h_small;  // pinned: [decode error flag | string segment totals]
   bool decode_err_pending = false;
   void check_decode_error();
@@ -656,13 +659,28 @@ void DeviceScan::Impl::upload() {
       PqZstdPage* d_zpages = static_cast<PqZstdPage*>(dalloc(sizeof(PqZstdPage) * zpages.size()));
       ZstdBlockDesc* d_zblocks = static_cast<ZstdBlockDesc*>(dalloc(sizeof(ZstdBlockDesc) * zblocks.size()));
       ZstdBlockPlan* d_zplans = static_cast<ZstdBlockPlan*>(dalloc(sizeof(ZstdBlockPlan) * zblocks.size()));
-      ZstdTables* d_ztables = static_cast<ZstdTables*>(dalloc(sizeof(ZstdTables) * zblocks.size()));
       uint8_t* d_zlit = static_cast<uint8_t*>(dalloc((size_t)zlit_bytes + 64));
       uint64_t* d_zseq = static_cast<uint64_t*>(dalloc(sizeof(uint64_t) * (size_t)(zseq_recs + 8)));
       h2d(d_zpages, zpages.data(), sizeof(PqZstdPage) * zpages.size());
       h2d(d_zblocks, zblocks.data(), sizeof(ZstdBlockDesc) * zblocks.size());
-      launch_zstd_pages(d_zpages, (int)zpages.size(), d_zblocks, d_zplans, d_ztables, d_zlit, d_zseq, d_err, stream);
-      ctr.kernel_launches += 1;
+      static const bool zstd_v1 = [] { const char* v = getenv("LAKESOUL_B200_ZSTD_V1"); return v && *v == '1'; }();
+      if (zstd_v1) {
+        ZstdTables* d_ztables = static_cast<ZstdTables*>(dalloc(sizeof(ZstdTables) * zblocks.size()));
+        launch_zstd_pages(d_zpages, (int)zpages.size(), d_zblocks, d_zplans, d_ztables, d_zlit, d_zseq, d_err, stream);
+        ctr.kernel_launches += 1;
+      } else {
+        // pages of one or two blocks run on two warps, larger ones on eight (one warp per 128 KiB block)
+        std::vector<int32_t> order_small, order_big;
+        for (size_t z = 0; z < zpages.size(); ++z) (zpages[z].nblocks <= 2 ? order_small : order_big).push_back((int32_t)z);
+        std::vector<int32_t>& order = scratch_order;
+        order = order_big;
+        order.insert(order.end(), order_small.begin(), order_small.end());
+        int32_t* d_order = static_cast<int32_t*>(dalloc(sizeof(int32_t) * order.size()));
+        h2d(d_order, order.data(), sizeof(int32_t) * order.size());
+        launch_zstd_pages_v2(d_zpages, d_order + order_big.size(), (int)order_small.size(), d_order, (int)order_big.size(), d_zblocks,
+                             d_zplans, d_zlit, d_zseq, d_err, stream);
+        ctr.kernel_launches += (order_small.empty() ? 0 : 1) + (order_big.empty() ? 0 : 1);
+      }
       ctr.device_decompressed_pages += (int64_t)zpages.size();
     }
     h2d(d_chunks, chunks.data(), sizeof(PqChunk) * chunks.size());

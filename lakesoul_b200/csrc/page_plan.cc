@@ -33,11 +33,23 @@ double device_zstd_share() {
   static const double share = [] {
     const char* v = getenv("LAKESOUL_B200_DEVICE_ZSTD_SHARE");
     if (!v) v = getenv("LAKESOUL_B200_DEVICE_ZSTD");  // 0 / 1
-    if (!v || !*v) return 0.0;
+    if (!v || !*v) return -1.0;  // unset: the size policy below decides
     const double x = atof(v);
     return x < 0 ? 0.0 : (x > 1 ? 1.0 : x);
   }();
   return share;
+}
+
+// Default split of the ZSTD work (r2 measurements): a frame is sequential per 128 KiB block, so the GPU
+// is efficient on LARGE column chunks (many blocks side by side, few thread blocks) and wasteful on the thousands of
+// few-KiB chunks of small delta files (one mostly idle thread block each), which the host expands in microseconds.
+// Column chunks of at least this many uncompressed bytes are expanded on the device, smaller ones on the host.
+int64_t device_zstd_min_bytes() {
+  static const int64_t v = [] {
+    const char* e = getenv("LAKESOUL_B200_DEVICE_ZSTD_MIN_BYTES");
+    return e && *e ? (int64_t)atoll(e) : (int64_t)(128 << 10);
+  }();
+  return v;
 }
 
 int32_t map_encoding(parquet::Encoding::type e) {
@@ -297,7 +309,7 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
   if (sd->num_columns() != schema_->num_fields()) { *why = "nested schema"; return false; }
   // which ZSTD column chunks the GPU expands: smallest payloads first, up to the configured share of the bytes
   std::set<std::pair<int, int>> device_chunks;  // (row group, column)
-  if (device_zstd_share() > 0) {
+  if (device_zstd_share() != 0) {
     std::vector<std::pair<int64_t, std::pair<int, int>>> cand;
     int64_t total = 0;
     for (size_t w = 0; w < want.size(); ++w) {
@@ -313,12 +325,17 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
       }
     }
     std::sort(cand.begin(), cand.end());
-    const double budget = device_zstd_share() * (double)total;
-    int64_t acc = 0;
-    for (const auto& c : cand) {
-      if (device_zstd_share() < 1.0 && (double)(acc + c.first) > budget) break;
-      device_chunks.insert(c.second);
-      acc += c.first;
+    if (device_zstd_share() < 0) {  // default policy: by chunk size
+      for (const auto& c : cand)
+        if (c.first >= device_zstd_min_bytes()) device_chunks.insert(c.second);
+    } else {
+      const double budget = device_zstd_share() * (double)total;
+      int64_t acc = 0;
+      for (const auto& c : cand) {
+        if (device_zstd_share() < 1.0 && (double)(acc + c.first) > budget) break;
+        device_chunks.insert(c.second);
+        acc += c.first;
+      }
     }
   }
   for (size_t w = 0; w < want.size(); ++w) {

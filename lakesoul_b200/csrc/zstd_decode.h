@@ -585,6 +585,15 @@ struct ZstdBlockPlan {      // one compressed block (plan)
   int32_t ll_log, ml_log, of_log;
   int32_t lit_base;         // where the block's literals start inside the page's literal scratch
   int32_t seq_base;         // where the block's sequences start inside the page's sequence scratch
+  // block-parallel execution (zstd_pages_kernel_v2): the repeat-offset history is the only state that crosses
+  // blocks. The sequence decoder resolves every offset relative to the block's INITIAL history (symbolically);
+  // the final history is a function of the initial one: rep_final[j] = rep_src[j] == 3 ? rep_val[j]
+  //                                                                   : rep_init[rep_src[j]] + rep_val[j]
+  int32_t out_size;         // bytes the block produces (regen + sum of match lengths)
+  int32_t out_base;         // where they start inside the page
+  int32_t rep_src[3];
+  int32_t rep_val[3];
+  uint32_t rep_init[3];     // history at the block's start (filled once the blocks before it are chained)
 };
 
 struct ZstdPlanScratch {
