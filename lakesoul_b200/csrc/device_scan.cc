@@ -92,6 +92,7 @@ namespace {
 struct ScanSlot {
   cudaStream_t stream = nullptr;
   DeviceArena arena;
+  HostStage stage;  // pinned staging of the descriptor uploads (see mor_engine.h)
   int device = -1;
 };
 class SlotPool {
@@ -124,6 +125,7 @@ class SlotPool {
   }
   void release(ScanSlot* s) {
     s->arena.reset();
+    s->stage.reset();
     std::lock_guard<std::mutex> g(mu_);
     free_.push_back(s);
   }
@@ -141,6 +143,7 @@ class ScanSession {
     if (!slot) return;
     stream_wait(slot->stream);
     if (arena_current() == &slot->arena) arena_install(nullptr);
+    if (host_stage_current() == &slot->stage) host_stage_install(nullptr);
     SlotPool::get().release(slot);
   }
 };
@@ -148,6 +151,7 @@ std::shared_ptr<ScanSession> begin_scan_session() {
   auto s = std::make_shared<ScanSession>();
   s->slot = SlotPool::get().acquire();
   arena_install(&s->slot->arena);
+  host_stage_install(&s->slot->stage);
   return s;
 }
 uint8_t* session_upload(ScanSession& s, const uint8_t* pinned, size_t bytes) {
@@ -345,7 +349,7 @@ struct DeviceScan::Impl : std::enable_shared_from_this<DeviceScan::Impl> {
   }
   void h2d(void* dst, const void* src, size_t n) {
     if (n == 0) return;
-    SCAN_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, stream));
+    SCAN_CUDA(h2d_staged(dst, src, n, stream));  // descriptors and host-decoded columns: never from pageable memory
     ctr.h2d_bytes += (int64_t)n;
   }
   void d2h(void* dst, const void* src, size_t n) {

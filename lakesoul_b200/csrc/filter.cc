@@ -229,7 +229,119 @@ std::string filter_to_string(const FilterExpr& e) {
     case FilterExpr::kIsNull: return "isnull(" + e.column + ")";
     case FilterExpr::kIsNotNull: return "isnotnull(" + e.column + ")";
     case FilterExpr::kTrue: return "true";
+    case FilterExpr::kNull: return "null";
     default: return "false";
+  }
+}
+
+namespace {
+
+// three-way compare of a constant column value with a literal of the column's family; false = not comparable
+bool compare_scalars(const arrow::Scalar& v, const arrow::Scalar& lit, int* out) {
+  using T = arrow::Type;
+  auto sgn = [](auto a, auto b) { return a < b ? -1 : (a > b ? 1 : 0); };
+  auto as_i64 = [](const arrow::Scalar& s, int64_t* x) {
+    switch (s.type->id()) {
+      case T::INT8: *x = static_cast<const arrow::Int8Scalar&>(s).value; return true;
+      case T::INT16: *x = static_cast<const arrow::Int16Scalar&>(s).value; return true;
+      case T::INT32: *x = static_cast<const arrow::Int32Scalar&>(s).value; return true;
+      case T::INT64: *x = static_cast<const arrow::Int64Scalar&>(s).value; return true;
+      case T::UINT8: *x = static_cast<const arrow::UInt8Scalar&>(s).value; return true;
+      case T::UINT16: *x = static_cast<const arrow::UInt16Scalar&>(s).value; return true;
+      case T::UINT32: *x = static_cast<const arrow::UInt32Scalar&>(s).value; return true;
+      case T::DATE32: *x = static_cast<const arrow::Date32Scalar&>(s).value; return true;
+      case T::BOOL: *x = static_cast<const arrow::BooleanScalar&>(s).value ? 1 : 0; return true;
+      case T::TIMESTAMP: {
+        int64_t t = static_cast<const arrow::TimestampScalar&>(s).value;
+        switch (static_cast<const arrow::TimestampType&>(*s.type).unit()) {  // literals are microseconds
+          case arrow::TimeUnit::SECOND: t *= 1000000; break;
+          case arrow::TimeUnit::MILLI: t *= 1000; break;
+          case arrow::TimeUnit::NANO: t = t / 1000 - ((t % 1000 != 0 && t < 0) ? 1 : 0); break;
+          default: break;
+        }
+        *x = t;
+        return true;
+      }
+      default: return false;
+    }
+  };
+  int64_t a, b;
+  if (as_i64(v, &a) && as_i64(lit, &b)) { *out = sgn(a, b); return true; }
+  auto as_f64 = [](const arrow::Scalar& s, double* x) {
+    if (s.type->id() == T::FLOAT) { *x = static_cast<const arrow::FloatScalar&>(s).value; return true; }
+    if (s.type->id() == T::DOUBLE) { *x = static_cast<const arrow::DoubleScalar&>(s).value; return true; }
+    return false;
+  };
+  double fa, fb;
+  if (as_f64(v, &fa) && as_f64(lit, &fb)) { *out = sgn(fa, fb); return fa == fa && fb == fb; }
+  auto is_bytes = [](const arrow::Scalar& s) { return s.type->id() == T::STRING || s.type->id() == T::BINARY; };
+  if (is_bytes(v) && is_bytes(lit)) {
+    const auto& x = static_cast<const arrow::BaseBinaryScalar&>(v).value;
+    const auto& y = static_cast<const arrow::BaseBinaryScalar&>(lit).value;
+    if (!x || !y) return false;
+    *out = sgn(x->ToString().compare(y->ToString()), 0);
+    return true;
+  }
+  if (v.type->id() == T::DECIMAL128 && lit.type->id() == T::DECIMAL128) {
+    const auto& x = static_cast<const arrow::Decimal128Scalar&>(v).value;
+    const auto& y = static_cast<const arrow::Decimal128Scalar&>(lit).value;
+    *out = x < y ? -1 : (x > y ? 1 : 0);
+    return true;
+  }
+  return false;
+}
+
+std::shared_ptr<FilterExpr> constant(FilterExpr::Kind k) {
+  auto e = std::make_shared<FilterExpr>();
+  e->kind = k;
+  return e;
+}
+
+}  // namespace
+
+std::shared_ptr<FilterExpr> fold_constant_columns(
+    const std::shared_ptr<FilterExpr>& e,
+    const std::function<bool(const std::string&, std::shared_ptr<arrow::Scalar>*)>& constant_of) {
+  if (!e) return e;
+  switch (e->kind) {
+    case FilterExpr::kAnd:
+    case FilterExpr::kOr: {
+      auto n = std::make_shared<FilterExpr>(*e);
+      n->left = fold_constant_columns(e->left, constant_of);
+      n->right = fold_constant_columns(e->right, constant_of);
+      return n;
+    }
+    case FilterExpr::kNot: {
+      auto n = std::make_shared<FilterExpr>(*e);
+      n->right = fold_constant_columns(e->right, constant_of);
+      return n;
+    }
+    case FilterExpr::kIsNull:
+    case FilterExpr::kIsNotNull: {
+      std::shared_ptr<arrow::Scalar> v;
+      if (!constant_of(e->column, &v)) return e;
+      const bool is_null = !v || !v->is_valid;
+      return constant((e->kind == FilterExpr::kIsNull) == is_null ? FilterExpr::kTrue : FilterExpr::kFalse);
+    }
+    case FilterExpr::kCmp: {
+      std::shared_ptr<arrow::Scalar> v;
+      if (!constant_of(e->column, &v)) return e;
+      if (!v || !v->is_valid || !e->literal || !e->literal->is_valid) return constant(FilterExpr::kNull);
+      int c = 0;
+      if (!compare_scalars(*v, *e->literal, &c))
+        bad("filter on the constant column '" + e->column + "' of type " + v->type->ToString() + " cannot be evaluated");
+      bool r = false;
+      switch (e->op) {
+        case FilterExpr::kEq: r = c == 0; break;
+        case FilterExpr::kNe: r = c != 0; break;
+        case FilterExpr::kGt: r = c > 0; break;
+        case FilterExpr::kGe: r = c >= 0; break;
+        case FilterExpr::kLt: r = c < 0; break;
+        case FilterExpr::kLe: r = c <= 0; break;
+      }
+      return constant(r ? FilterExpr::kTrue : FilterExpr::kFalse);
+    }
+    default: return e;
   }
 }
 

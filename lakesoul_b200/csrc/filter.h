@@ -8,6 +8,7 @@
 #pragma once
 #include <arrow/api.h>
 
+#include <functional>
 #include <memory>
 #include <set>
 #include <string>
@@ -15,7 +16,7 @@
 namespace lsb {
 
 struct FilterExpr {
-  enum Kind : int { kAnd, kOr, kNot, kCmp, kIsNull, kIsNotNull, kTrue, kFalse };
+  enum Kind : int { kAnd, kOr, kNot, kCmp, kIsNull, kIsNotNull, kTrue, kFalse, kNull };  // kNull: the constant NULL
   enum Op : int { kEq, kNe, kGt, kGe, kLt, kLe };
   Kind kind = kTrue;
   Op op = kEq;
@@ -29,5 +30,14 @@ std::shared_ptr<FilterExpr> parse_filter(const std::string& filter, const arrow:
 std::shared_ptr<FilterExpr> conjunction(const std::vector<std::shared_ptr<FilterExpr>>& exprs);
 void filter_columns(const FilterExpr& e, std::set<std::string>* out);
 std::string filter_to_string(const FilterExpr& e);
+
+// Replaces every predicate on a column whose value is the same for all rows of the scan -- a default-valued /
+// partition column (stream/default_column.rs:62-108, helpers/transform.rs:356-513) or a column no file carries
+// (all NULL) -- by the constant it evaluates to. The reference evaluates pushed filters over the merged schema
+// AFTER those columns were filled in, so such filters are legal; the device never sees the constant columns.
+// `constant_of(name, &scalar)` returns true when `name` is such a column (scalar: its value, null scalar = NULL).
+std::shared_ptr<FilterExpr> fold_constant_columns(
+    const std::shared_ptr<FilterExpr>& e,
+    const std::function<bool(const std::string&, std::shared_ptr<arrow::Scalar>*)>& constant_of);
 
 }  // namespace lsb

@@ -79,6 +79,7 @@ struct Builder {
       case FilterExpr::kNot: build(*e.right); in.opcode = FO_NOT; emit(in); return;
       case FilterExpr::kTrue: in.opcode = FO_TRUE; emit(in); return;
       case FilterExpr::kFalse: in.opcode = FO_FALSE; emit(in); return;
+      case FilterExpr::kNull: in.opcode = FO_NULL; emit(in); return;
       case FilterExpr::kIsNull: in.opcode = FO_ISNULL; in.col = slot_for(e.column); emit(in); return;
       case FilterExpr::kIsNotNull: in.opcode = FO_ISNOTNULL; in.col = slot_for(e.column); emit(in); return;
       case FilterExpr::kCmp: break;
@@ -148,9 +149,9 @@ int apply_filter(MergePlan* plan, const FilterExpr& expr, const std::vector<Filt
   d_prog = static_cast<FilterProgram*>(device_alloc_bytes(sizeof(FilterProgram), stream));
   d_keep = static_cast<uint8_t*>(device_alloc_bytes((size_t)U, stream));
   if (!b.pool.empty())
-    check(cudaMemcpyAsync(d_pool, b.pool.data(), b.pool.size(), cudaMemcpyHostToDevice, stream), "memcpy pool");
+    check(h2d_staged(d_pool, b.pool.data(), b.pool.size(), stream), "memcpy pool");
   b.prog.lit_pool = d_pool;
-  check(cudaMemcpyAsync(d_prog, &b.prog, sizeof(FilterProgram), cudaMemcpyHostToDevice, stream), "memcpy prog");
+  check(h2d_staged(d_prog, &b.prog, sizeof(FilterProgram), stream), "memcpy prog");
   launch_filter_kernel(d_prog, plan_winners(plan), plan_out_base_dev(plan), nb, U, d_keep, stream);
   plan_compact(plan, d_keep, extra_lists, stream);
   plan_sync_counts(plan, stream);

@@ -25,6 +25,7 @@
 #include <cstring>
 #include <deque>
 #include <stdexcept>
+#include <type_traits>
 
 namespace lsb {
 
@@ -372,7 +373,9 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int& 
 // ---------------------------------------------------------------------------------------
 template <typename KeyT, bool kGeneral>
 __global__ void __launch_bounds__(kTileThreads, 3) tile_kernel(PlanDev P, PkDesc pk, int level,
-                                                            int tile_ofs) {
+                                                            int tile_ofs, const uint8_t* __restrict__ tile_flag) {
+  // tile_flag != nullptr: only the tiles the fast kernel could not take (their flag is raised)
+  if (tile_flag && !tile_flag[tile_ofs + blockIdx.x]) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = P.tile_cap;
   KeyT* K = reinterpret_cast<KeyT*>(smem_raw);
@@ -616,6 +619,290 @@ __global__ void __launch_bounds__(kTileThreads, 3) tile_kernel(PlanDev P, PkDesc
       const int j = upper_idx(seg_start, k, e);
       wt[off] = (uint32_t)(frb[j] + seg_lo[j] + (e - seg_start[j]));
       wf[off] = (uint8_t)j;  // the string gather stages per-file source windows: no search per column there
+      ++off;
+    }
+  }
+  if (tid == 0) {
+    P.tile_cnt[t0] = total;
+    P.tile_gstart[t0] = gstart;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K_tile, fast path for fixed-width keys: the tile's keys are compressed to 64 bits RELATIVE TO THE TILE'S
+// SMALLEST KEY (a tile spans a narrow key range; composite 96/128-bit keys fit whenever the span is below 2^64)
+// and travel through the merge passes TOGETHER with their 16-bit element index: every step of the two-pointer
+// merge reads one 8-byte key and one index by position -- no index -> key double load, no 128-bit compares.
+// (r1 profile of tile_kernel<K128>: 590 thread instructions per key, issue-bound.)
+// A tile whose span does not fit raises its flag and is merged by tile_kernel afterwards.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ K128 k128_sub(const K128& a, const K128& b) {  // a - b, a >= b
+  K128 r;
+  r.lo = a.lo - b.lo;
+  r.hi = a.hi - b.hi - (a.lo < b.lo ? 1ull : 0ull);
+  return r;
+}
+__device__ __forceinline__ K128 widen(uint64_t v) { return K128{0ull, v}; }
+__device__ __forceinline__ K128 widen(const K128& v) { return v; }
+
+static size_t tile_fast_smem_bytes(int C) {
+  return (size_t)C * 8 * 2 + (size_t)C * 2 * 2 + kMaxFilesPerBucket * 8 + (kMaxFilesPerBucket + 1) * 4 +
+         kMaxFilesPerBucket * 4 + 16 * 4;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kTileThreads, 3) tile_fast_kernel(PlanDev P, PkDesc pk, int level, int tile_ofs,
+                                                                 uint8_t* __restrict__ tile_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C = P.tile_cap;
+  uint64_t* Ka = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* Kb = Ka + C;
+  uint16_t* Ia = reinterpret_cast<uint16_t*>(Kb + C);
+  uint16_t* Ib = Ia + C;
+  int64_t* frb = reinterpret_cast<int64_t*>(Ib + C);  // C is a multiple of 8
+  K128* hmin = reinterpret_cast<K128*>(Ka);            // per-file head / tail keys: live only until the keys are loaded
+  K128* hmax = hmin + kMaxFilesPerBucket;              // (2 * 256 * 16 bytes <= the key buffers, host-checked)
+  int32_t* seg_start = reinterpret_cast<int32_t*>(frb + kMaxFilesPerBucket);
+  int32_t* seg_lo = seg_start + kMaxFilesPerBucket + 1;
+  int32_t* scan_tmp = seg_lo + kMaxFilesPerBucket;
+  __shared__ int64_t s_tile_start;
+  __shared__ int s_has_next, s_fits;
+  __shared__ K128 s_min;
+  __shared__ unsigned long long s_next_rel;  // first key after the tile, relative to s_min (valid when s_has_next == 1)
+
+  const int t = tile_ofs + blockIdx.x;
+  const int b = P.tile_bucket[t];
+  const int i = P.tile_idx[t];
+  const BucketDesc& B = P.buckets[b];
+  const KeyOps<KeyT> ops(pk, b);
+  const int k = B.k;
+  const int32_t* sp_lo = P.splits + B.split_ofs[level] + (int64_t)i * k;
+  const int32_t* sp_hi = sp_lo + k;
+  const int sh = level * P.log_s;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+
+  // ---- segment table + head / tail key of every run ---------------------------------------------
+  for (int j = tid; j < k; j += kTileThreads) {
+    const int32_t lo = sp_lo[j], hi = sp_hi[j];
+    seg_lo[j] = lo;
+    seg_start[j + 1] = hi - lo;  // lengths, scanned below
+    const int64_t fb = P.file_row_base[B.file_begin + j];
+    frb[j] = fb;
+    if (hi > lo) {
+      hmin[j] = widen(ops.load(fb + ((((int64_t)lo + 1) << sh) - 1)));
+      hmax[j] = widen(ops.load(fb + ((((int64_t)hi) << sh) - 1)));
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int per = (k + 31) >> 5;
+    int sum = 0;
+    int64_t lsum = 0;
+    bool have = false;
+    K128 mn{0, 0}, mx{0, 0};
+    for (int x = 0; x < per; ++x) {
+      const int j = lane * per + x;
+      if (j < k) {
+        const int len = seg_start[j + 1];
+        sum += len;
+        lsum += seg_lo[j];
+        if (len > 0) {
+          const K128 a = hmin[j], z = hmax[j];
+          if (!have || key_lt(a, mn)) mn = a;
+          if (!have || key_lt(mx, z)) mx = z;
+          have = true;
+        }
+      }
+    }
+    int incl = sum;
+    int64_t lincl = lsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, d);
+      const int64_t ly = __shfl_up_sync(0xffffffffu, lincl, d);
+      if (lane >= d) { incl += y; lincl += ly; }
+    }
+    int run = incl - sum;
+    for (int x = 0; x < per; ++x) {
+      const int j = lane * per + x;
+      if (j < k) { const int len = seg_start[j + 1]; seg_start[j + 1] = run + len; run += len; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const bool oh = __shfl_xor_sync(0xffffffffu, (int)have, d);
+      const K128 omn = shfl_xor_key(mn, d), omx = shfl_xor_key(mx, d);
+      if (oh) {
+        if (!have || key_lt(omn, mn)) mn = omn;
+        if (!have || key_lt(mx, omx)) mx = omx;
+        have = true;
+      }
+    }
+    if (lane == 0) {
+      seg_start[0] = 0;
+      s_min = mn;
+      s_fits = (!have || k128_sub(mx, mn).hi == 0) ? 1 : 0;
+    }
+    if (lane == 31) s_tile_start = lincl;
+  }
+  __syncthreads();
+  const int L = seg_start[k];
+  if (L > C) {
+    if (tid == 0) atomicExch(P.err, kErrTileOverflow);
+    return;
+  }
+  if (!s_fits) {  // span of 2^64 or more: the generic kernel takes this tile
+    if (tid == 0) tile_flag[t] = 1;
+    return;
+  }
+  const K128 kmin = s_min;
+
+  // ---- load keys (coalesced inside a run), compress, pair with the element index ---------------
+  for (int e0 = tid; e0 < L; e0 += 4 * kTileThreads) {
+    int64_t row[4];
+    KeyT kv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * kTileThreads;
+      row[u] = 0;
+      if (e < L) {
+        const int j = upper_idx(seg_start, k, e);
+        row[u] = frb[j] + ((((int64_t)seg_lo[j] + (e - seg_start[j]) + 1) << sh) - 1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (e0 + u * kTileThreads < L) kv[u] = ops.load(row[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * kTileThreads;
+      if (e < L) {
+        Ka[e] = k128_sub(widen(kv[u]), kmin).lo;
+        Ia[e] = (uint16_t)e;
+      }
+    }
+  }
+  if (level == 0 && warp == (kTileThreads / 32 - 1)) {
+    // peek the first key after this tile (min over the k run heads)
+    bool have = false;
+    K128 best{0, 0};
+    for (int j = lane; j < k; j += 32) {
+      const int32_t h = sp_hi[j];
+      if (h < P.file_rows[B.file_begin + j]) {
+        const K128 kk = widen(ops.load(frb[j] + h));
+        if (!have || key_lt(kk, best)) { best = kk; have = true; }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const bool oh = __shfl_xor_sync(0xffffffffu, (int)have, d);
+      const K128 ob = shfl_xor_key(best, d);
+      if (oh && (!have || key_lt(ob, best))) { best = ob; have = true; }
+    }
+    if (lane == 0) {
+      // every later key is >= the tile's keys; one that is 2^64 or more above the tile's minimum differs from all of them
+      const K128 rel = have ? k128_sub(best, kmin) : K128{0, 0};
+      s_has_next = have ? (rel.hi == 0 ? 1 : 2) : 0;
+      s_next_rel = rel.lo;
+    }
+  }
+  __syncthreads();
+
+  // ---- pairwise merge tree over (key, index) pairs, merge-path co-ranking ------------------------
+  uint64_t* Kin = Ka; uint64_t* Kout = Kb;
+  uint16_t* Iin = Ia; uint16_t* Iout = Ib;
+  int nr = k;
+  const int EM = (L + kTileThreads - 1) / kTileThreads;
+  const int mo0 = min(tid * EM, L), mo1 = min(mo0 + EM, L);
+  for (int pass = 0; nr > 1; ++pass) {
+    auto rb = [&](int r) -> int {
+      const int s2 = r << pass;
+      return seg_start[s2 < k ? s2 : k];
+    };
+    int q = mo0;
+    while (q < mo1) {
+      int lo = 0, hi = nr;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (rb(mid) <= q) lo = mid; else hi = mid;
+      }
+      const int base = lo & ~1;
+      const int a0 = rb(base);
+      if (base + 1 >= nr) {  // unpaired last run: copy through
+        for (; q < mo1; ++q) { Kout[q] = Kin[q]; Iout[q] = Iin[q]; }
+        break;
+      }
+      const int m0 = rb(base + 1), e0 = rb(base + 2);
+      const int stop = min(mo1, e0);
+      const int na = m0 - a0, nbb = e0 - m0;
+      const int d = q - a0;
+      int ia = max(0, d - nbb), ihi = min(d, na);
+      while (ia < ihi) {  // co-rank: number of left-run elements among the first d outputs
+        const int mid = (ia + ihi) >> 1;
+        if (Kin[a0 + mid] <= Kin[m0 + d - 1 - mid]) ia = mid + 1; else ihi = mid;
+      }
+      int ja = d - ia;
+      uint64_t ka = ia < na ? Kin[a0 + ia] : ~0ull;
+      uint64_t kb = ja < nbb ? Kin[m0 + ja] : ~0ull;
+      uint16_t ea = ia < na ? Iin[a0 + ia] : (uint16_t)0;
+      uint16_t eb = ja < nbb ? Iin[m0 + ja] : (uint16_t)0;
+      for (; q < stop; ++q) {
+        const bool take_a = (ja >= nbb) || (ia < na && ka <= kb);  // stable: the left run (lower files) wins ties
+        Kout[q] = take_a ? ka : kb;
+        Iout[q] = take_a ? ea : eb;
+        ia += take_a ? 1 : 0;
+        ja += take_a ? 0 : 1;
+        const int nxt = take_a ? (a0 + ia) : (m0 + ja);
+        const bool more = take_a ? (ia < na) : (ja < nbb);
+        const uint64_t kn = Kin[more ? nxt : a0];
+        const uint16_t en = Iin[more ? nxt : a0];
+        if (take_a) { ka = kn; ea = en; } else { kb = kn; eb = en; }
+      }
+    }
+    __syncthreads();
+    uint64_t* tk = Kin; Kin = Kout; Kout = tk;
+    uint16_t* ti = Iin; Iin = Iout; Iout = ti;
+    nr = (nr + 1) >> 1;
+  }
+  // (Kin, Iin) now hold the merged order
+
+  if (level > 0) {
+    uint2* ml = P.mlist + B.mlist_ofs[level] + s_tile_start;
+    for (int q = tid; q < L; q += kTileThreads) {
+      const int e = Iin[q];
+      const int j = upper_idx(seg_start, k, e);
+      ml[q] = make_uint2((unsigned)j, (unsigned)(seg_lo[j] + (e - seg_start[j])));
+    }
+    return;
+  }
+
+  // ---- level 0: group ends -> winners ---------------------------------------------------------
+  const int E = (L + kTileThreads - 1) / kTileThreads;
+  const int q0 = min(tid * E, L), q1 = min(q0 + E, L);
+  const int has_next = s_has_next;
+  const unsigned long long next_rel = s_next_rel;
+  unsigned endmask = 0;  // E <= 11 for the tile capacities in use (host-checked: C <= 16 * kTileThreads)
+  int cnt = 0;
+  for (int q = q0; q < q1; ++q) {
+    const uint64_t kq = Kin[q];
+    bool end;
+    if (q + 1 < L) end = kq != Kin[q + 1];
+    else end = has_next == 0 ? true : (has_next == 2 ? true : kq != next_rel);
+    endmask |= end ? (1u << (q - q0)) : 0u;
+    cnt += end ? 1 : 0;
+  }
+  int total;
+  int off = block_exclusive_scan<kTileThreads>(cnt, scan_tmp, total);
+  const int t0 = blockIdx.x;
+  const int64_t gstart = B.row_base + s_tile_start;
+  uint32_t* wt = P.win_tmp + gstart;
+  uint8_t* wf = P.wfile_tmp + gstart;
+  for (int q = q0; q < q1; ++q) {
+    if (endmask & (1u << (q - q0))) {
+      const int e = Iin[q];
+      const int j = upper_idx(seg_start, k, e);
+      wt[off] = (uint32_t)(frb[j] + seg_lo[j] + (e - seg_start[j]));
+      wf[off] = (uint8_t)j;
       ++off;
     }
   }
@@ -1570,6 +1857,8 @@ struct MergePlan {
   int64_t *d_tile_gstart = nullptr, *d_tile_out = nullptr;
   uint32_t *d_win_tmp = nullptr, *d_win = nullptr;
   uint8_t *d_wfile_tmp = nullptr, *d_wfile = nullptr;
+  uint8_t* d_tile_flag = nullptr;  // per tile (all levels): 1 = the fast tile kernel left it to the generic one
+  bool use_fast_tiles = false;
   bool has_wfile = false;  // d_wfile matches d_win (merge path; the concat path leaves it unset)
   int64_t *d_out_base = nullptr, *d_batch_base = nullptr;
   int64_t* d_dense_base = nullptr;
@@ -1672,6 +1961,41 @@ void DeviceArena::reset() {
   cur_ = 0;
   off_ = 0;
   used_ = 0;
+}
+
+static thread_local HostStage* t_stage = nullptr;
+void host_stage_install(HostStage* s) { t_stage = s; }
+HostStage* host_stage_current() { return t_stage; }
+HostStage::~HostStage() {
+  for (auto& b : blocks_) cudaFreeHost(b.p);
+}
+void* HostStage::alloc(size_t bytes) {
+  bytes = (std::max<size_t>(bytes, 1) + 63) & ~(size_t)63;
+  while (true) {
+    if (cur_ < blocks_.size() && off_ + bytes <= blocks_[cur_].cap) {
+      void* p = blocks_[cur_].p + off_;
+      off_ += bytes;
+      return p;
+    }
+    if (cur_ + 1 < blocks_.size()) { ++cur_; off_ = 0; continue; }
+    size_t cap = std::max<size_t>(bytes, (size_t)1 << 20);
+    if (!blocks_.empty()) cap = std::max(cap, blocks_.back().cap * 2);
+    uint8_t* p = nullptr;
+    LSB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p), cap));
+    blocks_.push_back({p, cap});
+    cur_ = blocks_.size() - 1;
+    off_ = 0;
+  }
+}
+void HostStage::reset() { cur_ = 0; off_ = 0; }
+cudaError_t h2d_staged(void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0) return cudaSuccess;
+  if (t_stage) {
+    void* p = t_stage->alloc(bytes);
+    std::memcpy(p, src, bytes);
+    src = p;
+  }
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
 }
 
 void* device_alloc_bytes(size_t bytes, cudaStream_t stream) {
@@ -1850,6 +2174,12 @@ MergePlan* plan_create(int nb, const int32_t* bucket_file_begin, const int64_t* 
     P->d_win = dev_alloc<uint32_t>(P->n_total, stream);
     P->d_wfile_tmp = dev_alloc<uint8_t>(P->n_total, stream);
     P->d_wfile = dev_alloc<uint8_t>(P->n_total, stream);
+    P->d_tile_flag = dev_alloc<uint8_t>(tb.size(), stream);
+    LSB_CUDA(cudaMemsetAsync(P->d_tile_flag, 0, std::max<size_t>(tb.size(), 1), stream));
+    {
+      static const bool off = [] { const char* v = getenv("LAKESOUL_B200_FAST_TILES"); return v && *v == '0'; }();
+      P->use_fast_tiles = P->key128 && !off;
+    }
     P->d_out_base = dev_alloc<int64_t>(nb + 1, stream);
     P->d_batch_base = dev_alloc<int64_t>(nb + 1, stream);
     P->d_err = dev_alloc<int32_t>(1, stream);
@@ -1857,18 +2187,12 @@ MergePlan* plan_create(int nb, const int32_t* bucket_file_begin, const int64_t* 
     std::vector<int64_t>& dense = P->h_dense;
     dense.assign(P->F + 1, 0);
     for (int f = 0; f < P->F; ++f) dense[f + 1] = dense[f] + file_rows[f];
-    LSB_CUDA(cudaMemcpyAsync(P->d_dense_base, dense.data(), sizeof(int64_t) * (P->F + 1),
-                             cudaMemcpyHostToDevice, stream));
-    LSB_CUDA(cudaMemcpyAsync(P->d_buckets, P->buckets.data(), sizeof(BucketDesc) * nb,
-                             cudaMemcpyHostToDevice, stream));
-    LSB_CUDA(cudaMemcpyAsync(P->d_file_rows, fr32.data(), sizeof(int32_t) * P->F,
-                             cudaMemcpyHostToDevice, stream));
-    LSB_CUDA(cudaMemcpyAsync(P->d_file_row_base, frb.data(), sizeof(int64_t) * (P->F + 1),
-                             cudaMemcpyHostToDevice, stream));
-    LSB_CUDA(cudaMemcpyAsync(P->d_tile_bucket, tb.data(), sizeof(int32_t) * tb.size(),
-                             cudaMemcpyHostToDevice, stream));
-    LSB_CUDA(cudaMemcpyAsync(P->d_tile_idx, ti.data(), sizeof(int32_t) * ti.size(),
-                             cudaMemcpyHostToDevice, stream));
+    LSB_CUDA(h2d_staged(P->d_dense_base, dense.data(), sizeof(int64_t) * (P->F + 1), stream));
+    LSB_CUDA(h2d_staged(P->d_buckets, P->buckets.data(), sizeof(BucketDesc) * nb, stream));
+    LSB_CUDA(h2d_staged(P->d_file_rows, fr32.data(), sizeof(int32_t) * P->F, stream));
+    LSB_CUDA(h2d_staged(P->d_file_row_base, frb.data(), sizeof(int64_t) * (P->F + 1), stream));
+    LSB_CUDA(h2d_staged(P->d_tile_bucket, tb.data(), sizeof(int32_t) * tb.size(), stream));
+    LSB_CUDA(h2d_staged(P->d_tile_idx, ti.data(), sizeof(int32_t) * ti.size(), stream));
     LSB_CUDA(cudaMemsetAsync(P->d_err, 0, sizeof(int32_t), stream));
     // the host vectors are plan members: they outlive the asynchronous copies
 
@@ -1890,6 +2214,8 @@ MergePlan* plan_create(int nb, const int32_t* bucket_file_begin, const int64_t* 
                                   (int)tile_smem_bytes(3328, true)));
     LSB_CUDA(cudaFuncSetAttribute(tile_kernel<StrKey, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tile_smem_bytes(3328, true)));
+    LSB_CUDA(cudaFuncSetAttribute(tile_fast_kernel<K128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tile_fast_smem_bytes(3328)));
     }
     P->stats.n_rows = P->n_in;
     P->stats.tiles_l0 = T0;
@@ -1907,7 +2233,7 @@ void plan_destroy(MergePlan* P) {
   if (!P) return;
   cudaStream_t st = P->alloc_stream;
   void* ptrs[] = {P->d_buckets, P->d_file_rows, P->d_file_row_base, P->d_splits, P->d_mlist, P->d_tile_bucket,
-                  P->d_tile_idx, P->d_tile_cnt, P->d_tile_gstart, P->d_tile_out, P->d_win_tmp, P->d_win, P->d_wfile_tmp, P->d_wfile,
+                  P->d_tile_idx, P->d_tile_cnt, P->d_tile_gstart, P->d_tile_out, P->d_win_tmp, P->d_win, P->d_wfile_tmp, P->d_wfile, P->d_tile_flag,
                   P->d_out_base, P->d_batch_base, P->d_dense_base, P->d_ctmp, P->d_err, P->d_len, P->d_doff,
                   P->d_sums, P->d_cols};
   for (void* p : ptrs) dev_free(p, st);
@@ -1954,7 +2280,15 @@ static int run_levels(MergePlan* P, const PkDesc& pk, cudaStream_t stream) {
     const int ofs = P->level_tile_ofs[l];
     const int warps_per_block = 4;
     part_kernel<KeyT><<<(nt + warps_per_block - 1) / warps_per_block, 128, 0, stream>>>(D, pk, l, ofs, nt);
-    tile_kernel<KeyT, false><<<nt, kTileThreads, P->smem_bytes, stream>>>(D, pk, l, ofs);
+    if constexpr (std::is_same<KeyT, K128>::value) {
+      if (P->use_fast_tiles) {
+        tile_fast_kernel<KeyT><<<nt, kTileThreads, tile_fast_smem_bytes(P->tile_cap), stream>>>(D, pk, l, ofs, P->d_tile_flag);
+        tile_kernel<KeyT, false><<<nt, kTileThreads, P->smem_bytes, stream>>>(D, pk, l, ofs, P->d_tile_flag);
+        launches += 3;
+        continue;
+      }
+    }
+    tile_kernel<KeyT, false><<<nt, kTileThreads, P->smem_bytes, stream>>>(D, pk, l, ofs, nullptr);
     launches += 2;
   }
   return launches;
@@ -2081,7 +2415,7 @@ void gather_fixed(MergePlan* P, const FixedCol* cols, int ncols, cudaStream_t st
     P->d_cols = dev_alloc<FixedCol>(ncols, stream);
     P->d_cols_cap = ncols;
   }
-  LSB_CUDA(cudaMemcpyAsync(P->d_cols, cols, sizeof(FixedCol) * ncols, cudaMemcpyHostToDevice, stream));
+  LSB_CUDA(h2d_staged(P->d_cols, cols, sizeof(FixedCol) * ncols, stream));
   GatherGeom G = make_geom(P);
   const int64_t chunks = total_batches * G.chunks_per_batch;
   gather_fixed_kernel<<<(unsigned)chunks, kGatherThreads, 0, stream>>>(G, P->d_cols, ncols);
@@ -2157,7 +2491,7 @@ void gather_var_multi(MergePlan* P, const VarCol* cols, int ncols, cudaStream_t 
       VarColSet& set = P->h_varsets.back();
       set.n = n;
       for (int i = 0; i < n; ++i) set.col[i] = group[c0 + i];
-      LSB_CUDA(cudaMemcpyAsync(d_set, &set, sizeof(VarColSet), cudaMemcpyHostToDevice, stream));
+      LSB_CUDA(h2d_staged(d_set, &set, sizeof(VarColSet), stream));
       static const int win_variant = [] { const char* v = getenv("LAKESOUL_B200_WINDOW_VARIANT"); return v ? atoi(v) : 0; }();
       if (pass == 0 && win_variant == 1)
         var_window_kernel<14, 24576><<<(unsigned)(chunks * n), kGatherThreads, sizeof(WinSmem<14, 24576>), stream>>>(G, d_set, S, total_batches);
@@ -2495,11 +2829,11 @@ GeneralMerge* general_create(MergePlan* P, const PkDesc& pk, const std::vector<G
     G->d_R = dev_alloc<uint32_t>(rofs[nb], stream);
     G->d_rofs = dev_alloc<int64_t>(nb + 1, stream);
     LSB_CUDA(cudaMemsetAsync(G->d_R, 0xff, sizeof(uint32_t) * rofs[nb], stream));
-    LSB_CUDA(cudaMemcpyAsync(G->d_rofs, rofs.data(), sizeof(int64_t) * (nb + 1), cudaMemcpyHostToDevice, stream));
+    LSB_CUDA(h2d_staged(G->d_rofs, rofs.data(), sizeof(int64_t) * (nb + 1), stream));
     std::vector<char> present((size_t)G->C * P->F);
     for (int c = 0; c < G->C; ++c) std::memcpy(present.data() + (size_t)c * P->F, in[c].present, P->F);
     G->d_present = dev_alloc<char>(present.size(), stream);
-    LSB_CUDA(cudaMemcpyAsync(G->d_present, present.data(), present.size(), cudaMemcpyHostToDevice, stream));
+    LSB_CUDA(h2d_staged(G->d_present, present.data(), present.size(), stream));
     LSB_CUDA(stream_wait(stream));  // host vectors go out of scope below
 
     P->d_R = G->d_R;
@@ -2507,9 +2841,9 @@ GeneralMerge* general_create(MergePlan* P, const PkDesc& pk, const std::vector<G
     PlanDev D = plan_dev(P);
     const int T0 = P->level_tile_cnt[0];
     const int ofs0 = P->level_tile_ofs[0];
-    if (P->key_bytes) tile_kernel<StrKey, true><<<T0, kTileThreads, P->smem_bytes, stream>>>(D, pk, 0, ofs0);
-    else if (P->key128) tile_kernel<K128, true><<<T0, kTileThreads, P->smem_bytes, stream>>>(D, pk, 0, ofs0);
-    else tile_kernel<uint64_t, true><<<T0, kTileThreads, P->smem_bytes, stream>>>(D, pk, 0, ofs0);
+    if (P->key_bytes) tile_kernel<StrKey, true><<<T0, kTileThreads, P->smem_bytes, stream>>>(D, pk, 0, ofs0, nullptr);
+    else if (P->key128) tile_kernel<K128, true><<<T0, kTileThreads, P->smem_bytes, stream>>>(D, pk, 0, ofs0, nullptr);
+    else tile_kernel<uint64_t, true><<<T0, kTileThreads, P->smem_bytes, stream>>>(D, pk, 0, ofs0, nullptr);
     ++G->launches;
 
     for (int c = 0; c < G->C; ++c) {

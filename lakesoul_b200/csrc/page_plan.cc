@@ -23,27 +23,25 @@ namespace lsb {
 namespace {
 [[noreturn]] void fail(const std::string& m) { throw std::runtime_error(m); }
 
-// ZSTD page payloads are expanded by Arrow's codec on the host or by the GPU (zstd_pages_kernel). Measured on config-2
-// PLAIN+ZSTD buckets: all-host 73-83 M rows/s (13-15 cores busy), all-device 51-54 M rows/s (1.4 cores busy), and
-// splits that send the 30-50 % smallest column chunks to the device stay at 46-54 M rows/s -- the device decoder's
-// per-page latency, not its share of the bytes, is what holds a reader back. Until the execute step of the kernel is
-// parallel the default is the host codec; LAKESOUL_B200_DEVICE_ZSTD_SHARE=<0..1> sends that share of a file's
-// compressed-chunk bytes (smallest chunks first) to the GPU, 1 = everything.
+// ZSTD page payloads are expanded on the GPU (zstd_pages_kernel_v2) by default: with 32 hardware work queues the
+// all-device path reads config-5 buckets at 51 M rows/s on 16 task slots with 5 host cores busy, the host codec
+// (Arrow) at 40 M rows/s with 12 cores busy, and splits by chunk size at 36 M rows/s (r2 sweep).
+// LAKESOUL_B200_DEVICE_ZSTD_SHARE=<0..1> sends that share of a file's compressed-chunk bytes (smallest chunks first)
+// to the GPU (0 = host codec only); LAKESOUL_B200_DEVICE_ZSTD_MIN_BYTES=<n> instead sends the chunks of at least n
+// uncompressed bytes.
 double device_zstd_share() {
   static const double share = [] {
     const char* v = getenv("LAKESOUL_B200_DEVICE_ZSTD_SHARE");
     if (!v) v = getenv("LAKESOUL_B200_DEVICE_ZSTD");  // 0 / 1
-    if (!v || !*v) return -1.0;  // unset: the size policy below decides
+    if (!v || !*v) return getenv("LAKESOUL_B200_DEVICE_ZSTD_MIN_BYTES") ? -1.0 : 1.0;  // default: everything on the GPU
     const double x = atof(v);
     return x < 0 ? 0.0 : (x > 1 ? 1.0 : x);
   }();
   return share;
 }
 
-// Default split of the ZSTD work (r2 measurements): a frame is sequential per 128 KiB block, so the GPU
-// is efficient on LARGE column chunks (many blocks side by side, few thread blocks) and wasteful on the thousands of
-// few-KiB chunks of small delta files (one mostly idle thread block each), which the host expands in microseconds.
-// Column chunks of at least this many uncompressed bytes are expanded on the device, smaller ones on the host.
+// Optional split of the ZSTD work by chunk size: column chunks of at least this many uncompressed bytes are expanded
+// on the device, smaller ones by the host codec.
 int64_t device_zstd_min_bytes() {
   static const int64_t v = [] {
     const char* e = getenv("LAKESOUL_B200_DEVICE_ZSTD_MIN_BYTES");

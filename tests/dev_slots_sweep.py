@@ -17,6 +17,8 @@ for t in slots:
     with open(job, "w") as f:
         f.write(f"{t} 8192 3\n" + "\t".join(spec.primary_keys) + "\n\n\n" + "\n".join("\t".join(p) for p in paths) + "\n")
     out = subprocess.run([drv, job], capture_output=True, text=True)
+    if os.environ.get("LAKESOUL_B200_TRACE") == "1":
+        sys.stderr.write(out.stderr)
     if out.returncode != 0:
         print("FAILED", out.stderr[-400:]); continue
     r = json.loads(out.stdout.strip().splitlines()[-1])

@@ -136,6 +136,33 @@ def test_composite_key_128bit():
     _run(buckets, composite=True)
 
 
+def test_composite_key_wide_span_takes_the_generic_tile_kernel():
+    """First key column spread over the whole int64 range: a tile's key span exceeds 2^64 in the packed 96-bit space,
+    so the fast (tile-relative 64-bit) kernel hands those tiles to the generic one; dense ranges in the same scan stay
+    on the fast path. Negative values in both key columns (sign-flipped images)."""
+    rng = np.random.default_rng(17)
+    buckets = []
+    for wide in (True, False, True):
+        files = []
+        for n in (20_000, 6_000, 3_000, 3_000, 500):
+            if wide:
+                c0 = rng.integers(-2**62, 2**62, size=n)
+                c0[: n // 4] = rng.choice(c0, size=n // 4)  # duplicates across and inside files
+            else:
+                c0 = rng.integers(-3_000, 3_000, size=n)
+            a = np.stack([c0, rng.integers(-3, 4, size=n)], axis=1).astype(np.int64)
+            a = a[np.lexsort((a[:, 1], a[:, 0]))]
+            files.append(a)
+        buckets.append(files)
+    pool = np.stack([rng.integers(-2**62, 2**62, size=6_000), rng.integers(-3, 4, size=6_000)], axis=1).astype(np.int64)
+    shared = []
+    for _ in range(6):  # the same wide keys in many files: long equal-key groups across tile boundaries
+        a = pool[rng.integers(0, len(pool), size=9_000)]
+        shared.append(a[np.lexsort((a[:, 1], a[:, 0]))])
+    buckets.append(shared)
+    _run(buckets, composite=True, pad=True)
+
+
 def test_gather_fixed_and_strings_match_numpy():
     import torch
     from lakesoul_b200.engine import PK_SIGNED, ScanPlan
