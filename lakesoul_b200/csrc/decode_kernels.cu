@@ -827,11 +827,11 @@ constexpr int kZstdThreads = 64;
 __device__ unsigned long long g_zstd_prof[16];
 __global__ void __launch_bounds__(kZstdThreads) zstd_pages_kernel(const PqZstdPage* pages, const ZstdBlockDesc* blocks_all,
                                                                   ZstdBlockPlan* plans_all, ZstdTables* tables_all, uint8_t* lit_all,
-                                                                  uint64_t* seq_all, int32_t* err) {
+                                                                  uint64_t* seq_all, int32_t* err, const int32_t* order = nullptr) {
   __shared__ ZstdPlanScratch s_plan;
   __shared__ int s_fail;
   __shared__ uint32_t s_round[96];  // ll | ml | resolved offset of the 32 sequences of a round
-  const PqZstdPage pg = pages[blockIdx.x];
+  const PqZstdPage pg = pages[order ? order[blockIdx.x] : blockIdx.x];
   const uint8_t* src = reinterpret_cast<const uint8_t*>(pg.src_off);
   uint8_t* dst = reinterpret_cast<uint8_t*>(pg.dst_off);
   const ZstdBlockDesc* blocks = blocks_all + pg.first_block;
@@ -1515,7 +1515,8 @@ __global__ void __launch_bounds__(kWarps * 32) zstd_pages_kernel_v2(const PqZstd
 }
 
 void launch_zstd_pages_v2(const PqZstdPage* pages, const int32_t* order_small, int nsmall, const int32_t* order_big, int nbig,
-                          const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, uint8_t* lit, uint64_t* seq, int32_t* err, cudaStream_t s) {
+                          const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, ZstdTables* tables_v1, uint8_t* lit, uint64_t* seq, int32_t* err,
+                          cudaStream_t s) {
   static thread_local int attr_device = -1;
   int cur = 0;
   cudaGetDevice(&cur);
@@ -1538,7 +1539,9 @@ void launch_zstd_pages_v2(const PqZstdPage* pages, const int32_t* order_small, i
                       what, h[3], h[0] / 1e3 / h[3], h[1] / 1e3 / h[3], h[2] / 1e3 / h[3], h[4] / 1e3, h[5] / 1e3, h[6] / 1e3, h[7] / 1e3);
   };
   if (prof) dump("big");
-  if (nsmall > 0)
+  if (nsmall > 0 && tables_v1)  // experiment: pages of one or two blocks on the first-generation kernel
+    zstd_pages_kernel<<<nsmall, kZstdThreads, 0, s>>>(pages, blocks, plans, tables_v1, lit, seq, err, order_small);
+  else if (nsmall > 0)
     zstd_pages_kernel_v2<2><<<nsmall, 2 * 32, 2 * sizeof(ZstdTables), s>>>(pages, order_small, blocks, plans, lit, seq, err);
   if (prof) dump("small");
 }

@@ -200,7 +200,8 @@ void launch_block_decode(const DecodeArgs& A, cudaStream_t s);
 void launch_zstd_pages(const PqZstdPage* pages, int npages, const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, ZstdTables* tables,
                        uint8_t* lit, uint64_t* seq, int32_t* err, cudaStream_t s);
 void launch_zstd_pages_v2(const PqZstdPage* pages, const int32_t* order_small, int nsmall, const int32_t* order_big, int nbig,
-                          const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, uint8_t* lit, uint64_t* seq, int32_t* err, cudaStream_t s);
+                          const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, ZstdTables* tables_v1, uint8_t* lit, uint64_t* seq, int32_t* err,
+                          cudaStream_t s);
 
 namespace {
 
@@ -681,8 +682,10 @@ void DeviceScan::Impl::upload() {
         order.insert(order.end(), order_small.begin(), order_small.end());
         int32_t* d_order = static_cast<int32_t*>(dalloc(sizeof(int32_t) * order.size()));
         h2d(d_order, order.data(), sizeof(int32_t) * order.size());
+        static const bool small_v1 = [] { const char* v = getenv("LAKESOUL_B200_ZSTD_SMALL_V1"); return v && *v == '1'; }();
+        ZstdTables* d_ztables = small_v1 ? static_cast<ZstdTables*>(dalloc(sizeof(ZstdTables) * zblocks.size())) : nullptr;
         launch_zstd_pages_v2(d_zpages, d_order + order_big.size(), (int)order_small.size(), d_order, (int)order_big.size(), d_zblocks,
-                             d_zplans, d_zlit, d_zseq, d_err, stream);
+                             d_zplans, d_ztables, d_zlit, d_zseq, d_err, stream);
         ctr.kernel_launches += (order_small.empty() ? 0 : 1) + (order_big.empty() ? 0 : 1);
       }
       ctr.device_decompressed_pages += (int64_t)zpages.size();
@@ -826,46 +829,87 @@ void DeviceScan::Impl::merge_and_gather() {
   const bool general_path = do_merge && (!all_use_last || partial);
 
   // ---- primary key ------------------------------------------------------------------------
+  // Fast paths: up to 4 fixed-width columns packed into 64 / 128 bits, or one Utf8 / Binary column. Every other
+  // shape (a string inside a composite key, decimal keys, more than 128 bits or 4 columns) is merged on row-encoded
+  // keys (plan_encode_keys), the order the reference gets from arrow-row (stream/mod.rs:104-122).
   PkDesc pk{};
   int key_bits = 64;
+  bool encoded_keys = false;
+  std::vector<EncKeyCol> enc;
   if (do_merge) {
-    if ((int)spec.primary_keys.size() > kMaxPkCols)
-      fail("more than 4 primary key columns are not supported by the GPU reader");
-    pk.ncols = (int)spec.primary_keys.size();
-    key_bits = 0;
-    for (int i = 0; i < pk.ncols; ++i) {
+    const int npk = (int)spec.primary_keys.size();
+    std::vector<int> pk_cols;
+    for (int i = 0; i < npk; ++i) {
       const int c = spec.physical_schema->GetFieldIndex(spec.primary_keys[i]);
       if (c < 0) fail("primary key column '" + spec.primary_keys[i] + "' is not in the schema");
+      if (!cols[c].all_present) fail("primary key column '" + spec.primary_keys[i] + "' is missing from a file");
+      pk_cols.push_back(c);
+    }
+    int bits = 0;
+    bool fixed_ok = npk <= kMaxPkCols;
+    for (int c : pk_cols) {
       const DevColumn& dc = cols[c];
-      if (!dc.all_present) fail("primary key column '" + spec.primary_keys[i] + "' is missing from a file");
-      if (dc.kind.var && pk.ncols == 1) {
-        // Utf8 / Binary key: prefix + full byte-wise compare on the device
+      if (dc.kind.var || !dc.kind.pk_ok) fixed_ok = false;
+      bits += dc.kind.width * 8 + (dc.validity.p ? 1 : 0);
+    }
+    if (fixed_ok && bits > 128) fixed_ok = false;
+    const bool single_bytes = npk == 1 && cols[pk_cols[0]].kind.var;
+    if (single_bytes) {
+      const DevColumn& dc = cols[pk_cols[0]];
+      pk.ncols = 1;
+      pk.col[0].values = dc.values.p;
+      pk.col[0].validity = static_cast<const uint8_t*>(dc.validity.p);
+      pk.col[0].width = 0;
+      pk.col[0].kind = PK_BYTES;
+      pk.col[0].data = static_cast<const uint8_t*>(dc.data.p);
+      pk.col[0].bucket_data = static_cast<const int64_t*>(dc.d_bucket_data.p);
+      key_bits = 128;
+    } else if (fixed_ok) {
+      pk.ncols = npk;
+      for (int i = 0; i < npk; ++i) {
+        const DevColumn& dc = cols[pk_cols[i]];
         pk.col[i].values = dc.values.p;
         pk.col[i].validity = static_cast<const uint8_t*>(dc.validity.p);
-        pk.col[i].width = 0;
-        pk.col[i].kind = PK_BYTES;
-        pk.col[i].data = static_cast<const uint8_t*>(dc.data.p);
-        pk.col[i].bucket_data = static_cast<const int64_t*>(dc.d_bucket_data.p);
-        key_bits = 128;
-        continue;
+        pk.col[i].width = (uint8_t)dc.kind.width;
+        pk.col[i].kind = dc.kind.pk_kind;
       }
-      if (!dc.kind.pk_ok)
-        fail("primary key column '" + spec.primary_keys[i] + "' of type " +
-             spec.physical_schema->field(c)->type()->ToString() +
-             (dc.kind.var ? " inside a composite key" : "") + " is not supported by the GPU reader yet");
-      pk.col[i].values = dc.values.p;
-      pk.col[i].validity = static_cast<const uint8_t*>(dc.validity.p);
-      pk.col[i].width = (uint8_t)dc.kind.width;
-      pk.col[i].kind = dc.kind.pk_kind;
-      key_bits += dc.kind.width * 8 + (dc.validity.p ? 1 : 0);
+      key_bits = bits;
+    } else {
+      encoded_keys = true;
+      key_bits = 128;
+      for (int i = 0; i < npk; ++i) {
+        const int c = pk_cols[i];
+        const DevColumn& dc = cols[c];
+        const auto& type = *spec.physical_schema->field(c)->type();
+        EncKeyCol e{};
+        e.values = dc.values.p;
+        e.validity = static_cast<const uint8_t*>(dc.validity.p);
+        e.data = static_cast<const uint8_t*>(dc.data.p);
+        e.bucket_data = static_cast<const int64_t*>(dc.d_bucket_data.p);
+        e.width = dc.kind.width;
+        if (dc.kind.var) e.kind = ENC_BYTES;
+        else if (type.id() == arrow::Type::BOOL) e.kind = ENC_BOOL_BITS;
+        else if (type.id() == arrow::Type::FLOAT || type.id() == arrow::Type::DOUBLE) e.kind = ENC_FLOAT;
+        else if (arrow::is_unsigned_integer(type.id())) e.kind = ENC_UNSIGNED;
+        else if (arrow::is_signed_integer(type.id()) || arrow::is_decimal(type.id()) || arrow::is_temporal(type.id())) e.kind = ENC_SIGNED;
+        else
+          fail("primary key column '" + spec.primary_keys[i] + "' of type " + type.ToString() + " is not supported by the GPU reader");
+        enc.push_back(e);
+      }
     }
-    if (key_bits > 128) fail("primary key wider than 128 bits is not supported by the GPU reader");
     pk.key_bits = key_bits;
   }
 
   const double t0 = now_ms();
   plan = plan_create(nb, bucket_file_begin.data(), file_rows.data(), file_row_base.data(), span,
                      do_merge ? key_bits : 64, spec.batch_size, stream);
+  if (do_merge && encoded_keys) {
+    // the encoder walks string offsets of the key columns: a malformed page must surface as its own error first
+    SCAN_CUDA(stream_wait(stream));
+    check_decode_error();
+    plan_encode_keys(plan, enc.data(), (int)enc.size(), &pk, stream);
+    ctr.kernel_launches += 5;
+  }
   if (do_merge) plan_merge(plan, pk, stream);
   else plan_identity(plan, stream);
   plan_sync_counts(plan, stream);

@@ -2507,6 +2507,147 @@ void gather_var_multi(MergePlan* P, const VarCol* cols, int ncols, cudaStream_t 
 void gather_var(MergePlan* P, const VarCol& col, cudaStream_t stream) { gather_var_multi(P, &col, 1, stream); }
 
 // ---------------------------------------------------------------------------------------
+// row-encoded keys (general primary-key shapes)
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxEncCols = 16;
+struct EncKeySet {
+  int32_t n;
+  EncKeyCol col[kMaxEncCols];
+};
+
+__device__ __forceinline__ bool enc_valid(const EncKeyCol& c, int64_t g) {
+  return !c.validity || ((c.validity[g >> 3] >> (g & 7)) & 1);
+}
+
+// dense row u (files packed back to back) -> global row, file
+__device__ __forceinline__ int64_t dense_to_global(const PlanDev& P, int F, int64_t u, int* f_out) {
+  const int f = upper_idx(P.dense_base, F + 1, u);
+  *f_out = f;
+  return P.file_row_base[f] + (u - P.dense_base[f]);
+}
+
+template <bool kWrite>
+__global__ void __launch_bounds__(256) encode_keys_kernel(PlanDev P, int F, int64_t n_in, const EncKeySet* __restrict__ set,
+                                                          const int32_t* __restrict__ file_bucket, int32_t* __restrict__ len,
+                                                          const int64_t* __restrict__ off, int32_t* __restrict__ enc_off,
+                                                          uint8_t* __restrict__ enc_data) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_in) return;
+  int f;
+  const int64_t g = dense_to_global(P, F, u, &f);
+  uint8_t* out = kWrite ? enc_data + off[u] : nullptr;
+  if (kWrite) {
+    enc_off[g] = (int32_t)off[u];
+    if (u + 1 == P.dense_base[f + 1]) enc_off[g + 1] = (int32_t)off[u + 1];  // closing entry in the file's spare row
+  }
+  int64_t n = 0;
+  for (int c = 0; c < set->n; ++c) {
+    const EncKeyCol& col = set->col[c];
+    const bool valid = enc_valid(col, g);
+    if (kWrite) out[n] = valid ? 1 : 0;
+    ++n;
+    if (col.kind == ENC_BYTES) {
+      if (valid) {
+        const int32_t* offs = reinterpret_cast<const int32_t*>(col.values);
+        const uint8_t* p = col.data + col.bucket_data[file_bucket[f]] + offs[g];
+        const int32_t l = offs[g + 1] - offs[g];
+        for (int32_t i = 0; i < l; ++i) {
+          const uint8_t b = p[i];
+          if (kWrite) out[n] = b;
+          ++n;
+          if (b == 0) { if (kWrite) out[n] = 0xFF; ++n; }
+        }
+      }
+      if (kWrite) { out[n] = 0; out[n + 1] = 0; }
+      n += 2;
+    } else if (col.kind == ENC_BOOL_BITS) {
+      const uint8_t v = valid ? ((reinterpret_cast<const uint8_t*>(col.values)[g >> 3] >> (g & 7)) & 1) : 0;
+      if (kWrite) out[n] = v;
+      ++n;
+    } else {
+      const int w = col.width;
+      if (kWrite) {
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(col.values) + g * w;
+        const bool neg = (p[w - 1] & 0x80) != 0;
+        for (int i = 0; i < w; ++i) {  // big endian, most significant byte first
+          uint8_t b = valid ? p[w - 1 - i] : 0;
+          if (valid) {
+            if (col.kind == ENC_SIGNED) { if (i == 0) b ^= 0x80; }
+            else if (col.kind == ENC_FLOAT) { b = neg ? (uint8_t)~b : (i == 0 ? (uint8_t)(b ^ 0x80) : b); }
+          }
+          out[n + i] = b;
+        }
+      }
+      n += w;
+    }
+  }
+  if (!kWrite) len[u] = (int32_t)min(n, (int64_t)INT32_MAX);
+}
+
+void plan_encode_keys(MergePlan* P, const EncKeyCol* cols, int ncols, PkDesc* pk, cudaStream_t stream) {
+  if (ncols <= 0 || ncols > kMaxEncCols) {
+    g_last_error = "primary key with more than 16 columns is not supported";
+    throw std::runtime_error(g_last_error);
+  }
+  const int64_t n = P->n_in;
+  EncKeySet set{};
+  set.n = ncols;
+  for (int i = 0; i < ncols; ++i) set.col[i] = cols[i];
+  EncKeySet* d_set = dev_alloc<EncKeySet>(1, stream);
+  LSB_CUDA(h2d_staged(d_set, &set, sizeof(set), stream));
+  std::vector<int32_t> fb((size_t)std::max(P->F, 1), 0);
+  for (int b = 0; b < P->nb; ++b)
+    for (int j = 0; j < P->buckets[b].k; ++j) fb[(size_t)P->buckets[b].file_begin + j] = b;
+  int32_t* d_fb = dev_alloc<int32_t>(fb.size(), stream);
+  LSB_CUDA(h2d_staged(d_fb, fb.data(), sizeof(int32_t) * fb.size(), stream));
+  int32_t* d_off32 = dev_alloc<int32_t>((size_t)P->n_total + 2, stream);
+  int64_t* d_zero = dev_alloc<int64_t>((size_t)std::max(P->nb, 1), stream);
+  LSB_CUDA(cudaMemsetAsync(d_zero, 0, sizeof(int64_t) * (size_t)std::max(P->nb, 1), stream));
+  LSB_CUDA(cudaMemsetAsync(d_off32, 0, sizeof(int32_t) * ((size_t)P->n_total + 2), stream));
+  uint8_t* d_data = nullptr;
+  P->var_scratch.push_back(d_set);
+  P->var_scratch.push_back(d_fb);
+  P->var_scratch.push_back(d_off32);
+  P->var_scratch.push_back(d_zero);
+  if (n > 0) {
+    PlanDev D = plan_dev(P);
+    int32_t* d_len = dev_alloc<int32_t>((size_t)n, stream);
+    const int nblocks = (int)((n + kScanChunk - 1) / kScanChunk);
+    int64_t* d_sums = dev_alloc<int64_t>((size_t)nblocks + 2, stream);
+    int64_t* d_doff = dev_alloc<int64_t>((size_t)n + 1, stream);
+    P->var_scratch.push_back(d_len);
+    P->var_scratch.push_back(d_sums);
+    P->var_scratch.push_back(d_doff);
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    encode_keys_kernel<false><<<grid, 256, 0, stream>>>(D, P->F, n, d_set, d_fb, d_len, nullptr, nullptr, nullptr);
+    scan_block_sums<<<nblocks, 256, 0, stream>>>(d_len, n, d_sums);
+    scan_sums_inplace<<<1, 1024, 0, stream>>>(d_sums, nblocks, 0);
+    scan_apply<<<nblocks, 256, 0, stream>>>(d_len, n, d_sums, d_doff);
+    int64_t* h_total = pinned_counts(4) + 3;  // (the plan's count read-back uses the front of the same block later)
+    LSB_CUDA(cudaMemcpyAsync(h_total, d_doff + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    LSB_CUDA(stream_wait(stream));
+    const int64_t total = *h_total;
+    if (total > 0x7fffff00ll) {
+      g_last_error = "row-encoded primary keys exceed 2 GiB in one scan";
+      throw std::runtime_error(g_last_error);
+    }
+    d_data = dev_alloc<uint8_t>((size_t)total + 64, stream);
+    P->var_scratch.push_back(d_data);
+    encode_keys_kernel<true><<<grid, 256, 0, stream>>>(D, P->F, n, d_set, d_fb, nullptr, d_doff, d_off32, d_data);
+    LSB_CUDA(cudaGetLastError());
+  }
+  *pk = PkDesc{};
+  pk->ncols = 1;
+  pk->key_bits = 128;
+  pk->col[0].values = d_off32;
+  pk->col[0].validity = nullptr;
+  pk->col[0].width = 0;
+  pk->col[0].kind = PK_BYTES;
+  pk->col[0].data = d_data;
+  pk->col[0].bucket_data = d_zero;
+}
+
+// ---------------------------------------------------------------------------------------
 // winner compaction after the post-merge predicate
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) keep_to_i32(const uint8_t* keep, int64_t n, int32_t* out) {

@@ -99,6 +99,24 @@ void plan_destroy(MergePlan*);
 // Run partition + tile merge + scan + compaction. Asynchronous on `stream`.
 void plan_merge(MergePlan*, const PkDesc& pk, cudaStream_t stream);
 
+// Primary keys the fixed-width fast paths do not cover (a string inside a composite key, decimal keys, more than
+// 128 key bits, more than 4 columns): every row's key is materialised as ONE byte string whose bytewise order is
+// the reference's row order (arrow-row through RowCursorStream, stream/mod.rs:104-122: columns in order, nulls
+// first, signed / float / decimal values as order-preserving big-endian images, strings bytewise), and the merge
+// runs on that column like on a single Binary key. Per column: 1 validity byte, then the fixed-width image or the
+// escaped string (0x00 -> 0x00 0xFF) closed by 0x00 0x00.
+enum EncKind : int32_t { ENC_UNSIGNED = 0, ENC_SIGNED = 1, ENC_FLOAT = 2, ENC_BYTES = 3, ENC_BOOL_BITS = 4 };
+struct EncKeyCol {
+  const void* values;          // fixed width: `width` bytes per global row (little endian); ENC_BYTES: int32 offsets
+  const uint8_t* validity;     // or nullptr
+  const uint8_t* data;         // ENC_BYTES
+  const int64_t* bucket_data;  // ENC_BYTES: device, per bucket
+  int32_t width;               // 1, 2, 4, 8, 16, 32 (ENC_SIGNED covers the decimals)
+  int32_t kind;
+};
+// Fills `pk` (one PK_BYTES column, key_bits 128) with device buffers owned by the plan. Blocks once on `stream`.
+void plan_encode_keys(MergePlan*, const EncKeyCol* cols, int ncols, PkDesc* pk, cudaStream_t stream);
+
 // "No merge" variant (skip_merge_on_read / no primary key, merge/mod.rs:297-312): every input row
 // survives, in file order.
 void plan_identity(MergePlan*, cudaStream_t stream);
