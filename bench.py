@@ -53,7 +53,7 @@ def parse_args():
                     help="distinct bucket contents generated; the remaining bucket ids are hard links to them")
     ap.add_argument("--e2e-passes", type=int, default=5, help="timed passes over the whole table (median reported)")
     ap.add_argument("--e2e-threads", type=int, default=0,
-                    help="concurrent per-bucket readers (task slots) per rank; 0 = min(cores/ranks, --e2e-slot-cap)")
+                    help="concurrent per-bucket readers (task slots) per rank; 0 = --e2e-slot-cap")
     ap.add_argument("--e2e-slot-cap", type=int, default=24)
     ap.add_argument("--side-buckets", type=int, default=64, help="buckets of the E1/E2/E3 side comparison (1 GPU only)")
     ap.add_argument("--keep-data", action="store_true")
@@ -87,15 +87,19 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self) -> dict:
+    def stop(self, t0: float = None, t1: float = None) -> dict:
+        """clocks over the samples taken inside [t0, t1] (the timed region); if the region was too short to catch
+        one, over every sample since the sampler started (warm-up steps: same kernels, same load)"""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        inside = [ln for ts, ln in self.lines if t0 is not None and t0 <= ts <= t1 + 0.05]
+        window = "timed region" if inside else "warm-up + timed region"
+        for ln in (inside or [ln for _, ln in self.lines]):
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 9:
                 continue
@@ -108,7 +112,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -512,12 +516,12 @@ def main():
         sizes = my_sizes.cpu().numpy()
     lo, hi = balanced_ranges(sizes, world)[rank]
     shard = Shard(hi - lo, seed=20260921 + 2000 + rank)
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # nvidia-smi needs a moment to start: it samples from the warm-up steps on (same kernels, same load)
     for _ in range(args.warmup):
         shard.step()
     rec = {"merge_ms": [], "gather_ms": []}
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     ev0.record()
@@ -530,8 +534,9 @@ def main():
         launches += st["launches"] + 1 + 1  # merge kernels + fixed-width gather + string gather
     ev1.record()
     barrier()
-    wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
+    t_wall1 = time.perf_counter()
+    wall = t_wall1 - t_wall0
+    clocks = sampler.stop(t_wall0, t_wall1)
     ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
     tot = torch.tensor([rows_in, rows_out], dtype=torch.int64, device="cuda")
     if world > 1:
@@ -599,7 +604,10 @@ def main():
         lo, hi = balanced_ranges(bsizes, world)[rank]
         paths = [bucket_paths(root, "E3", b) for b in range(lo, hi)]
         cpus, numa = rank_cpus(local_rank, world)
-        slots = args.e2e_threads or max(2, min(cores_total // world, len(cpus), args.e2e_slot_cap))
+        # task slots per rank: with page decompression on the GPU a slot mostly sleeps on its stream, so the number in
+        # flight is what saturates the GPU (measured optimum 24 on one B200: 45 / 53 / 58 / 60 / 54 M rows/s at
+        # 12 / 16 / 20 / 24 / 32 slots), not the core count
+        slots = args.e2e_threads or args.e2e_slot_cap
         readers = NativeReaders(paths, slots, cpus, e2e_env("E3"))
         readers.run_pass(min(len(paths), 2 * slots))  # warm-up: pinned pool, arenas, page cache
         passes = []

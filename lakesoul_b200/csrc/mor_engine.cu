@@ -1029,6 +1029,7 @@ __global__ void __launch_bounds__(256) compact_kernel(PlanDev P) {
 // gather: fixed width
 // ---------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
+constexpr int kGatherFixedBlocksDefault = 2;
 constexpr int kRowsPerChunk = 2048;
 
 struct GatherGeom {
@@ -1078,9 +1079,10 @@ __device__ __forceinline__ int var_row_len(const VarCol& col, uint32_t g, bool& 
 // One block = 2048 output rows of one batch x ALL fixed-width columns.
 // (Fusing pass 1 of the string gather in here was measured slower: the latency-bound string sizing
 //  then runs at this kernel's 2 blocks/SM instead of 8 -- gather 7.99 ms vs 7.2 ms per bench step.)
-__global__ void __launch_bounds__(kGatherThreads) gather_fixed_kernel(GatherGeom G,
-                                                                      const FixedCol* __restrict__ cols,
-                                                                      int ncols) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kGatherThreads, kMinBlocks) gather_fixed_kernel(GatherGeom G,
+                                                                                  const FixedCol* __restrict__ cols,
+                                                                                  int ncols) {
   int b, r_begin, r_end, rows;
   int64_t gb, u0;
   if (!chunk_geometry(G, blockIdx.x, b, gb, u0, r_begin, r_end, rows)) return;
@@ -1361,11 +1363,20 @@ __global__ void __launch_bounds__(kGatherThreads) var_write_kernel(GatherGeom G,
   __shared__ int32_t s_src[kRowsPerChunk];       // bucket-relative source offset of every row
   __shared__ __align__(16) uint8_t s_stage[kStageBytes + 16];
   __shared__ long long s_c0, s_rel;
-  int b, r_begin, r_end, rows;
-  int64_t gb, u0;
+  __shared__ int g_b, g_r_begin, g_rows, g_live;   // chunk geometry: one thread searches, everybody reads
+  __shared__ long long g_gb, g_u0;
   const int ci = (int)(blockIdx.x % (unsigned)S.ncols);
   const int64_t chunk = blockIdx.x / (unsigned)S.ncols;
-  const bool live = chunk_geometry(G, chunk, b, gb, u0, r_begin, r_end, rows);
+  if (threadIdx.x == 0) {
+    int b0, rb0, re0, rows0;
+    int64_t gb0, u00;
+    g_live = chunk_geometry(G, chunk, b0, gb0, u00, rb0, re0, rows0) ? 1 : 0;
+    g_b = b0; g_r_begin = rb0; g_rows = rows0; g_gb = gb0; g_u0 = u00;
+  }
+  __syncthreads();
+  const bool live = g_live != 0;
+  const int b = g_b, r_begin = g_r_begin, rows = g_rows;
+  const int64_t gb = g_gb, u0 = g_u0;
   const VarCol col = set->col[ci];
   unsigned long long* agg = S.agg + (int64_t)ci * S.stride;
   unsigned long long* incl = S.incl + (int64_t)ci * S.stride;
@@ -1423,12 +1434,13 @@ __global__ void __launch_bounds__(kGatherThreads) var_write_kernel(GatherGeom G,
   uint8_t* dst_bytes = col.dst_data + c0;       // chunk-relative byte p lives at dst_bytes[p]
   const int mis = (int)((reinterpret_cast<uintptr_t>(dst_bytes)) & 15);  // stage[mis + (p - w0)] <-> p
   int w0 = 0;
+  int r_lo = 0;
   while (w0 < tot) {
     const int first_pad = (w0 == 0) ? mis : 0;   // later windows start on a 16-byte boundary
     const int w1 = min(tot, w0 + kStageBytes - first_pad);
-    // rows intersecting [w0, w1)
-    const int r_lo = upper_idx(s_off, nloc + 1, w0);
-    const int r_hi = upper_idx(s_off, nloc + 1, w1 - 1);
+    // rows intersecting [w0, w1): most chunks are one window (no search at all); the row that straddles a window
+    // boundary is the first row of the next window
+    const int r_hi = (w1 >= tot) ? nloc - 1 : upper_idx(s_off, nloc + 1, w1 - 1);
     for (int r = r_lo + threadIdx.x; r <= r_hi; r += 2 * kGatherThreads) {
       // two rows per trip: all loads of both rows are issued before the first store
       RowCopy c0r, c1r;
@@ -1463,6 +1475,7 @@ __global__ void __launch_bounds__(kGatherThreads) var_write_kernel(GatherGeom G,
     }
     __syncthreads();
     w0 = w1;
+    r_lo = r_hi;
   }
 }
 
@@ -2418,7 +2431,11 @@ void gather_fixed(MergePlan* P, const FixedCol* cols, int ncols, cudaStream_t st
   LSB_CUDA(h2d_staged(P->d_cols, cols, sizeof(FixedCol) * ncols, stream));
   GatherGeom G = make_geom(P);
   const int64_t chunks = total_batches * G.chunks_per_batch;
-  gather_fixed_kernel<<<(unsigned)chunks, kGatherThreads, 0, stream>>>(G, P->d_cols, ncols);
+  // occupancy variants: r1 profile 90 registers -> 2 blocks per SM, latency-bound (24.8 % warps active)
+  static const int min_blocks = [] { const char* v = getenv("LAKESOUL_B200_GATHER_BLOCKS"); return v ? atoi(v) : kGatherFixedBlocksDefault; }();
+  if (min_blocks >= 4) gather_fixed_kernel<4><<<(unsigned)chunks, kGatherThreads, 0, stream>>>(G, P->d_cols, ncols);
+  else if (min_blocks == 3) gather_fixed_kernel<3><<<(unsigned)chunks, kGatherThreads, 0, stream>>>(G, P->d_cols, ncols);
+  else gather_fixed_kernel<2><<<(unsigned)chunks, kGatherThreads, 0, stream>>>(G, P->d_cols, ncols);
   LSB_CUDA(cudaGetLastError());
   // the descriptor table is reused by the next call: order the copy behind this launch
 }
