@@ -592,3 +592,32 @@ def read_bucket(files: Sequence[str], schema: pa.Schema, primary_keys: Sequence[
     for e in exprs:
         full = full.filter(e)  # keeps rows where the predicate is TRUE (null -> dropped)
     return full.select(schema.names) if schema.names else pa.table({"__rows": pa.nulls(full.num_rows)}).select([])
+
+
+# ------------------------------------------------------------------------------------------------
+# search bounds of one sorted run (v2/batch_range.rs:120-190; pinned by G8): the two questions the tile partition
+# asks of every delta file -- how many rows are < / <= a splitter key (mor_engine.cu part_kernel)
+# ------------------------------------------------------------------------------------------------
+def find_ge_start_index(values: Sequence, target, begin: int = 0) -> Optional[int]:
+    """first index >= begin whose value is >= target (BatchRange::find_ge_start_index), None when there is none"""
+    lo, hi = begin, len(values)
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if values[mid] < target:
+            lo = mid + 1
+        else:
+            hi = mid
+    return lo if lo < len(values) else None
+
+
+def find_le_start_index(values: Sequence, target, begin: int = 0, end_row_for_merge: Optional[int] = None) -> Optional[int]:
+    """last index in [begin, end_row_for_merge] whose value is <= target (BatchRange::find_le_start_index)"""
+    end = len(values) - 1 if end_row_for_merge is None else end_row_for_merge
+    lo, hi = begin, end + 1
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if values[mid] <= target:
+            lo = mid + 1
+        else:
+            hi = mid
+    return lo - 1 if lo - 1 >= begin else None

@@ -114,3 +114,16 @@ def test_reader_level_oracle_matches_reference_upsert_golden(case, tmp_path):
     paths, schema, expected = upsert_case_files(case, tmp_path)
     got = mo.read_bucket(paths, schema, case["primary_keys"], default_columns=case["partition"], filters=case["filters"])
     assert_tables_equal(got, expected, case["name"])
+
+
+def test_g8_batch_range_search_bounds():
+    """v2/batch_range.rs:269-342: first index >= target / last index <= target inside the merge window."""
+    import json
+    import os
+    from conftest import ROOT
+    with open(os.path.join(ROOT, "tests", "golden", "reference_unit_goldens.json")) as f:
+        g8 = json.load(f)["G8_batch_range_bounds"]
+    for c in g8["find_ge_start_index"]:
+        assert mo.find_ge_start_index(c["values"], c["target"], c["begin"]) == c["expect"], c
+    for c in g8["find_le_start_index"]:
+        assert mo.find_le_start_index(c["values"], c["target"], c["begin"], c["end"]) == c["expect"], c

@@ -23,13 +23,16 @@ _T = {"int32": pa.int32(), "utf8": pa.string(), "timestamp_us": pa.timestamp("us
 
 
 def _cases():
-    with open(os.path.join(ROOT, "tests", "golden", "reference_upsert_scenarios.json")) as f:
-        return json.load(f)["cases"]
+    out = []
+    for name in ("reference_upsert_scenarios.json", "reference_cdc_goldens.json"):  # G9, G10 (CDC deletes)
+        with open(os.path.join(ROOT, "tests", "golden", name)) as f:
+            out += json.load(f)["cases"]
+    return out
 
 
 CASES = _cases()
 CHECKS = [(c, i) for c in CASES for i in range(len(c["checks"]))]
-IDS = [f"{c['name'][5:]}#{i}" for c, i in CHECKS]
+IDS = [f"{c['name'].removeprefix('test_')}#{i}" for c, i in CHECKS]
 
 
 def _partition_files(case, n_upserts, tmp_path):
@@ -106,7 +109,7 @@ def _read_all(read_fn, case, check, tmp_path):
     for key, files in _partition_files(case, check["after_upserts"], tmp_path).items():
         defaults = dict(zip(ranges, key))
         t = read_fn(files, schema, case["primary_keys"], default_columns=defaults, filters=filters,
-                    partition_schema=part_schema if ranges else None)
+                    partition_schema=part_schema if ranges else None, options=case.get("options"))
         rows += _rows(t, selected)
     return selected, sorted(rows, key=_key)
 
