@@ -34,6 +34,7 @@ typedef struct LsbReaderStats {
   int64_t host_decoded_files;   /* files that needed the Arrow C++ host decoder (unsupported encodings) */
   int64_t pruned_row_groups;    /* row groups skipped by primary-key min/max statistics (pushed key filters) */
   int64_t device_decompressed_pages; /* ZSTD page payloads expanded by the GPU (the rest is decompressed on the host) */
+  int64_t pruned_buckets;       /* 1: an equality filter on the whole primary key selects another hash bucket: nothing was read */
 } LsbReaderStats;
 int32_t lsb_reader_get_stats(CResult_Reader *reader, LsbReaderStats *out);
 

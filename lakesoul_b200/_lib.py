@@ -28,7 +28,7 @@ class LsbReaderStats(Structure):
                 ("kernel_launches", c_int32), ("pad", c_int32), ("decode_ms", c_double), ("upload_ms", c_double),
                 ("merge_ms", c_double), ("gather_ms", c_double), ("download_ms", c_double),
                 ("device_decoded_pages", c_int64), ("host_decoded_files", c_int64), ("pruned_row_groups", c_int64),
-                ("device_decompressed_pages", c_int64)]
+                ("device_decompressed_pages", c_int64), ("pruned_buckets", c_int64)]
 
 
 I32_CALLBACK = ctypes.CFUNCTYPE(None, c_int32, c_char_p)

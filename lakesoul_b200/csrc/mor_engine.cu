@@ -1029,7 +1029,7 @@ __global__ void __launch_bounds__(256) compact_kernel(PlanDev P) {
 // gather: fixed width
 // ---------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
-constexpr int kGatherFixedBlocksDefault = 2;
+constexpr int kGatherFixedBlocksDefault = 3;  // 80 registers: 5.92 ms gather vs 6.11 (2 blocks, 114 regs) and 6.03 (4 blocks, spills)
 constexpr int kRowsPerChunk = 2048;
 
 struct GatherGeom {

@@ -23,6 +23,7 @@
 
 #include <arrow/io/memory.h>
 
+#include "bucket_hash.h"
 #include "device_scan.h"
 #include "filter.h"
 #include "page_plan.h"
@@ -139,6 +140,16 @@ struct FileInfo {
   int64_t rows = 0;
 };
 
+// eq(column, literal) terms at the top level of a conjunction
+void collect_eq_terms(const FilterExpr& e, std::map<std::string, std::shared_ptr<arrow::Scalar>>* out) {
+  if (e.kind == FilterExpr::kAnd) {
+    collect_eq_terms(*e.left, out);
+    collect_eq_terms(*e.right, out);
+  } else if (e.kind == FilterExpr::kCmp && e.op == FilterExpr::kEq && e.literal && e.literal->is_valid) {
+    out->emplace(e.column, e.literal);
+  }
+}
+
 bool force_host_decode() {
   const char* v = getenv("LAKESOUL_B200_HOST_DECODE");
   return v && (v[0] == '1' || v[0] == 't');
@@ -249,6 +260,48 @@ void Reader::Start() {
   if (cfg.filter_protos > 0)
     fail("substrait filters (add_filter_proto) are not supported by the GPU reader; "
          "refusing to read without applying a pushed filter");
+  // ---- hash-bucket elimination (N2), before a single byte is read: an equality filter on the WHOLE primary key
+  // selects one hash bucket; when every file of this reader belongs to another one, no row can match
+  // (helpers/mod.rs:929-1065 drops such files while planning). Needs the table's bucket count
+  // (set_hash_bucket_num), LakeSoul file names and the key columns in the requested schema.
+  if (!cfg.filter_strs.empty() && !cfg.primary_keys.empty() && !cfg.inferring_schema && cfg.target_schema &&
+      getenv("LAKESOUL_B200_NO_PRUNING") == nullptr) {
+    const long nbuckets = atol(cfg.hash_bucket_num.c_str());
+    std::map<std::string, std::shared_ptr<arrow::Scalar>> eqs;
+    bool ok = nbuckets > 1;
+    if (ok) {
+      try {
+        for (const auto& fs : cfg.filter_strs) collect_eq_terms(*parse_filter(fs, *cfg.target_schema), &eqs);
+      } catch (const std::exception&) {
+        ok = false;  // the full parse below reports the error
+      }
+    }
+    uint32_t h = kHashSeed;
+    for (const auto& pkc : cfg.primary_keys) {
+      if (!ok) break;
+      auto it = eqs.find(pkc);
+      auto fld = cfg.target_schema->GetFieldByName(pkc);
+      if (it == eqs.end() || !fld || !it->second->type->Equals(*fld->type())) { ok = false; break; }
+      ok = hash_scalar(*it->second, h, &h);
+    }
+    if (ok) {
+      const int want = (int)(h % (uint32_t)nbuckets);
+      bool all_other = true;
+      for (const auto& raw : cfg.files) {
+        const int id = bucket_id_of_file(raw);
+        if (id < 0 || id == want) { all_other = false; break; }
+      }
+      if (all_other) {
+        std::vector<std::shared_ptr<arrow::Field>> out_f;
+        for (const auto& f : cfg.target_schema->fields()) out_f.push_back(uniform_field(f));
+        I.out_schema = arrow::schema(out_f);
+        I.stats.pruned_buckets = 1;
+        I.stats.path = "bucket-pruned";
+        I.started = true;  // empty stream
+        return;
+      }
+    }
+  }
   ensure_device();
 
   // ---- open files, read footers (session.rs:546-593) -----------------------------------------

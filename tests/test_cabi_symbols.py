@@ -80,3 +80,65 @@ def test_library_exports_nothing_but_the_declared_symbols():
     exported = {ln.split()[-1].split("@")[0] for ln in out.splitlines() if ln.strip()}
     declared = _declared("lakesoul_c_bindings.h") | _declared("lakesoul_b200_ext.h")
     assert exported == declared, (sorted(exported - declared)[:10], sorted(declared - exported)[:10])
+
+
+def test_hash_bucket_elimination_needs_no_gpu_and_matches_the_table_hash(tmp_path, lib):
+    """N2: eq filters on the whole primary key select one bucket (spark murmur3, utils/hash/mod.rs; KATs G11). A
+    reader whose files belong to another bucket returns an empty stream without touching the files or the GPU; for
+    the matching bucket it must go on (and, without a GPU, fail on the device -- never silently return nothing)."""
+    import pyarrow as pa
+    from lakesoul_b200 import hashing
+    from lakesoul_b200.native_io import NativeIOReader
+
+    def reader_for(bucket, nbuckets, schema, pks, filters):
+        r = NativeIOReader()
+        r.addFile(str(tmp_path / f"part-abcdefghijklmnop_{bucket:04d}.parquet"))  # never opened when pruned
+        r.setPrimaryKeys(pks)
+        r.setSchema(schema)
+        r.ioConfigBuilder = lib.lakesoul_config_builder_set_hash_bucket_num(r.ioConfigBuilder, nbuckets)
+        for f in filters:
+            r.addFilter(f)
+        return r
+
+    nb = 16
+    schema = pa.schema([pa.field("k", pa.int64()), pa.field("l", pa.int32()), pa.field("v", pa.string())])
+    for k, l in ((1, 1), (123456789, 7), (-5, 0)):
+        import numpy as np
+        want = int(hashing.bucket_of([np.array([k], dtype=np.int64), np.array([l], dtype=np.int32)], nb)[0])
+        flt = [f"and(eq(k, {k}), and(eq(l, {l}), noteq(v, null)))"]
+        for bucket in range(nb):
+            r = reader_for(bucket, nb, schema, ["k", "l"], flt)
+            if bucket != want:
+                r.initializeReader()  # no file access, no GPU
+                assert r.stats()["pruned_buckets"] == 1
+                holder = (ctypes.c_byte * 80)()
+                assert r.nextBatchBlocked(ctypes.addressof(holder)) == 0
+                assert r.getSchema().names == ["k", "l", "v"]
+            else:
+                try:
+                    r.initializeReader()
+                    raise AssertionError("the selected bucket must be read, not pruned")
+                except IOError as e:
+                    assert "not found" in str(e) or "CUDA" in str(e), e
+            r.close()
+    # string keys: the reference's own known answers (hash_tests.rs:48-90): "321" chained after "321" -> -218318595
+    sschema = pa.schema([pa.field("a", pa.string()), pa.field("b", pa.string())])
+    want = (-218318595 & 0xFFFFFFFF) % 7
+    for bucket in range(7):
+        r = reader_for(bucket, 7, sschema, ["a", "b"], ['and(eq(a, Binary{"321"}), eq(b, Binary{"321"}))'])
+        try:
+            r.initializeReader()
+            pruned = r.stats()["pruned_buckets"] == 1
+        except IOError:
+            pruned = False
+        r.close()
+        assert pruned == (bucket != want), (bucket, want)
+    # a filter that does not pin the whole key prunes nothing
+    r = reader_for(3, nb, schema, ["k", "l"], ["eq(k, 1)"])
+    with_gpu_or_file_error = False
+    try:
+        r.initializeReader()
+    except IOError:
+        with_gpu_or_file_error = True
+    r.close()
+    assert with_gpu_or_file_error
