@@ -1546,6 +1546,140 @@ void launch_zstd_pages_v2(const PqZstdPage* pages, const int32_t* order_small, i
   if (prof) dump("small");
 }
 
+// ---------------------------------------------------------------------------------------------------
+// SNAPPY page payloads (pyarrow / Spark default files): one warp per payload. The element stream (tag byte, length,
+// literal bytes or copy offset) can only be walked in order, so lane 0 frames 32 elements at a time into shared
+// memory; the warp then places them like the ZSTD execute phase does: output positions by a scan, literal runs in
+// parallel straight from the compressed stream, copies whose source lies before the round in parallel, the rest in
+// order (overlapping copies replicate their period). Format: github.com/google/snappy format_description.txt.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) snappy_pages_kernel(const PqZstdPage* pages, int32_t* err) {
+  __shared__ uint32_t s_len[32], s_off[32], s_src[32];
+  const PqZstdPage pg = pages[blockIdx.x];
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(pg.src_off);
+  uint8_t* dst = reinterpret_cast<uint8_t*>(pg.dst_off);
+  const int64_t n = pg.comp_size, cap = pg.raw_size;
+  const int lane = threadIdx.x;
+  // preamble: uncompressed length, base-128 varint
+  int64_t ip = 0;
+  {
+    uint64_t v = 0;
+    int sh = 0;
+    bool ok = false;
+    for (int i = 0; i < 5 && ip < n; ++i, sh += 7) {
+      const uint8_t b = src[ip++];
+      v |= (uint64_t)(b & 0x7f) << sh;
+      if (!(b & 0x80)) { ok = true; break; }
+    }
+    if (!ok || (int64_t)v != cap) {
+      if (lane == 0) atomicExch(err, kErrBadPage);
+      return;
+    }
+  }
+  int64_t op = 0;
+  while (ip < n) {
+    int cnt = 0;
+    int bad = 0;
+    if (lane == 0) {
+      int64_t p = ip;
+      while (cnt < 32 && p < n) {
+        const uint32_t tag = src[p];
+        uint32_t len, off = 0, lsrc = 0;
+        if ((tag & 3) == 0) {
+          len = (tag >> 2) + 1;
+          int extra = 0;
+          if (len > 60) {
+            extra = (int)len - 60;
+            if (p + 1 + extra > n) { bad = 1; break; }
+            uint32_t v = 0;
+            for (int i = 0; i < extra; ++i) v |= (uint32_t)src[p + 1 + i] << (8 * i);
+            len = v + 1;
+          }
+          p += 1 + extra;
+          if (len > (uint32_t)(n - p)) { bad = 1; break; }
+          lsrc = (uint32_t)p;
+          p += len;
+        } else if ((tag & 3) == 1) {
+          if (p + 2 > n) { bad = 1; break; }
+          len = ((tag >> 2) & 7) + 4;
+          off = ((tag >> 5) << 8) | src[p + 1];
+          p += 2;
+          if (off == 0) { bad = 1; break; }
+        } else if ((tag & 3) == 2) {
+          if (p + 3 > n) { bad = 1; break; }
+          len = (tag >> 2) + 1;
+          off = (uint32_t)src[p + 1] | ((uint32_t)src[p + 2] << 8);
+          p += 3;
+          if (off == 0) { bad = 1; break; }
+        } else {
+          if (p + 5 > n) { bad = 1; break; }
+          len = (tag >> 2) + 1;
+          off = (uint32_t)src[p + 1] | ((uint32_t)src[p + 2] << 8) | ((uint32_t)src[p + 3] << 16) | ((uint32_t)src[p + 4] << 24);
+          p += 5;
+          if (off == 0) { bad = 1; break; }
+        }
+        s_len[cnt] = len;
+        s_off[cnt] = off;
+        s_src[cnt] = lsrc;
+        ++cnt;
+      }
+      ip = p;
+    }
+    cnt = __shfl_sync(0xffffffffu, cnt, 0);
+    bad = __shfl_sync(0xffffffffu, bad, 0);
+    ip = __shfl_sync(0xffffffffu, ip, 0);
+    __syncwarp();
+    const uint32_t len = lane < cnt ? s_len[lane] : 0u;
+    const uint32_t off = lane < cnt ? s_off[lane] : 0u;
+    const uint32_t lsrc = lane < cnt ? s_src[lane] : 0u;
+    __syncwarp();
+    uint32_t incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += y;
+    }
+    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+    const int64_t my = op + (incl - len);
+    if (bad || op + tot > cap || __any_sync(0xffffffffu, lane < cnt && off != 0 && (int64_t)off > my)) {
+      if (lane == 0) atomicExch(err, kErrBadPage);
+      return;
+    }
+    // literals: independent of everything
+    const bool lit = lane < cnt && off == 0;
+    if (lit && len <= 64) copy_lane_cg(dst + my, src + lsrc, len);
+    unsigned big = __ballot_sync(0xffffffffu, lit && len > 64);
+    while (big) {
+      const int j = __ffs(big) - 1;
+      big &= big - 1;
+      copy_warp_cg(dst + __shfl_sync(0xffffffffu, my, j), src + __shfl_sync(0xffffffffu, lsrc, j), __shfl_sync(0xffffffffu, len, j), lane);
+    }
+    __syncwarp();
+    // copies whose whole source was produced before this round
+    const bool cp = lane < cnt && off != 0;
+    const bool indep = cp && len <= 64 && (my - (int64_t)off + len <= op);
+    if (indep) copy_lane_cg(dst + my, dst + my - off, len);
+    __syncwarp();
+    unsigned serial = __ballot_sync(0xffffffffu, cp && !indep);
+    while (serial) {
+      const int j = __ffs(serial) - 1;
+      serial &= serial - 1;
+      const int64_t md = __shfl_sync(0xffffffffu, my, j);
+      const uint32_t o = __shfl_sync(0xffffffffu, off, j), l = __shfl_sync(0xffffffffu, len, j);
+      const uint8_t* m = dst + md - o;
+      if (o >= l) copy_warp_cg(dst + md, m, l, lane);
+      else for (uint32_t i = lane; i < l; i += 32) dst[md + i] = m[i % o];
+      __syncwarp();
+    }
+    op += tot;
+  }
+  if (op != cap && lane == 0) atomicExch(err, kErrBadPage);
+}
+
+void launch_snappy_pages(const PqZstdPage* pages, int npages, int32_t* err, cudaStream_t s) {
+  if (npages > 0) snappy_pages_kernel<<<npages, 32, 0, s>>>(pages, err);
+}
+
 void launch_zstd_pages(const PqZstdPage* pages, int npages, const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, ZstdTables* tables,
                        uint8_t* lit, uint64_t* seq, int32_t* err, cudaStream_t s) {
   if (npages > 0) zstd_pages_kernel<<<npages, kZstdThreads, 0, s>>>(pages, blocks, plans, tables, lit, seq, err);

@@ -199,6 +199,7 @@ void launch_block_scan(const DecodeArgs& A, const int32_t* seg_bounds, const int
 void launch_block_decode(const DecodeArgs& A, cudaStream_t s);
 void launch_zstd_pages(const PqZstdPage* pages, int npages, const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, ZstdTables* tables,
                        uint8_t* lit, uint64_t* seq, int32_t* err, cudaStream_t s);
+void launch_snappy_pages(const PqZstdPage* pages, int npages, int32_t* err, cudaStream_t s);
 void launch_zstd_pages_v2(const PqZstdPage* pages, const int32_t* order_small, int nsmall, const int32_t* order_big, int nbig,
                           const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, ZstdTables* tables_v1, uint8_t* lit, uint64_t* seq, int32_t* err,
                           cudaStream_t s);
@@ -537,10 +538,41 @@ void DeviceScan::Impl::upload() {
     }
     int64_t dict_entries = 0, nblocks = 0, vpos_entries = 0, zstd_bytes = 0;
     bool any_dict_var = false;
-    std::vector<PqZstdPage> zpages;
-    std::vector<int32_t> zstd_page_of;
     std::vector<ZstdBlockDesc> zblocks;
     int64_t zlit_bytes = 0, zseq_recs = 0;
+    std::vector<PqZstdPage> zpages, spages;     // ZSTD / SNAPPY payloads expanded on the device
+    struct Fixup { bool snappy; size_t z; bool is_dict; size_t target; };  // whose address becomes the expansion's
+    std::vector<Fixup> fixups;
+    // registers one compressed payload of file image `fi`; the expansion lands at a 64-byte aligned slot of one buffer
+    auto add_expansion = [&](const FileInput& fi, int f, uint8_t codec, int64_t src_off, int32_t comp_size, int32_t raw_size,
+                             bool is_dict, size_t target, int c) {
+      PqZstdPage zp{};
+      zp.src_off = img_off[f] + src_off;
+      zp.comp_size = comp_size;
+      zp.raw_size = raw_size;
+      zp.dst_off = zstd_bytes;  // relative for now; the buffer is allocated once the total is known
+      zstd_bytes = (zstd_bytes + raw_size + 64 + 63) & ~63ll;
+      if (codec == kCodecZstd) {
+        // block headers of the frame (three bytes each), read from the pinned image
+        zblocks.resize(zblocks.size() + 4096);
+        int64_t frame_end = 0;
+        const size_t b0 = zblocks.size() - 4096;
+        const int64_t nblk = zstd_scan_frame(fi.raw->image() + src_off, comp_size, zblocks.data() + b0, 4096, &frame_end);
+        if (nblk < 0) fail("malformed ZSTD page in " + spec.physical_schema->field(c)->name());
+        zblocks.resize(b0 + (size_t)nblk);
+        zp.first_block = (int32_t)b0;
+        zp.nblocks = (int32_t)nblk;
+        zp.lit_off = zlit_bytes;
+        zp.seq_off = zseq_recs;
+        zlit_bytes += ((int64_t)raw_size + 63) & ~63ll;
+        zseq_recs += raw_size / 3 + 8;
+        fixups.push_back({false, zpages.size(), is_dict, target});
+        zpages.push_back(zp);
+      } else {
+        fixups.push_back({true, spages.size(), is_dict, target});
+        spages.push_back(zp);
+      }
+    };
     for (int c = 0; c < C; ++c) {
       if (!cols[c].has_raw) continue;
       for (int b = 0; b < nb; ++b) {
@@ -573,6 +605,7 @@ void DeviceScan::Impl::upload() {
                   pc.dict_index = dict_entries;
                   dict_entries += d.num_values + 1;
                 }
+                if (d.codec) add_expansion(fi, f, d.codec, d.src_off, d.comp_size, d.size, true, chunks.size(), c);
               }
               chunks.push_back(pc);
               ci = (int)chunks.size() - 1;
@@ -580,29 +613,8 @@ void DeviceScan::Impl::upload() {
             PqPage pg{};
             pg.src_off = (rp.aux ? aux_off[f] : img_off[f]) + rp.src_off;
             pg.size = rp.size;
-            if (rp.zstd) {  // expanded on the device: the decoders read the expansion, not the file image
-              PqZstdPage zp{};
-              zp.src_off = img_off[f] + rp.src_off;
-              zp.comp_size = rp.comp_size;
-              zp.raw_size = rp.size;
-              zp.dst_off = zstd_bytes;  // relative for now; the buffer is allocated once the total is known
-              zstd_bytes = (zstd_bytes + rp.size + 64 + 63) & ~63ll;
-              // block headers of the frame (three bytes each), read from the pinned image
-              zblocks.resize(zblocks.size() + 4096);
-              int64_t frame_end = 0;
-              const size_t b0 = zblocks.size() - 4096;
-              const int64_t nblk = zstd_scan_frame(fi.raw->image() + rp.src_off, rp.comp_size, zblocks.data() + b0, 4096, &frame_end);
-              if (nblk < 0) fail("malformed ZSTD page in " + spec.physical_schema->field(c)->name());
-              zblocks.resize(b0 + (size_t)nblk);
-              zp.first_block = (int32_t)b0;
-              zp.nblocks = (int32_t)nblk;
-              zp.lit_off = zlit_bytes;
-              zp.seq_off = zseq_recs;
-              zlit_bytes += ((int64_t)rp.size + 63) & ~63ll;
-              zseq_recs += rp.size / 3 + 8;
-              zstd_page_of.push_back((int32_t)pages.size());
-              zpages.push_back(zp);
-            }
+            if (rp.codec)  // expanded on the device: the decoders read the expansion, not the file image
+              add_expansion(fi, f, rp.codec, rp.src_off, rp.comp_size, rp.size, false, pages.size(), c);
             pg.num_values = rp.num_values;
             pg.encoding = rp.encoding;
             pg.def_encoding = rp.def_encoding;
@@ -654,13 +666,24 @@ void DeviceScan::Impl::upload() {
     PqBlock* d_blocks = static_cast<PqBlock*>(dalloc(sizeof(PqBlock) * (size_t)(nblocks + 1)));
     int32_t* d_vpos = static_cast<int32_t*>(dalloc(sizeof(int32_t) * (size_t)(vpos_entries + 1)));
     SCAN_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int32_t), stream));
-    if (!zpages.empty()) {
-      // ZSTD frames -> plain page payloads, one thread block per page, before anything reads the pages
+    if (!zpages.empty() || !spages.empty()) {
+      // compressed payloads -> plain payloads, before anything reads the pages / dictionaries
       uint8_t* d_zout = static_cast<uint8_t*>(dalloc((size_t)zstd_bytes + 64));
-      for (size_t z = 0; z < zpages.size(); ++z) {
-        zpages[z].dst_off += (int64_t)reinterpret_cast<uintptr_t>(d_zout);
-        pages[(size_t)zstd_page_of[z]].src_off = zpages[z].dst_off;
+      for (const Fixup& fx : fixups) {
+        PqZstdPage& zp = fx.snappy ? spages[fx.z] : zpages[fx.z];
+        zp.dst_off += (int64_t)reinterpret_cast<uintptr_t>(d_zout);
+        if (fx.is_dict) chunks[fx.target].dict_off = zp.dst_off;
+        else pages[fx.target].src_off = zp.dst_off;
       }
+    }
+    if (!spages.empty()) {
+      PqZstdPage* d_spages = static_cast<PqZstdPage*>(dalloc(sizeof(PqZstdPage) * spages.size()));
+      h2d(d_spages, spages.data(), sizeof(PqZstdPage) * spages.size());
+      launch_snappy_pages(d_spages, (int)spages.size(), d_err, stream);
+      ctr.kernel_launches += 1;
+      ctr.device_decompressed_pages += (int64_t)spages.size();
+    }
+    if (!zpages.empty()) {
       PqZstdPage* d_zpages = static_cast<PqZstdPage*>(dalloc(sizeof(PqZstdPage) * zpages.size()));
       ZstdBlockDesc* d_zblocks = static_cast<ZstdBlockDesc*>(dalloc(sizeof(ZstdBlockDesc) * zblocks.size()));
       ZstdBlockPlan* d_zplans = static_cast<ZstdBlockPlan*>(dalloc(sizeof(ZstdBlockPlan) * zblocks.size()));

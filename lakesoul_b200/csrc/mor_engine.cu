@@ -1269,6 +1269,39 @@ __device__ __forceinline__ void row_store(RowCopy& rc) {
   if (rc.tail > 2) td[2] = rc.t2;
 }
 
+// TMA bulk copies (cp.async.bulk; SASS UBLKCP) and the mbarrier that completes the loads
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(smem_src)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+
 // pass 2 (grid.y = column): batch-rebased offsets + the bytes of one chunk.
 // Thread t owns the 8 consecutive rows [8t, 8t+8) for the offsets; the bytes are staged through a
 // shared-memory window that is address-congruent (mod 16) with the destination, so the flush to HBM
@@ -1457,22 +1490,21 @@ __global__ void __launch_bounds__(kGatherThreads) var_write_kernel(GatherGeom G,
       row_store(c0r);
       row_store(c1r);
     }
+    fence_proxy_async();  // the stage was written through the generic proxy; the bulk store reads it asynchronously
     __syncthreads();
-    // flush: global address of stage[first_pad] is dst_bytes + w0
+    // flush: global address of stage[first_pad] is dst_bytes + w0. The 16-byte aligned middle leaves with ONE TMA
+    // bulk store (cp.async.bulk shared -> global) issued by a single thread; the <= 15 bytes that share a vector with
+    // the neighbouring chunks are stored by hand.
     uint8_t* gdst = dst_bytes + w0 - first_pad;  // 16-byte aligned
     const int nbytes = first_pad + (w1 - w0);
-    const int nvec = nbytes >> 4;
-    for (int v = threadIdx.x; v < nvec; v += kGatherThreads) {
-      if (v == 0 && first_pad) {
-        for (int t = first_pad; t < 16; ++t) gdst[t] = s_stage[t];
-      } else {
-        reinterpret_cast<uint4*>(gdst)[v] = reinterpret_cast<const uint4*>(s_stage)[v];
-      }
-    }
-    if (threadIdx.x == 0) {
-      const int start = (nvec == 0) ? first_pad : (nvec << 4);
-      for (int t = start; t < nbytes; ++t) gdst[t] = s_stage[t];
-    }
+    const int v_lo = first_pad ? 16 : 0;
+    const int v_hi = nbytes & ~15;
+    if (threadIdx.x == 0 && v_hi > v_lo) bulk_store(gdst + v_lo, s_stage + v_lo, (uint32_t)(v_hi - v_lo));
+    if (first_pad)
+      for (int t = first_pad + threadIdx.x; t < min(16, nbytes); t += kGatherThreads) gdst[t] = s_stage[t];
+    for (int t = max(v_hi, v_lo) + threadIdx.x; t < nbytes; t += kGatherThreads)
+      if (t >= first_pad) gdst[t] = s_stage[t];
+    if (threadIdx.x == 0) bulk_store_wait_read();  // the stage is rewritten by the next window
     __syncthreads();
     w0 = w1;
     r_lo = r_hi;
@@ -1493,37 +1525,6 @@ __global__ void __launch_bounds__(kGatherThreads) var_write_kernel(GatherGeom G,
 // Replaces the sector-granular random DRAM reads of var_write_kernel (r01: 38 % long-scoreboard stalls).
 // ---------------------------------------------------------------------------------------
 constexpr int kWinDirect = INT32_MIN;    // s_wbase marker: this file's rows are read straight from HBM
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_addr(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_addr(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
-               : "memory");
-}
-__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(smem_src)),
-               "r"(bytes)
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 constexpr int kWinMaxPieces = 64;
 constexpr bool kWindowGatherDefault = false;  // flipped once the windowed kernel beats the direct one

@@ -18,6 +18,8 @@
 #include <functional>
 #include <stdexcept>
 
+#include "zstd_decode.h"
+
 namespace lsb {
 
 namespace {
@@ -48,6 +50,24 @@ int64_t device_zstd_min_bytes() {
     return e && *e ? (int64_t)atoll(e) : (int64_t)(128 << 10);
   }();
   return v;
+}
+
+// SNAPPY page payloads (pyarrow / Spark default files) are expanded by snappy_pages_kernel unless
+// LAKESOUL_B200_DEVICE_SNAPPY=0 sends them to the host codec.
+bool device_snappy() {
+  static const bool on = [] { const char* v = getenv("LAKESOUL_B200_DEVICE_SNAPPY"); return !(v && *v == '0'); }();
+  return on;
+}
+
+// uncompressed size announced by a compressed payload itself, or -1
+int64_t announced_size(uint8_t codec, const uint8_t* p, int64_t n) {
+  if (codec == kCodecZstd) return zstd_frame_content_size(p, n);
+  uint64_t v = 0;  // snappy preamble: little-endian base-128 varint
+  for (int i = 0, sh = 0; i < 5 && i < n; ++i, sh += 7) {
+    v |= (uint64_t)(p[i] & 0x7f) << sh;
+    if (!(p[i] & 0x80)) return v <= 0x7fffffffull ? (int64_t)v : -1;
+  }
+  return -1;
 }
 
 int32_t map_encoding(parquet::Encoding::type e) {
@@ -305,8 +325,22 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
   cols_.resize(want.size());
   // flat schemas only: leaf index == field index
   if (sd->num_columns() != schema_->num_fields()) { *why = "nested schema"; return false; }
-  // which ZSTD column chunks the GPU expands: smallest payloads first, up to the configured share of the bytes
+  // which compressed column chunks the GPU expands. SNAPPY: all of them; ZSTD: by the configured share / size policy
   std::set<std::pair<int, int>> device_chunks;  // (row group, column)
+  std::map<std::pair<int, int>, uint8_t> chunk_codec;
+  if (device_snappy()) {
+    for (size_t w = 0; w < want.size(); ++w) {
+      const int ci = schema_->GetFieldIndex(want[w]->name());
+      if (ci < 0) continue;
+      for (int rg : kept_rg_) {
+        auto ccm = md->RowGroup(rg)->ColumnChunk(ci);
+        const int64_t first = ccm->has_dictionary_page() ? ccm->dictionary_page_offset() : ccm->data_page_offset();
+        if (ccm->compression() != parquet::Compression::SNAPPY || first <= 0 || first + ccm->total_compressed_size() > image_bytes_) continue;
+        device_chunks.insert({rg, ci});
+        chunk_codec[{rg, ci}] = kCodecSnappy;
+      }
+    }
+  }
   if (device_zstd_share() != 0) {
     std::vector<std::pair<int64_t, std::pair<int, int>>> cand;
     int64_t total = 0;
@@ -315,9 +349,10 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
       if (ci < 0) continue;
       for (int rg : kept_rg_) {
         auto ccm = md->RowGroup(rg)->ColumnChunk(ci);
-        if (ccm->compression() != parquet::Compression::ZSTD || ccm->has_dictionary_page() || ccm->data_page_offset() <= 0 ||
-            ccm->data_page_offset() + ccm->total_compressed_size() > image_bytes_)
+        const int64_t first = ccm->has_dictionary_page() ? ccm->dictionary_page_offset() : ccm->data_page_offset();
+        if (ccm->compression() != parquet::Compression::ZSTD || first <= 0 || first + ccm->total_compressed_size() > image_bytes_)
           continue;
+        chunk_codec[{rg, ci}] = kCodecZstd;
         cand.push_back({ccm->total_uncompressed_size(), {rg, ci}});
         total += ccm->total_uncompressed_size();
       }
@@ -408,13 +443,16 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
         if (!proven) rc.may_have_nulls = true;
       }
       std::unique_ptr<parquet::PageReader> pr;
-      // ZSTD chunks without a dictionary page (what the LakeSoul writer emits): the pages stay compressed in the
-      // file image and are expanded by the GPU (zstd_pages_kernel); everything else is decompressed here
-      bool raw_zstd = device_chunks.count({rg, ci}) > 0;
+      // ZSTD (what the LakeSoul writer emits) and SNAPPY chunks chosen above: the pages stay compressed in the file
+      // image and are expanded by the GPU (zstd_pages_kernel_v2 / snappy_pages_kernel); everything else is
+      // decompressed here by Arrow's codecs
+      bool raw_zstd = device_chunks.count({rg, ci}) > 0;  // (name kept: "raw" = still compressed, either codec)
+      const uint8_t codec = raw_zstd ? chunk_codec[{rg, ci}] : (uint8_t)0;
       try {
         if (raw_zstd) {
           auto whole = std::make_shared<arrow::Buffer>(image_.get(), image_bytes_);
-          auto chunk = arrow::SliceBuffer(whole, ccm->data_page_offset(), ccm->total_compressed_size());
+          const int64_t first = ccm->has_dictionary_page() ? ccm->dictionary_page_offset() : ccm->data_page_offset();
+          auto chunk = arrow::SliceBuffer(whole, first, ccm->total_compressed_size());
           pr = parquet::PageReader::Open(std::make_shared<arrow::io::BufferReader>(chunk), ccm->num_values(),
                                          parquet::Compression::UNCOMPRESSED);
         } else {
@@ -455,6 +493,23 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
           place(&d.src_off, &d.aux);
           d.size = (int32_t)size;
           d.num_values = dp->num_values();
+          if (raw_zstd) {
+            const int64_t usz = d.aux ? -1 : announced_size(codec, data, size);
+            if (usz < 0 || usz > ((int64_t)1 << 30)) {
+              // the payload does not say how large it gets: let libparquet decompress this chunk
+              raw_zstd = false;
+              try {
+                pr = rd->RowGroup(rg)->GetColumnPageReader(ci);
+              } catch (const std::exception& e) {
+                *why = std::string("page reader: ") + e.what();
+                return false;
+              }
+              continue;
+            }
+            d.codec = codec;
+            d.comp_size = (int32_t)size;
+            d.size = (int32_t)usz;
+          }
           rc.dicts.push_back(d);
           dict_idx = (int)rc.dicts.size() - 1;
         } else if (page->type() == parquet::PageType::DATA_PAGE || page->type() == parquet::PageType::DATA_PAGE_V2) {
@@ -500,7 +555,7 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
               *why = "ZSTD page shape in column " + rc.name;
               return false;
             }
-            pg.zstd = true;
+            pg.codec = codec;
             pg.comp_size = (int32_t)size;
             pg.size = (int32_t)dp->uncompressed_size();
           }

@@ -19,6 +19,8 @@ namespace lsb {
 
 std::shared_ptr<uint8_t> pinned_alloc(size_t bytes);  // recycled cudaMallocHost blocks (device_scan.cc)
 
+constexpr uint8_t kCodecZstd = 1, kCodecSnappy = 2;
+
 struct RawColumn {                    // one requested column of one file
   std::string name;
   bool present = false;
@@ -28,13 +30,20 @@ struct RawColumn {                    // one requested column of one file
   struct Page {
     int64_t src_off = 0;              // inside the file image (aux = false) or the aux arena (aux = true)
     bool aux = false;
-    bool zstd = false;                // src_off/comp_size = ZSTD frame inside the file image, expanded on the device
+    uint8_t codec = 0;                // 0: src_off/size = plain payload; kCodecZstd / kCodecSnappy: src_off/comp_size =
+                                      // compressed payload inside the file image, expanded on the device to `size` bytes
     int32_t comp_size = 0;
     int32_t size = 0, num_values = 0, encoding = 0, def_encoding = 0, v2_def_len = -1;
     int32_t row_group = 0;
     int64_t first_row = 0;            // row inside the file
   };
-  struct Dict { int64_t src_off = 0; bool aux = false; int32_t size = 0, num_values = 0; };
+  struct Dict {
+    int64_t src_off = 0;
+    bool aux = false;
+    uint8_t codec = 0;  // like Page::codec
+    int32_t comp_size = 0;
+    int32_t size = 0, num_values = 0;
+  };
   std::vector<Page> pages;
   std::vector<Dict> dicts;            // one per row group (or size/num_values 0)
   std::vector<int32_t> page_dict;     // page -> index into dicts, -1 none
