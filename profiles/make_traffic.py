@@ -1,8 +1,8 @@
 # SPDX-License-Identifier: Apache-2.0
-"""profiles/r01_traffic.json from an ncu launch list of ONE bench step
+"""profiles/r0N_traffic.json from an ncu launch list of ONE bench step
 (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none ... --steps 1 --warmup 1):
 DRAM bytes and serialised time per kernel of the LAST step in the list.
-usage: python profiles/make_traffic.py profiles/r01_launches_step_kernels.csv > profiles/r01_traffic.json"""
+usage: python profiles/make_traffic.py profiles/r01_launches_step_kernels.csv > profiles/r0N_traffic.json"""
 import csv, collections, json, sys
 lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
