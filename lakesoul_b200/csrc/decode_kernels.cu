@@ -1514,6 +1514,179 @@ __global__ void __launch_bounds__(kWarps * 32) zstd_pages_kernel_v2(const PqZstd
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// One-block pages, eight to a thread block. The delta files of a hash bucket are small (config 5: 63 files of
+// 1 162 rows -> a thousand pages of a few KiB, one ZSTD block each); given a thread block of their own they keep
+// one lane of one warp busy. Here warp w plans and executes page w of the batch, and the two entropy roles run
+// across the batch exactly as they run across the blocks of a large page: warp 0 = the Huffman streams of all eight
+// pages (lane = page * 4 + stream), warp 1 = their eight FSE sequence streams (8 x fewer warp instructions there).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kZstdBatch = 8;
+
+// the sequences of one block -> output (a whole page here: no history before it, no other block to wait for)
+__device__ bool zstd_execute_single_block(const ZstdBlockPlan& P, const uint8_t* lits, const uint64_t* sq, uint8_t* dst,
+                                          int64_t out_k, int lane) {
+  const uint32_t rep_i0 = 1, rep_i1 = 4, rep_i2 = 8;
+  int64_t op = 0, lpos = 0;
+  uint64_t v_next = (lane < P.nseq) ? sq[lane] : 0ull;
+  for (int q0 = 0; q0 < P.nseq; q0 += 32) {
+    const int cnt = min(32, P.nseq - q0);
+    const uint64_t v = v_next;
+    v_next = (q0 + 32 + lane < P.nseq) ? sq[q0 + 32 + lane] : 0ull;
+    const uint32_t ll = (uint32_t)(v & 0x1ffff), ml = (uint32_t)((v >> 17) & 0x1ffff);
+    const uint32_t tag = (uint32_t)(v >> 34) & 3u;
+    const int32_t val = (int32_t)((uint32_t)(v >> 36) << 4) >> 4;
+    const uint32_t rep_t = tag == 1 ? rep_i0 : (tag == 2 ? rep_i1 : rep_i2);
+    const uint32_t offset = lane < cnt ? (tag == 0 ? (uint32_t)val : rep_t + (uint32_t)val) : 1u;
+    uint32_t io = ll + ml, il = ll;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t yo = __shfl_up_sync(0xffffffffu, io, d), yl = __shfl_up_sync(0xffffffffu, il, d);
+      if (lane >= d) { io += yo; il += yl; }
+    }
+    const uint32_t tot_out = __shfl_sync(0xffffffffu, io, 31), tot_lit = __shfl_sync(0xffffffffu, il, 31);
+    const int64_t my_out = op + (io - ll - ml);
+    const int64_t my_lit = lpos + (il - ll);
+    const int64_t my_match = my_out + ll;
+    const bool bad = lpos + tot_lit > P.regen || op + tot_out > out_k ||
+                     (lane < cnt && (offset == 0 || (int64_t)offset > my_match));
+    if (__any_sync(0xffffffffu, bad)) return false;
+    if (ll <= 64) copy_lane_cg(dst + my_out, lits + my_lit, ll);
+    unsigned big = __ballot_sync(0xffffffffu, ll > 64);
+    while (big) {
+      const int j = __ffs(big) - 1;
+      big &= big - 1;
+      const int64_t o = __shfl_sync(0xffffffffu, my_out, j), l0 = __shfl_sync(0xffffffffu, my_lit, j);
+      const uint32_t n = __shfl_sync(0xffffffffu, ll, j);
+      copy_warp_cg(dst + o, lits + l0, n, lane);
+    }
+    __syncwarp();
+    const bool indep = lane < cnt && ml <= 64 && (my_match - (int64_t)offset + ml <= op);
+    if (indep) copy_lane_cg(dst + my_match, dst + my_match - offset, ml);
+    __syncwarp();
+    unsigned serial = __ballot_sync(0xffffffffu, lane < cnt && !indep && ml > 0);
+    while (serial) {
+      const int j = __ffs(serial) - 1;
+      serial &= serial - 1;
+      const int64_t md = __shfl_sync(0xffffffffu, my_match, j);
+      const uint32_t off = __shfl_sync(0xffffffffu, offset, j), n = __shfl_sync(0xffffffffu, ml, j);
+      const uint8_t* m = dst + md - off;
+      if (off >= n) copy_warp_cg(dst + md, m, n, lane);
+      else for (uint32_t i = lane; i < n; i += 32) dst[md + i] = m[i % off];
+      __syncwarp();
+    }
+    op += tot_out;
+    lpos += tot_lit;
+  }
+  const int64_t rest = P.regen - lpos;
+  if (rest < 0 || op + rest != out_k) return false;
+  copy_warp_cg(dst + op, lits + lpos, (uint32_t)rest, lane);
+  return true;
+}
+
+__global__ void __launch_bounds__(kZstdBatch * 32) zstd_batch_kernel(const PqZstdPage* pages, const int32_t* order, int npages,
+                                                                     const ZstdBlockDesc* blocks_all, ZstdBlockPlan* plans_all,
+                                                                     uint8_t* lit_all, uint64_t* seq_all, int32_t* err) {
+  extern __shared__ __align__(16) unsigned char zsm_raw[];
+  ZstdTables* s_tabs = reinterpret_cast<ZstdTables*>(zsm_raw);  // one slot per page of the batch
+  __shared__ ZstdPlanScratch s_scr[kZstdBatch];
+  __shared__ ZstdBlockPlan s_plans[kZstdBatch];
+  __shared__ int s_state[kZstdBatch];  // 0 = no page, 1 = compressed block planned, 2 = raw / RLE block, -1 = corrupt
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int first = blockIdx.x * kZstdBatch;
+  auto page_of = [&](int u) -> const PqZstdPage& { return pages[order[first + u]]; };
+  // ---- plan: warp w, one lane, page w ----
+  if (lane == 0) {
+    int st = 0;
+    if (first + warp < npages) {
+      const PqZstdPage& pg = page_of(warp);
+      const ZstdBlockDesc& blk = blocks_all[pg.first_block];
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(pg.src_off);
+      if (blk.type != 2) {
+        st = blk.out_size == pg.raw_size ? 2 : -1;
+      } else {
+        ZstdBlockPlan& P = s_plans[warp];
+        const int64_t r = zstd_plan_block(src + blk.src_off, blk.size, P, s_tabs[warp], nullptr, nullptr, s_scr[warp]);
+        P.lit_base = 0;
+        P.seq_base = 0;
+        st = (r < 0 || P.regen > pg.raw_size || P.nseq > pg.raw_size / 3 + 1) ? -1 : 1;
+      }
+    }
+    s_state[warp] = st;
+  }
+  __syncthreads();
+  // ---- entropy across the batch ----
+  if (warp == 0) {
+    const int u = lane >> 2, role = lane & 3;
+    if (s_state[u] == 1) {
+      const ZstdBlockPlan& P = s_plans[u];
+      if (P.lit_type == 2 && role < P.streams) {
+        const PqZstdPage& pg = page_of(u);
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(pg.src_off) + blocks_all[pg.first_block].src_off;
+        uint8_t* L = lit_all + pg.lit_off;
+        const int64_t per = P.streams == 4 ? (P.regen + 3) / 4 : P.regen;
+        int64_t so = 0;
+        for (int st = 0; st < role; ++st) so += P.stream_size[st];
+        const int64_t n = P.streams == 4 ? (role < 3 ? per : P.regen - 3 * per) : P.regen;
+        if (huf_stream_v2(s_tabs[u].huf, P.huf_log, b + P.lit_src + so, P.stream_size[role], L + role * per, n) < 0) s_state[u] = -1;
+      }
+    }
+  } else if (warp == 1 && lane < kZstdBatch) {
+    const int u = lane;
+    if (s_state[u] == 1) {
+      ZstdBlockPlan& P = s_plans[u];
+      const PqZstdPage& pg = page_of(u);
+      const uint8_t* b = reinterpret_cast<const uint8_t*>(pg.src_off) + blocks_all[pg.first_block].src_off;
+      int64_t mls = 0;
+      RepSym fin[3] = {{0, 0}, {1, 0}, {2, 0}};
+      int64_t r = 0;
+      if (P.nseq > 0) r = sequences_v2(b + P.seq_src, P.seq_size, P, s_tabs[u].ll, s_tabs[u].ml, s_tabs[u].of, seq_all + pg.seq_off, &mls, fin);
+      P.out_size = (int32_t)min((int64_t)INT32_MAX, (int64_t)P.regen + mls);
+      if (r < 0 || P.out_size != pg.raw_size) s_state[u] = -1;
+      if (P.lit_type == 1) {
+        uint8_t* L = lit_all + pg.lit_off;
+        const uint8_t v = b[P.lit_src];
+        for (int i = 0; i < P.regen; ++i) L[i] = v;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- execute: warp w, page w ----
+  const int st = s_state[warp];
+  if (st == 0) return;
+  bool ok = st > 0;
+  if (ok) {
+    const PqZstdPage& pg = page_of(warp);
+    const ZstdBlockDesc& blk = blocks_all[pg.first_block];
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(pg.src_off) + blk.src_off;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(pg.dst_off);
+    if (st == 2) {
+      if (blk.type == 0) for (int64_t i = lane; i < blk.out_size; i += 32) dst[i] = b[i];
+      else { const uint8_t v = b[0]; for (int64_t i = lane; i < blk.out_size; i += 32) dst[i] = v; }
+    } else {
+      const ZstdBlockPlan& P = s_plans[warp];
+      const uint8_t* lits = P.lit_type == 0 ? b + P.lit_src : lit_all + pg.lit_off;
+      ok = zstd_execute_single_block(P, lits, seq_all + pg.seq_off, dst, pg.raw_size, lane);
+    }
+  }
+  if (!ok && lane == 0) atomicExch(err, kErrBadPage);
+  (void)plans_all;
+}
+
+void launch_zstd_batch(const PqZstdPage* pages, const int32_t* order_one, int none, const ZstdBlockDesc* blocks, ZstdBlockPlan* plans,
+                       uint8_t* lit, uint64_t* seq, int32_t* err, cudaStream_t s) {
+  if (none <= 0) return;
+  static thread_local int attr_device = -1;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (attr_device != cur) {
+    attr_device = cur;
+    cudaFuncSetAttribute(zstd_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kZstdBatch * sizeof(ZstdTables)));
+  }
+  zstd_batch_kernel<<<(none + kZstdBatch - 1) / kZstdBatch, kZstdBatch * 32, kZstdBatch * sizeof(ZstdTables), s>>>(
+      pages, order_one, none, blocks, plans, lit, seq, err);
+}
+
 void launch_zstd_pages_v2(const PqZstdPage* pages, const int32_t* order_small, int nsmall, const int32_t* order_big, int nbig,
                           const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, ZstdTables* tables_v1, uint8_t* lit, uint64_t* seq, int32_t* err,
                           cudaStream_t s) {

@@ -200,6 +200,8 @@ void launch_block_decode(const DecodeArgs& A, cudaStream_t s);
 void launch_zstd_pages(const PqZstdPage* pages, int npages, const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, ZstdTables* tables,
                        uint8_t* lit, uint64_t* seq, int32_t* err, cudaStream_t s);
 void launch_snappy_pages(const PqZstdPage* pages, int npages, int32_t* err, cudaStream_t s);
+void launch_zstd_batch(const PqZstdPage* pages, const int32_t* order_one, int none, const ZstdBlockDesc* blocks, ZstdBlockPlan* plans,
+                       uint8_t* lit, uint64_t* seq, int32_t* err, cudaStream_t s);
 void launch_zstd_pages_v2(const PqZstdPage* pages, const int32_t* order_small, int nsmall, const int32_t* order_big, int nbig,
                           const ZstdBlockDesc* blocks, ZstdBlockPlan* plans, ZstdTables* tables_v1, uint8_t* lit, uint64_t* seq, int32_t* err,
                           cudaStream_t s);
@@ -697,18 +699,29 @@ void DeviceScan::Impl::upload() {
         launch_zstd_pages(d_zpages, (int)zpages.size(), d_zblocks, d_zplans, d_ztables, d_zlit, d_zseq, d_err, stream);
         ctr.kernel_launches += 1;
       } else {
-        // pages of one or two blocks run on two warps, larger ones on eight (one warp per 128 KiB block)
-        std::vector<int32_t> order_small, order_big;
-        for (size_t z = 0; z < zpages.size(); ++z) (zpages[z].nblocks <= 2 ? order_small : order_big).push_back((int32_t)z);
+        // one-block pages are batched eight to a thread block (zstd_batch_kernel), pages of two blocks run on two
+        // warps, larger ones on eight (one warp per 128 KiB block)
+        static const bool no_batch = [] { const char* v = getenv("LAKESOUL_B200_ZSTD_NO_BATCH"); return v && *v == '1'; }();
+        std::vector<int32_t> order_one, order_small, order_big;
+        for (size_t z = 0; z < zpages.size(); ++z) {
+          const int nbk = zpages[z].nblocks;
+          (nbk == 1 && !no_batch ? order_one : (nbk <= 2 ? order_small : order_big)).push_back((int32_t)z);
+        }
+        // largest pages first inside a batch class: pages of similar size share a thread block
+        std::sort(order_one.begin(), order_one.end(), [&](int32_t a, int32_t b) { return zpages[(size_t)a].raw_size > zpages[(size_t)b].raw_size; });
         std::vector<int32_t>& order = scratch_order;
         order = order_big;
         order.insert(order.end(), order_small.begin(), order_small.end());
+        order.insert(order.end(), order_one.begin(), order_one.end());
         int32_t* d_order = static_cast<int32_t*>(dalloc(sizeof(int32_t) * order.size()));
         h2d(d_order, order.data(), sizeof(int32_t) * order.size());
         static const bool small_v1 = [] { const char* v = getenv("LAKESOUL_B200_ZSTD_SMALL_V1"); return v && *v == '1'; }();
         ZstdTables* d_ztables = small_v1 ? static_cast<ZstdTables*>(dalloc(sizeof(ZstdTables) * zblocks.size())) : nullptr;
         launch_zstd_pages_v2(d_zpages, d_order + order_big.size(), (int)order_small.size(), d_order, (int)order_big.size(), d_zblocks,
                              d_zplans, d_ztables, d_zlit, d_zseq, d_err, stream);
+        launch_zstd_batch(d_zpages, d_order + order_big.size() + order_small.size(), (int)order_one.size(), d_zblocks, d_zplans, d_zlit,
+                          d_zseq, d_err, stream);
+        ctr.kernel_launches += order_one.empty() ? 0 : 1;
         ctr.kernel_launches += (order_small.empty() ? 0 : 1) + (order_big.empty() ? 0 : 1);
       }
       ctr.device_decompressed_pages += (int64_t)zpages.size();
