@@ -329,6 +329,7 @@ struct DeviceScan::Impl : std::enable_shared_from_this<DeviceScan::Impl> {
   std::vector<int64_t> out_base, batch_base;
   int64_t vstride = 0;
   bool ran = false;
+  std::shared_ptr<uint8_t> h_sorted_buckets;  // sort mode with buckets: uint32 per output row (pinned)
 
   std::shared_ptr<ScanSession> session;
   ScanSlot* slot = nullptr;
@@ -872,26 +873,55 @@ void DeviceScan::Impl::merge_and_gather() {
   int key_bits = 64;
   bool encoded_keys = false;
   std::vector<EncKeyCol> enc;
-  if (do_merge) {
-    const int npk = (int)spec.primary_keys.size();
-    std::vector<int> pk_cols;
-    for (int i = 0; i < npk; ++i) {
-      const int c = spec.physical_schema->GetFieldIndex(spec.primary_keys[i]);
-      if (c < 0) fail("primary key column '" + spec.primary_keys[i] + "' is not in the schema");
-      if (!cols[c].all_present) fail("primary key column '" + spec.primary_keys[i] + "' is missing from a file");
-      pk_cols.push_back(c);
+  // one key item = a physical column, or (c < 0) a device-computed uint32 column over global rows (the hash bucket of
+  // the write side)
+  struct KeyItem { int c; const void* syn; std::string name; };
+  auto enc_col_of = [&](const KeyItem& it) -> EncKeyCol {
+    EncKeyCol e{};
+    if (it.c < 0) {
+      e.values = it.syn;
+      e.width = 4;
+      e.kind = ENC_UNSIGNED;
+      return e;
     }
+    const DevColumn& dc = cols[it.c];
+    const auto& type = *spec.physical_schema->field(it.c)->type();
+    e.values = dc.values.p;
+    e.validity = static_cast<const uint8_t*>(dc.validity.p);
+    e.data = static_cast<const uint8_t*>(dc.data.p);
+    e.bucket_data = static_cast<const int64_t*>(dc.d_bucket_data.p);
+    e.width = dc.kind.width;
+    if (dc.kind.var) e.kind = ENC_BYTES;
+    else if (type.id() == arrow::Type::BOOL) e.kind = ENC_BOOL_BITS;
+    else if (type.id() == arrow::Type::FLOAT || type.id() == arrow::Type::DOUBLE || type.id() == arrow::Type::HALF_FLOAT) e.kind = ENC_FLOAT;
+    else if (arrow::is_unsigned_integer(type.id())) e.kind = ENC_UNSIGNED;
+    else if (arrow::is_signed_integer(type.id()) || arrow::is_decimal(type.id()) || arrow::is_temporal(type.id())) e.kind = ENC_SIGNED;
+    else
+      fail("key column '" + it.name + "' of type " + type.ToString() + " is not supported by the GPU engine");
+    return e;
+  };
+  auto key_items_of = [&](const std::vector<std::string>& names, std::vector<KeyItem>& items) {
+    for (const auto& nme : names) {
+      const int c = spec.physical_schema->GetFieldIndex(nme);
+      if (c < 0) fail("primary key column '" + nme + "' is not in the schema");
+      if (!cols[c].all_present) fail("primary key column '" + nme + "' is missing from a file");
+      items.push_back(KeyItem{c, nullptr, nme});
+    }
+  };
+  auto build_key = [&](const std::vector<KeyItem>& items) {
+    const int nk = (int)items.size();
     int bits = 0;
-    bool fixed_ok = npk <= kMaxPkCols;
-    for (int c : pk_cols) {
-      const DevColumn& dc = cols[c];
+    bool fixed_ok = nk <= kMaxPkCols;
+    for (const auto& it : items) {
+      if (it.c < 0) { bits += 32; continue; }
+      const DevColumn& dc = cols[it.c];
       if (dc.kind.var || !dc.kind.pk_ok) fixed_ok = false;
       bits += dc.kind.width * 8 + (dc.validity.p ? 1 : 0);
     }
     if (fixed_ok && bits > 128) fixed_ok = false;
-    const bool single_bytes = npk == 1 && cols[pk_cols[0]].kind.var;
+    const bool single_bytes = nk == 1 && items[0].c >= 0 && cols[items[0].c].kind.var;
     if (single_bytes) {
-      const DevColumn& dc = cols[pk_cols[0]];
+      const DevColumn& dc = cols[items[0].c];
       pk.ncols = 1;
       pk.col[0].values = dc.values.p;
       pk.col[0].validity = static_cast<const uint8_t*>(dc.validity.p);
@@ -901,9 +931,16 @@ void DeviceScan::Impl::merge_and_gather() {
       pk.col[0].bucket_data = static_cast<const int64_t*>(dc.d_bucket_data.p);
       key_bits = 128;
     } else if (fixed_ok) {
-      pk.ncols = npk;
-      for (int i = 0; i < npk; ++i) {
-        const DevColumn& dc = cols[pk_cols[i]];
+      pk.ncols = nk;
+      for (int i = 0; i < nk; ++i) {
+        if (items[i].c < 0) {
+          pk.col[i].values = items[i].syn;
+          pk.col[i].validity = nullptr;
+          pk.col[i].width = 4;
+          pk.col[i].kind = PK_UNSIGNED;
+          continue;
+        }
+        const DevColumn& dc = cols[items[i].c];
         pk.col[i].values = dc.values.p;
         pk.col[i].validity = static_cast<const uint8_t*>(dc.validity.p);
         pk.col[i].width = (uint8_t)dc.kind.width;
@@ -913,27 +950,14 @@ void DeviceScan::Impl::merge_and_gather() {
     } else {
       encoded_keys = true;
       key_bits = 128;
-      for (int i = 0; i < npk; ++i) {
-        const int c = pk_cols[i];
-        const DevColumn& dc = cols[c];
-        const auto& type = *spec.physical_schema->field(c)->type();
-        EncKeyCol e{};
-        e.values = dc.values.p;
-        e.validity = static_cast<const uint8_t*>(dc.validity.p);
-        e.data = static_cast<const uint8_t*>(dc.data.p);
-        e.bucket_data = static_cast<const int64_t*>(dc.d_bucket_data.p);
-        e.width = dc.kind.width;
-        if (dc.kind.var) e.kind = ENC_BYTES;
-        else if (type.id() == arrow::Type::BOOL) e.kind = ENC_BOOL_BITS;
-        else if (type.id() == arrow::Type::FLOAT || type.id() == arrow::Type::DOUBLE) e.kind = ENC_FLOAT;
-        else if (arrow::is_unsigned_integer(type.id())) e.kind = ENC_UNSIGNED;
-        else if (arrow::is_signed_integer(type.id()) || arrow::is_decimal(type.id()) || arrow::is_temporal(type.id())) e.kind = ENC_SIGNED;
-        else
-          fail("primary key column '" + spec.primary_keys[i] + "' of type " + type.ToString() + " is not supported by the GPU reader");
-        enc.push_back(e);
-      }
+      for (const auto& it : items) enc.push_back(enc_col_of(it));
     }
     pk.key_bits = key_bits;
+  };
+  if (do_merge) {
+    std::vector<KeyItem> items;
+    key_items_of(spec.primary_keys, items);
+    build_key(items);
   }
 
   const double t0 = now_ms();
@@ -950,6 +974,33 @@ void DeviceScan::Impl::merge_and_gather() {
   else plan_identity(plan, stream);
   plan_sync_counts(plan, stream);
   check_decode_error();  // same stream, enqueued before the merge
+  // ---- write side: hash buckets + sort of the row list ----------------------------
+  uint32_t* d_row_bucket = nullptr;
+  if (spec.sort.enabled) {
+    if (do_merge || nb != 1) fail("sort mode takes one group of unmerged inputs");
+    std::vector<KeyItem> items;
+    key_items_of(spec.sort.prefix_cols, items);
+    if (spec.sort.with_buckets) {
+      std::vector<KeyItem> hitems;
+      key_items_of(spec.sort.hash_cols, hitems);
+      std::vector<EncKeyCol> henc;
+      for (const auto& it : hitems) henc.push_back(enc_col_of(it));
+      d_row_bucket = static_cast<uint32_t*>(dalloc(sizeof(uint32_t) * (size_t)std::max<int64_t>(span, 1)));
+      plan_hash_buckets(plan, henc.data(), (int)henc.size(), std::max<uint32_t>(spec.sort.bucket_num, 1), d_row_bucket, stream);
+      ctr.kernel_launches += 1;
+      items.push_back(KeyItem{-1, d_row_bucket, "<hash bucket>"});
+    }
+    key_items_of(spec.sort.hash_cols, items);
+    key_items_of(spec.sort.suffix_cols, items);
+    if (!items.empty()) {
+      build_key(items);
+      if (encoded_keys) {
+        plan_encode_keys(plan, enc.data(), (int)enc.size(), &pk, stream);
+        ctr.kernel_launches += 5;
+      }
+      plan_sort(plan, pk, stream);
+    }
+  }
   ctr.kernel_launches += plan_stats(plan).launches;
 
   // per-column winner lists / operator results (partial merge, non-UseLast operators)
@@ -1101,6 +1152,13 @@ void DeviceScan::Impl::merge_and_gather() {
       }
     }
   }
+  if (d_row_bucket && U > 0) {  // bucket of every output row, in output order
+    uint32_t* d_sorted = static_cast<uint32_t*>(dalloc(sizeof(uint32_t) * (size_t)U));
+    plan_take_u32(plan, d_row_bucket, d_sorted, stream);
+    h_sorted_buckets = pool.alloc(sizeof(uint32_t) * (size_t)U);
+    d2h(h_sorted_buckets.get(), d_sorted, sizeof(uint32_t) * (size_t)U);
+    ctr.kernel_launches += 1;
+  }
   // error flag of the gather kernels (a look-back scan that never saw its predecessor publish), same wait
   std::shared_ptr<uint8_t> h_gerr = pinned_alloc(64);
   *reinterpret_cast<int32_t*>(h_gerr.get()) = 0;
@@ -1176,6 +1234,9 @@ int DeviceScan::num_buckets() const { return impl_->nb; }
 int64_t DeviceScan::num_rows(int b) const { return impl_->out_base[b + 1] - impl_->out_base[b]; }
 int64_t DeviceScan::num_batches(int b) const { return impl_->batch_base[b + 1] - impl_->batch_base[b]; }
 const ScanCounters& DeviceScan::counters() const { return impl_->ctr; }
+const uint32_t* DeviceScan::sorted_buckets() const {
+  return impl_->h_sorted_buckets ? reinterpret_cast<const uint32_t*>(impl_->h_sorted_buckets.get()) : nullptr;
+}
 
 std::shared_ptr<arrow::RecordBatch> DeviceScan::Batch(int b, int64_t i) const {
   const Impl& I = *impl_;

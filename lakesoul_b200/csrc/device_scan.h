@@ -31,6 +31,19 @@ void trace_flush(const char* tag);
 // merge_operator.rs:41-53 -- unknown names are an error (the reference panics)
 MergeOp merge_op_from_name(const std::string& name);
 
+// Write side: the rows of ONE group of unmerged inputs come out sorted by
+// (prefix_cols, [hash bucket of hash_cols], hash_cols, suffix_cols), ascending, nulls first, ties in input order
+// -- the order SortExec + RepartitionByRangeAndHashExec give the reference's writers (sort_writer.rs:59-76,
+// partitioning_writer.rs:139-241).
+struct SortSpec {
+  bool enabled = false;
+  std::vector<std::string> prefix_cols;   // range partition columns
+  std::vector<std::string> hash_cols;     // primary keys
+  std::vector<std::string> suffix_cols;   // aux sort columns
+  bool with_buckets = false;              // hash the rows into buckets and sort by bucket before the primary key
+  uint32_t bucket_num = 1;
+};
+
 struct ScanSpec {
   std::shared_ptr<arrow::Schema> physical_schema;  // columns carried through the merge, target order
   std::vector<std::string> primary_keys;
@@ -38,6 +51,7 @@ struct ScanSpec {
   bool merge = true;            // false = plain concatenation in file order (merge/mod.rs:297-312)
   int batch_size = 8192;
   std::shared_ptr<FilterExpr> filter;  // evaluated on the merged rows (session.rs:839-877), may be null
+  SortSpec sort;                // merge must be false
 };
 
 class RawParquetFile;
@@ -83,6 +97,8 @@ class DeviceScan {
   // zero-copy over pinned host memory; columns == spec.physical_schema
   std::shared_ptr<arrow::RecordBatch> Batch(int bucket, int64_t i) const;
   const ScanCounters& counters() const;
+  // sort mode with buckets: hash bucket of every output row of bucket 0, in output order (valid while the scan lives)
+  const uint32_t* sorted_buckets() const;
 
  private:
   struct Impl;

@@ -1389,7 +1389,7 @@ __device__ __forceinline__ void scan_lookback(unsigned long long* agg, unsigned 
   }
 }
 
-__global__ void __launch_bounds__(kGatherThreads) var_write_kernel(GatherGeom G, const VarColSet* __restrict__ set,
+__global__ void __launch_bounds__(kGatherThreads) var_write_kernel_v1(GatherGeom G, const VarColSet* __restrict__ set,
                                                                    VarScan S, int64_t total_batches) {
   __shared__ int s_scan[kGatherThreads / 32 + 2];
   __shared__ int32_t s_off[kRowsPerChunk + 1];   // chunk-relative destination offset of every row
@@ -1508,6 +1508,326 @@ __global__ void __launch_bounds__(kGatherThreads) var_write_kernel(GatherGeom G,
     __syncthreads();
     w0 = w1;
     r_lo = r_hi;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// var_write_kernel (r2b): same chunk protocol as v1 (look-back positions, 16-byte congruent stage, TMA bulk-store
+// flush), rebuilt around the instruction count per (row, column) cell -- the r2 profile of v1 showed ~350 thread
+// instructions per cell at 36 % issue utilisation, a fixed cost that a 1-byte flag pays like a 40-byte comment:
+//   * row pass with rows STRIDED over the block (row = x * 256 + thread): winner and offset loads of a warp fall into
+//     one or two lines instead of ten, eight independent load chains per thread, validity words by ballot;
+//   * chunks whose rows are all one byte long (flag columns) skip the row copies: a thread assembles one stage word
+//     from four byte loads;
+//   * general rows: destination-word grid -- one dst word = funnel shift of two aligned source words; only the first
+//     and the last word of a row are partial (byte stores), everything between is a full STS.32; all loads of two
+//     rows are in flight before the first store.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_word_part(uint8_t* p, uint32_t v, int lo, int hi) {  // bytes [lo, hi) of the word at p
+  if (lo == 0 && hi == 4) {
+    *reinterpret_cast<uint32_t*>(p) = v;
+    return;
+  }
+  if (lo <= 0 && hi > 0) p[0] = (uint8_t)v;
+  if (lo <= 1 && hi > 1) p[1] = (uint8_t)(v >> 8);
+  if (lo <= 2 && hi > 2) p[2] = (uint8_t)(v >> 16);
+  if (hi > 3) p[3] = (uint8_t)(v >> 24);
+}
+
+__device__ __forceinline__ void store_word_mask(uint32_t* p, uint32_t v, uint32_t m) {  // the bytes of v selected by m
+  if (m == 0xffffffffu) {
+    *p = v;
+    return;
+  }
+  uint8_t* b = reinterpret_cast<uint8_t*>(p);
+  if (m & 0xffu) b[0] = (uint8_t)v;
+  if (m & 0xff00u) b[1] = (uint8_t)(v >> 8);
+  if (m & 0xff0000u) b[2] = (uint8_t)(v >> 16);
+  if (m & 0xff000000u) b[3] = (uint8_t)(v >> 24);
+}
+
+// One row on the destination-word grid of the (zeroed) stage. W = destination words whose source words are loaded up
+// front (W + 1 aligned source words + the two under the row's last word); the first and the last word of a row are
+// OR-ed into the stage under a byte mask (shared-memory atomics: neighbouring rows complete the word), the words
+// between are plain stores.
+// experiment switches (tools/build_variant.sh); the defaults are the measured best
+#ifndef VARW_ATOMIC
+#define VARW_ATOMIC 0
+#endif
+#ifndef VARW_R_SHORT
+#define VARW_R_SHORT 1
+#endif
+#ifndef VARW_R_MID
+#define VARW_R_MID 1
+#endif
+#ifndef VARW_W_LONG
+#define VARW_W_LONG 6
+#endif
+#ifndef VARW_PREFETCH
+#define VARW_PREFETCH 2
+#endif
+template <int W, bool kLoop>
+struct RowWords {
+  uint32_t* p0;         // stage word that holds the row's first byte
+  int nk;               // destination words - 1 (-1: nothing to copy)
+  unsigned sh;
+  uint32_t m0, ml;      // byte masks of the first / last destination word
+  const uint32_t* wp;   // aligned source word under the first destination word (kLoop only)
+  uint32_t w[W + 1], wl0, wl1;
+};
+
+template <int W, bool kLoop>
+__device__ __forceinline__ void roww_load(RowWords<W, kLoop>& rc, uint8_t* stage, int a, int n, const uint8_t* s) {
+  rc.nk = -1;
+  if (n <= 0) return;
+  const int lo = a & 3;
+  rc.p0 = reinterpret_cast<uint32_t*>(stage + (a - lo));
+  rc.nk = (lo + n - 1) >> 2;
+  const uintptr_t sa0 = reinterpret_cast<uintptr_t>(s) - (uintptr_t)lo;
+  rc.sh = (unsigned)(sa0 & 3) * 8;
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>(sa0 & ~(uintptr_t)3);
+  if (kLoop) rc.wp = wp;
+  // source word i covers row bytes [4i - d0, 4i - d0 + 4): it is read only if it holds a byte of the row (never before
+  // / beyond the column's byte buffer): i == 0 needs d0 < 4, i >= 1 needs 4i < d0 + n
+  const int d0 = lo + (int)(sa0 & 3);  // 0..6
+  const int lim = d0 + n;
+  rc.w[0] = d0 < 4 ? __ldg(wp) : 0u;
+#pragma unroll
+  for (int i = 1; i <= W; ++i) rc.w[i] = (4 * i < lim) ? __ldg(wp + i) : 0u;
+  rc.wl0 = rc.wl1 = 0u;
+  if (rc.nk > 0) {
+    rc.wl0 = __ldg(wp + rc.nk);
+    if (4 * (rc.nk + 1) < lim) rc.wl1 = __ldg(wp + rc.nk + 1);
+  }
+  const int hi = min(4, lo + n);
+  rc.m0 = (0xffffffffu << (8 * lo)) & (0xffffffffu >> (8 * (4 - hi)));
+  rc.ml = 0xffffffffu >> (8 * (3 - ((lo + n - 1) & 3)));
+}
+
+template <int W, bool kLoop>
+__device__ __forceinline__ void roww_store(const RowWords<W, kLoop>& rc) {
+  if (rc.nk < 0) return;
+#if VARW_ATOMIC
+  atomicOr(rc.p0, __funnelshift_r(rc.w[0], rc.w[1], rc.sh) & rc.m0);
+#else
+  store_word_mask(rc.p0, __funnelshift_r(rc.w[0], rc.w[1], rc.sh), rc.m0);
+#endif
+  if (rc.nk == 0) return;
+#pragma unroll
+  for (int i = 1; i < W; ++i)
+    if (i < rc.nk) rc.p0[i] = __funnelshift_r(rc.w[i], rc.w[i + 1], rc.sh);
+  if (kLoop) {
+    for (int base = W; base < rc.nk; base += 4) {  // rows longer than the preload: four full words per trip
+      uint32_t w[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) w[i] = (base + i <= rc.nk) ? __ldg(rc.wp + base + i) : 0u;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (base + i < rc.nk) rc.p0[base + i] = __funnelshift_r(w[i], w[i + 1], rc.sh);
+    }
+  }
+#if VARW_ATOMIC
+  atomicOr(rc.p0 + rc.nk, __funnelshift_r(rc.wl0, rc.wl1, rc.sh) & rc.ml);
+#else
+  store_word_mask(rc.p0 + rc.nk, __funnelshift_r(rc.wl0, rc.wl1, rc.sh), rc.ml);
+#endif
+}
+
+// rows [r_lo, r_hi] of the chunk, clipped to the window [w0, w1) of its bytes; R rows per thread and trip, all loads of
+// a trip in flight before the first store
+template <int W, int R, bool kLoop>
+__device__ __forceinline__ void copy_rows(const int32_t* s_off, const int32_t* s_src, uint8_t* s_stage, const uint8_t* src_base,
+                                          int r_lo, int r_hi, int w0, int w1, int first_pad) {
+  for (int r = r_lo + threadIdx.x; r <= r_hi; r += R * kGatherThreads) {
+    RowWords<W, kLoop> rc[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const int rq = r + q * kGatherThreads;
+      rc[q].nk = -1;
+      if (rq <= r_hi) {
+        const int o = s_off[rq], a = max(o, w0), e = min(s_off[rq + 1], w1);
+        roww_load<W, kLoop>(rc[q], s_stage, first_pad + (a - w0), e - a, src_base + s_src[rq] + (a - o));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) roww_store<W, kLoop>(rc[q]);
+  }
+}
+
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kGatherThreads, kMinBlocks) var_write_kernel(const __grid_constant__ GatherGeom G,
+                                                                              const __grid_constant__ VarColSet set, const __grid_constant__ VarScan S,
+                                                                              int64_t total_batches) {
+  __shared__ int s_scan[kGatherThreads / 32 + 2];
+  __shared__ __align__(16) int32_t s_off[kRowsPerChunk + 4];   // row lengths, then chunk-relative destination offsets
+  __shared__ __align__(16) int32_t s_src[kRowsPerChunk];       // bucket-relative source offset of every row
+  __shared__ __align__(16) uint8_t s_stage[kStageBytes + 16];
+  __shared__ long long s_c0, s_rel;
+  __shared__ int g_b, g_r_begin, g_rows, g_live;   // chunk geometry: one thread searches, everybody reads
+  __shared__ long long g_gb, g_u0;
+  __shared__ int s_maxlen;
+  const int ci = (int)(blockIdx.x % (unsigned)S.ncols);
+  const int64_t chunk = blockIdx.x / (unsigned)S.ncols;
+  if (threadIdx.x == 0) {
+    int b0, rb0, re0, rows0;
+    int64_t gb0, u00;
+    g_live = chunk_geometry(G, chunk, b0, gb0, u00, rb0, re0, rows0) ? 1 : 0;
+    g_b = b0; g_r_begin = rb0; g_rows = rows0; g_gb = gb0; g_u0 = u00;
+    s_maxlen = 0;
+  }
+#if VARW_ATOMIC
+  // the stage starts zeroed: partial words are OR-ed into it
+  for (int t = threadIdx.x; t < (kStageBytes + 16) / 16; t += kGatherThreads) reinterpret_cast<uint4*>(s_stage)[t] = make_uint4(0, 0, 0, 0);
+#endif
+  __syncthreads();
+  const bool live = g_live != 0;
+  const int b = g_b, r_begin = g_r_begin, rows = g_rows;
+  const int64_t gb = g_gb, u0 = g_u0;
+  const VarCol& col = set.col[ci];
+  unsigned long long* agg = S.agg + (int64_t)ci * S.stride;
+  unsigned long long* incl = S.incl + (int64_t)ci * S.stride;
+  const uint32_t* win = (col.win ? col.win : G.win) + u0 + r_begin;
+  const int c_in = (int)(chunk % G.chunks_per_batch);
+  const uint8_t* src_base = col.src_data + col.src_data_base[b];
+  const int nloc = live ? min(rows - r_begin, kRowsPerChunk) : 0;  // rows of this chunk
+  const int lane = threadIdx.x & 31;
+  // ---- row pass: row = x * 256 + thread ----
+  uint32_t g[kRowsPerThread];
+#pragma unroll
+  for (int x = 0; x < kRowsPerThread; ++x) {
+    const int r = x * kGatherThreads + threadIdx.x;
+    g[x] = r < nloc ? __ldg(win + r) : kNoRow;
+  }
+  bool ones = true;
+  int maxlen = 0;
+  uint32_t* vwords = col.dst_valid ? reinterpret_cast<uint32_t*>(col.dst_valid + gb * G.valid_stride) + (r_begin >> 5) : nullptr;
+  // three phases, each over all eight rows, so that the eight offset-pair loads are in flight together (r2c profile:
+  // one exposed DRAM round trip per row when loads, shared stores and the validity store alternate)
+  unsigned vmask = 0;
+#pragma unroll
+  for (int x = 0; x < kRowsPerThread; ++x) {
+    bool valid = g[x] != kNoRow;
+    if (valid && col.src_valid) valid = (__ldg(col.src_valid + (g[x] >> 3)) >> (g[x] & 7)) & 1;
+    vmask |= valid ? (1u << x) : 0u;
+  }
+  int o0[kRowsPerThread], o1[kRowsPerThread];
+#pragma unroll
+  for (int x = 0; x < kRowsPerThread; ++x) {
+    o0[x] = o1[x] = 0;
+    if (vmask & (1u << x)) {
+      o0[x] = __ldg(col.src_offsets + g[x]);
+      o1[x] = __ldg(col.src_offsets + (int64_t)g[x] + 1);
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < kRowsPerThread; ++x) {
+    const int r = x * kGatherThreads + threadIdx.x;
+#if VARW_PREFETCH == 1
+    if (o1[x] > o0[x]) asm volatile("prefetch.global.L1 [%0];" ::"l"(src_base + o0[x]));
+#elif VARW_PREFETCH == 2
+    if (o1[x] > o0[x]) asm volatile("prefetch.global.L2 [%0];" ::"l"(src_base + o0[x]));
+#endif
+    s_src[r] = o0[x];
+    s_off[r] = o1[x] - o0[x];
+    ones = ones && (r >= nloc || o1[x] - o0[x] == 1);
+    maxlen = max(maxlen, o1[x] - o0[x]);
+    if (vwords) {
+      const unsigned word = __ballot_sync(0xffffffffu, (vmask >> x) & 1u);
+      if (lane == 0 && r < ((nloc + 31) & ~31)) vwords[r >> 5] = word;
+    }
+  }
+  maxlen = __reduce_max_sync(0xffffffffu, maxlen);
+  if (lane == 0 && maxlen > 0) atomicMax(&s_maxlen, maxlen);
+  const bool all_one = __syncthreads_and(ones) != 0;
+  const int maxlen_all = s_maxlen;
+  // ---- lengths -> chunk-relative offsets (thread t scans rows [8t, 8t+8)) ----
+  int tot;
+  {
+    int4* po = reinterpret_cast<int4*>(s_off) + 2 * threadIdx.x;
+    int4 l0 = po[0], l1 = po[1];
+    const int mine = l0.x + l0.y + l0.z + l0.w + l1.x + l1.y + l1.z + l1.w;
+    int run = block_exclusive_scan<kGatherThreads>(mine, s_scan, tot);
+    int4 e0, e1;
+    e0.x = run; run += l0.x;
+    e0.y = run; run += l0.y;
+    e0.z = run; run += l0.z;
+    e0.w = run; run += l0.w;
+    e1.x = run; run += l1.x;
+    e1.y = run; run += l1.y;
+    e1.z = run; run += l1.z;
+    e1.w = run;
+    po[0] = e0;
+    po[1] = e1;
+    if (threadIdx.x == 0) s_off[kRowsPerChunk] = tot;
+  }
+  // publish the chunk total, then resolve the chunk's position by looking back
+  if (threadIdx.x < 32) scan_lookback(agg, incl, chunk, c_in, tot, &s_c0, &s_rel, S.err);
+  __syncthreads();
+  if (!live) return;
+  const int64_t c0 = s_c0;
+  const int32_t rel = (int32_t)s_rel;
+  // offsets (every earlier batch contributed one extra entry)
+  int32_t* dst_off = col.dst_offsets + u0 + gb + r_begin;
+  for (int r = threadIdx.x; r < nloc; r += kGatherThreads) dst_off[r] = rel + s_off[r];
+  const bool last_chunk = r_begin + nloc == rows;
+  if (threadIdx.x == 0) {
+    if (last_chunk) dst_off[nloc] = rel + tot;
+    if (c_in == 0) col.batch_data_start[gb] = c0 - rel;
+    if (last_chunk && gb == total_batches - 1) col.batch_data_start[total_batches] = c0 + tot;
+  }
+  // ---- bytes: windows of the chunk's output range, staged in shared memory --------------------
+  uint8_t* dst_bytes = col.dst_data + c0;       // chunk-relative byte p lives at dst_bytes[p]
+  const int mis = (int)((reinterpret_cast<uintptr_t>(dst_bytes)) & 15);  // stage[mis + (p - w0)] <-> p
+  int w0 = 0;
+  int r_lo = 0;
+  while (w0 < tot) {
+    const int first_pad = (w0 == 0) ? mis : 0;   // later windows start on a 16-byte boundary
+    const int w1 = min(tot, w0 + kStageBytes - first_pad);
+    if (all_one) {
+      // one byte per row (one window: tot = nloc <= 2048): stage word j = rows 4j - mis .. 4j - mis + 3
+      const int jw1 = (mis + nloc + 3) >> 2;
+      for (int j = (mis >> 2) + threadIdx.x; j < jw1; j += kGatherThreads) {
+        const int rb = 4 * j - mis;
+        uint32_t v = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = rb + q;
+          if (r >= 0 && r < nloc) v |= (uint32_t)__ldg(src_base + s_src[r]) << (8 * q);
+        }
+        store_word_part(s_stage + 4 * j, v, max(-rb, 0), min(nloc - rb, 4));
+      }
+    } else {
+      // rows intersecting [w0, w1): most chunks are one window (no search at all); the row that straddles a window
+      // boundary is the first row of the next window
+      const int r_hi = (w1 >= tot) ? nloc - 1 : upper_idx(s_off, nloc + 1, w1 - 1);
+      // preload depth by the longest row of the chunk (block-uniform): rows up to 8 / 20 / 44 bytes never loop
+      if (maxlen_all <= 8) copy_rows<3, VARW_R_SHORT, false>(s_off, s_src, s_stage, src_base, r_lo, r_hi, w0, w1, first_pad);
+      else if (maxlen_all <= 20) copy_rows<6, VARW_R_MID, false>(s_off, s_src, s_stage, src_base, r_lo, r_hi, w0, w1, first_pad);
+      else copy_rows<VARW_W_LONG, 1, true>(s_off, s_src, s_stage, src_base, r_lo, r_hi, w0, w1, first_pad);
+      r_lo = r_hi;
+    }
+    fence_proxy_async();  // the stage was written through the generic proxy; the bulk store reads it asynchronously
+    __syncthreads();
+    // flush: global address of stage[first_pad] is dst_bytes + w0. The 16-byte aligned middle leaves with ONE TMA
+    // bulk store (cp.async.bulk shared -> global) issued by a single thread; the <= 15 bytes that share a vector with
+    // the neighbouring chunks are stored by hand.
+    uint8_t* gdst = dst_bytes + w0 - first_pad;  // 16-byte aligned
+    const int nbytes = first_pad + (w1 - w0);
+    const int v_lo = first_pad ? 16 : 0;
+    const int v_hi = nbytes & ~15;
+    if (threadIdx.x == 0 && v_hi > v_lo) bulk_store(gdst + v_lo, s_stage + v_lo, (uint32_t)(v_hi - v_lo));
+    if (first_pad)
+      for (int t = first_pad + threadIdx.x; t < min(16, nbytes); t += kGatherThreads) gdst[t] = s_stage[t];
+    for (int t = max(v_hi, v_lo) + threadIdx.x; t < nbytes; t += kGatherThreads)
+      if (t >= first_pad) gdst[t] = s_stage[t];
+    if (threadIdx.x == 0) bulk_store_wait_read();  // the stage is rewritten by the next window / released at exit
+    if (w1 >= tot) break;
+    __syncthreads();
+#if VARW_ATOMIC
+    for (int t = threadIdx.x; t < (kStageBytes + 16) / 16; t += kGatherThreads) reinterpret_cast<uint4*>(s_stage)[t] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+#endif
+    w0 = w1;
   }
 }
 
@@ -2419,7 +2739,15 @@ static void require_synced(const MergePlan* P) {
   }
 }
 
+static void gather_fixed_on(MergePlan* P, const FixedCol* cols, int ncols, cudaStream_t stream, cudaStream_t launch_stream,
+                            cudaEvent_t fork);
 void gather_fixed(MergePlan* P, const FixedCol* cols, int ncols, cudaStream_t stream) {
+  gather_fixed_on(P, cols, ncols, stream, stream, nullptr);
+}
+
+// Descriptor upload on `stream`; the kernel on `launch_stream` (behind `fork`, recorded on `stream`, when they differ).
+static void gather_fixed_on(MergePlan* P, const FixedCol* cols, int ncols, cudaStream_t stream, cudaStream_t launch_stream,
+                            cudaEvent_t fork) {
   require_synced(P);
   if (ncols <= 0) return;
   const int64_t total_batches = P->batch_base[P->nb];
@@ -2434,9 +2762,13 @@ void gather_fixed(MergePlan* P, const FixedCol* cols, int ncols, cudaStream_t st
   const int64_t chunks = total_batches * G.chunks_per_batch;
   // occupancy variants: r1 profile 90 registers -> 2 blocks per SM, latency-bound (24.8 % warps active)
   static const int min_blocks = [] { const char* v = getenv("LAKESOUL_B200_GATHER_BLOCKS"); return v ? atoi(v) : kGatherFixedBlocksDefault; }();
-  if (min_blocks >= 4) gather_fixed_kernel<4><<<(unsigned)chunks, kGatherThreads, 0, stream>>>(G, P->d_cols, ncols);
-  else if (min_blocks == 3) gather_fixed_kernel<3><<<(unsigned)chunks, kGatherThreads, 0, stream>>>(G, P->d_cols, ncols);
-  else gather_fixed_kernel<2><<<(unsigned)chunks, kGatherThreads, 0, stream>>>(G, P->d_cols, ncols);
+  if (launch_stream != stream) {
+    LSB_CUDA(cudaEventRecord(fork, stream));
+    LSB_CUDA(cudaStreamWaitEvent(launch_stream, fork, 0));
+  }
+  if (min_blocks >= 4) gather_fixed_kernel<4><<<(unsigned)chunks, kGatherThreads, 0, launch_stream>>>(G, P->d_cols, ncols);
+  else if (min_blocks == 3) gather_fixed_kernel<3><<<(unsigned)chunks, kGatherThreads, 0, launch_stream>>>(G, P->d_cols, ncols);
+  else gather_fixed_kernel<2><<<(unsigned)chunks, kGatherThreads, 0, launch_stream>>>(G, P->d_cols, ncols);
   LSB_CUDA(cudaGetLastError());
   // the descriptor table is reused by the next call: order the copy behind this launch
 }
@@ -2444,7 +2776,39 @@ void gather_fixed(MergePlan* P, const FixedCol* cols, int ncols, cudaStream_t st
 void gather_var_multi(MergePlan* P, const VarCol* cols, int ncols, cudaStream_t stream);
 
 // Fixed-width and variable-width columns of one scan: 2 launches.
+// The fixed-width gather is HBM-bound, the string gather instruction / latency-bound: they run side by side, the
+// fixed-width kernel on a side stream of the calling thread (fork / join by events; LAKESOUL_B200_GATHER_OVERLAP=0
+// puts them back in sequence).
+struct SideStream {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream& side_stream() {
+  static thread_local SideStream ss;
+  int cur = 0;
+  LSB_CUDA(cudaGetDevice(&cur));
+  if (ss.device != cur) {  // streams of a previous device are left to the context
+    LSB_CUDA(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking));
+    LSB_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+    LSB_CUDA(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+    ss.device = cur;
+  }
+  return ss;
+}
+
 void gather_all(MergePlan* P, const FixedCol* fixed, int nfixed, const VarCol* vars, int nvars, cudaStream_t stream) {
+  static const bool overlap = [] { const char* v = getenv("LAKESOUL_B200_GATHER_OVERLAP"); return !v || *v != '0'; }();
+  // (small scans -- one bucket of a reader -- stay on one stream: many readers already share the hardware queues)
+  const bool both = nfixed > 0 && nvars > 0 && P->synced && P->batch_base[P->nb] > 0 && P->out_base[P->nb] >= (1 << 20);
+  if (both && overlap) {
+    SideStream& ss = side_stream();
+    gather_fixed_on(P, fixed, nfixed, stream, ss.stream, ss.fork);
+    gather_var_multi(P, vars, nvars, stream);
+    LSB_CUDA(cudaEventRecord(ss.join, ss.stream));
+    LSB_CUDA(cudaStreamWaitEvent(stream, ss.join, 0));
+    return;
+  }
   if (nfixed > 0) gather_fixed(P, fixed, nfixed, stream);
   if (nvars > 0) gather_var_multi(P, vars, nvars, stream);
 }
@@ -2510,13 +2874,19 @@ void gather_var_multi(MergePlan* P, const VarCol* cols, int ncols, cudaStream_t 
       set.n = n;
       for (int i = 0; i < n; ++i) set.col[i] = group[c0 + i];
       LSB_CUDA(h2d_staged(d_set, &set, sizeof(VarColSet), stream));
+      static const bool var_v1 = [] { const char* v = getenv("LAKESOUL_B200_VAR_V1"); return v && *v == '1'; }();
+      static const int var_blocks = [] { const char* v = getenv("LAKESOUL_B200_VAR_BLOCKS"); return v ? atoi(v) : 4; }();
       static const int win_variant = [] { const char* v = getenv("LAKESOUL_B200_WINDOW_VARIANT"); return v ? atoi(v) : 0; }();
       if (pass == 0 && win_variant == 1)
         var_window_kernel<14, 24576><<<(unsigned)(chunks * n), kGatherThreads, sizeof(WinSmem<14, 24576>), stream>>>(G, d_set, S, total_batches);
       else if (pass == 0)
         var_window_kernel<13, 16384><<<(unsigned)(chunks * n), kGatherThreads, sizeof(WinSmem<13, 16384>), stream>>>(G, d_set, S, total_batches);
+      else if (var_v1)
+        var_write_kernel_v1<<<(unsigned)(chunks * n), kGatherThreads, 0, stream>>>(G, d_set, S, total_batches);
+      else if (var_blocks >= 4)
+        var_write_kernel<4><<<(unsigned)(chunks * n), kGatherThreads, 0, stream>>>(G, set, S, total_batches);
       else
-        var_write_kernel<<<(unsigned)(chunks * n), kGatherThreads, 0, stream>>>(G, d_set, S, total_batches);
+        var_write_kernel<3><<<(unsigned)(chunks * n), kGatherThreads, 0, stream>>>(G, set, S, total_batches);
     }
   }
   LSB_CUDA(cudaGetLastError());
@@ -2729,6 +3099,269 @@ void plan_compact(MergePlan* P, const uint8_t* keep, const std::vector<uint32_t*
   batch_base_kernel<<<1, 1024, 0, stream>>>(D);
   LSB_CUDA(cudaGetLastError());
   P->synced = false;
+}
+
+// ---------------------------------------------------------------------------------------
+// write side: hash buckets of rows and a device sort of the row list
+//   * plan_hash_buckets: spark murmur3_32 chained over the key columns (seed 42 for the first column, the running
+//     hash for the next, a null leaves it unchanged; utils/hash/mod.rs:22-178, spark_murmur3.rs:42-87), mod the
+//     bucket count as u32 (physical_plan/repartition/mod.rs:260);
+//   * plan_sort: the identity row list of the plan sorted by (key, input position) -- what SortExec over
+//     (range partitions, primary keys, aux sort columns) gives the reference's writers (sort_writer.rs:59-76,
+//     partitioning_writer.rs:139-171). Tiles of 2048 rows are sorted in shared memory by a bitonic network, then
+//     log2(runs) passes merge neighbouring runs pairwise: one block per 2048 outputs, merge-path split by two binary
+//     searches through the row list, merge of the two segments in shared memory.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mm3_mix(uint32_t state, uint32_t k) {
+  k *= 0xcc9e2d51u;
+  k = __funnelshift_l(k, k, 15);
+  k *= 0x1b873593u;
+  state ^= k;
+  state = __funnelshift_l(state, state, 13);
+  return state * 5u + 0xe6546b64u;
+}
+__device__ __forceinline__ uint32_t mm3_fin(uint32_t state, uint32_t n) {
+  uint32_t h = state ^ n;
+  h ^= h >> 16;
+  h *= 0x85ebca6bu;
+  h ^= h >> 13;
+  h *= 0xc2b2ae35u;
+  h ^= h >> 16;
+  return h;
+}
+
+__global__ void __launch_bounds__(256) hash_buckets_kernel(PlanDev P, int F, int64_t n_in, const EncKeySet* __restrict__ set,
+                                                           const int32_t* __restrict__ file_bucket, uint32_t nbuckets,
+                                                           uint32_t* __restrict__ out) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_in) return;
+  int f;
+  const int64_t g = dense_to_global(P, F, u, &f);
+  uint32_t h = 0;  // the hash buffer starts at 0 (repartition/mod.rs:247-248): a null first column leaves 0
+  for (int c = 0; c < set->n; ++c) {
+    const EncKeyCol& col = set->col[c];
+    if (!enc_valid(col, g)) continue;
+    const uint32_t seed = c == 0 ? 42u : h;
+    if (col.kind == ENC_BYTES) {
+      const int32_t* offs = reinterpret_cast<const int32_t*>(col.values);
+      const uint8_t* p = col.data + col.bucket_data[file_bucket[f]] + offs[g];
+      const int32_t l = offs[g + 1] - offs[g];
+      uint32_t st = seed;
+      int32_t i = 0;
+      for (; i + 4 <= l; i += 4)
+        st = mm3_mix(st, (uint32_t)p[i] | ((uint32_t)p[i + 1] << 8) | ((uint32_t)p[i + 2] << 16) | ((uint32_t)p[i + 3] << 24));
+      for (; i < l; ++i) st = mm3_mix(st, (uint32_t)p[i]);
+      h = mm3_fin(st, (uint32_t)l);
+    } else if (col.kind == ENC_BOOL_BITS) {
+      const uint32_t v = (reinterpret_cast<const uint8_t*>(col.values)[g >> 3] >> (g & 7)) & 1;
+      h = mm3_fin(mm3_mix(seed, v), 4);
+    } else {
+      const int w = col.width;
+      const uint8_t* p = reinterpret_cast<const uint8_t*>(col.values) + g * w;
+      if (w <= 4) {
+        uint32_t v;
+        if (w == 1) v = col.kind == ENC_SIGNED ? (uint32_t)(int32_t)(int8_t)p[0] : (uint32_t)p[0];
+        else if (w == 2) {
+          const uint16_t x = *reinterpret_cast<const uint16_t*>(p);
+          v = col.kind == ENC_SIGNED ? (uint32_t)(int32_t)(int16_t)x : (uint32_t)x;
+          if (col.kind == ENC_FLOAT && x == 0x8000u) v = 0;  // f16 -0.0
+        } else {
+          v = *reinterpret_cast<const uint32_t*>(p);
+          if (col.kind == ENC_FLOAT && v == 0x80000000u) v = 0;  // -0.0 hashes like 0.0 (utils/hash/mod.rs:76-88)
+        }
+        h = mm3_fin(mm3_mix(seed, v), 4);
+      } else {
+        uint32_t st = seed;
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+        if (w == 8 && col.kind == ENC_FLOAT && q[0] == 0u && q[1] == 0x80000000u) {
+          st = mm3_mix(mm3_mix(st, 0u), 0u);
+        } else {
+          for (int i = 0; i < w / 4; ++i) st = mm3_mix(st, q[i]);
+        }
+        h = mm3_fin(st, (uint32_t)w);
+      }
+    }
+  }
+  out[g] = h % nbuckets;
+}
+
+void plan_hash_buckets(MergePlan* P, const EncKeyCol* cols, int ncols, uint32_t nbuckets, uint32_t* d_out, cudaStream_t stream) {
+  if (ncols < 0 || ncols > kMaxEncCols || nbuckets == 0) {
+    g_last_error = "plan_hash_buckets: bad arguments";
+    throw std::runtime_error(g_last_error);
+  }
+  const int64_t n = P->n_in;
+  if (n == 0) return;
+  EncKeySet set{};
+  set.n = ncols;
+  for (int i = 0; i < ncols; ++i) set.col[i] = cols[i];
+  EncKeySet* d_set = dev_alloc<EncKeySet>(1, stream);
+  LSB_CUDA(h2d_staged(d_set, &set, sizeof(set), stream));
+  std::vector<int32_t> fb((size_t)std::max(P->F, 1), 0);
+  for (int b = 0; b < P->nb; ++b)
+    for (int j = 0; j < P->buckets[b].k; ++j) fb[(size_t)P->buckets[b].file_begin + j] = b;
+  int32_t* d_fb = dev_alloc<int32_t>(fb.size(), stream);
+  LSB_CUDA(h2d_staged(d_fb, fb.data(), sizeof(int32_t) * fb.size(), stream));
+  P->var_scratch.push_back(d_set);
+  P->var_scratch.push_back(d_fb);
+  hash_buckets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(plan_dev(P), P->F, n, d_set, d_fb, nbuckets, d_out);
+  LSB_CUDA(cudaGetLastError());
+}
+
+constexpr int kSortTile = 2048;
+constexpr int kSortThreads = 256;
+constexpr int kSortPer = kSortTile / kSortThreads;  // 8
+
+// (key, row) of the sort: rows are global row ids; kNoRow pads a tile and sorts last. Equal keys keep their input
+// order (the row list starts increasing), which also makes the order total -- a bitonic network needs no stability.
+template <typename KeyT>
+__device__ __forceinline__ bool sort_lt(const KeyOps<KeyT>& ops, const KeyT& ka, uint32_t ra, const KeyT& kb, uint32_t rb) {
+  if (ra == kNoRow || rb == kNoRow) return rb == kNoRow && ra != kNoRow;
+  if (ops.lt(ka, kb)) return true;
+  if (ops.lt(kb, ka)) return false;
+  return ra < rb;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads) sort_tiles_kernel(PkDesc pk, const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                                 int64_t n) {
+  __shared__ KeyT s_key[kSortTile];
+  __shared__ uint32_t s_row[kSortTile];
+  const KeyOps<KeyT> ops(pk, 0);
+  const int64_t base = (int64_t)blockIdx.x * kSortTile;
+  for (int i = threadIdx.x; i < kSortTile; i += kSortThreads) {
+    const int64_t q = base + i;
+    const uint32_t r = q < n ? in[q] : kNoRow;
+    s_row[i] = r;
+    if (r != kNoRow) s_key[i] = ops.load(r);
+  }
+  __syncthreads();
+  for (int size = 2; size <= kSortTile; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < kSortTile / 2; t += kSortThreads) {
+        const int lo = 2 * t - (t & (stride - 1));  // element with bit `stride` clear
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;           // ascending block of the bitonic sequence
+        const KeyT ka = s_key[lo], kb = s_key[hi];
+        const uint32_t ra = s_row[lo], rb = s_row[hi];
+        const bool swap = up ? sort_lt(ops, kb, rb, ka, ra) : sort_lt(ops, ka, ra, kb, rb);
+        if (swap) {
+          s_key[lo] = kb; s_key[hi] = ka;
+          s_row[lo] = rb; s_row[hi] = ra;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < kSortTile; i += kSortThreads) {
+    const int64_t q = base + i;
+    if (q < n) out[q] = s_row[i];
+  }
+}
+
+// number of elements taken from run A among the first d outputs of merge(A, B): A = list[a0, a0 + na), B = list[b0, b0 + nb)
+template <typename KeyT>
+__device__ int64_t sort_corank_global(const KeyOps<KeyT>& ops, const uint32_t* list, int64_t a0, int64_t na, int64_t b0, int64_t nb, int64_t d) {
+  int64_t lo = d > nb ? d - nb : 0, hi = d < na ? d : na;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;  // take mid + 1 from A?  A[mid] must precede B[d - 1 - mid]
+    const uint32_t ra = list[a0 + mid], rb = list[b0 + d - 1 - mid];
+    const KeyT ka = ops.load(ra), kb = ops.load(rb);
+    if (sort_lt(ops, ka, ra, kb, rb)) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads) sort_merge_kernel(PkDesc pk, const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                                 int64_t n, int64_t run) {
+  __shared__ KeyT s_key[kSortTile];
+  __shared__ uint32_t s_row[kSortTile];
+  __shared__ long long s_split[2];
+  const KeyOps<KeyT> ops(pk, 0);
+  const int64_t o0 = (int64_t)blockIdx.x * kSortTile;   // first output of this block
+  const int64_t pair0 = o0 / (2 * run) * (2 * run);     // the pair of runs it belongs to
+  const int64_t a0 = pair0, na = min(run, n - pair0);
+  const int64_t b0 = pair0 + na, nb = max((int64_t)0, min(run, n - b0));
+  const int64_t d0 = o0 - pair0, d1 = min(d0 + kSortTile, na + nb);
+  if (threadIdx.x < 2) s_split[threadIdx.x] = sort_corank_global(ops, in, a0, na, b0, nb, threadIdx.x == 0 ? d0 : d1);
+  __syncthreads();
+  const int64_t ia0 = s_split[0], ia1 = s_split[1];
+  const int64_t ib0 = d0 - ia0, ib1 = d1 - ia1;
+  const int ca = (int)(ia1 - ia0), cb = (int)(ib1 - ib0);  // ca + cb = d1 - d0 <= kSortTile
+  for (int i = threadIdx.x; i < ca + cb; i += kSortThreads) {
+    const uint32_t r = i < ca ? in[a0 + ia0 + i] : in[b0 + ib0 + (i - ca)];
+    s_row[i] = r;
+    s_key[i] = ops.load(r);
+  }
+  __syncthreads();
+  const int total = ca + cb;
+  const int q0 = min((int)threadIdx.x * kSortPer, total), q1 = min(q0 + kSortPer, total);
+  if (q0 < q1) {
+    int lo = max(0, q0 - cb), hi = min(q0, ca);
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (sort_lt(ops, s_key[mid], s_row[mid], s_key[ca + q0 - 1 - mid], s_row[ca + q0 - 1 - mid])) lo = mid + 1; else hi = mid;
+    }
+    int ia = lo, ib = q0 - lo;
+    for (int q = q0; q < q1; ++q) {
+      bool take_a;
+      if (ia >= ca) take_a = false;
+      else if (ib >= cb) take_a = true;
+      else take_a = sort_lt(ops, s_key[ia], s_row[ia], s_key[ca + ib], s_row[ca + ib]);
+      out[pair0 + d0 + q] = take_a ? s_row[ia] : s_row[ca + ib];
+      ia += take_a ? 1 : 0;
+      ib += take_a ? 0 : 1;
+    }
+  }
+}
+
+template <typename KeyT>
+static int run_sort(MergePlan* P, const PkDesc& pk, cudaStream_t stream) {
+  const int64_t n = P->out_base[P->nb];
+  if (n <= 1) return 0;
+  const unsigned tiles = (unsigned)((n + kSortTile - 1) / kSortTile);
+  uint32_t* a = P->d_win;
+  uint32_t* b = P->d_win_tmp;
+  sort_tiles_kernel<KeyT><<<tiles, kSortThreads, 0, stream>>>(pk, a, b, n);
+  std::swap(a, b);  // a = sorted tiles
+  int launches = 1;
+  for (int64_t run = kSortTile; run < n; run *= 2) {
+    sort_merge_kernel<KeyT><<<tiles, kSortThreads, 0, stream>>>(pk, a, b, n, run);
+    std::swap(a, b);
+    ++launches;
+  }
+  if (a != P->d_win) LSB_CUDA(cudaMemcpyAsync(P->d_win, a, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+  LSB_CUDA(cudaGetLastError());
+  return launches;
+}
+
+// Sorts the plan's row list (plan_identity + plan_sync_counts first: every input row, file order) by `pk`.
+void plan_sort(MergePlan* P, const PkDesc& pk, cudaStream_t stream) {
+  require_synced(P);
+  if (P->nb != 1) {
+    g_last_error = "plan_sort: one bucket per plan";
+    throw std::runtime_error(g_last_error);
+  }
+  int launches;
+  if (pk.ncols == 1 && pk.col[0].kind == PK_BYTES) launches = run_sort<StrKey>(P, pk, stream);
+  else if (pk.key_bits > 64) launches = run_sort<K128>(P, pk, stream);
+  else launches = run_sort<uint64_t>(P, pk, stream);
+  P->stats.launches += launches;
+  P->has_wfile = false;
+}
+
+// out[u] = src[win[u]] for a 4-byte column indexed by global row (the bucket ids of the sorted rows)
+__global__ void __launch_bounds__(256) take_u32_kernel(const uint32_t* __restrict__ win, const uint32_t* __restrict__ src, int64_t n,
+                                                       uint32_t* __restrict__ out) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < n) out[u] = src[win[u]];
+}
+void plan_take_u32(MergePlan* P, const uint32_t* d_src, uint32_t* d_out, cudaStream_t stream) {
+  require_synced(P);
+  const int64_t n = P->out_base[P->nb];
+  if (n > 0) take_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(P->d_win, d_src, n, d_out);
+  LSB_CUDA(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------------------

@@ -117,6 +117,14 @@ struct EncKeyCol {
 // Fills `pk` (one PK_BYTES column, key_bits 128) with device buffers owned by the plan. Blocks once on `stream`.
 void plan_encode_keys(MergePlan*, const EncKeyCol* cols, int ncols, PkDesc* pk, cudaStream_t stream);
 
+// Write side. plan_hash_buckets: d_out[global row] = spark murmur3_32 of the key columns (chained,
+// seed 42, nulls skipped; utils/hash/mod.rs:22-178) mod nbuckets. plan_sort: after plan_identity + plan_sync_counts,
+// reorders the plan's row list by `pk` (ties keep the input order); the gathers then emit the rows sorted.
+// plan_take_u32: d_out[u] = d_src[row list[u]].
+void plan_hash_buckets(MergePlan*, const EncKeyCol* cols, int ncols, uint32_t nbuckets, uint32_t* d_out, cudaStream_t stream);
+void plan_sort(MergePlan*, const PkDesc& pk, cudaStream_t stream);
+void plan_take_u32(MergePlan*, const uint32_t* d_src, uint32_t* d_out, cudaStream_t stream);
+
 // "No merge" variant (skip_merge_on_read / no primary key, merge/mod.rs:297-312): every input row
 // survives, in file order.
 void plan_identity(MergePlan*, cudaStream_t stream);
