@@ -38,6 +38,15 @@ typedef struct LsbReaderStats {
 } LsbReaderStats;
 int32_t lsb_reader_get_stats(CResult_Reader *reader, LsbReaderStats *out);
 
+/* write side (create_lakesoul_writer_from_config .. flush_and_close_writer): what the GPU did for this writer */
+typedef struct LsbWriterStats {
+  int64_t rows_in, rows_out, files, flush_cycles; /* a flush cycle = one device pass (hash + sort + gather) over the buffered rows */
+  int64_t h2d_bytes, d2h_bytes;
+  int32_t kernel_launches, pad;
+  double sort_ms, encode_ms;                      /* device pass incl. copies; host Parquet encode */
+} LsbWriterStats;
+int32_t lsb_writer_get_stats(CResult_Writer *writer, LsbWriterStats *out);
+
 /* ---- device-level plan --------------------------------------------------------------------- */
 typedef struct LsbPlan LsbPlan;
 

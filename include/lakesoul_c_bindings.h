@@ -108,8 +108,8 @@ void free_tokio_runtime(TokioRuntime *runtime);                                 
 void free_c_status(CStatus *status);                                                                /* lib.rs:1070 */
 void free_bytes_result(CResult_BytesResult *bytes);                                                 /* lib.rs:1477 */
 
-/* ---- writer side: out of scope for this engine -- every entry reports an error, never silently
- *      succeeds (SURVEY.md section 8b "Writer-side / misc exports") ----------------------------- */
+/* ---- writer side: murmur3 bucketing + sort on the GPU, Parquet (ZSTD, no dictionaries) encoded on
+ *      the host; same writers, file names and flush summary as writer/mod.rs:61-400 ------------------------------- */
 CResult_Writer *create_lakesoul_writer_from_config(IOConfig *io_config, TokioRuntime *runtime);    /* lib.rs:1081 */
 CStatus *check_writer_created(CResult_Writer *writer);                                              /* lib.rs:1101 */
 void write_record_batch(CResult_Writer *writer, c_ptrdiff_t schema_addr, c_ptrdiff_t array_addr, ResultCallback callback); /* lib.rs:1125 */

@@ -31,6 +31,12 @@ class LsbReaderStats(Structure):
                 ("device_decompressed_pages", c_int64), ("pruned_buckets", c_int64)]
 
 
+class LsbWriterStats(Structure):
+    _fields_ = [("rows_in", c_int64), ("rows_out", c_int64), ("files", c_int64), ("flush_cycles", c_int64),
+                ("h2d_bytes", c_int64), ("d2h_bytes", c_int64), ("kernel_launches", c_int32), ("pad", c_int32),
+                ("sort_ms", c_double), ("encode_ms", c_double)]
+
+
 I32_CALLBACK = ctypes.CFUNCTYPE(None, c_int32, c_char_p)
 BOOL_CALLBACK = ctypes.CFUNCTYPE(None, c_bool, c_char_p)
 
@@ -99,6 +105,7 @@ EXT_SYMBOLS = {
     "lsb_init_device": (c_int32, []),
     "lsb_version": (c_char_p, []),
     "lsb_reader_get_stats": (c_int32, [POINTER(CResult), POINTER(LsbReaderStats)]),
+    "lsb_writer_get_stats": (c_int32, [c_void_p, POINTER(LsbWriterStats)]),
     "lsb_plan_create": (c_void_p, [c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     "lsb_plan_destroy": (None, [c_void_p]),
     "lsb_plan_merge": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

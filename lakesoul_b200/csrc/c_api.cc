@@ -4,6 +4,8 @@
 // (include/lakesoul_c_bindings.h, rust/lakesoul-io-c/src/lib.rs:164-1508) plus the B200
 // extensions (include/lakesoul_b200_ext.h).
 #include <arrow/c/bridge.h>
+#include <arrow/io/memory.h>
+#include <arrow/ipc/reader.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -17,6 +19,7 @@
 #pragma GCC visibility pop
 #include "mor_engine.h"
 #include "reader.h"
+#include "writer.h"
 
 namespace {
 
@@ -45,6 +48,11 @@ struct ReaderImpl {
 BuilderImpl* B(IOConfigBuilder* b) { return reinterpret_cast<BuilderImpl*>(b); }
 IOConfigBuilder* O(BuilderImpl* b) { return reinterpret_cast<IOConfigBuilder*>(b); }
 ReaderImpl* R(CResult_Reader* r) { return r ? reinterpret_cast<ReaderImpl*>(r->ptr) : nullptr; }
+struct WriterImpl {
+  std::unique_ptr<lsb::Writer> writer;
+  std::mutex mu;
+};
+WriterImpl* W(CResult_Writer* w) { return w ? reinterpret_cast<WriterImpl*>(w->ptr) : nullptr; }
 
 std::shared_ptr<arrow::Schema> import_schema(c_ptrdiff_t addr) {
   // takes ownership like FFI_ArrowSchema::from_raw (lib.rs:295): ImportSchema releases it
@@ -81,10 +89,6 @@ int32_t next_into(ReaderImpl* ri, c_ptrdiff_t array_addr, c_ptrdiff_t schema_add
   if (!st.ok()) throw std::runtime_error(st.ToString());
   return (int32_t)batch->num_rows();
 }
-
-const char* kWriterError =
-    "lakesoul_b200: the write path is not part of the B200 merge-on-read engine; "
-    "use the reference liblakesoul_io_c for writers";
 
 }  // namespace
 
@@ -294,6 +298,7 @@ void free_lakesoul_reader(CResult_Reader* reader) {
 }
 void free_lakesoul_writer(CResult_Writer* writer) {
   if (!writer) return;
+  delete reinterpret_cast<WriterImpl*>(writer->ptr);
   free(const_cast<char*>(writer->err));
   free(writer);
 }
@@ -308,57 +313,158 @@ void free_c_status(CStatus* status) {
   free(const_cast<char*>(status->err));
   free(status);
 }
-void free_bytes_result(CResult_BytesResult* bytes) {
-  if (!bytes) return;
-  free(const_cast<char*>(bytes->err));
-  free(bytes);
-}
 
-// ---- writer side: explicit errors ------------------------------------------------------------
+// ---- writer side (lib.rs:1081-1377) -----------------------------------------------
 CResult_Writer* create_lakesoul_writer_from_config(IOConfig* io_config, TokioRuntime* runtime) {
-  delete reinterpret_cast<ConfigImpl*>(io_config);
+  auto* c = reinterpret_cast<ConfigImpl*>(io_config);
   delete reinterpret_cast<RuntimeImpl*>(runtime);
   auto* res = static_cast<CResult_Writer*>(malloc(sizeof(CResult_Writer)));
   res->ptr = nullptr;
-  res->err = dup_cstr(kWriterError);
+  res->err = nullptr;
+  try {
+    auto* wi = new WriterImpl();
+    wi->writer.reset(new lsb::Writer(std::move(c->cfg)));
+    res->ptr = reinterpret_cast<Writer*>(wi);
+  } catch (const std::exception& e) {
+    res->err = dup_cstr(e.what());
+  }
+  delete c;
   return res;
 }
 CStatus* check_writer_created(CResult_Writer* writer) {
-  if (!writer || writer->err) {
-    std::string m = writer && writer->err ? writer->err : kWriterError;
+  if (!writer || writer->err || !writer->ptr) {
+    std::string m = writer && writer->err ? writer->err : "writer was not created";
     return new_status(-1, &m);
   }
   return new_status(0);
 }
-void write_record_batch(CResult_Writer*, c_ptrdiff_t, c_ptrdiff_t, ResultCallback callback) {
-  callback(false, kWriterError);
+// the C structs are moved from, like ptr::replace(.., FFI_ArrowArray::empty()) (lib.rs:1136-1141)
+static void write_imported(WriterImpl* wi, c_ptrdiff_t schema_addr, c_ptrdiff_t array_addr) {
+  auto batch = arrow::ImportRecordBatch(reinterpret_cast<struct ArrowArray*>(array_addr), reinterpret_cast<struct ArrowSchema*>(schema_addr));
+  if (!batch.ok()) throw std::runtime_error(batch.status().ToString());
+  std::lock_guard<std::mutex> g(wi->mu);
+  wi->writer->Write(*batch);
 }
-CStatus* write_record_batch_blocked(CResult_Writer*, c_ptrdiff_t, c_ptrdiff_t) {
-  std::string m = kWriterError;
-  return new_status(-1, &m);
+void write_record_batch(CResult_Writer* writer, c_ptrdiff_t schema_addr, c_ptrdiff_t array_addr, ResultCallback callback) {
+  try {
+    auto* wi = W(writer);
+    if (!wi) throw std::runtime_error("writer was not created");
+    write_imported(wi, schema_addr, array_addr);
+    callback(true, nullptr);
+  } catch (const std::exception& e) {
+    callback(false, e.what());
+  }
 }
-CStatus* write_record_batch_ipc_blocked(CResult_Writer*, c_ptrdiff_t, int64_t) {
-  std::string m = kWriterError;
-  return new_status(-1, &m);
+CStatus* write_record_batch_blocked(CResult_Writer* writer, c_ptrdiff_t schema_addr, c_ptrdiff_t array_addr) {
+  try {
+    auto* wi = W(writer);
+    if (!wi) throw std::runtime_error("writer was not created");
+    write_imported(wi, schema_addr, array_addr);
+    return new_status(0);
+  } catch (const std::exception& e) {
+    std::string m = e.what();
+    return new_status(-1, &m);
+  }
 }
-void export_bytes_result(void (*callback)(bool, const char*), CResult_BytesResult* bytes, int32_t, c_ptrdiff_t) {
-  free_bytes_result(bytes);
-  callback(false, kWriterError);
+// an Arrow IPC stream; status = rows written (lib.rs:1211-1250)
+CStatus* write_record_batch_ipc_blocked(CResult_Writer* writer, c_ptrdiff_t ipc_addr, int64_t len) {
+  try {
+    auto* wi = W(writer);
+    if (!wi) throw std::runtime_error("writer was not created");
+    auto buf = std::make_shared<arrow::Buffer>(reinterpret_cast<const uint8_t*>(ipc_addr), len);
+    auto in = std::make_shared<arrow::io::BufferReader>(buf);
+    auto rd = arrow::ipc::RecordBatchStreamReader::Open(in);
+    if (!rd.ok()) throw std::runtime_error(rd.status().ToString());
+    int64_t rows = 0;
+    while (true) {
+      std::shared_ptr<arrow::RecordBatch> rb;
+      auto st = (*rd)->ReadNext(&rb);
+      if (!st.ok()) throw std::runtime_error(st.ToString());
+      if (!rb) break;
+      // the batch borrows the caller's buffer: copy before buffering
+      std::vector<std::shared_ptr<arrow::Array>> cols;
+      for (const auto& c : rb->columns()) {
+        auto cc = arrow::Concatenate({c});
+        if (!cc.ok()) throw std::runtime_error(cc.status().ToString());
+        cols.push_back(*cc);
+      }
+      auto copy = arrow::RecordBatch::Make(rb->schema(), rb->num_rows(), std::move(cols));
+      std::lock_guard<std::mutex> g(wi->mu);
+      wi->writer->Write(copy);
+      rows += rb->num_rows();
+    }
+    return new_status((int32_t)rows);
+  } catch (const std::exception& e) {
+    std::string m = e.what();
+    return new_status(-1, &m);
+  }
 }
-static CResult_BytesResult* empty_bytes() {
+struct BytesImpl { std::string bytes; };
+static CResult_BytesResult* make_bytes(std::string v) {
   auto* res = static_cast<CResult_BytesResult*>(malloc(sizeof(CResult_BytesResult)));
-  res->ptr = nullptr;
+  auto* bi = new BytesImpl();
+  bi->bytes = std::move(v);
+  res->ptr = reinterpret_cast<BytesResult*>(bi);
   res->err = nullptr;
   return res;
 }
+void free_bytes_result(CResult_BytesResult* bytes) {
+  if (!bytes) return;
+  delete reinterpret_cast<BytesImpl*>(bytes->ptr);
+  free(const_cast<char*>(bytes->err));
+  free(bytes);
+}
+// copies the bytes (+ a closing 0) to `addr` and frees the result (lib.rs:1262-1300)
+void export_bytes_result(void (*callback)(bool, const char*), CResult_BytesResult* bytes, int32_t len, c_ptrdiff_t addr) {
+  auto* bi = bytes ? reinterpret_cast<BytesImpl*>(bytes->ptr) : nullptr;
+  if (!bi || (int64_t)bi->bytes.size() != (int64_t)len) {
+    free_bytes_result(bytes);
+    callback(false, "Size of buffer and result mismatch at export_bytes_result.");
+    return;
+  }
+  memcpy(reinterpret_cast<void*>(addr), bi->bytes.c_str(), (size_t)len + 1);
+  free_bytes_result(bytes);
+  callback(true, nullptr);
+}
+static CResult_BytesResult* empty_bytes() { return make_bytes(std::string()); }
 CResult_BytesResult* flush_and_close_writer(CResult_Writer* writer, I32ResultCallback callback) {
+  auto* wi = W(writer);
+  std::string out, err;
+  bool ok = false;
+  if (wi) {
+    try {
+      std::lock_guard<std::mutex> g(wi->mu);
+      out = wi->writer->FlushAndClose();
+      ok = true;
+    } catch (const std::exception& e) {
+      err = e.what();
+    }
+  } else {
+    err = writer && writer->err ? writer->err : "writer was not created";
+  }
   free_lakesoul_writer(writer);
-  callback(-1, kWriterError);
-  return empty_bytes();
+  if (!ok) {
+    callback(-1, err.c_str());
+    return empty_bytes();
+  }
+  callback((int32_t)out.size(), nullptr);
+  return make_bytes(std::move(out));
 }
 void abort_and_close_writer(CResult_Writer* writer, ResultCallback callback) {
+  auto* wi = W(writer);
+  std::string err;
+  bool ok = true;
+  if (wi) {
+    try {
+      std::lock_guard<std::mutex> g(wi->mu);
+      wi->writer->AbortAndClose();
+    } catch (const std::exception& e) {
+      ok = false;
+      err = e.what();
+    }
+  }
   free_lakesoul_writer(writer);
-  callback(false, kWriterError);
+  callback(ok, ok ? nullptr : err.c_str());
 }
 CResult_BytesResult* apply_partition_filter(void (*callback)(int32_t, const char*), int32_t, c_ptrdiff_t,
                                             c_ptrdiff_t, int32_t, c_ptrdiff_t) {
@@ -388,6 +494,17 @@ int32_t lsb_reader_get_stats(CResult_Reader* reader, LsbReaderStats* out) {
   out->pruned_row_groups = s.pruned_row_groups;
   out->pruned_buckets = s.pruned_buckets;
   out->device_decompressed_pages = s.device_decompressed_pages;
+  return 0;
+}
+
+int32_t lsb_writer_get_stats(CResult_Writer* writer, LsbWriterStats* out) {
+  auto* wi = W(writer);
+  if (!wi) { g_ext_error = "writer was not created"; return -1; }
+  const lsb::WriterStats& s = wi->writer->stats();
+  out->rows_in = s.rows_in; out->rows_out = s.rows_out; out->files = s.files; out->flush_cycles = s.flush_cycles;
+  out->h2d_bytes = s.h2d_bytes; out->d2h_bytes = s.d2h_bytes;
+  out->kernel_launches = s.kernel_launches; out->pad = 0;
+  out->sort_ms = s.sort_ms; out->encode_ms = s.encode_ms;
   return 0;
 }
 

@@ -1062,6 +1062,40 @@ __device__ __forceinline__ bool chunk_geometry(const GatherGeom& G, int64_t chun
   return r_begin < r_end;
 }
 
+// same as upper_idx over a global array, by one warp: 32-ary search, one round trip per level instead of one per bit
+// (r2c profile of var_write_kernel: 9 % of the stall samples sat behind thread 0's bit-by-bit search of batch_base)
+__device__ __forceinline__ int warp_upper_idx(const int64_t* __restrict__ arr, int n, int64_t q) {
+  const int lane = threadIdx.x & 31;
+  int lo = 0, hi = n;  // invariant arr[lo] <= q, answer in [lo, hi)
+  while (hi - lo > 1) {
+    const int span = hi - lo;
+    const int step = (span + 31) >> 5;
+    const int idx = lo + lane * step;
+    const bool le = idx < hi && __ldg(arr + idx) <= q;
+    const unsigned m = __ballot_sync(0xffffffffu, le);  // lanes are monotone: a prefix of ones (lane 0 always)
+    const int last = 31 - __clz((int)m);
+    lo = lo + last * step;
+    hi = min(hi, lo + step);
+  }
+  return lo;
+}
+
+// chunk geometry by one warp (lanes agree on the result)
+__device__ __forceinline__ bool chunk_geometry_warp(const GatherGeom& G, int64_t chunk, int& b, int64_t& gb, int64_t& u0, int& r_begin,
+                                                    int& r_end, int& rows_in_batch) {
+  gb = chunk / G.chunks_per_batch;
+  const int c_in = (int)(chunk % G.chunks_per_batch);
+  b = warp_upper_idx(G.batch_base, G.nb + 1, gb);
+  const int64_t ob0 = __ldg(G.out_base + b), ob1 = __ldg(G.out_base + b + 1);
+  const int64_t i = gb - __ldg(G.batch_base + b);
+  const int64_t first = i * G.batch_size;
+  rows_in_batch = (int)min((int64_t)G.batch_size, ob1 - ob0 - first);
+  u0 = ob0 + first;
+  r_begin = c_in * kRowsPerChunk;
+  r_end = min(r_begin + kRowsPerChunk, (rows_in_batch + 31) & ~31);
+  return r_begin < r_end;
+}
+
 constexpr int kRowsPerThread = kRowsPerChunk / kGatherThreads;  // 8
 
 constexpr int kMaxVarCols = 16;
@@ -1306,7 +1340,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // Thread t owns the 8 consecutive rows [8t, 8t+8) for the offsets; the bytes are staged through a
 // shared-memory window that is address-congruent (mod 16) with the destination, so the flush to HBM
 // is made of full, aligned 16-byte stores whatever the string lengths are.
-constexpr int kStageBytes = 24 * 1024;
 
 // The byte position of a chunk is resolved inside the kernel with a decoupled look-back scan over the
 // per-chunk totals of the column (status word = bit 63 "published" | bytes): no separate sizing pass.
@@ -1389,130 +1422,8 @@ __device__ __forceinline__ void scan_lookback(unsigned long long* agg, unsigned 
   }
 }
 
-__global__ void __launch_bounds__(kGatherThreads) var_write_kernel_v1(GatherGeom G, const VarColSet* __restrict__ set,
-                                                                   VarScan S, int64_t total_batches) {
-  __shared__ int s_scan[kGatherThreads / 32 + 2];
-  __shared__ int32_t s_off[kRowsPerChunk + 1];   // chunk-relative destination offset of every row
-  __shared__ int32_t s_src[kRowsPerChunk];       // bucket-relative source offset of every row
-  __shared__ __align__(16) uint8_t s_stage[kStageBytes + 16];
-  __shared__ long long s_c0, s_rel;
-  __shared__ int g_b, g_r_begin, g_rows, g_live;   // chunk geometry: one thread searches, everybody reads
-  __shared__ long long g_gb, g_u0;
-  const int ci = (int)(blockIdx.x % (unsigned)S.ncols);
-  const int64_t chunk = blockIdx.x / (unsigned)S.ncols;
-  if (threadIdx.x == 0) {
-    int b0, rb0, re0, rows0;
-    int64_t gb0, u00;
-    g_live = chunk_geometry(G, chunk, b0, gb0, u00, rb0, re0, rows0) ? 1 : 0;
-    g_b = b0; g_r_begin = rb0; g_rows = rows0; g_gb = gb0; g_u0 = u00;
-  }
-  __syncthreads();
-  const bool live = g_live != 0;
-  const int b = g_b, r_begin = g_r_begin, rows = g_rows;
-  const int64_t gb = g_gb, u0 = g_u0;
-  const VarCol col = set->col[ci];
-  unsigned long long* agg = S.agg + (int64_t)ci * S.stride;
-  unsigned long long* incl = S.incl + (int64_t)ci * S.stride;
-  const uint32_t* win = col.win ? col.win : G.win;
-  const int c_in = (int)(chunk % G.chunks_per_batch);
-  const uint8_t* src_base = col.src_data + col.src_data_base[b];
-  const int nloc = live ? min(rows - r_begin, kRowsPerChunk) : 0;  // rows of this chunk
-  const int rl0 = threadIdx.x * kRowsPerThread;
-  int len[kRowsPerThread];
-  int mine = 0;
-  unsigned vbits = 0;
-#pragma unroll
-  for (int x = 0; x < kRowsPerThread; ++x) {
-    len[x] = 0;
-    if (rl0 + x < nloc) {
-      const uint32_t g = win[u0 + r_begin + rl0 + x];
-      bool valid;
-      len[x] = var_row_len(col, g, valid);
-      s_src[rl0 + x] = valid ? col.src_offsets[g] : 0;
-      vbits |= valid ? (1u << x) : 0u;
-    }
-    mine += len[x];
-  }
-  // validity: a thread owns 8 consecutive rows = one byte of the batch's bitmap (words are completed up to
-  // the 32-row boundary after the last row)
-  if (col.dst_valid && rl0 < ((nloc + 31) & ~31))
-    (col.dst_valid + gb * G.valid_stride)[(r_begin + rl0) >> 3] = (uint8_t)vbits;
-  int tot;
-  int run = block_exclusive_scan<kGatherThreads>(mine, s_scan, tot);
-  // chunk-relative offsets first (shared memory), so that nothing but `tot` is live across the look-back
-#pragma unroll
-  for (int x = 0; x < kRowsPerThread; ++x) {
-    if (rl0 + x < nloc) {
-      s_off[rl0 + x] = run;
-      run += len[x];
-    }
-  }
-  if (threadIdx.x == 0) s_off[nloc] = tot;
-  // publish the chunk total, then resolve the chunk's position by looking back
-  if (threadIdx.x < 32) scan_lookback(agg, incl, chunk, c_in, tot, &s_c0, &s_rel, S.err);
-  __syncthreads();
-  if (!live) return;
-  const int64_t c0 = s_c0;
-  const int32_t rel = (int32_t)s_rel;
-  // offsets (every earlier batch contributed one extra entry)
-  int32_t* dst_off = col.dst_offsets + u0 + gb + r_begin;
-  for (int r = threadIdx.x; r < nloc; r += kGatherThreads) dst_off[r] = rel + s_off[r];
-  const bool last_chunk = r_begin + nloc == rows;
-  if (threadIdx.x == 0) {
-    if (last_chunk) dst_off[nloc] = rel + tot;
-    if (c_in == 0) col.batch_data_start[gb] = c0 - rel;
-    if (last_chunk && gb == total_batches - 1) col.batch_data_start[total_batches] = c0 + tot;
-  }
-  // ---- bytes: windows of the chunk's output range, staged in shared memory --------------------
-  uint8_t* dst_bytes = col.dst_data + c0;       // chunk-relative byte p lives at dst_bytes[p]
-  const int mis = (int)((reinterpret_cast<uintptr_t>(dst_bytes)) & 15);  // stage[mis + (p - w0)] <-> p
-  int w0 = 0;
-  int r_lo = 0;
-  while (w0 < tot) {
-    const int first_pad = (w0 == 0) ? mis : 0;   // later windows start on a 16-byte boundary
-    const int w1 = min(tot, w0 + kStageBytes - first_pad);
-    // rows intersecting [w0, w1): most chunks are one window (no search at all); the row that straddles a window
-    // boundary is the first row of the next window
-    const int r_hi = (w1 >= tot) ? nloc - 1 : upper_idx(s_off, nloc + 1, w1 - 1);
-    for (int r = r_lo + threadIdx.x; r <= r_hi; r += 2 * kGatherThreads) {
-      // two rows per trip: all loads of both rows are issued before the first store
-      RowCopy c0r, c1r;
-      {
-        const int a = max(s_off[r], w0), e = min(s_off[r + 1], w1);
-        row_load(c0r, s_stage + first_pad + (a - w0), src_base + s_src[r] + (a - s_off[r]), max(e - a, 0));
-      }
-      const int r2 = r + kGatherThreads;
-      c1r.n = 0;
-      if (r2 <= r_hi) {
-        const int a = max(s_off[r2], w0), e = min(s_off[r2 + 1], w1);
-        row_load(c1r, s_stage + first_pad + (a - w0), src_base + s_src[r2] + (a - s_off[r2]), max(e - a, 0));
-      }
-      row_store(c0r);
-      row_store(c1r);
-    }
-    fence_proxy_async();  // the stage was written through the generic proxy; the bulk store reads it asynchronously
-    __syncthreads();
-    // flush: global address of stage[first_pad] is dst_bytes + w0. The 16-byte aligned middle leaves with ONE TMA
-    // bulk store (cp.async.bulk shared -> global) issued by a single thread; the <= 15 bytes that share a vector with
-    // the neighbouring chunks are stored by hand.
-    uint8_t* gdst = dst_bytes + w0 - first_pad;  // 16-byte aligned
-    const int nbytes = first_pad + (w1 - w0);
-    const int v_lo = first_pad ? 16 : 0;
-    const int v_hi = nbytes & ~15;
-    if (threadIdx.x == 0 && v_hi > v_lo) bulk_store(gdst + v_lo, s_stage + v_lo, (uint32_t)(v_hi - v_lo));
-    if (first_pad)
-      for (int t = first_pad + threadIdx.x; t < min(16, nbytes); t += kGatherThreads) gdst[t] = s_stage[t];
-    for (int t = max(v_hi, v_lo) + threadIdx.x; t < nbytes; t += kGatherThreads)
-      if (t >= first_pad) gdst[t] = s_stage[t];
-    if (threadIdx.x == 0) bulk_store_wait_read();  // the stage is rewritten by the next window
-    __syncthreads();
-    w0 = w1;
-    r_lo = r_hi;
-  }
-}
-
 // ---------------------------------------------------------------------------------------
-// var_write_kernel (r2b): same chunk protocol as v1 (look-back positions, 16-byte congruent stage, TMA bulk-store
+// var_write_kernel (r2b): same chunk protocol as the r1 / r2a kernel (look-back positions, 16-byte congruent stage, TMA bulk-store
 // flush), rebuilt around the instruction count per (row, column) cell -- the r2 profile of v1 showed ~350 thread
 // instructions per cell at 36 % issue utilisation, a fixed cost that a 1-byte flag pays like a 40-byte comment:
 //   * row pass with rows STRIDED over the block (row = x * 256 + thread): winner and offset loads of a warp fall into
@@ -1546,26 +1457,12 @@ __device__ __forceinline__ void store_word_mask(uint32_t* p, uint32_t v, uint32_
   if (m & 0xff000000u) b[3] = (uint8_t)(v >> 24);
 }
 
-// One row on the destination-word grid of the (zeroed) stage. W = destination words whose source words are loaded up
-// front (W + 1 aligned source words + the two under the row's last word); the first and the last word of a row are
-// OR-ed into the stage under a byte mask (shared-memory atomics: neighbouring rows complete the word), the words
-// between are plain stores.
-// experiment switches (tools/build_variant.sh); the defaults are the measured best
-#ifndef VARW_ATOMIC
-#define VARW_ATOMIC 0
-#endif
-#ifndef VARW_R_SHORT
-#define VARW_R_SHORT 1
-#endif
-#ifndef VARW_R_MID
-#define VARW_R_MID 1
-#endif
-#ifndef VARW_W_LONG
-#define VARW_W_LONG 6
-#endif
-#ifndef VARW_PREFETCH
-#define VARW_PREFETCH 2
-#endif
+// One row on the destination-word grid of the stage. W = destination words whose source words are loaded up front
+// (W + 1 aligned source words + the two under the row's last word); the first and the last word of a row are stored
+// under a byte mask (neighbouring rows complete the word), the words between are plain stores. (Measured and
+// dropped: shared-memory atomicOr for the partial words on a zeroed stage, two rows per thread in flight -- it
+// spills at 64 registers --, and a cp.async raw-word scratch that keeps every load of a batch in flight: all within
+// 2 % of this version; the kernel is bound by its instruction count and barriers, not by the copy's load latency.)
 template <int W, bool kLoop>
 struct RowWords {
   uint32_t* p0;         // stage word that holds the row's first byte
@@ -1607,11 +1504,7 @@ __device__ __forceinline__ void roww_load(RowWords<W, kLoop>& rc, uint8_t* stage
 template <int W, bool kLoop>
 __device__ __forceinline__ void roww_store(const RowWords<W, kLoop>& rc) {
   if (rc.nk < 0) return;
-#if VARW_ATOMIC
-  atomicOr(rc.p0, __funnelshift_r(rc.w[0], rc.w[1], rc.sh) & rc.m0);
-#else
   store_word_mask(rc.p0, __funnelshift_r(rc.w[0], rc.w[1], rc.sh), rc.m0);
-#endif
   if (rc.nk == 0) return;
 #pragma unroll
   for (int i = 1; i < W; ++i)
@@ -1626,11 +1519,7 @@ __device__ __forceinline__ void roww_store(const RowWords<W, kLoop>& rc) {
         if (base + i < rc.nk) rc.p0[base + i] = __funnelshift_r(w[i], w[i + 1], rc.sh);
     }
   }
-#if VARW_ATOMIC
-  atomicOr(rc.p0 + rc.nk, __funnelshift_r(rc.wl0, rc.wl1, rc.sh) & rc.ml);
-#else
   store_word_mask(rc.p0 + rc.nk, __funnelshift_r(rc.wl0, rc.wl1, rc.sh), rc.ml);
-#endif
 }
 
 // rows [r_lo, r_hi] of the chunk, clipped to the window [w0, w1) of its bytes; R rows per thread and trip, all loads of
@@ -1654,6 +1543,9 @@ __device__ __forceinline__ void copy_rows(const int32_t* s_off, const int32_t* s
   }
 }
 
+constexpr int kStage2Bytes = 24 * 1024;
+constexpr int kVarWriteDynSmem = kStage2Bytes + 16;
+
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kGatherThreads, kMinBlocks) var_write_kernel(const __grid_constant__ GatherGeom G,
                                                                               const __grid_constant__ VarColSet set, const __grid_constant__ VarScan S,
@@ -1661,24 +1553,23 @@ __global__ void __launch_bounds__(kGatherThreads, kMinBlocks) var_write_kernel(c
   __shared__ int s_scan[kGatherThreads / 32 + 2];
   __shared__ __align__(16) int32_t s_off[kRowsPerChunk + 4];   // row lengths, then chunk-relative destination offsets
   __shared__ __align__(16) int32_t s_src[kRowsPerChunk];       // bucket-relative source offset of every row
-  __shared__ __align__(16) uint8_t s_stage[kStageBytes + 16];
+  extern __shared__ __align__(16) uint8_t s_stage[];   // kStage2Bytes + 16
   __shared__ long long s_c0, s_rel;
   __shared__ int g_b, g_r_begin, g_rows, g_live;   // chunk geometry: one thread searches, everybody reads
   __shared__ long long g_gb, g_u0;
   __shared__ int s_maxlen;
   const int ci = (int)(blockIdx.x % (unsigned)S.ncols);
   const int64_t chunk = blockIdx.x / (unsigned)S.ncols;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
     int b0, rb0, re0, rows0;
     int64_t gb0, u00;
-    g_live = chunk_geometry(G, chunk, b0, gb0, u00, rb0, re0, rows0) ? 1 : 0;
-    g_b = b0; g_r_begin = rb0; g_rows = rows0; g_gb = gb0; g_u0 = u00;
-    s_maxlen = 0;
+    const bool lv = chunk_geometry_warp(G, chunk, b0, gb0, u00, rb0, re0, rows0);
+    if (threadIdx.x == 0) {
+      g_live = lv ? 1 : 0;
+      g_b = b0; g_r_begin = rb0; g_rows = rows0; g_gb = gb0; g_u0 = u00;
+      s_maxlen = 0;
+    }
   }
-#if VARW_ATOMIC
-  // the stage starts zeroed: partial words are OR-ed into it
-  for (int t = threadIdx.x; t < (kStageBytes + 16) / 16; t += kGatherThreads) reinterpret_cast<uint4*>(s_stage)[t] = make_uint4(0, 0, 0, 0);
-#endif
   __syncthreads();
   const bool live = g_live != 0;
   const int b = g_b, r_begin = g_r_begin, rows = g_rows;
@@ -1722,11 +1613,8 @@ __global__ void __launch_bounds__(kGatherThreads, kMinBlocks) var_write_kernel(c
 #pragma unroll
   for (int x = 0; x < kRowsPerThread; ++x) {
     const int r = x * kGatherThreads + threadIdx.x;
-#if VARW_PREFETCH == 1
-    if (o1[x] > o0[x]) asm volatile("prefetch.global.L1 [%0];" ::"l"(src_base + o0[x]));
-#elif VARW_PREFETCH == 2
+    // the row's bytes are wanted two barriers from now: start them towards L2 (4.54 -> 4.38 ms gather on config 2)
     if (o1[x] > o0[x]) asm volatile("prefetch.global.L2 [%0];" ::"l"(src_base + o0[x]));
-#endif
     s_src[r] = o0[x];
     s_off[r] = o1[x] - o0[x];
     ones = ones && (r >= nloc || o1[x] - o0[x] == 1);
@@ -1782,7 +1670,7 @@ __global__ void __launch_bounds__(kGatherThreads, kMinBlocks) var_write_kernel(c
   int r_lo = 0;
   while (w0 < tot) {
     const int first_pad = (w0 == 0) ? mis : 0;   // later windows start on a 16-byte boundary
-    const int w1 = min(tot, w0 + kStageBytes - first_pad);
+    const int w1 = min(tot, w0 + kStage2Bytes - first_pad);
     if (all_one) {
       // one byte per row (one window: tot = nloc <= 2048): stage word j = rows 4j - mis .. 4j - mis + 3
       const int jw1 = (mis + nloc + 3) >> 2;
@@ -1801,9 +1689,9 @@ __global__ void __launch_bounds__(kGatherThreads, kMinBlocks) var_write_kernel(c
       // boundary is the first row of the next window
       const int r_hi = (w1 >= tot) ? nloc - 1 : upper_idx(s_off, nloc + 1, w1 - 1);
       // preload depth by the longest row of the chunk (block-uniform): rows up to 8 / 20 / 44 bytes never loop
-      if (maxlen_all <= 8) copy_rows<3, VARW_R_SHORT, false>(s_off, s_src, s_stage, src_base, r_lo, r_hi, w0, w1, first_pad);
-      else if (maxlen_all <= 20) copy_rows<6, VARW_R_MID, false>(s_off, s_src, s_stage, src_base, r_lo, r_hi, w0, w1, first_pad);
-      else copy_rows<VARW_W_LONG, 1, true>(s_off, s_src, s_stage, src_base, r_lo, r_hi, w0, w1, first_pad);
+      if (maxlen_all <= 8) copy_rows<3, 1, false>(s_off, s_src, s_stage, src_base, r_lo, r_hi, w0, w1, first_pad);
+      else if (maxlen_all <= 20) copy_rows<6, 1, false>(s_off, s_src, s_stage, src_base, r_lo, r_hi, w0, w1, first_pad);
+      else copy_rows<6, 1, true>(s_off, s_src, s_stage, src_base, r_lo, r_hi, w0, w1, first_pad);
       r_lo = r_hi;
     }
     fence_proxy_async();  // the stage was written through the generic proxy; the bulk store reads it asynchronously
@@ -1823,10 +1711,6 @@ __global__ void __launch_bounds__(kGatherThreads, kMinBlocks) var_write_kernel(c
     if (threadIdx.x == 0) bulk_store_wait_read();  // the stage is rewritten by the next window / released at exit
     if (w1 >= tot) break;
     __syncthreads();
-#if VARW_ATOMIC
-    for (int t = threadIdx.x; t < (kStageBytes + 16) / 16; t += kGatherThreads) reinterpret_cast<uint4*>(s_stage)[t] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-#endif
     w0 = w1;
   }
 }
@@ -2840,6 +2724,8 @@ void gather_var_multi(MergePlan* P, const VarCol* cols, int ncols, cudaStream_t 
                                   (int)sizeof(WinSmem<14, 24576>)));
     LSB_CUDA(cudaFuncSetAttribute(var_window_kernel<13, 16384>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(WinSmem<13, 16384>)));
+    LSB_CUDA(cudaFuncSetAttribute(var_write_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVarWriteDynSmem));
+    LSB_CUDA(cudaFuncSetAttribute(var_write_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVarWriteDynSmem));
   }
   // columns whose rows are file rows of the plan take the windowed kernel; computed columns (merge operators:
   // rows of a scan-wide scratch column) keep the direct one. Each group: one launch per 16 columns.
@@ -2859,9 +2745,9 @@ void gather_var_multi(MergePlan* P, const VarCol* cols, int ncols, cudaStream_t 
       // gather has its own state and descriptor block (the launches are asynchronous)
       const int64_t words = 2 * chunks * n;
       int64_t* state = dev_alloc<int64_t>(words, stream);
-      VarColSet* d_set = dev_alloc<VarColSet>(1, stream);
+      VarColSet* d_set = pass == 0 ? dev_alloc<VarColSet>(1, stream) : nullptr;  // var_write takes the set as a kernel parameter
       P->var_scratch.push_back(state);
-      P->var_scratch.push_back(d_set);
+      if (d_set) P->var_scratch.push_back(d_set);
       LSB_CUDA(cudaMemsetAsync(state, 0, sizeof(int64_t) * words, stream));
       VarScan S{};
       S.agg = reinterpret_cast<unsigned long long*>(state);
@@ -2873,20 +2759,17 @@ void gather_var_multi(MergePlan* P, const VarCol* cols, int ncols, cudaStream_t 
       VarColSet& set = P->h_varsets.back();
       set.n = n;
       for (int i = 0; i < n; ++i) set.col[i] = group[c0 + i];
-      LSB_CUDA(h2d_staged(d_set, &set, sizeof(VarColSet), stream));
-      static const bool var_v1 = [] { const char* v = getenv("LAKESOUL_B200_VAR_V1"); return v && *v == '1'; }();
+      if (d_set) LSB_CUDA(h2d_staged(d_set, &set, sizeof(VarColSet), stream));
       static const int var_blocks = [] { const char* v = getenv("LAKESOUL_B200_VAR_BLOCKS"); return v ? atoi(v) : 4; }();
       static const int win_variant = [] { const char* v = getenv("LAKESOUL_B200_WINDOW_VARIANT"); return v ? atoi(v) : 0; }();
       if (pass == 0 && win_variant == 1)
         var_window_kernel<14, 24576><<<(unsigned)(chunks * n), kGatherThreads, sizeof(WinSmem<14, 24576>), stream>>>(G, d_set, S, total_batches);
       else if (pass == 0)
         var_window_kernel<13, 16384><<<(unsigned)(chunks * n), kGatherThreads, sizeof(WinSmem<13, 16384>), stream>>>(G, d_set, S, total_batches);
-      else if (var_v1)
-        var_write_kernel_v1<<<(unsigned)(chunks * n), kGatherThreads, 0, stream>>>(G, d_set, S, total_batches);
       else if (var_blocks >= 4)
-        var_write_kernel<4><<<(unsigned)(chunks * n), kGatherThreads, 0, stream>>>(G, set, S, total_batches);
+        var_write_kernel<4><<<(unsigned)(chunks * n), kGatherThreads, kVarWriteDynSmem, stream>>>(G, set, S, total_batches);
       else
-        var_write_kernel<3><<<(unsigned)(chunks * n), kGatherThreads, 0, stream>>>(G, set, S, total_batches);
+        var_write_kernel<3><<<(unsigned)(chunks * n), kGatherThreads, kVarWriteDynSmem, stream>>>(G, set, S, total_batches);
     }
   }
   LSB_CUDA(cudaGetLastError());

@@ -14,7 +14,7 @@ from typing import Dict, Iterable, Iterator, List, Optional
 
 import pyarrow as pa
 
-from ._lib import CStatus, LsbReaderStats, load_library
+from ._lib import BOOL_CALLBACK, I32_CALLBACK, CStatus, LsbReaderStats, LsbWriterStats, load_library
 
 
 class _ArrowSchemaStruct(ctypes.Structure):
@@ -263,3 +263,141 @@ def read_bucket(files: List[str], schema: pa.Schema, primary_keys: Iterable[str]
         return table, r
     r.close()
     return table
+
+
+class FlushResult:
+    """NativeIOWriter.java FlushResult: one data file of a flush."""
+
+    def __init__(self, filePath: str, fileSize: int, fileExistCols: str):
+        self.filePath, self.fileSize, self.fileExistCols = filePath, fileSize, fileExistCols
+
+    def __repr__(self):
+        return f"FlushResult(filePath={self.filePath!r}, fileSize={self.fileSize}, fileExistCols={self.fileExistCols!r})"
+
+
+class NativeIOWriter(NativeIOReader):
+    """Mirror of NativeIOWriter.java (native-io/lakesoul-io-java/.../NativeIOWriter.java): the NativeIOBase setters are
+    shared with the reader; write() hands a batch over through the Arrow C data interface, flush() decodes the
+    summary of flush_and_close_writer into {partition_desc: [FlushResult]}."""
+
+    def __init__(self, schema: pa.Schema):
+        super().__init__()
+        self.writer = None
+        self.setSchema(schema)
+
+    def setAuxSortColumns(self, cols: Iterable[str]):
+        for c in cols:
+            self.ioConfigBuilder = self.lib.lakesoul_config_builder_add_single_aux_sort_column(self.ioConfigBuilder, c.encode())
+
+    def setHashBucketNum(self, n: int):
+        self.ioConfigBuilder = self.lib.lakesoul_config_builder_set_hash_bucket_num(self.ioConfigBuilder, max(int(n), 1))
+
+    def setRowGroupRowNumber(self, n: int):
+        self.ioConfigBuilder = self.lib.lakesoul_config_builder_set_max_row_group_size(self.ioConfigBuilder, n)
+
+    def setRowGroupValueNumber(self, n: int):
+        self.ioConfigBuilder = self.lib.lakesoul_config_builder_set_max_row_group_num_values(self.ioConfigBuilder, n)
+
+    def initializeWriter(self):
+        runtime = self.lib.create_tokio_runtime_from_builder(self.tokioRuntimeBuilder)
+        self.tokioRuntimeBuilder = None
+        config = self.lib.create_lakesoul_io_config_from_builder(self.ioConfigBuilder)
+        self.ioConfigBuilder = None
+        w = self.lib.create_lakesoul_writer_from_config(config, runtime)
+        status = self.lib.check_writer_created(w)
+        try:
+            if status.contents.status < 0:
+                msg = (status.contents.err or b"unknown").decode()
+                self.lib.free_lakesoul_writer(w)
+                raise IOError("Init native writer failed with error: " + msg)
+        finally:
+            self.lib.free_c_status(status)
+        self.writer = w
+
+    def write(self, batch: pa.RecordBatch):
+        arr, sch = _ArrowArrayStruct(), _ArrowSchemaStruct()
+        batch._export_to_c(ctypes.addressof(arr), ctypes.addressof(sch))
+        status = self.lib.write_record_batch_blocked(self.writer, ctypes.addressof(sch), ctypes.addressof(arr))
+        try:
+            if status.contents.status < 0:
+                raise IOError("Native writer write batch failed with error: " + (status.contents.err or b"unknown").decode())
+        finally:
+            self.lib.free_c_status(status)
+
+    def writeIpc(self, encoded: bytes) -> int:
+        buf = ctypes.create_string_buffer(encoded, len(encoded))
+        status = self.lib.write_record_batch_ipc_blocked(self.writer, ctypes.addressof(buf), len(encoded))
+        try:
+            if status.contents.status < 0:
+                raise IOError("Native writer write batch failed with error: " + (status.contents.err or b"unknown").decode())
+            return status.contents.status
+        finally:
+            self.lib.free_c_status(status)
+
+    def writer_stats(self) -> dict:
+        st = LsbWriterStats()
+        if self.lib.lsb_writer_get_stats(self.writer, ctypes.byref(st)) != 0:
+            raise RuntimeError(self.lib.lsb_last_error().decode())
+        return {name: getattr(st, name) for name, _ in LsbWriterStats._fields_ if name != "pad"}
+
+    def flush(self) -> Dict[str, List[FlushResult]]:
+        """NativeIOWriter.java flush(): flush_and_close_writer + export_bytes_result, then the summary is decoded."""
+        got = {}
+
+        def on_len(n, err):
+            got["len"], got["err"] = n, (err.decode() if err else None)
+
+        cb = I32_CALLBACK(on_len)
+        res = self.lib.flush_and_close_writer(self.writer, cb)
+        self.writer = None
+        if got.get("len", -1) < 0:
+            self.lib.free_bytes_result(res)
+            raise IOError("Flush native writer failed with error: " + str(got.get("err")))
+        n = got["len"]
+        out: Dict[str, List[FlushResult]] = {}
+        if n == 0:
+            self.lib.free_bytes_result(res)
+            return out
+        buf = ctypes.create_string_buffer(n + 1)
+        ok = {}
+
+        def on_done(status, err):
+            ok["ok"], ok["err"] = status, (err.decode() if err else None)
+
+        cb2 = BOOL_CALLBACK(on_done)
+        self.lib.export_bytes_result(cb2, res, n, ctypes.addressof(buf))
+        if not ok.get("ok"):
+            raise IOError("Export flush result failed: " + str(ok.get("err")))
+        text = buf.raw[:n].decode()
+        parts = text.split("\x01")
+        count = int(parts[0])
+        assert count == len(parts) - 1
+        for p in parts[1:]:
+            fields = p.split("\x02")
+            desc = fields[0]
+            files = []
+            for enc in fields[1:]:
+                f = enc.split("\x03")
+                assert len(f) == 3
+                files.append(FlushResult(f[0], int(f[1]), f[2]))
+            out[desc] = files
+        return out
+
+    def abort(self):
+        if self.writer is None:
+            return
+        got = {}
+
+        def on_done(status, err):
+            got["ok"], got["err"] = status, (err.decode() if err else None)
+
+        cb = BOOL_CALLBACK(on_done)
+        self.lib.abort_and_close_writer(self.writer, cb)
+        self.writer = None
+        if not got.get("ok"):
+            raise IOError("Abort native writer failed with error: " + str(got.get("err")))
+
+    def close(self):
+        if self.writer is not None:
+            self.abort()
+        super().close()
