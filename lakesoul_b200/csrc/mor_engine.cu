@@ -1543,6 +1543,29 @@ __device__ __forceinline__ void copy_rows(const int32_t* s_off, const int32_t* s
   }
 }
 
+// Short rows (the chunk's longest row has at most kMax bytes) of a single-window chunk, byte by byte: kMax predicated
+// byte loads, then kMax predicated byte stores. For rows of a few bytes this is a third of the instructions of the
+// word-grid copy (whose alignment bookkeeping is a fixed cost per row), and the byte loads of neighbouring lanes fall
+// into the same sectors. (The same idea for rows of up to 20 bytes -- a 20-register byte array, or a four-byte loop --
+// made the kernel slower: at 64 registers any addition to this kernel spills somewhere else.)
+template <int kMax>
+__device__ __forceinline__ void copy_rows_bytes(const int32_t* s_off, const int32_t* s_src, uint8_t* s_stage, const uint8_t* __restrict__ src_base,
+                                                int nloc, int first_pad) {
+  for (int r = threadIdx.x; r < nloc; r += kGatherThreads) {
+    const int o = s_off[r];
+    const int n = s_off[r + 1] - o;
+    const uint8_t* sp = src_base + s_src[r];
+    uint8_t* dp = s_stage + first_pad + o;
+    uint8_t v[kMax];
+#pragma unroll
+    for (int i = 0; i < kMax; ++i)
+      if (i < n) v[i] = __ldg(sp + i);
+#pragma unroll
+    for (int i = 0; i < kMax; ++i)
+      if (i < n) dp[i] = v[i];
+  }
+}
+
 constexpr int kStage2Bytes = 24 * 1024;
 constexpr int kVarWriteDynSmem = kStage2Bytes + 16;
 
@@ -1689,7 +1712,8 @@ __global__ void __launch_bounds__(kGatherThreads, kMinBlocks) var_write_kernel(c
       // boundary is the first row of the next window
       const int r_hi = (w1 >= tot) ? nloc - 1 : upper_idx(s_off, nloc + 1, w1 - 1);
       // preload depth by the longest row of the chunk (block-uniform): rows up to 8 / 20 / 44 bytes never loop
-      if (maxlen_all <= 8) copy_rows<3, 1, false>(s_off, s_src, s_stage, src_base, r_lo, r_hi, w0, w1, first_pad);
+      if (maxlen_all <= 8 && w1 >= tot && w0 == 0) copy_rows_bytes<8>(s_off, s_src, s_stage, src_base, nloc, first_pad);
+      else if (maxlen_all <= 8) copy_rows<3, 1, false>(s_off, s_src, s_stage, src_base, r_lo, r_hi, w0, w1, first_pad);
       else if (maxlen_all <= 20) copy_rows<6, 1, false>(s_off, s_src, s_stage, src_base, r_lo, r_hi, w0, w1, first_pad);
       else copy_rows<6, 1, true>(s_off, s_src, s_stage, src_base, r_lo, r_hi, w0, w1, first_pad);
       r_lo = r_hi;

@@ -15,7 +15,7 @@ drv = os.path.join(ROOT, "lakesoul_b200", "lib", "cabi_driver")
 for t in slots:
     job = os.path.join(tmp, "job.txt")
     with open(job, "w") as f:
-        f.write(f"{t} 8192 3\n" + "\t".join(spec.primary_keys) + "\n\n\n" + "\n".join("\t".join(p) for p in paths) + "\n")
+        f.write(f"{t} 8192 {os.environ.get('SWEEP_PASSES', '3')}\n" + "\t".join(spec.primary_keys) + "\n\n\n" + "\n".join("\t".join(p) for p in paths) + "\n")
     out = subprocess.run([drv, job], capture_output=True, text=True)
     if os.environ.get("LAKESOUL_B200_TRACE") == "1":
         sys.stderr.write(out.stderr)
@@ -23,4 +23,5 @@ for t in slots:
         print("FAILED", out.stderr[-400:]); continue
     r = json.loads(out.stdout.strip().splitlines()[-1])
     print(f"slots {t:3d}: {r['rows_in'] / r['seconds'] / 1e6:7.1f} M rows/s  ({r['seconds']*1e3/nb:6.2f} ms/bucket, host cores busy "
-          f"{r['cpu_seconds'] / r['seconds']:.1f}, device-decompressed pages {r['device_decompressed_pages']})", flush=True)
+          f"{r['cpu_seconds'] / r['seconds']:.1f}, device-decompressed pages {r['device_decompressed_pages']}) passes "
+          + " ".join(f"{x*1e3/nb:.2f}" for x in r["pass_seconds"]), flush=True)
