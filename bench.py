@@ -38,7 +38,7 @@ K = 8
 BASE_ROWS = 117_188
 DELTA_ROWS = 16_741
 BATCH_SIZE = 8192
-TRAFFIC_FILE = "r02_traffic.json"  # ncu dram bytes of the step kernels (profiles/make_traffic.py)
+TRAFFIC_FILE = "r03_traffic.json"  # ncu dram bytes of the step kernels (profiles/make_traffic.py)
 
 
 def parse_args():

@@ -138,6 +138,7 @@ struct FileInfo {
   std::shared_ptr<RawParquetFile> raw;    // whole file in pinned memory + parsed footer
   std::shared_ptr<arrow::Schema> schema;  // partition columns removed
   int64_t rows = 0;
+  int group = 0;                          // hash bucket of the reader's file list this file belongs to (b200_file_groups)
 };
 
 // eq(column, literal) terms at the top level of a conjunction
@@ -228,7 +229,8 @@ struct Reader::Impl {
   ReaderStats stats;
   std::shared_ptr<arrow::Schema> out_schema;
   std::unique_ptr<DeviceScan> scan;
-  int64_t next_batch = 0, n_batches = 0;
+  int64_t next_batch = 0, n_batches = 0;  // inside the current bucket of the scan
+  int cur_bucket = 0;
   bool started = false;
 
   // count-only reads (empty projection, nothing to merge)
@@ -311,8 +313,33 @@ void Reader::Start() {
   // it is in pinned memory, overlapping the read of the next file
   std::shared_ptr<ScanSession> session = begin_scan_session();
   const bool early_upload = !force_host_decode();
+  // Extension (option b200_file_groups = "n0,n1,..."): the file list is several hash buckets back to back, n_i files
+  // each; every bucket is merged on its own, in ONE device scan (one framing pass, one launch set -- SURVEY.md 7.2
+  // "tiny units at scale"), and the stream returns bucket 0's batches, then bucket 1's, ... (no batch spans two buckets).
+  std::vector<int> group_of(cfg.files.size(), 0);
+  int ngroups = 1;
+  {
+    std::string gs;
+    if (cfg.option("b200_file_groups", &gs) && !gs.empty()) {
+      size_t pos = 0, f = 0;
+      int g = 0;
+      while (pos < gs.size()) {
+        const size_t comma = gs.find(',', pos);
+        const long n = atol(gs.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos).c_str());
+        if (n <= 0 || f + (size_t)n > cfg.files.size()) fail("b200_file_groups does not match the file list");
+        for (long i = 0; i < n; ++i) group_of[f++] = g;
+        ++g;
+        if (comma == std::string::npos) break;
+        pos = comma + 1;
+      }
+      if (f != cfg.files.size()) fail("b200_file_groups does not match the file list");
+      ngroups = g;
+    }
+  }
   std::vector<FileInfo> files;
+  size_t file_no = 0;
   for (const auto& raw : cfg.files) {
+    const int this_group = group_of[file_no++];
     const std::string path = strip_scheme(raw);
     struct stat st;
     if (stat(path.c_str(), &st) != 0) fail("Object at location " + path + " not found");
@@ -322,6 +349,7 @@ void Reader::Start() {
     }
     FileInfo fi;
     fi.path = path;
+    fi.group = this_group;
     fi.raw = RawParquetFile::Open(path);
     if (early_upload)
       fi.raw->set_device_image(session_upload(*session, fi.raw->image(), (size_t)fi.raw->image_bytes()));
@@ -446,6 +474,7 @@ void Reader::Start() {
   bool merge_on_read;
   if (cfg.skip_merge_on_read() || cfg.primary_keys.empty()) merge_on_read = false;
   else merge_on_read = !(cfg.files.size() == 1 && cfg.merge_operators.empty() && cfg.is_compacted());
+  // (with file groups a one-file bucket is merged like the others: a sorted, compacted file comes out unchanged)
 
   if (files.empty()) {  // no valid file: empty stream with the requested schema
     I.started = true;
@@ -463,7 +492,7 @@ void Reader::Start() {
   }
 
   // ---- frame every file for the device decoders; host Arrow decode only where they do not apply
-  BucketFiles bucket;
+  std::vector<BucketFiles> groups((size_t)ngroups);
   const bool host_only = force_host_decode();
   for (auto& fi : files) {
     bool any = false;
@@ -473,7 +502,7 @@ void Reader::Start() {
     if (!host_only && fi.raw->Plan(phys_fields, &why)) {
       FileInput in;
       in.raw = fi.raw;
-      bucket.files.push_back(std::move(in));
+      groups[(size_t)fi.group].files.push_back(std::move(in));
       continue;
     }
     if (!host_only && getenv("LAKESOUL_B200_VERBOSE"))
@@ -526,7 +555,7 @@ void Reader::Start() {
     }
     FileInput in;
     in.table = arrow::Table::Make(arrow::schema(flds), cols, table->num_rows());
-    bucket.files.push_back(std::move(in));
+    groups[(size_t)fi.group].files.push_back(std::move(in));
   }
   I.stats.decode_ms = now_ms() - t_dec0;
   trace_mark("frame");
@@ -542,11 +571,13 @@ void Reader::Start() {
     spec.ops.push_back(it == cfg.merge_operators.end() ? MergeOp::UseLast : merge_op_from_name(it->second));
   }
   std::vector<BucketFiles> buckets;
-  buckets.push_back(std::move(bucket));
+  for (auto& g : groups)
+    if (!g.files.empty()) buckets.push_back(std::move(g));  // a bucket whose files were all skipped has no rows
   I.scan.reset(new DeviceScan(std::move(spec), std::move(buckets), std::move(session)));
   I.scan->Run();
   trace_mark("cleanup");
   trace_flush("reader");
+  I.cur_bucket = 0;
   I.n_batches = I.scan->num_batches(0);
   const ScanCounters& c = I.scan->counters();
   I.stats.rows_in = c.rows_in;
@@ -576,8 +607,14 @@ std::shared_ptr<arrow::RecordBatch> Reader::Next() {
     rows = std::min(bs, I.count_rows_left);
     I.count_rows_left -= rows;
   } else {
-    if (!I.scan || I.next_batch >= I.n_batches) return nullptr;
-    phys = I.scan->Batch(0, I.next_batch++);
+    if (!I.scan) return nullptr;
+    while (I.next_batch >= I.n_batches) {  // next bucket of the scan
+      if (I.cur_bucket + 1 >= I.scan->num_buckets()) return nullptr;
+      I.cur_bucket += 1;
+      I.next_batch = 0;
+      I.n_batches = I.scan->num_batches(I.cur_bucket);
+    }
+    phys = I.scan->Batch(I.cur_bucket, I.next_batch++);
     rows = phys->num_rows();
   }
   std::vector<std::shared_ptr<arrow::Array>> arrays;

@@ -14,7 +14,7 @@ for x in rows:
     e[x["Metric Name"]] = v
 ids = sorted(d)
 # one step = the launches after the last var_write of the previous step
-ends = [i for i in ids if d[i]["name"].startswith("var_write_kernel")]
+ends = [i for i in ids if "var_write_kernel" in d[i]["name"]]
 lo = ends[-2] + 1 if len(ends) > 1 else ids[0]
 step = [d[i] for i in ids if lo <= i <= ends[-1]]
 byt, ms = collections.OrderedDict(), collections.OrderedDict()

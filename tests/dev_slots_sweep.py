@@ -15,7 +15,7 @@ drv = os.path.join(ROOT, "lakesoul_b200", "lib", "cabi_driver")
 for t in slots:
     job = os.path.join(tmp, "job.txt")
     with open(job, "w") as f:
-        f.write(f"{t} 8192 {os.environ.get('SWEEP_PASSES', '3')}\n" + "\t".join(spec.primary_keys) + "\n\n\n" + "\n".join("\t".join(p) for p in paths) + "\n")
+        f.write(f"{t} 8192 {os.environ.get('SWEEP_PASSES', '3')} {os.environ.get('SWEEP_GROUP', '1')}\n" + "\t".join(spec.primary_keys) + "\n\n\n" + "\n".join("\t".join(p) for p in paths) + "\n")
     out = subprocess.run([drv, job], capture_output=True, text=True)
     if os.environ.get("LAKESOUL_B200_TRACE") == "1":
         sys.stderr.write(out.stderr)

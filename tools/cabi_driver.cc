@@ -56,6 +56,7 @@ static std::vector<std::string> split_tabs(const std::string& line) {
 
 struct Job {
   int threads = 1, batch_size = 8192, passes = 1;
+  int group = 1;  // hash buckets per reader (option b200_file_groups of the library): one device scan for `group` buckets
   std::vector<std::string> pks, opts, filters;
   std::vector<std::vector<std::string>> buckets;
 };
@@ -91,10 +92,16 @@ static PassResult run_pass(const Job& job, size_t nbuckets) {
   };
   auto worker = [&]() {
     while (!failed) {
-      const size_t b = next.fetch_add(1);
+      const size_t b = next.fetch_add((size_t)job.group);
       if (b >= nbuckets) break;
+      const size_t b_end = std::min(nbuckets, b + (size_t)job.group);
       IOConfigBuilder* cb = new_lakesoul_io_config_builder();
-      for (const auto& f : job.buckets[b]) cb = lakesoul_config_builder_add_single_file(cb, f.c_str());
+      std::string groups;
+      for (size_t bb = b; bb < b_end; ++bb) {
+        for (const auto& f : job.buckets[bb]) cb = lakesoul_config_builder_add_single_file(cb, f.c_str());
+        groups += (groups.empty() ? "" : ",") + std::to_string(job.buckets[bb].size());
+      }
+      if (b_end - b > 1) cb = lakesoul_config_builder_set_option(cb, "b200_file_groups", groups.c_str());
       for (const auto& p : job.pks) cb = lakesoul_config_builder_add_single_primary_key(cb, p.c_str());
       cb = lakesoul_config_builder_set_inferring_schema(cb, true);
       cb = lakesoul_config_builder_set_batch_size(cb, (c_size_t)job.batch_size);
@@ -191,7 +198,7 @@ int main(int argc, char** argv) {
   Job job;
   std::string line;
   std::getline(in, line);
-  { std::stringstream ss(line); ss >> job.threads >> job.batch_size >> job.passes; }
+  { std::stringstream ss(line); ss >> job.threads >> job.batch_size >> job.passes; if (!(ss >> job.group) || job.group < 1) job.group = 1; }
   std::getline(in, line);
   job.pks = split_tabs(line);
   std::getline(in, line);
