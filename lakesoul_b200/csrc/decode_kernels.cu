@@ -1234,6 +1234,47 @@ __device__ __forceinline__ void copy_warp_cg(uint8_t* d, const uint8_t* s, uint3
   for (; i < n; i += 32) d[i] = s[i];
 }
 
+// Matches of one round (<= 32 sequences, one per lane) in dependency LEVELS instead of one at a time: a match whose
+// source overlaps the output of an earlier match of the same round (columnar data repeats values a few bytes back: most
+// matches do) must wait for it -- but only for it. level = 1 + the highest level among the earlier matches it reads
+// from (one pass over the lanes: lane i's level is final when it is broadcast); every level is then copied by all its
+// lanes at once. A round of 32 sequences costs (levels) memory round trips instead of (dependent matches) round
+// trips (r3: the three ZSTD launches of a config-5 bucket are 9-13 ms chains of such round trips).
+__device__ __forceinline__ void zstd_copy_matches(uint8_t* dst, int64_t op, int64_t my_match, uint32_t offset, uint32_t ml, int cnt, int lane) {
+  const bool has = lane < cnt && ml > 0;
+  const int64_t src0 = my_match - (int64_t)offset;
+  const int64_t src1 = src0 + (int64_t)(ml < offset ? ml : offset);  // an overlapping match reads [src0, my_match) only
+  int level = 0;
+  if (__any_sync(0xffffffffu, has && src1 > op)) {  // some source reaches into this round
+    for (int i = 0; i + 1 < cnt; ++i) {
+      const int64_t o0 = __shfl_sync(0xffffffffu, my_match, i);
+      const uint32_t oml = __shfl_sync(0xffffffffu, ml, i);
+      const int li = __shfl_sync(0xffffffffu, level, i);
+      if (has && lane > i && oml > 0 && src0 < o0 + (int64_t)oml && src1 > o0) level = max(level, li + 1);
+    }
+  }
+  const int maxl = __reduce_max_sync(0xffffffffu, has ? level : 0);
+  for (int L = 0; L <= maxl; ++L) {
+    const bool mine = has && level == L;
+    const bool small = mine && ml <= 64 && offset >= ml;
+    if (small) copy_lane_cg(dst + my_match, dst + src0, ml);
+    unsigned big = __ballot_sync(0xffffffffu, mine && !small);
+    while (big) {
+      const int j = __ffs(big) - 1;
+      big &= big - 1;
+      const int64_t md = __shfl_sync(0xffffffffu, my_match, j);
+      const uint32_t off = __shfl_sync(0xffffffffu, offset, j), n = __shfl_sync(0xffffffffu, ml, j);
+      const uint8_t* m = dst + md - off;
+      if (off >= n) {
+        copy_warp_cg(dst + md, m, n, lane);
+      } else {  // overlapping match: only bytes that existed before this sequence are read
+        for (uint32_t i = lane; i < n; i += 32) dst[md + i] = m[i % off];
+      }
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace
 
 template <int kWarps>
@@ -1472,23 +1513,7 @@ __global__ void __launch_bounds__(kWarps * 32) zstd_pages_kernel_v2(const PqZstd
         copy_warp_cg(dst + o, lits + l0, n, lane);
       }
       __syncwarp();
-      const bool indep = lane < cnt && ml <= 64 && (my_match - (int64_t)offset + ml <= op);
-      if (indep) copy_lane_cg(dst + my_match, dst + my_match - offset, ml);
-      __syncwarp();
-      unsigned serial = __ballot_sync(0xffffffffu, lane < cnt && !indep && ml > 0);
-      while (serial) {
-        const int j = __ffs(serial) - 1;
-        serial &= serial - 1;
-        const int64_t md = __shfl_sync(0xffffffffu, my_match, j);
-        const uint32_t off = __shfl_sync(0xffffffffu, offset, j), n = __shfl_sync(0xffffffffu, ml, j);
-        const uint8_t* m = dst + md - off;
-        if (off >= n) {
-          copy_warp_cg(dst + md, m, n, lane);
-        } else {  // overlapping match: only bytes that existed before this sequence are read
-          for (uint32_t i = lane; i < n; i += 32) dst[md + i] = m[i % off];
-        }
-        __syncwarp();
-      }
+      zstd_copy_matches(dst, op, my_match, offset, ml, cnt, lane);
       op += tot_out;
       lpos += tot_lit;
       __threadfence_block();
@@ -1561,20 +1586,7 @@ __device__ bool zstd_execute_single_block(const ZstdBlockPlan& P, const uint8_t*
       copy_warp_cg(dst + o, lits + l0, n, lane);
     }
     __syncwarp();
-    const bool indep = lane < cnt && ml <= 64 && (my_match - (int64_t)offset + ml <= op);
-    if (indep) copy_lane_cg(dst + my_match, dst + my_match - offset, ml);
-    __syncwarp();
-    unsigned serial = __ballot_sync(0xffffffffu, lane < cnt && !indep && ml > 0);
-    while (serial) {
-      const int j = __ffs(serial) - 1;
-      serial &= serial - 1;
-      const int64_t md = __shfl_sync(0xffffffffu, my_match, j);
-      const uint32_t off = __shfl_sync(0xffffffffu, offset, j), n = __shfl_sync(0xffffffffu, ml, j);
-      const uint8_t* m = dst + md - off;
-      if (off >= n) copy_warp_cg(dst + md, m, n, lane);
-      else for (uint32_t i = lane; i < n; i += 32) dst[md + i] = m[i % off];
-      __syncwarp();
-    }
+    zstd_copy_matches(dst, op, my_match, offset, ml, cnt, lane);
     op += tot_out;
     lpos += tot_lit;
   }

@@ -94,6 +94,10 @@ struct ScanSlot {
   DeviceArena arena;
   HostStage stage;  // pinned staging of the descriptor uploads (see mor_engine.h)
   int device = -1;
+  // two side streams + events: the three ZSTD launches of a scan (large pages, two-block pages, one-block pages) are
+  // independent and each is a ~10 ms chain of serial work -- side by side they cost the longest instead of the sum
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
 };
 class SlotPool {
  public:
@@ -121,6 +125,12 @@ class SlotPool {
       delete s;
       fail(std::string("cudaStreamCreate failed: ") + cudaGetErrorString(e));
     }
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+      e = cudaStreamCreateWithFlags(&s->side[i], cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->join[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming);
+    if (e != cudaSuccess) fail(std::string("side stream creation failed: ") + cudaGetErrorString(e));
     return s;
   }
   void release(ScanSlot* s) {
@@ -718,10 +728,39 @@ void DeviceScan::Impl::upload() {
         h2d(d_order, order.data(), sizeof(int32_t) * order.size());
         static const bool small_v1 = [] { const char* v = getenv("LAKESOUL_B200_ZSTD_SMALL_V1"); return v && *v == '1'; }();
         ZstdTables* d_ztables = small_v1 ? static_cast<ZstdTables*>(dalloc(sizeof(ZstdTables) * zblocks.size())) : nullptr;
-        launch_zstd_pages_v2(d_zpages, d_order + order_big.size(), (int)order_small.size(), d_order, (int)order_big.size(), d_zblocks,
-                             d_zplans, d_ztables, d_zlit, d_zseq, d_err, stream);
-        launch_zstd_batch(d_zpages, d_order + order_big.size() + order_small.size(), (int)order_one.size(), d_zblocks, d_zplans, d_zlit,
-                          d_zseq, d_err, stream);
+        static const bool side_streams = [] { const char* v = getenv("LAKESOUL_B200_ZSTD_STREAMS"); return !v || *v != '1'; }();
+        const int classes = (order_big.empty() ? 0 : 1) + (order_small.empty() ? 0 : 1) + (order_one.empty() ? 0 : 1);
+        if (side_streams && classes > 1 && !small_v1) {
+          SCAN_CUDA(cudaEventRecord(slot->fork, stream));
+          int used = 0;
+          cudaStream_t where[3] = {stream, stream, stream};  // big, small, one
+          bool first = true;
+          const bool have[3] = {!order_big.empty(), !order_small.empty(), !order_one.empty()};
+          for (int c = 0; c < 3; ++c) {
+            if (!have[c]) continue;
+            if (first) { first = false; continue; }  // the first class stays on the scan's stream
+            where[c] = slot->side[used];
+            SCAN_CUDA(cudaStreamWaitEvent(slot->side[used], slot->fork, 0));
+            ++used;
+          }
+          if (have[0])
+            launch_zstd_pages_v2(d_zpages, nullptr, 0, d_order, (int)order_big.size(), d_zblocks, d_zplans, nullptr, d_zlit, d_zseq, d_err, where[0]);
+          if (have[1])
+            launch_zstd_pages_v2(d_zpages, d_order + order_big.size(), (int)order_small.size(), nullptr, 0, d_zblocks, d_zplans, nullptr, d_zlit,
+                                 d_zseq, d_err, where[1]);
+          if (have[2])
+            launch_zstd_batch(d_zpages, d_order + order_big.size() + order_small.size(), (int)order_one.size(), d_zblocks, d_zplans, d_zlit,
+                              d_zseq, d_err, where[2]);
+          for (int i = 0; i < used; ++i) {
+            SCAN_CUDA(cudaEventRecord(slot->join[i], slot->side[i]));
+            SCAN_CUDA(cudaStreamWaitEvent(stream, slot->join[i], 0));
+          }
+        } else {
+          launch_zstd_pages_v2(d_zpages, d_order + order_big.size(), (int)order_small.size(), d_order, (int)order_big.size(), d_zblocks,
+                               d_zplans, d_ztables, d_zlit, d_zseq, d_err, stream);
+          launch_zstd_batch(d_zpages, d_order + order_big.size() + order_small.size(), (int)order_one.size(), d_zblocks, d_zplans, d_zlit,
+                            d_zseq, d_err, stream);
+        }
         ctr.kernel_launches += order_one.empty() ? 0 : 1;
         ctr.kernel_launches += (order_small.empty() ? 0 : 1) + (order_big.empty() ? 0 : 1);
       }
