@@ -1598,9 +1598,10 @@ __device__ bool zstd_execute_single_block(const ZstdBlockPlan& P, const uint8_t*
 
 __global__ void __launch_bounds__(kZstdBatch * 32) zstd_batch_kernel(const PqZstdPage* pages, const int32_t* order, int npages,
                                                                      const ZstdBlockDesc* blocks_all, ZstdBlockPlan* plans_all,
-                                                                     uint8_t* lit_all, uint64_t* seq_all, int32_t* err) {
+                                                                     uint8_t* lit_all, uint64_t* seq_all, int32_t* err, int prof) {
   extern __shared__ __align__(16) unsigned char zsm_raw[];
   ZstdTables* s_tabs = reinterpret_cast<ZstdTables*>(zsm_raw);  // one slot per page of the batch
+  const long long t_start = prof ? clock64() : 0;
   __shared__ ZstdPlanScratch s_scr[kZstdBatch];
   __shared__ ZstdBlockPlan s_plans[kZstdBatch];
   __shared__ int s_state[kZstdBatch];  // 0 = no page, 1 = compressed block planned, 2 = raw / RLE block, -1 = corrupt
@@ -1631,6 +1632,7 @@ __global__ void __launch_bounds__(kZstdBatch * 32) zstd_batch_kernel(const PqZst
     s_state[u] = st;
   }
   __syncthreads();
+  const long long t_plan = prof ? clock64() : 0;
   // ---- entropy across the batch ----
   if (warp == 0) {
     const int u = lane >> 2, role = lane & 3;
@@ -1667,6 +1669,9 @@ __global__ void __launch_bounds__(kZstdBatch * 32) zstd_batch_kernel(const PqZst
     }
   }
   __syncthreads();
+  const long long t_entropy = prof ? clock64() : 0;
+  if (prof && threadIdx.x == 32) {  // warp 1: how long did the FSE lanes take vs the barrier (Huffman warp)
+  }
   // ---- execute: warp w, page w ----
   const int st = s_state[warp];
   if (st == 0) return;
@@ -1687,6 +1692,15 @@ __global__ void __launch_bounds__(kZstdBatch * 32) zstd_batch_kernel(const PqZst
   }
   if (!ok && lane == 0) atomicExch(err, kErrBadPage);
   (void)plans_all;
+  if (prof && lane == 0) {
+    const long long t_end = clock64();
+    if (warp == 0) {
+      atomicAdd(&g_zstd_prof[12], (unsigned long long)(t_plan - t_start));
+      atomicAdd(&g_zstd_prof[13], (unsigned long long)(t_entropy - t_plan));
+      atomicAdd(&g_zstd_prof[15], 1ull);
+    }
+    atomicMax(&g_zstd_prof[14], (unsigned long long)(t_end - t_entropy));
+  }
 }
 
 void launch_zstd_batch(const PqZstdPage* pages, const int32_t* order_one, int none, const ZstdBlockDesc* blocks, ZstdBlockPlan* plans,
@@ -1699,8 +1713,18 @@ void launch_zstd_batch(const PqZstdPage* pages, const int32_t* order_one, int no
     attr_device = cur;
     cudaFuncSetAttribute(zstd_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kZstdBatch * sizeof(ZstdTables)));
   }
+  static const bool prof = [] { const char* v = getenv("LAKESOUL_B200_ZSTD_PROFILE"); return v && *v == '1'; }();
   zstd_batch_kernel<<<(none + kZstdBatch - 1) / kZstdBatch, kZstdBatch * 32, kZstdBatch * sizeof(ZstdTables), s>>>(
-      pages, order_one, none, blocks, plans, lit, seq, err);
+      pages, order_one, none, blocks, plans, lit, seq, err, prof ? 1 : 0);
+  if (prof) {
+    unsigned long long h[16] = {0};
+    cudaStreamSynchronize(s);
+    cudaMemcpyFromSymbol(h, g_zstd_prof, sizeof(h));
+    if (h[15]) fprintf(stderr, "ZSTDPROF batch: %llu thread blocks, mean kcycles plan %.0f entropy %.0f; slowest execute %.0f\n", h[15],
+                       h[12] / 1e3 / h[15], h[13] / 1e3 / h[15], h[14] / 1e3);
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_zstd_prof, z, sizeof(z));
+  }
 }
 
 void launch_zstd_pages_v2(const PqZstdPage* pages, const int32_t* order_small, int nsmall, const int32_t* order_big, int nbig,
