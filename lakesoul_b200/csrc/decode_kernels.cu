@@ -1154,10 +1154,16 @@ __device__ __forceinline__ uint64_t pack_seq_v2(uint32_t ll, uint32_t ml, const 
   return (uint64_t)ll | ((uint64_t)ml << 17) | (tag << 34) | ((uint64_t)((uint32_t)o.val & kSeqValMask) << 36);
 }
 
+// literal-length codes 0..35 then match-length codes 0..52: extra bits << 24 | base value (RFC 8878 3.1.1.3.2.1.1;
+// the same numbers as ll_base / ll_bits / ml_base / ml_bits of zstd_decode.h). The kernels copy the table to shared
+// memory: one LDS per code instead of two global loads with 64-bit address arithmetic on the bit-consumption chain.
+constexpr int kSeqCodeTabSize = 89;
+__constant__ uint32_t kSeqCodeTab[kSeqCodeTabSize] = {0x0u, 0x1u, 0x2u, 0x3u, 0x4u, 0x5u, 0x6u, 0x7u, 0x8u, 0x9u, 0xau, 0xbu, 0xcu, 0xdu, 0xeu, 0xfu, 0x1000010u, 0x1000012u, 0x1000014u, 0x1000016u, 0x2000018u, 0x200001cu, 0x3000020u, 0x3000028u, 0x4000030u, 0x6000040u, 0x7000080u, 0x8000100u, 0x9000200u, 0xa000400u, 0xb000800u, 0xc001000u, 0xd002000u, 0xe004000u, 0xf008000u, 0x10010000u, 0x3u, 0x4u, 0x5u, 0x6u, 0x7u, 0x8u, 0x9u, 0xau, 0xbu, 0xcu, 0xdu, 0xeu, 0xfu, 0x10u, 0x11u, 0x12u, 0x13u, 0x14u, 0x15u, 0x16u, 0x17u, 0x18u, 0x19u, 0x1au, 0x1bu, 0x1cu, 0x1du, 0x1eu, 0x1fu, 0x20u, 0x21u, 0x22u, 0x1000023u, 0x1000025u, 0x1000027u, 0x1000029u, 0x200002bu, 0x200002fu, 0x3000033u, 0x300003bu, 0x4000043u, 0x4000053u, 0x5000063u, 0x7000083u, 0x8000103u, 0x9000203u, 0xa000403u, 0xb000803u, 0xc001003u, 0xd002003u, 0xe004003u, 0xf008003u, 0x10010003u};
+
 // FSE bit stream of one block -> records with offsets resolved against the block's initial repeat history.
 // Returns 0 or < 0; *ml_total = sum of the match lengths; fin[3] = the final history (symbolic).
 __device__ int64_t sequences_v2(const uint8_t* bits, int64_t size, const ZstdBlockPlan& P, const FseEntry* tll, const FseEntry* tml,
-                                const FseEntry* tof, uint64_t* out, int64_t* ml_total, RepSym* fin) {
+                                const FseEntry* tof, uint64_t* out, int64_t* ml_total, RepSym* fin, const uint32_t* codetab) {
   using namespace zstd_detail;
   BitD d;
   if (!d.init(bits, size)) return ZSTD_E_CORRUPT;
@@ -1169,10 +1175,13 @@ __device__ int64_t sequences_v2(const uint8_t* bits, int64_t size, const ZstdBlo
     const FseEntry eo = tof[so], em = tml[sm], el = tll[sl];
     const int oc = eo.symbol, mc = em.symbol, lc = el.symbol;
     if (oc > 27 || mc > 52 || lc > 35) return ZSTD_E_CORRUPT;  // offsets >= 256 MiB cannot occur inside a page
-    const uint32_t ov = (1u << oc) + d.read(oc);              // <= 27 bits
-    const uint32_t ml = ml_base(mc) + d.read(ml_bits(mc));    // <= 16 bits
-    d.reload();
-    const uint32_t ll = ll_base(lc) + d.read(ll_bits(lc));    // <= 16 bits
+    const uint32_t cm = codetab[36 + mc], cl = codetab[lc];
+    const uint32_t ov = (1u << oc) + d.read(oc);                        // <= 27 bits
+    const uint32_t ml = (cm & 0xffffffu) + d.read((int)(cm >> 24));     // <= 16 bits
+    // the second refill of the sequence only when the four fields still to come do not fit what is left of the
+    // container (they almost always do: a refill is ~40 of the ~200 instructions of a sequence)
+    if (d.consumed + (cl >> 24) + el.nbits + em.nbits + eo.nbits > 64u) d.reload();
+    const uint32_t ll = (cl & 0xffffffu) + d.read((int)(cl >> 24));     // <= 16 bits
     if (q + 1 < P.nseq) {                                      // <= 9 + 9 + 8 bits
       sl = el.baseline + d.read(el.nbits);
       sm = em.baseline + d.read(em.nbits);
@@ -1288,6 +1297,8 @@ __global__ void __launch_bounds__(kWarps * 32) zstd_pages_kernel_v2(const PqZstd
   __shared__ ZstdPlanScratch s_plan;
   __shared__ ZstdBlockPlan s_cur_plan, s_prev_plan;
   __shared__ int s_fail, s_have_prev, s_prev_slot;
+  __shared__ uint32_t s_codetab[kSeqCodeTabSize];
+  for (int i = threadIdx.x; i < kSeqCodeTabSize; i += kWarps * 32) s_codetab[i] = kSeqCodeTab[i];  // read after the first barrier
   __shared__ int s_done[kZstdMaxTracked];  // absolute output position every block has completed
   __shared__ int s_abort;                  // a block met corrupt data: nobody waits for anybody any more
   const PqZstdPage pg = pages[order[blockIdx.x]];
@@ -1362,7 +1373,7 @@ __global__ void __launch_bounds__(kWarps * 32) zstd_pages_kernel_v2(const PqZstd
         RepSym fin[3] = {{0, 0}, {1, 0}, {2, 0}};
         int64_t r = 0;
         const long long ts0 = clock64();
-        if (P.nseq > 0) r = sequences_v2(b + P.seq_src, P.seq_size, P, T.ll, T.ml, T.of, seq + P.seq_base, &mls, fin);
+        if (P.nseq > 0) r = sequences_v2(b + P.seq_src, P.seq_size, P, T.ll, T.ml, T.of, seq + P.seq_base, &mls, fin, s_codetab);
         if (prof) {
           const unsigned long long c = (unsigned long long)(clock64() - ts0);
           if (atomicMax(&g_zstd_prof[8], c) < c) g_zstd_prof[9] = (unsigned long long)P.nseq;
@@ -1605,7 +1616,9 @@ __global__ void __launch_bounds__(kZstdBatch * 32) zstd_batch_kernel(const PqZst
   __shared__ ZstdPlanScratch s_scr[kZstdBatch];
   __shared__ ZstdBlockPlan s_plans[kZstdBatch];
   __shared__ int s_state[kZstdBatch];  // 0 = no page, 1 = compressed block planned, 2 = raw / RLE block, -1 = corrupt
+  __shared__ uint32_t s_codetab[kSeqCodeTabSize];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kSeqCodeTabSize; i += kZstdBatch * 32) s_codetab[i] = kSeqCodeTab[i];  // read after the plan barrier
   const int first = blockIdx.x * kZstdBatch;
   auto page_of = [&](int u) -> const PqZstdPage& { return pages[order[first + u]]; };
   // ---- plan: ONE warp, lane u plans page u (section headers + entropy tables into the page's shared-memory slot). The
@@ -1658,7 +1671,7 @@ __global__ void __launch_bounds__(kZstdBatch * 32) zstd_batch_kernel(const PqZst
       int64_t mls = 0;
       RepSym fin[3] = {{0, 0}, {1, 0}, {2, 0}};
       int64_t r = 0;
-      if (P.nseq > 0) r = sequences_v2(b + P.seq_src, P.seq_size, P, s_tabs[u].ll, s_tabs[u].ml, s_tabs[u].of, seq_all + pg.seq_off, &mls, fin);
+      if (P.nseq > 0) r = sequences_v2(b + P.seq_src, P.seq_size, P, s_tabs[u].ll, s_tabs[u].ml, s_tabs[u].of, seq_all + pg.seq_off, &mls, fin, s_codetab);
       P.out_size = (int32_t)min((int64_t)INT32_MAX, (int64_t)P.regen + mls);
       if (r < 0 || P.out_size != pg.raw_size) s_state[u] = -1;
       if (P.lit_type == 1) {
