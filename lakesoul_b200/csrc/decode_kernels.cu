@@ -1171,16 +1171,18 @@ __device__ int64_t sequences_v2(const uint8_t* bits, int64_t size, const ZstdBlo
   RepSym r0{0, 0}, r1{1, 0}, r2{2, 0};
   int64_t mls = 0;
   for (int32_t q = 0; q < P.nseq; ++q) {
-    d.reload();
     const FseEntry eo = tof[so], em = tml[sm], el = tll[sl];
     const int oc = eo.symbol, mc = em.symbol, lc = el.symbol;
     if (oc > 27 || mc > 52 || lc > 35) return ZSTD_E_CORRUPT;  // offsets >= 256 MiB cannot occur inside a page
     const uint32_t cm = codetab[36 + mc], cl = codetab[lc];
+    // The container is refilled only when the fields of this sequence do not fit what is left of it (a refill is ~40 of
+    // the ~200 instructions of a sequence; a typical sequence reads 20-30 bits, so every other one skips it), and a
+    // second time in the middle only for the rare sequence of more than 57 bits.
+    const uint32_t n1 = (uint32_t)oc + (cm >> 24), n2 = (cl >> 24) + el.nbits + em.nbits + eo.nbits;
+    if (d.consumed + n1 + n2 > 64u) d.reload();
     const uint32_t ov = (1u << oc) + d.read(oc);                        // <= 27 bits
     const uint32_t ml = (cm & 0xffffffu) + d.read((int)(cm >> 24));     // <= 16 bits
-    // the second refill of the sequence only when the four fields still to come do not fit what is left of the
-    // container (they almost always do: a refill is ~40 of the ~200 instructions of a sequence)
-    if (d.consumed + (cl >> 24) + el.nbits + em.nbits + eo.nbits > 64u) d.reload();
+    if (d.consumed + n2 > 64u) d.reload();
     const uint32_t ll = (cl & 0xffffffu) + d.read((int)(cl >> 24));     // <= 16 bits
     if (q + 1 < P.nseq) {                                      // <= 9 + 9 + 8 bits
       sl = el.baseline + d.read(el.nbits);
