@@ -336,6 +336,24 @@ void Reader::Start() {
       ngroups = g;
     }
   }
+  // The whole scan group is resident at once (file images in pinned memory, decoded columns and outputs in HBM): a
+  // group far beyond what that can hold is refused up front with a clear message instead of failing in an allocator
+  // (streaming by primary-key range is not built).
+  {
+    static const int64_t max_bytes = [] {
+      const char* v = getenv("LAKESOUL_B200_MAX_SCAN_BYTES");
+      return v ? atoll(v) : ((int64_t)24 << 30);
+    }();
+    int64_t total = 0;
+    for (const auto& raw : cfg.files) {
+      struct stat st0;
+      if (raw.find("://") == std::string::npos || raw.rfind("file:", 0) == 0)
+        if (stat(strip_scheme(raw).c_str(), &st0) == 0) total += (int64_t)st0.st_size;
+    }
+    if (total > max_bytes)
+      fail("the files of this reader hold " + std::to_string(total >> 20) + " MiB, more than LAKESOUL_B200_MAX_SCAN_BYTES (" +
+           std::to_string(max_bytes >> 20) + " MiB): the GPU reader keeps a whole scan group resident; compact the bucket or raise the limit");
+  }
   std::vector<FileInfo> files;
   size_t file_no = 0;
   for (const auto& raw : cfg.files) {

@@ -298,3 +298,26 @@ def test_general_primary_key_shapes_use_row_encoded_keys(tmp_path, shape):
     assert_tables_equal(got, want, f"primary key shape {shape}")
     assert 0 < got.num_rows < sum(pq.read_metadata(f).num_rows for f in files)
     assert st["kernel_launches"] > 0
+
+
+def test_oversized_scan_group_is_refused_up_front(tmp_path):
+    """the whole scan group is resident at once: a group beyond LAKESOUL_B200_MAX_SCAN_BYTES fails with a message, not in
+    an allocator (the variable is read once per process: a child process carries it)"""
+    import subprocess
+    import sys
+    t = pa.table({"id": pa.array(range(5000), pa.int64()), "v": pa.array([1.5] * 5000)})
+    p = str(tmp_path / "part-aaaaaaaaaaaaaaaa_0000.parquet")
+    pq.write_table(t, p)
+    code = ("import sys, pyarrow as pa\n"
+            "sys.path.insert(0, %r)\n"
+            "from lakesoul_b200 import read_bucket\n"
+            "s = pa.schema([('id', pa.int64()), ('v', pa.float64())])\n"
+            "try:\n"
+            "    read_bucket([%r], s, ['id'])\n"
+            "    print('READ')\n"
+            "except IOError as e:\n"
+            "    print('REFUSED' if 'LAKESOUL_B200_MAX_SCAN_BYTES' in str(e) else 'OTHER ' + str(e))\n") % (
+        __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))), p)
+    env = dict(__import__("os").environ, LAKESOUL_B200_MAX_SCAN_BYTES="1000")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert out.stdout.strip().endswith("REFUSED"), (out.stdout, out.stderr[-300:])
