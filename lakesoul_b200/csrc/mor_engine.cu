@@ -650,7 +650,23 @@ static size_t tile_fast_smem_bytes(int C) {
          kMaxFilesPerBucket * 4 + 16 * 4;
 }
 
-template <typename KeyT, int kThreads>
+// Key of one row for tile_fast_kernel. kShape 1 = (8-byte, 4-byte) integer columns without validity bitmaps -- the
+// composite key of config 2 and of most fact tables: the same 96-bit image KeyLoader<K128> builds, without its loops
+// over columns, widths and kinds (r3 profile: the generic loader carried 46 % of the kernel's stall samples).
+template <int kShape, typename KeyT>
+__device__ __forceinline__ KeyT load_key_shape(const KeyOps<KeyT>& ops, const PkDesc& pk, int64_t row) {
+  if constexpr (kShape == 1 && std::is_same<KeyT, K128>::value) {
+    uint64_t a = __ldg(reinterpret_cast<const uint64_t*>(pk.col[0].values) + row);
+    uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(pk.col[1].values) + row);
+    if (pk.col[0].kind == PK_SIGNED) a ^= 1ull << 63;
+    if (pk.col[1].kind == PK_SIGNED) b ^= 1u << 31;
+    return K128{a >> 32, (a << 32) | b};
+  } else {
+    return load_key_shape<kShape>(ops, pk, row);
+  }
+}
+
+template <typename KeyT, int kThreads, int kShape>
 __global__ void __launch_bounds__(kThreads, 3) tile_fast_kernel(PlanDev P, PkDesc pk, int level, int tile_ofs,
                                                                  uint8_t* __restrict__ tile_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -690,8 +706,8 @@ __global__ void __launch_bounds__(kThreads, 3) tile_fast_kernel(PlanDev P, PkDes
     const int64_t fb = P.file_row_base[B.file_begin + j];
     frb[j] = fb;
     if (hi > lo) {
-      hmin[j] = widen(ops.load(fb + ((((int64_t)lo + 1) << sh) - 1)));
-      hmax[j] = widen(ops.load(fb + ((((int64_t)hi) << sh) - 1)));
+      hmin[j] = widen(load_key_shape<kShape>(ops, pk, fb + ((((int64_t)lo + 1) << sh) - 1)));
+      hmax[j] = widen(load_key_shape<kShape>(ops, pk, fb + ((((int64_t)hi) << sh) - 1)));
     }
   }
   __syncthreads();
@@ -772,7 +788,7 @@ __global__ void __launch_bounds__(kThreads, 3) tile_fast_kernel(PlanDev P, PkDes
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (e0 + u * kThreads < L) kv[u] = ops.load(row[u]);
+      if (e0 + u * kThreads < L) kv[u] = load_key_shape<kShape>(ops, pk, row[u]);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int e = e0 + u * kThreads;
@@ -789,7 +805,7 @@ __global__ void __launch_bounds__(kThreads, 3) tile_fast_kernel(PlanDev P, PkDes
     for (int j = lane; j < k; j += 32) {
       const int32_t h = sp_hi[j];
       if (h < P.file_rows[B.file_begin + j]) {
-        const K128 kk = widen(ops.load(frb[j] + h));
+        const K128 kk = widen(load_key_shape<kShape>(ops, pk, frb[j] + h));
         if (!have || key_lt(kk, best)) { best = kk; have = true; }
       }
     }
@@ -2456,7 +2472,9 @@ MergePlan* plan_create(int nb, const int32_t* bucket_file_begin, const int64_t* 
                                   (int)tile_smem_bytes(3328, true)));
     LSB_CUDA(cudaFuncSetAttribute(tile_kernel<StrKey, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tile_smem_bytes(3328, true)));
-    LSB_CUDA(cudaFuncSetAttribute(tile_fast_kernel<K128, kTileThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LSB_CUDA(cudaFuncSetAttribute(tile_fast_kernel<K128, kTileThreads, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tile_fast_smem_bytes(3328)));
+    LSB_CUDA(cudaFuncSetAttribute(tile_fast_kernel<K128, kTileThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tile_fast_smem_bytes(3328)));
     }
     P->stats.n_rows = P->n_in;
@@ -2526,7 +2544,12 @@ static int run_levels(MergePlan* P, const PkDesc& pk, cudaStream_t stream) {
       if (P->use_fast_tiles) {
         // (256 threads per tile -- twice the elements per thread, half the co-rank searches -- measured 2.38 vs 2.09 ms
         //  merge: the kernel needs the 48 warps per SM more than it needs the amortisation)
-        tile_fast_kernel<KeyT, kTileThreads><<<nt, kTileThreads, tile_fast_smem_bytes(P->tile_cap), stream>>>(D, pk, l, ofs, P->d_tile_flag);
+        const bool shape1 = pk.ncols == 2 && pk.col[0].width == 8 && pk.col[1].width == 4 && !pk.col[0].validity && !pk.col[1].validity &&
+                            pk.col[0].kind != PK_FLOAT && pk.col[1].kind != PK_FLOAT;
+        if (shape1)
+          tile_fast_kernel<KeyT, kTileThreads, 1><<<nt, kTileThreads, tile_fast_smem_bytes(P->tile_cap), stream>>>(D, pk, l, ofs, P->d_tile_flag);
+        else
+          tile_fast_kernel<KeyT, kTileThreads, 0><<<nt, kTileThreads, tile_fast_smem_bytes(P->tile_cap), stream>>>(D, pk, l, ofs, P->d_tile_flag);
         tile_kernel<KeyT, false><<<nt, kTileThreads, P->smem_bytes, stream>>>(D, pk, l, ofs, P->d_tile_flag);
         launches += 3;
         continue;

@@ -16,6 +16,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <mutex>
 #include <stdexcept>
 
 #include "zstd_decode.h"
@@ -108,9 +110,31 @@ std::shared_ptr<RawParquetFile> RawParquetFile::Open(const std::string& path) {
   }
   auto md = rd->metadata();
   f->rows_ = md->num_rows();
-  auto st2 = parquet::arrow::FromParquetSchema(md->schema(), parquet::default_arrow_reader_properties(),
-                                               md->key_value_metadata(), &f->schema_);
-  if (!st2.ok()) fail(st2.ToString());
+  // The Arrow schema of a file written by an Arrow writer (parquet-rs ArrowWriter of the LakeSoul writer, Arrow C++) is
+  // fully described by its ARROW:schema key-value entry: the 64 delta files of a bucket carry the same one, and
+  // rebuilding it costs as much as parsing the footer (23 of 73 us per file, tools: r3 host profile). One cache per process.
+  std::string schema_key;
+  if (auto kv = md->key_value_metadata()) {
+    auto v = kv->Get("ARROW:schema");
+    if (v.ok()) schema_key = std::to_string(md->schema()->num_columns()) + ":" + *v;
+  }
+  static std::mutex cache_mu;
+  static std::map<std::string, std::shared_ptr<arrow::Schema>> cache;
+  if (!schema_key.empty()) {
+    std::lock_guard<std::mutex> g(cache_mu);
+    auto it = cache.find(schema_key);
+    if (it != cache.end()) f->schema_ = it->second;
+  }
+  if (!f->schema_) {
+    auto st2 = parquet::arrow::FromParquetSchema(md->schema(), parquet::default_arrow_reader_properties(),
+                                                 md->key_value_metadata(), &f->schema_);
+    if (!st2.ok()) fail(st2.ToString());
+    if (!schema_key.empty()) {
+      std::lock_guard<std::mutex> g(cache_mu);
+      if (cache.size() > 256) cache.clear();
+      cache[schema_key] = f->schema_;
+    }
+  }
   f->kept_rg_.resize((size_t)md->num_row_groups());
   for (int rg = 0; rg < md->num_row_groups(); ++rg) f->kept_rg_[(size_t)rg] = rg;
   f->reader_ = std::shared_ptr<parquet::ParquetFileReader>(std::move(rd));
@@ -326,18 +350,39 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
   // flat schemas only: leaf index == field index
   if (sd->num_columns() != schema_->num_fields()) { *why = "nested schema"; return false; }
   // which compressed column chunks the GPU expands. SNAPPY: all of them; ZSTD: by the configured share / size policy
-  std::set<std::pair<int, int>> device_chunks;  // (row group, column)
-  std::map<std::pair<int, int>, uint8_t> chunk_codec;
+  // the metadata objects of every (kept row group, column) are built once (libparquet allocates one per call)
+  const int ncols_file = sd->num_columns();
+  const int nrg_all = md->num_row_groups();
+  std::vector<std::unique_ptr<parquet::RowGroupMetaData>> rg_md((size_t)nrg_all);
+  std::vector<std::unique_ptr<parquet::ColumnChunkMetaData>> cc_md((size_t)nrg_all * (size_t)ncols_file);
+  auto chunk_md = [&](int rg, int ci) -> parquet::ColumnChunkMetaData* {
+    auto& slot = cc_md[(size_t)rg * (size_t)ncols_file + (size_t)ci];
+    if (!slot) {
+      if (!rg_md[(size_t)rg]) rg_md[(size_t)rg] = md->RowGroup(rg);
+      slot = rg_md[(size_t)rg]->ColumnChunk(ci);
+    }
+    return slot.get();
+  };
+  // (row group, column) -> expanded on the device? with which codec?
+  struct ChunkTable {
+    std::vector<uint8_t> device, codec;
+    int ncols;
+    size_t at(int rg, int ci) const { return (size_t)rg * (size_t)ncols + (size_t)ci; }
+    struct Ref { int rg, ci; };
+    void insert(const Ref& r) { device[at(r.rg, r.ci)] = 1; }
+    size_t count(const Ref& r) const { return device[at(r.rg, r.ci)]; }
+  } device_chunks{std::vector<uint8_t>((size_t)nrg_all * (size_t)ncols_file, 0), std::vector<uint8_t>((size_t)nrg_all * (size_t)ncols_file, 0), ncols_file};
+  auto& chunk_codec_v = device_chunks.codec;
   if (device_snappy()) {
     for (size_t w = 0; w < want.size(); ++w) {
       const int ci = schema_->GetFieldIndex(want[w]->name());
       if (ci < 0) continue;
       for (int rg : kept_rg_) {
-        auto ccm = md->RowGroup(rg)->ColumnChunk(ci);
+        auto* ccm = chunk_md(rg, ci);
         const int64_t first = ccm->has_dictionary_page() ? ccm->dictionary_page_offset() : ccm->data_page_offset();
         if (ccm->compression() != parquet::Compression::SNAPPY || first <= 0 || first + ccm->total_compressed_size() > image_bytes_) continue;
         device_chunks.insert({rg, ci});
-        chunk_codec[{rg, ci}] = kCodecSnappy;
+        chunk_codec_v[device_chunks.at(rg, ci)] = kCodecSnappy;
       }
     }
   }
@@ -348,11 +393,11 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
       const int ci = schema_->GetFieldIndex(want[w]->name());
       if (ci < 0) continue;
       for (int rg : kept_rg_) {
-        auto ccm = md->RowGroup(rg)->ColumnChunk(ci);
+        auto* ccm = chunk_md(rg, ci);
         const int64_t first = ccm->has_dictionary_page() ? ccm->dictionary_page_offset() : ccm->data_page_offset();
         if (ccm->compression() != parquet::Compression::ZSTD || first <= 0 || first + ccm->total_compressed_size() > image_bytes_)
           continue;
-        chunk_codec[{rg, ci}] = kCodecZstd;
+        chunk_codec_v[device_chunks.at(rg, ci)] = kCodecZstd;
         cand.push_back({ccm->total_uncompressed_size(), {rg, ci}});
         total += ccm->total_uncompressed_size();
       }
@@ -360,13 +405,13 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
     std::sort(cand.begin(), cand.end());
     if (device_zstd_share() < 0) {  // default policy: by chunk size
       for (const auto& c : cand)
-        if (c.first >= device_zstd_min_bytes()) device_chunks.insert(c.second);
+        if (c.first >= device_zstd_min_bytes()) device_chunks.insert({c.second.first, c.second.second});
     } else {
       const double budget = device_zstd_share() * (double)total;
       int64_t acc = 0;
       for (const auto& c : cand) {
         if (device_zstd_share() < 1.0 && (double)(acc + c.first) > budget) break;
-        device_chunks.insert(c.second);
+        device_chunks.insert({c.second.first, c.second.second});
         acc += c.first;
       }
     }
@@ -430,8 +475,7 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
     // pages
     int64_t first_row = 0;
     for (int rg : kept_rg_) {
-      auto rgm = md->RowGroup(rg);
-      auto ccm = rgm->ColumnChunk(ci);
+      auto* ccm = chunk_md(rg, ci);
       for (auto e : ccm->encodings())
         if (map_encoding(e) < 0) { *why = "encoding " + parquet::EncodingToString(e) + " in column " + rc.name; return false; }
       if (rc.optional) {
@@ -447,7 +491,7 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
       // image and are expanded by the GPU (zstd_pages_kernel_v2 / snappy_pages_kernel); everything else is
       // decompressed here by Arrow's codecs
       bool raw_zstd = device_chunks.count({rg, ci}) > 0;  // (name kept: "raw" = still compressed, either codec)
-      const uint8_t codec = raw_zstd ? chunk_codec[{rg, ci}] : (uint8_t)0;
+      const uint8_t codec = raw_zstd ? chunk_codec_v[device_chunks.at(rg, ci)] : (uint8_t)0;
       try {
         if (raw_zstd) {
           auto whole = std::make_shared<arrow::Buffer>(image_.get(), image_bytes_);
@@ -566,8 +610,8 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
           rc.page_dict.push_back(is_dict ? dict_idx : -1);
         }
       }
-      if (row_in_rg != rgm->num_rows()) { *why = "page row count mismatch in column " + rc.name; return false; }
-      first_row += rgm->num_rows();
+      if (row_in_rg != rg_md[(size_t)rg]->num_rows()) { *why = "page row count mismatch in column " + rc.name; return false; }
+      first_row += rg_md[(size_t)rg]->num_rows();
     }
   }
   return true;

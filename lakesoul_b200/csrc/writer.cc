@@ -471,6 +471,10 @@ std::string Writer::FlushAndClose() {
     throw;
   }
   I.closed = true;
+  if (const char* tr = getenv("LAKESOUL_B200_TRACE"); tr && *tr == '1')
+    fprintf(stderr, "LSBTRACE writer rows_in=%lld rows_out=%lld files=%lld flush_cycles=%lld device_pass_ms=%.2f encode_ms=%.2f h2d=%lld d2h=%lld launches=%d\n",
+            (long long)I.st.rows_in, (long long)I.st.rows_out, (long long)I.st.files, (long long)I.st.flush_cycles, I.st.sort_ms, I.st.encode_ms,
+            (long long)I.st.h2d_bytes, (long long)I.st.d2h_bytes, I.st.kernel_launches);
   // writer/mod.rs:346-378 (insertion order of the partitions instead of a hash map's)
   std::vector<std::string> order;
   std::vector<std::vector<std::string>> files;

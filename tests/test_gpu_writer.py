@@ -217,3 +217,35 @@ def test_ipc_entry_point_and_abort(tmp_path):
     w2.abort()
     w2.close()
     assert not d2.exists() or not any(p.suffix == ".parquet" for p in d2.rglob("*"))
+
+
+def test_partition_descriptions_follow_format_scalar_value(tmp_path):
+    """helpers/mod.rs:205-274: strings (',' -> the EQ marker, '' -> the empty marker), integers, booleans, microsecond
+    timestamps and nulls in the partition description and in the directory names (helpers/mod.rs:452-488)"""
+    import datetime as dt
+    ts = [dt.datetime(2024, 1, 2, 3, 4, 5, 123456), dt.datetime(1969, 12, 31, 23, 59, 59, 500000)]
+    rows = [("a,b", 5, True, ts[0]), ("", -7, False, ts[1]), (None, 5, True, ts[0]), ("plain", 0, False, ts[1])]
+    t = pa.table({
+        "id": pa.array(range(len(rows) * 50), pa.int64()),
+        "s": pa.array([rows[i % 4][0] for i in range(len(rows) * 50)], pa.string()),
+        "i": pa.array([rows[i % 4][1] for i in range(len(rows) * 50)], pa.int32()),
+        "b": pa.array([rows[i % 4][2] for i in range(len(rows) * 50)]),
+        "ts": pa.array([rows[i % 4][3] for i in range(len(rows) * 50)], pa.timestamp("us")),
+    })
+    w = _writer(t.schema, tmp_path, pks=["id"], ranges=["s", "i", "b", "ts"], buckets=1, dynamic=True)
+    _write_all(w, t)
+    res = w.flush()
+    w.close()
+    want = {
+        "s=a__L@KE$OUL_EQ__b,i=5,b=true,ts=2024-01-02T03:04:05.123456",
+        "s=__L@KE$OUL_EMPTY_STRING__,i=-7,b=false,ts=1969-12-31T23:59:59.500000",
+        "s=NULL,i=5,b=true,ts=2024-01-02T03:04:05.123456",
+        "s=plain,i=0,b=false,ts=1969-12-31T23:59:59.500000",
+    }
+    assert set(res) == want
+    for desc, files in res.items():
+        assert len(files) == 1
+        sub = "/".join(desc.split(","))
+        assert files[0].filePath == os.path.join(str(tmp_path), sub, os.path.basename(files[0].filePath))
+        assert files[0].fileExistCols == "id"
+        assert pq.ParquetFile(files[0].filePath).read().num_rows == 50
