@@ -47,6 +47,12 @@ typedef struct LsbWriterStats {
 } LsbWriterStats;
 int32_t lsb_writer_get_stats(CResult_Writer *writer, LsbWriterStats *out);
 
+/* test hook: walks the Parquet page headers of the byte range [off, off + len) of a file image with the library's own
+ * compact-thrift reader; out[8 * i ..] = {page type, uncompressed size, compressed size, num_values, encoding,
+ * definition-level encoding, v2 definition-levels byte length, header length}. Returns the page count, -1 on a
+ * malformed header, -2 when the pages do not end exactly at off + len. */
+int64_t lsb_test_walk_page_heads(const uint8_t *image, int64_t off, int64_t len, int32_t *out, int64_t max_pages);
+
 /* ---- device-level plan --------------------------------------------------------------------- */
 typedef struct LsbPlan LsbPlan;
 

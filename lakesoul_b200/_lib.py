@@ -106,6 +106,7 @@ EXT_SYMBOLS = {
     "lsb_version": (c_char_p, []),
     "lsb_reader_get_stats": (c_int32, [POINTER(CResult), POINTER(LsbReaderStats)]),
     "lsb_writer_get_stats": (c_int32, [c_void_p, POINTER(LsbWriterStats)]),
+    "lsb_test_walk_page_heads": (c_int64, [c_void_p, c_int64, c_int64, c_void_p, c_int64]),
     "lsb_plan_create": (c_void_p, [c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     "lsb_plan_destroy": (None, [c_void_p]),
     "lsb_plan_merge": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

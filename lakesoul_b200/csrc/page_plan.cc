@@ -84,6 +84,151 @@ int32_t map_encoding(parquet::Encoding::type e) {
 }
 }  // namespace
 
+// ---------------------------------------------------------------------------------------
+// Page headers read straight from the file image (thrift compact protocol, parquet.thrift PageHeader): the framing of a
+// config-5 bucket walks 1 072 of them, and parquet::PageReader costs ~1 us of allocations and statistics copies per
+// page on top of the decode (r3 host profile). Used for chunks whose payloads stay where they are (uncompressed, or
+// expanded on the GPU); chunks libparquet has to decompress keep going through parquet::PageReader.
+// ---------------------------------------------------------------------------------------
+namespace {
+struct PageHead {
+  int type = -1;                  // parquet::PageType: 0 data, 1 index, 2 dictionary, 3 data v2
+  int32_t uncompressed = -1, compressed = -1;
+  int32_t num_values = -1;
+  int encoding = -1, def_encoding = -1;
+  int32_t v2_def_len = 0, v2_rep_len = 0;
+  bool have_sub = false;
+  int64_t header_len = 0;
+};
+
+class CompactReader {
+ public:
+  CompactReader(const uint8_t* p, const uint8_t* end) : p_(p), end_(end) {}
+  bool ok() const { return ok_; }
+  const uint8_t* pos() const { return p_; }
+  uint64_t varint() {
+    uint64_t v = 0;
+    for (int sh = 0; sh < 64; sh += 7) {
+      if (p_ >= end_) { ok_ = false; return 0; }
+      const uint8_t b = *p_++;
+      v |= (uint64_t)(b & 0x7f) << sh;
+      if (!(b & 0x80)) return v;
+    }
+    ok_ = false;
+    return 0;
+  }
+  int64_t zigzag() { const uint64_t v = varint(); return (int64_t)(v >> 1) ^ -(int64_t)(v & 1); }
+  // next field of the current struct: returns false at STOP; *type = compact type, *id = field id
+  bool field(int* type, int* id, int* last_id) {
+    if (p_ >= end_) { ok_ = false; return false; }
+    const uint8_t b = *p_++;
+    if (b == 0) return false;
+    *type = b & 0x0f;
+    const int delta = b >> 4;
+    if (delta) *id = *last_id + delta;
+    else *id = (int)zigzag();
+    *last_id = *id;
+    return ok_;
+  }
+  void skip(int type, int depth = 0) {
+    if (!ok_ || depth > 8) { ok_ = false; return; }
+    switch (type) {
+      case 1: case 2: break;                  // bool in the field header
+      case 3: if (p_ < end_) ++p_; else ok_ = false; break;
+      case 4: case 5: case 6: (void)varint(); break;
+      case 7: if (end_ - p_ >= 8) p_ += 8; else ok_ = false; break;
+      case 8: { const uint64_t n = varint(); if ((uint64_t)(end_ - p_) >= n) p_ += n; else ok_ = false; } break;
+      case 9: case 10: {
+        if (p_ >= end_) { ok_ = false; break; }
+        const uint8_t h = *p_++;
+        uint64_t n = h >> 4;
+        if (n == 15) n = varint();
+        const int et = h & 0x0f;
+        for (uint64_t i = 0; i < n && ok_; ++i) skip_elem(et, depth + 1);
+      } break;
+      case 11: {
+        const uint64_t n = varint();
+        if (n == 0) break;
+        if (p_ >= end_) { ok_ = false; break; }
+        const uint8_t kv = *p_++;
+        for (uint64_t i = 0; i < n && ok_; ++i) { skip_elem(kv >> 4, depth + 1); skip_elem(kv & 0x0f, depth + 1); }
+      } break;
+      case 12: {
+        int t, id, last = 0;
+        while (field(&t, &id, &last)) skip(t, depth + 1);
+      } break;
+      default: ok_ = false;
+    }
+  }
+ private:
+  void skip_elem(int type, int depth) {  // inside a container a bool takes a byte
+    if (type == 1 || type == 2) { if (p_ < end_) ++p_; else ok_ = false; }
+    else skip(type, depth);
+  }
+  const uint8_t* p_;
+  const uint8_t* end_;
+  bool ok_ = true;
+};
+
+// parses one PageHeader at `p`; false = malformed / truncated
+bool read_page_head(const uint8_t* p, const uint8_t* end, PageHead* h) {
+  CompactReader r(p, end);
+  int t, id, last = 0;
+  while (r.field(&t, &id, &last)) {
+    if (!r.ok()) return false;
+    if (id == 1 && t == 5) h->type = (int)r.zigzag();
+    else if (id == 2 && t == 5) h->uncompressed = (int32_t)r.zigzag();
+    else if (id == 3 && t == 5) h->compressed = (int32_t)r.zigzag();
+    else if ((id == 5 || id == 7 || id == 8) && t == 12) {
+      h->have_sub = true;
+      int t2, id2, last2 = 0;
+      while (r.field(&t2, &id2, &last2)) {
+        if (!r.ok()) return false;
+        const bool i32 = t2 == 5;
+        if (id == 5) {          // DataPageHeader
+          if (id2 == 1 && i32) h->num_values = (int32_t)r.zigzag();
+          else if (id2 == 2 && i32) h->encoding = (int)r.zigzag();
+          else if (id2 == 3 && i32) h->def_encoding = (int)r.zigzag();
+          else r.skip(t2);
+        } else if (id == 7) {   // DictionaryPageHeader
+          if (id2 == 1 && i32) h->num_values = (int32_t)r.zigzag();
+          else if (id2 == 2 && i32) h->encoding = (int)r.zigzag();
+          else r.skip(t2);
+        } else {                // DataPageHeaderV2
+          if (id2 == 1 && i32) h->num_values = (int32_t)r.zigzag();
+          else if (id2 == 4 && i32) h->encoding = (int)r.zigzag();
+          else if (id2 == 5 && i32) h->v2_def_len = (int32_t)r.zigzag();
+          else if (id2 == 6 && i32) h->v2_rep_len = (int32_t)r.zigzag();
+          else r.skip(t2);
+        }
+      }
+    } else {
+      r.skip(t);
+    }
+    if (!r.ok()) return false;
+  }
+  if (!r.ok() || h->type < 0 || h->uncompressed < 0 || h->compressed < 0) return false;
+  h->header_len = r.pos() - p;
+  return true;
+}
+}  // namespace
+
+// test hook (tests/test_page_heads.py through ctypes): page headers of the byte range [off, off + len) of a file image
+extern "C" __attribute__((visibility("default"))) int64_t lsb_test_walk_page_heads(const uint8_t* image, int64_t off, int64_t len, int32_t* out,
+                                                                                   int64_t max_pages) {
+  int64_t n = 0, p = off;
+  while (p < off + len && n < max_pages) {
+    PageHead h;
+    if (!read_page_head(image + p, image + off + len, &h)) return -1;
+    int32_t* o = out + n * 8;
+    o[0] = h.type; o[1] = h.uncompressed; o[2] = h.compressed; o[3] = h.num_values; o[4] = h.encoding; o[5] = h.def_encoding;
+    o[6] = h.v2_def_len; o[7] = (int32_t)h.header_len;
+    p += h.header_len + h.compressed;
+    ++n;
+  }
+  return p == off + len ? n : -2;
+}
+
 std::shared_ptr<RawParquetFile> RawParquetFile::Open(const std::string& path) {
   auto f = std::make_shared<RawParquetFile>();
   f->path_ = path;
@@ -486,39 +631,108 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
         }
         if (!proven) rc.may_have_nulls = true;
       }
-      std::unique_ptr<parquet::PageReader> pr;
       // ZSTD (what the LakeSoul writer emits) and SNAPPY chunks chosen above: the pages stay compressed in the file
-      // image and are expanded by the GPU (zstd_pages_kernel_v2 / snappy_pages_kernel); everything else is
-      // decompressed here by Arrow's codecs
+      // image and are expanded by the GPU (zstd_pages_kernel_v2 / snappy_pages_kernel); uncompressed chunks are used
+      // in place; everything else is decompressed here by Arrow's codecs (parquet::PageReader).
       bool raw_zstd = device_chunks.count({rg, ci}) > 0;  // (name kept: "raw" = still compressed, either codec)
       const uint8_t codec = raw_zstd ? chunk_codec_v[device_chunks.at(rg, ci)] : (uint8_t)0;
-      try {
-        if (raw_zstd) {
-          auto whole = std::make_shared<arrow::Buffer>(image_.get(), image_bytes_);
-          const int64_t first = ccm->has_dictionary_page() ? ccm->dictionary_page_offset() : ccm->data_page_offset();
-          auto chunk = arrow::SliceBuffer(whole, first, ccm->total_compressed_size());
-          pr = parquet::PageReader::Open(std::make_shared<arrow::io::BufferReader>(chunk), ccm->num_values(),
-                                         parquet::Compression::UNCOMPRESSED);
-        } else {
+      const int64_t chunk_first = ccm->has_dictionary_page() ? ccm->dictionary_page_offset() : ccm->data_page_offset();
+      const int64_t chunk_bytes = ccm->total_compressed_size();
+      const bool in_image = chunk_first > 0 && chunk_first + chunk_bytes <= image_bytes_;
+      // own header walk (read_page_head) when the payloads are not touched on the host
+      bool walk = in_image && (raw_zstd || ccm->compression() == parquet::Compression::UNCOMPRESSED);
+      const uint8_t* wp = image_.get() + chunk_first;
+      const uint8_t* const wend = wp + chunk_bytes;
+      std::unique_ptr<parquet::PageReader> pr;
+      auto open_libparquet = [&]() -> bool {
+        try {
           pr = rd->RowGroup(rg)->GetColumnPageReader(ci);
+        } catch (const std::exception& e) {
+          *why = std::string("page reader: ") + e.what();
+          return false;
         }
-      } catch (const std::exception& e) {
-        *why = std::string("page reader: ") + e.what();
-        return false;
+        walk = false;
+        return true;
+      };
+      if (!walk) {
+        raw_zstd = false;  // (a device chunk outside the image cannot happen: the candidates were checked above)
+        if (!open_libparquet()) return false;
       }
+      struct PageView {
+        int type = -1;
+        const uint8_t* data = nullptr;
+        int64_t size = 0, uncompressed = 0;
+        int32_t num_values = 0, v2_def_len = 0, v2_rep_len = 0;
+        parquet::Encoding::type enc = parquet::Encoding::PLAIN, def_enc = parquet::Encoding::RLE;
+      };
+      std::shared_ptr<parquet::Page> hold;
+      // 1 = a page, 0 = end of the chunk, -1 = error (*why set)
+      auto next_page = [&](PageView* v) -> int {
+        if (walk) {
+          while (true) {
+            if (wp >= wend) return 0;
+            PageHead h;
+            if (!read_page_head(wp, wend, &h) || wp + h.header_len + h.compressed > wend) { *why = "malformed page header in column " + rc.name; return -1; }
+            const uint8_t* payload = wp + h.header_len;
+            wp = payload + h.compressed;
+            if (h.type == 1) continue;  // index page: skipped, as libparquet does
+            if (!h.have_sub || h.num_values < 0 || h.encoding < 0) { *why = "page header without its page-type section in column " + rc.name; return -1; }
+            v->type = h.type;
+            v->data = payload;
+            v->size = h.compressed;
+            v->uncompressed = h.uncompressed;
+            v->num_values = h.num_values;
+            v->enc = (parquet::Encoding::type)h.encoding;
+            v->def_enc = h.def_encoding >= 0 ? (parquet::Encoding::type)h.def_encoding : parquet::Encoding::RLE;
+            v->v2_def_len = h.v2_def_len;
+            v->v2_rep_len = h.v2_rep_len;
+            return 1;
+          }
+        }
+        try {
+          hold = pr->NextPage();
+        } catch (const std::exception& e) {
+          *why = std::string("page decode: ") + e.what();
+          return -1;
+        }
+        if (!hold) return 0;
+        v->data = hold->data();
+        v->size = hold->size();
+        v->type = (int)hold->type();
+        if (hold->type() == parquet::PageType::DICTIONARY_PAGE) {
+          auto* dp = static_cast<parquet::DictionaryPage*>(hold.get());
+          v->num_values = dp->num_values();
+          v->enc = dp->encoding();
+        } else if (hold->type() == parquet::PageType::DATA_PAGE) {
+          auto* p1 = static_cast<parquet::DataPageV1*>(hold.get());
+          v->num_values = p1->num_values();
+          v->enc = p1->encoding();
+          v->def_enc = p1->definition_level_encoding();
+          v->uncompressed = p1->uncompressed_size();
+        } else if (hold->type() == parquet::PageType::DATA_PAGE_V2) {
+          auto* p2 = static_cast<parquet::DataPageV2*>(hold.get());
+          v->num_values = p2->num_values();
+          v->enc = p2->encoding();
+          v->v2_def_len = p2->definition_levels_byte_length();
+          v->v2_rep_len = p2->repetition_levels_byte_length();
+          v->uncompressed = p2->uncompressed_size();
+        }
+        return 1;
+      };
+      // a chunk the device cannot expand after all is started over with libparquet's decompressing reader
+      auto restart_on_host = [&]() -> bool {
+        raw_zstd = false;
+        return open_libparquet();
+      };
       int dict_idx = -1;
       int64_t row_in_rg = 0;
       while (true) {
-        std::shared_ptr<parquet::Page> page;
-        try {
-          page = pr->NextPage();
-        } catch (const std::exception& e) {
-          *why = std::string("page decode: ") + e.what();
-          return false;
-        }
-        if (!page) break;
-        const uint8_t* data = page->data();
-        const int64_t size = page->size();
+        PageView page;
+        const int got = next_page(&page);
+        if (got < 0) return false;
+        if (got == 0) break;
+        const uint8_t* data = page.data;
+        const int64_t size = page.size;
         auto place = [&](int64_t* off, bool* aux) {
           if (data >= image_.get() && data + size <= image_.get() + image_bytes_) {
             *off = data - image_.get();
@@ -528,26 +742,19 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
             *aux = true;
           }
         };
-        if (page->type() == parquet::PageType::DICTIONARY_PAGE) {
-          auto* dp = static_cast<parquet::DictionaryPage*>(page.get());
-          if (dp->encoding() != parquet::Encoding::PLAIN && dp->encoding() != parquet::Encoding::PLAIN_DICTIONARY) {
+        if (page.type == (int)parquet::PageType::DICTIONARY_PAGE) {
+          if (page.enc != parquet::Encoding::PLAIN && page.enc != parquet::Encoding::PLAIN_DICTIONARY) {
             *why = "dictionary page encoding"; return false;
           }
           RawColumn::Dict d;
           place(&d.src_off, &d.aux);
           d.size = (int32_t)size;
-          d.num_values = dp->num_values();
+          d.num_values = page.num_values;
           if (raw_zstd) {
             const int64_t usz = d.aux ? -1 : announced_size(codec, data, size);
             if (usz < 0 || usz > ((int64_t)1 << 30)) {
               // the payload does not say how large it gets: let libparquet decompress this chunk
-              raw_zstd = false;
-              try {
-                pr = rd->RowGroup(rg)->GetColumnPageReader(ci);
-              } catch (const std::exception& e) {
-                *why = std::string("page reader: ") + e.what();
-                return false;
-              }
+              if (!restart_on_host()) return false;
               continue;
             }
             d.codec = codec;
@@ -556,22 +763,18 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
           }
           rc.dicts.push_back(d);
           dict_idx = (int)rc.dicts.size() - 1;
-        } else if (page->type() == parquet::PageType::DATA_PAGE || page->type() == parquet::PageType::DATA_PAGE_V2) {
+        } else if (page.type == (int)parquet::PageType::DATA_PAGE || page.type == (int)parquet::PageType::DATA_PAGE_V2) {
+          const bool v2 = page.type == (int)parquet::PageType::DATA_PAGE_V2;
           RawColumn::Page pg;
-          parquet::Encoding::type enc;
-          if (page->type() == parquet::PageType::DATA_PAGE) {
-            auto* p1 = static_cast<parquet::DataPageV1*>(page.get());
-            pg.num_values = p1->num_values();
-            enc = p1->encoding();
-            pg.def_encoding = map_encoding(p1->definition_level_encoding());
+          pg.num_values = page.num_values;
+          const parquet::Encoding::type enc = page.enc;
+          if (!v2) {
+            pg.def_encoding = map_encoding(page.def_enc);
             pg.v2_def_len = -1;
           } else {
-            auto* p2 = static_cast<parquet::DataPageV2*>(page.get());
-            pg.num_values = p2->num_values();
-            enc = p2->encoding();
             pg.def_encoding = ENC_RLE;
-            pg.v2_def_len = p2->definition_levels_byte_length();
-            if (p2->repetition_levels_byte_length() != 0) { *why = "repetition levels"; return false; }
+            pg.v2_def_len = page.v2_def_len;
+            if (page.v2_rep_len != 0) { *why = "repetition levels"; return false; }
           }
           pg.encoding = map_encoding(enc);
           const bool is_dict = pg.encoding == ENC_PLAIN_DICT || pg.encoding == ENC_RLE_DICT;
@@ -581,27 +784,19 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
           if (pc.conv == CONV_BOOL && is_dict) { *why = "dictionary coded boolean"; return false; }
           place(&pg.src_off, &pg.aux);
           pg.size = (int32_t)size;
-          if (raw_zstd && page->type() == parquet::PageType::DATA_PAGE_V2 && row_in_rg == 0) {
+          if (raw_zstd && v2 && row_in_rg == 0) {
             // v2 pages keep their levels outside the compressed section: let libparquet decompress this chunk
-            raw_zstd = false;
-            try {
-              pr = rd->RowGroup(rg)->GetColumnPageReader(ci);
-            } catch (const std::exception& e) {
-              *why = std::string("page reader: ") + e.what();
-              return false;
-            }
+            if (!restart_on_host()) return false;
             continue;
           }
           if (raw_zstd) {
-            auto* dp = static_cast<parquet::DataPage*>(page.get());
-            if (page->type() != parquet::PageType::DATA_PAGE || pg.aux || dp->uncompressed_size() <= 0 ||
-                dp->uncompressed_size() > (int64_t)1 << 30) {
+            if (v2 || pg.aux || page.uncompressed <= 0 || page.uncompressed > (int64_t)1 << 30) {
               *why = "ZSTD page shape in column " + rc.name;
               return false;
             }
             pg.codec = codec;
             pg.comp_size = (int32_t)size;
-            pg.size = (int32_t)dp->uncompressed_size();
+            pg.size = (int32_t)page.uncompressed;
           }
           pg.row_group = rg;
           pg.first_row = first_row + row_in_rg;
