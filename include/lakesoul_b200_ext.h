@@ -28,7 +28,8 @@ const char *lsb_version(void);
 
 typedef struct LsbReaderStats {
   int64_t rows_in, rows_out, h2d_bytes, d2h_bytes;
-  int32_t kernel_launches, pad;
+  int32_t kernel_launches;
+  int32_t stream_passes;        /* > 1: the bucket was read in that many scans over ascending primary-key ranges */
   double decode_ms, upload_ms, merge_ms, gather_ms, download_ms;
   int64_t device_decoded_pages; /* Parquet data pages decoded by the GPU kernels */
   int64_t host_decoded_files;   /* files that needed the Arrow C++ host decoder (unsupported encodings) */
@@ -52,6 +53,11 @@ int32_t lsb_writer_get_stats(CResult_Writer *writer, LsbWriterStats *out);
  * definition-level encoding, v2 definition-levels byte length, header length}. Returns the page count, -1 on a
  * malformed header, -2 when the pages do not end exactly at off + len. */
 int64_t lsb_test_walk_page_heads(const uint8_t *image, int64_t off, int64_t len, int32_t *out, int64_t max_pages);
+/* test hook: frames row groups [rg_lo, rg_hi) of a file from the whole image (lazy = 0) or from the byte span of those row
+ * groups (lazy = 1) and prints one position-independent line per page; returns the text length, -1 on error. */
+int64_t lsb_test_plan_digest(const char *path, int32_t lazy, int32_t rg_lo, int32_t rg_hi, char *out, int64_t cap);
+/* test hook: the key-range filters of the passes a bucket with these files (newline separated) is streamed in, one per line */
+int64_t lsb_test_stream_passes(const char *files, const char *pk, const char *opts, int64_t pass_bytes, char *out, int64_t cap);
 
 /* ---- device-level plan --------------------------------------------------------------------- */
 typedef struct LsbPlan LsbPlan;

@@ -25,7 +25,7 @@ class CStatus(Structure):  # lib.rs:77-81 ; Java mirror LibLakeSoulIO.java:86-94
 
 class LsbReaderStats(Structure):
     _fields_ = [("rows_in", c_int64), ("rows_out", c_int64), ("h2d_bytes", c_int64), ("d2h_bytes", c_int64),
-                ("kernel_launches", c_int32), ("pad", c_int32), ("decode_ms", c_double), ("upload_ms", c_double),
+                ("kernel_launches", c_int32), ("stream_passes", c_int32), ("decode_ms", c_double), ("upload_ms", c_double),
                 ("merge_ms", c_double), ("gather_ms", c_double), ("download_ms", c_double),
                 ("device_decoded_pages", c_int64), ("host_decoded_files", c_int64), ("pruned_row_groups", c_int64),
                 ("device_decompressed_pages", c_int64), ("pruned_buckets", c_int64)]
@@ -107,6 +107,8 @@ EXT_SYMBOLS = {
     "lsb_reader_get_stats": (c_int32, [POINTER(CResult), POINTER(LsbReaderStats)]),
     "lsb_writer_get_stats": (c_int32, [c_void_p, POINTER(LsbWriterStats)]),
     "lsb_test_walk_page_heads": (c_int64, [c_void_p, c_int64, c_int64, c_void_p, c_int64]),
+    "lsb_test_plan_digest": (c_int64, [c_char_p, c_int32, c_int32, c_int32, c_void_p, c_int64]),
+    "lsb_test_stream_passes": (c_int64, [c_char_p, c_char_p, c_char_p, c_int64, c_void_p, c_int64]),
     "lsb_plan_create": (c_void_p, [c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     "lsb_plan_destroy": (None, [c_void_p]),
     "lsb_plan_merge": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -487,7 +487,7 @@ int32_t lsb_reader_get_stats(CResult_Reader* reader, LsbReaderStats* out) {
   const lsb::ReaderStats& s = ri->reader->stats();
   out->rows_in = s.rows_in; out->rows_out = s.rows_out;
   out->h2d_bytes = s.h2d_bytes; out->d2h_bytes = s.d2h_bytes;
-  out->kernel_launches = s.kernel_launches; out->pad = 0;
+  out->kernel_launches = s.kernel_launches; out->stream_passes = s.stream_passes;
   out->decode_ms = s.decode_ms; out->upload_ms = s.upload_ms; out->merge_ms = s.merge_ms;
   out->gather_ms = s.gather_ms; out->download_ms = s.download_ms;
   out->device_decoded_pages = s.device_decoded_pages; out->host_decoded_files = s.host_decoded_files;

@@ -229,24 +229,76 @@ extern "C" __attribute__((visibility("default"))) int64_t lsb_test_walk_page_hea
   return p == off + len ? n : -2;
 }
 
-std::shared_ptr<RawParquetFile> RawParquetFile::Open(const std::string& path) {
-  auto f = std::make_shared<RawParquetFile>();
-  f->path_ = path;
-  const int fd = ::open(path.c_str(), O_RDONLY);
-  if (fd < 0) fail("Object at location " + path + " not found");
-  struct stat st;
-  if (fstat(fd, &st) != 0) { ::close(fd); fail("cannot stat " + path); }
-  f->image_bytes_ = st.st_size;
-  f->image_ = pinned_alloc((size_t)st.st_size + 64);
-  int64_t got = 0;
-  while (got < st.st_size) {
-    const ssize_t n = ::pread(fd, f->image_.get() + got, (size_t)(st.st_size - got), got);
-    if (n <= 0) { ::close(fd); fail("short read on " + path); }
-    got += n;
+// A file of which only a window [base, base + len) sits in (pinned) memory: reads inside the window are served from it
+// without a copy -- Plan() recognises such pages as part of the image --, everything else (the footer, a chunk the
+// caller did not load) by pread.
+namespace {
+class WindowFile : public arrow::io::RandomAccessFile {
+ public:
+  WindowFile(int fd, int64_t size) : fd_(fd), size_(size) {}
+  ~WindowFile() override { if (fd_ >= 0) ::close(fd_); }
+  void set_window(const uint8_t* p, int64_t base, int64_t len) { win_ = p; base_ = base; len_ = len; }
+  arrow::Status Close() override {
+    if (fd_ >= 0) ::close(fd_);
+    fd_ = -1;
+    return arrow::Status::OK();
   }
-  ::close(fd);
-  auto buf = std::make_shared<arrow::Buffer>(f->image_.get(), f->image_bytes_);
-  auto src = std::make_shared<arrow::io::BufferReader>(buf);
+  bool closed() const override { return fd_ < 0; }
+  arrow::Result<int64_t> Tell() const override { return pos_; }
+  arrow::Status Seek(int64_t position) override {
+    if (position < 0 || position > size_) return arrow::Status::IOError("seek out of bounds");
+    pos_ = position;
+    return arrow::Status::OK();
+  }
+  arrow::Result<int64_t> GetSize() override { return size_; }
+  arrow::Result<int64_t> Read(int64_t nbytes, void* out) override {
+    ARROW_ASSIGN_OR_RAISE(int64_t n, ReadAt(pos_, nbytes, out));
+    pos_ += n;
+    return n;
+  }
+  arrow::Result<std::shared_ptr<arrow::Buffer>> Read(int64_t nbytes) override {
+    ARROW_ASSIGN_OR_RAISE(auto b, ReadAt(pos_, nbytes));
+    pos_ += b->size();
+    return b;
+  }
+  arrow::Result<int64_t> ReadAt(int64_t position, int64_t nbytes, void* out) override {
+    if (position < 0 || nbytes < 0) return arrow::Status::IOError("bad read");
+    nbytes = std::max<int64_t>(0, std::min(nbytes, size_ - position));
+    if (nbytes == 0) return 0;
+    if (win_ && position >= base_ && position + nbytes <= base_ + len_) {
+      memcpy(out, win_ + (position - base_), (size_t)nbytes);
+      return nbytes;
+    }
+    if (fd_ < 0) return arrow::Status::IOError("file is closed");
+    int64_t got = 0;
+    while (got < nbytes) {
+      const ssize_t n = ::pread(fd_, static_cast<uint8_t*>(out) + got, (size_t)(nbytes - got), position + got);
+      if (n <= 0) return arrow::Status::IOError("short read");
+      got += n;
+    }
+    return got;
+  }
+  arrow::Result<std::shared_ptr<arrow::Buffer>> ReadAt(int64_t position, int64_t nbytes) override {
+    if (position < 0 || nbytes < 0) return arrow::Status::IOError("bad read");
+    nbytes = std::max<int64_t>(0, std::min(nbytes, size_ - position));
+    if (win_ && nbytes > 0 && position >= base_ && position + nbytes <= base_ + len_)
+      return std::make_shared<arrow::Buffer>(win_ + (position - base_), nbytes);  // the owner outlives every reader
+    ARROW_ASSIGN_OR_RAISE(auto buf, arrow::AllocateResizableBuffer(nbytes));
+    ARROW_ASSIGN_OR_RAISE(int64_t n, ReadAt(position, nbytes, buf->mutable_data()));
+    if (n != nbytes) ARROW_RETURN_NOT_OK(buf->Resize(n));
+    return std::shared_ptr<arrow::Buffer>(std::move(buf));
+  }
+
+ private:
+  int fd_;
+  int64_t size_, pos_ = 0;
+  const uint8_t* win_ = nullptr;
+  int64_t base_ = 0, len_ = 0;
+};
+
+// footer -> row count, Arrow schema, row-group list
+void parse_footer(const std::shared_ptr<arrow::io::RandomAccessFile>& src, std::shared_ptr<void>* reader_out, int64_t* rows,
+                  std::shared_ptr<arrow::Schema>* schema, std::vector<int>* kept) {
   std::unique_ptr<parquet::ParquetFileReader> rd;
   try {
     rd = parquet::ParquetFileReader::Open(src);
@@ -254,7 +306,7 @@ std::shared_ptr<RawParquetFile> RawParquetFile::Open(const std::string& path) {
     fail(std::string("Parquet error: ") + e.what());
   }
   auto md = rd->metadata();
-  f->rows_ = md->num_rows();
+  *rows = md->num_rows();
   // The Arrow schema of a file written by an Arrow writer (parquet-rs ArrowWriter of the LakeSoul writer, Arrow C++) is
   // fully described by its ARROW:schema key-value entry: the 64 delta files of a bucket carry the same one, and
   // rebuilding it costs as much as parsing the footer (23 of 73 us per file, tools: r3 host profile). One cache per process.
@@ -268,23 +320,92 @@ std::shared_ptr<RawParquetFile> RawParquetFile::Open(const std::string& path) {
   if (!schema_key.empty()) {
     std::lock_guard<std::mutex> g(cache_mu);
     auto it = cache.find(schema_key);
-    if (it != cache.end()) f->schema_ = it->second;
+    if (it != cache.end()) *schema = it->second;
   }
-  if (!f->schema_) {
+  if (!*schema) {
     auto st2 = parquet::arrow::FromParquetSchema(md->schema(), parquet::default_arrow_reader_properties(),
-                                                 md->key_value_metadata(), &f->schema_);
+                                                 md->key_value_metadata(), schema);
     if (!st2.ok()) fail(st2.ToString());
     if (!schema_key.empty()) {
       std::lock_guard<std::mutex> g(cache_mu);
       if (cache.size() > 256) cache.clear();
-      cache[schema_key] = f->schema_;
+      cache[schema_key] = *schema;
     }
   }
-  f->kept_rg_.resize((size_t)md->num_row_groups());
-  for (int rg = 0; rg < md->num_row_groups(); ++rg) f->kept_rg_[(size_t)rg] = rg;
-  f->reader_ = std::shared_ptr<parquet::ParquetFileReader>(std::move(rd));
+  kept->resize((size_t)md->num_row_groups());
+  for (int rg = 0; rg < md->num_row_groups(); ++rg) (*kept)[(size_t)rg] = rg;
+  *reader_out = std::shared_ptr<parquet::ParquetFileReader>(std::move(rd));
+}
+}  // namespace
+
+std::shared_ptr<RawParquetFile> RawParquetFile::Open(const std::string& path) {
+  auto f = std::make_shared<RawParquetFile>();
+  f->path_ = path;
+  const int fd = ::open(path.c_str(), O_RDONLY);
+  if (fd < 0) fail("Object at location " + path + " not found");
+  struct stat st;
+  if (fstat(fd, &st) != 0) { ::close(fd); fail("cannot stat " + path); }
+  f->image_bytes_ = f->file_bytes_ = st.st_size;
+  f->image_ = pinned_alloc((size_t)st.st_size + 64);
+  int64_t got = 0;
+  while (got < st.st_size) {
+    const ssize_t n = ::pread(fd, f->image_.get() + got, (size_t)(st.st_size - got), got);
+    if (n <= 0) { ::close(fd); fail("short read on " + path); }
+    got += n;
+  }
+  ::close(fd);
+  auto buf = std::make_shared<arrow::Buffer>(f->image_.get(), f->image_bytes_);
+  f->source_ = std::make_shared<arrow::io::BufferReader>(buf);
+  parse_footer(f->source_, &f->reader_, &f->rows_, &f->schema_, &f->kept_rg_);
   return f;
 }
+
+std::shared_ptr<RawParquetFile> RawParquetFile::OpenLazy(const std::string& path) {
+  auto f = std::make_shared<RawParquetFile>();
+  f->path_ = path;
+  const int fd = ::open(path.c_str(), O_RDONLY);
+  if (fd < 0) fail("Object at location " + path + " not found");
+  struct stat st;
+  if (fstat(fd, &st) != 0) { ::close(fd); fail("cannot stat " + path); }
+  f->file_bytes_ = st.st_size;
+  f->lazy_ = true;
+  f->loaded_ = false;
+  f->source_ = std::make_shared<WindowFile>(fd, (int64_t)st.st_size);  // owns fd
+  parse_footer(f->source_, &f->reader_, &f->rows_, &f->schema_, &f->kept_rg_);
+  return f;
+}
+
+void RawParquetFile::LoadKept() {
+  if (!lazy_ || loaded_) return;
+  auto* rd = static_cast<parquet::ParquetFileReader*>(reader_.get());
+  auto md = rd->metadata();
+  int64_t lo = INT64_MAX, hi = 0;
+  for (int rg : kept_rg_) {
+    auto rgm = md->RowGroup(rg);
+    for (int ci = 0; ci < rgm->num_columns(); ++ci) {
+      auto ccm = rgm->ColumnChunk(ci);
+      int64_t first = ccm->data_page_offset();
+      if (ccm->has_dictionary_page() && ccm->dictionary_page_offset() > 0) first = std::min(first, ccm->dictionary_page_offset());
+      if (first <= 0) continue;
+      lo = std::min(lo, first);
+      hi = std::max(hi, first + ccm->total_compressed_size());
+    }
+  }
+  if (lo >= hi) { lo = 0; hi = 0; }
+  hi = std::min(hi, file_bytes_);
+  base_ = lo;
+  image_bytes_ = hi - lo;
+  image_ = pinned_alloc((size_t)image_bytes_ + 64);
+  auto* wf = static_cast<WindowFile*>(source_.get());
+  if (image_bytes_ > 0) {
+    auto r = wf->ReadAt(lo, image_bytes_, image_.get());
+    if (!r.ok() || *r != image_bytes_) fail("short read on " + path_);
+    wf->set_window(image_.get(), base_, image_bytes_);
+  }
+  loaded_ = true;
+}
+
+std::shared_ptr<arrow::io::RandomAccessFile> RawParquetFile::source() const { return source_; }
 
 int64_t RawParquetFile::aux_append(const uint8_t* p, int64_t n) {
   if (aux_used_ + n + 64 > aux_cap_) {
@@ -314,13 +435,17 @@ struct Bound {          // min / max of one column chunk, comparable with a lite
   int64_t imin = 0, imax = 0;
   double rmin = 0, rmax = 0;
   std::string bmin, bmax;
+  int64_t nulls = -1;   // null count of the chunk, -1 unknown
 };
 
 Bound chunk_bound(const parquet::ColumnChunkMetaData& ccm, const parquet::ColumnDescriptor& cd, const arrow::DataType& type) {
   Bound b;
   if (!ccm.is_stats_set()) return b;
   auto st = ccm.statistics();
-  if (!st || !st->HasMinMax()) return b;
+  if (!st) return b;
+  if (st->HasNullCount()) b.nulls = st->null_count();
+  else if (cd.max_definition_level() == 0) b.nulls = 0;
+  if (!st->HasMinMax()) return b;
   using AT = arrow::Type;
   switch (cd.physical_type()) {
     case parquet::Type::INT32: {
@@ -454,7 +579,15 @@ Possible possible(const FilterExpr& e, const BoundFn& bound_of) {
       }
       return unknown;
     }
-    default: return unknown;  // null tests: statistics of key columns say nothing useful here
+    case FilterExpr::kIsNull: {  // a chunk proven free of nulls cannot satisfy it
+      const Bound b = bound_of(e.column);
+      return b.nulls == 0 ? Possible{false, true} : unknown;
+    }
+    case FilterExpr::kIsNotNull: {
+      const Bound b = bound_of(e.column);
+      return b.nulls == 0 ? Possible{true, false} : unknown;
+    }
+    default: return unknown;
   }
 }
 
@@ -486,7 +619,43 @@ int RawParquetFile::PruneRowGroups(const FilterExpr& filter, const std::set<std:
   return dropped;
 }
 
+void RawParquetFile::KeepRowGroups(int lo, int hi) {
+  auto* rd = static_cast<parquet::ParquetFileReader*>(reader_.get());
+  auto md = rd->metadata();
+  std::vector<int> kept;
+  int64_t rows = 0;
+  for (int rg : kept_rg_)
+    if (rg >= lo && rg < hi) { kept.push_back(rg); rows += md->RowGroup(rg)->num_rows(); }
+  kept_rg_ = std::move(kept);
+  rows_ = rows;
+}
+
+std::vector<RowGroupKeyRange> RawParquetFile::KeyRanges(const std::string& column) const {
+  std::vector<RowGroupKeyRange> out;
+  auto* rd = static_cast<parquet::ParquetFileReader*>(reader_.get());
+  auto md = rd->metadata();
+  const auto* sd = md->schema();
+  if (sd->num_columns() != schema_->num_fields()) return out;
+  const int ci = schema_->GetFieldIndex(column);
+  if (ci < 0) return out;
+  for (int rg : kept_rg_) {
+    auto rgm = md->RowGroup(rg);
+    const Bound b = chunk_bound(*rgm->ColumnChunk(ci), *sd->Column(ci), *schema_->field(ci)->type());
+    RowGroupKeyRange r;
+    r.rows = rgm->num_rows();
+    r.nulls = b.nulls;
+    r.bytes = rgm->total_byte_size();
+    if (b.fam == Bound::kInt) { r.fam = RowGroupKeyRange::kInt; r.imin = b.imin; r.imax = b.imax; }
+    else if (b.fam == Bound::kBytes) { r.fam = RowGroupKeyRange::kBytes; r.bmin = b.bmin; r.bmax = b.bmax; }
+    out.push_back(std::move(r));
+  }
+  return out;
+}
+
 bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want, std::string* why) {
+  if (lazy_ && !loaded_) LoadKept();
+  // a chunk [first, first + bytes) of the file lies inside the image?
+  auto in_window = [&](int64_t first, int64_t bytes) { return first > 0 && first >= base_ && first - base_ + bytes <= image_bytes_; };
   auto* rd = static_cast<parquet::ParquetFileReader*>(reader_.get());
   auto md = rd->metadata();
   const auto* sd = md->schema();
@@ -525,7 +694,7 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
       for (int rg : kept_rg_) {
         auto* ccm = chunk_md(rg, ci);
         const int64_t first = ccm->has_dictionary_page() ? ccm->dictionary_page_offset() : ccm->data_page_offset();
-        if (ccm->compression() != parquet::Compression::SNAPPY || first <= 0 || first + ccm->total_compressed_size() > image_bytes_) continue;
+        if (ccm->compression() != parquet::Compression::SNAPPY || !in_window(first, ccm->total_compressed_size())) continue;
         device_chunks.insert({rg, ci});
         chunk_codec_v[device_chunks.at(rg, ci)] = kCodecSnappy;
       }
@@ -540,8 +709,7 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
       for (int rg : kept_rg_) {
         auto* ccm = chunk_md(rg, ci);
         const int64_t first = ccm->has_dictionary_page() ? ccm->dictionary_page_offset() : ccm->data_page_offset();
-        if (ccm->compression() != parquet::Compression::ZSTD || first <= 0 || first + ccm->total_compressed_size() > image_bytes_)
-          continue;
+        if (ccm->compression() != parquet::Compression::ZSTD || !in_window(first, ccm->total_compressed_size())) continue;
         chunk_codec_v[device_chunks.at(rg, ci)] = kCodecZstd;
         cand.push_back({ccm->total_uncompressed_size(), {rg, ci}});
         total += ccm->total_uncompressed_size();
@@ -638,10 +806,10 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
       const uint8_t codec = raw_zstd ? chunk_codec_v[device_chunks.at(rg, ci)] : (uint8_t)0;
       const int64_t chunk_first = ccm->has_dictionary_page() ? ccm->dictionary_page_offset() : ccm->data_page_offset();
       const int64_t chunk_bytes = ccm->total_compressed_size();
-      const bool in_image = chunk_first > 0 && chunk_first + chunk_bytes <= image_bytes_;
+      const bool in_image = in_window(chunk_first, chunk_bytes);
       // own header walk (read_page_head) when the payloads are not touched on the host
       bool walk = in_image && (raw_zstd || ccm->compression() == parquet::Compression::UNCOMPRESSED);
-      const uint8_t* wp = image_.get() + chunk_first;
+      const uint8_t* wp = image_.get() + (chunk_first - base_);
       const uint8_t* const wend = wp + chunk_bytes;
       std::unique_ptr<parquet::PageReader> pr;
       auto open_libparquet = [&]() -> bool {
@@ -810,6 +978,49 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
     }
   }
   return true;
+}
+
+// test hook (tests/test_lazy_files.py through ctypes): frames the row groups [rg_lo, rg_hi) of every flat column of a
+// file, from a whole-file image (lazy = 0) or from the loaded byte span of those row groups (lazy = 1), and prints
+// one line per page -- position-independent, with a hash of the payload bytes the device would read -- so that the two
+// can be compared. Returns the text length, -1 on error (message in `out`).
+extern "C" __attribute__((visibility("default"))) int64_t lsb_test_plan_digest(const char* path, int32_t lazy, int32_t rg_lo, int32_t rg_hi,
+                                                                               char* out, int64_t cap) {
+  std::string text;
+  try {
+    auto f = lazy ? RawParquetFile::OpenLazy(path) : RawParquetFile::Open(path);
+    f->KeepRowGroups(rg_lo, rg_hi);
+    f->LoadKept();
+    std::vector<std::shared_ptr<arrow::Field>> want = f->schema()->fields();
+    std::string why;
+    if (!f->Plan(want, &why)) throw std::runtime_error("not framed: " + why);
+    auto hash = [&](bool aux, int64_t off, int64_t n) {
+      const uint8_t* p = (aux ? f->aux() : f->image()) + off;
+      uint64_t h = 1469598103934665603ull;
+      for (int64_t i = 0; i < n; ++i) h = (h ^ p[i]) * 1099511628211ull;
+      return h;
+    };
+    text += "rows " + std::to_string(f->num_rows()) + " window " + std::to_string(f->image_bytes()) + " of " + std::to_string(f->file_bytes()) + "\n";
+    for (const auto& c : f->columns()) {
+      for (size_t i = 0; i < c.dicts.size(); ++i) {
+        const auto& d = c.dicts[i];
+        text += "D " + c.name + " " + std::to_string(i) + " " + std::to_string(d.num_values) + " " + std::to_string(d.size) + " " +
+                std::to_string((int)d.codec) + " " + std::to_string(hash(d.aux, d.src_off, d.codec ? d.comp_size : d.size)) + "\n";
+      }
+      for (size_t i = 0; i < c.pages.size(); ++i) {
+        const auto& g = c.pages[i];
+        text += "P " + c.name + " " + std::to_string(g.row_group) + " " + std::to_string(g.first_row) + " " + std::to_string(g.num_values) + " " +
+                std::to_string(g.size) + " " + std::to_string(g.encoding) + " " + std::to_string((int)g.codec) + " " + std::to_string(c.page_dict[i]) + " " +
+                std::to_string(hash(g.aux, g.src_off, g.codec ? g.comp_size : g.size)) + "\n";
+      }
+    }
+  } catch (const std::exception& e) {
+    snprintf(out, (size_t)cap, "%s", e.what());
+    return -1;
+  }
+  if ((int64_t)text.size() + 1 > cap) { snprintf(out, (size_t)cap, "digest needs %zu bytes", text.size() + 1); return -1; }
+  memcpy(out, text.c_str(), text.size() + 1);
+  return (int64_t)text.size();
 }
 
 }  // namespace lsb

@@ -6,6 +6,7 @@
 // described by a POD record that points into the raw image. Values are never touched on the host.
 #pragma once
 #include <arrow/api.h>
+#include <arrow/io/interfaces.h>
 
 #include <memory>
 #include <set>
@@ -49,10 +50,29 @@ struct RawColumn {                    // one requested column of one file
   std::vector<int32_t> page_dict;     // page -> index into dicts, -1 none
 };
 
+// min / max statistics of one row group's chunk of a key column (streaming by key range, reader.cc)
+struct RowGroupKeyRange {
+  enum Fam { kNone, kInt, kBytes } fam = kNone;  // kNone: no usable statistics
+  int64_t imin = 0, imax = 0;                    // kInt (timestamps in microseconds, like filter literals)
+  std::string bmin, bmax;                        // kBytes (unsigned byte order)
+  int64_t rows = 0, nulls = -1;                  // nulls: -1 unknown
+  int64_t bytes = 0;                             // uncompressed bytes of the whole row group
+};
+
 class RawParquetFile {
  public:
   // reads the whole file into pinned memory and parses the footer; throws on IO / format errors
   static std::shared_ptr<RawParquetFile> Open(const std::string& path);
+  // reads the footer only; the image stays empty until LoadKept() reads the byte span of the kept row groups
+  // (files are sorted by primary key: the row groups a key range keeps are neighbours). Used when a bucket is
+  // streamed by key range (reader.cc) so that pinned memory holds one pass, not the bucket.
+  static std::shared_ptr<RawParquetFile> OpenLazy(const std::string& path);
+  void LoadKept();                                  // no-op for files opened with Open()
+  int64_t file_bytes() const { return file_bytes_; }
+  // the file as an Arrow source (host-decode fallback): the image when it is the whole file, else image + pread
+  std::shared_ptr<arrow::io::RandomAccessFile> source() const;
+  // one entry per kept row group; empty when the file has no such (flat) column
+  std::vector<RowGroupKeyRange> KeyRanges(const std::string& column) const;
 
   int64_t num_rows() const { return rows_; }
   const std::shared_ptr<arrow::Schema>& schema() const { return schema_; }  // full file schema (Arrow types)
@@ -64,6 +84,7 @@ class RawParquetFile {
   // num_rows() then counts the kept row groups. Returns the number of row groups dropped.
   int PruneRowGroups(const FilterExpr& filter, const std::set<std::string>& pk_columns);
   const std::vector<int>& kept_row_groups() const { return kept_rg_; }  // indices, ascending (all by default)
+  void KeepRowGroups(int lo, int hi);  // keeps the kept row groups with lo <= index < hi (before LoadKept / Plan)
 
   // Frames the pages of the requested columns (missing columns are allowed: present = false).
   // Returns false and fills `why` when some column chunk needs a decoder the device does not have;
@@ -71,8 +92,10 @@ class RawParquetFile {
   bool Plan(const std::vector<std::shared_ptr<arrow::Field>>& want, std::string* why);
 
   const std::vector<RawColumn>& columns() const { return cols_; }
+  // bytes [image_base(), image_base() + image_bytes()) of the file; page records hold offsets into image()
   const uint8_t* image() const { return image_.get(); }
   int64_t image_bytes() const { return image_bytes_; }
+  int64_t image_base() const { return base_; }
   const uint8_t* aux() const { return aux_.get(); }
   int64_t aux_bytes() const { return aux_used_; }
   int64_t host_decompressed_bytes() const { return aux_used_; }
@@ -85,6 +108,9 @@ class RawParquetFile {
   std::string path_;
   std::shared_ptr<uint8_t> image_, aux_;
   int64_t image_bytes_ = 0, aux_cap_ = 0, aux_used_ = 0, rows_ = 0;
+  int64_t base_ = 0, file_bytes_ = 0;
+  bool lazy_ = false, loaded_ = true;
+  std::shared_ptr<arrow::io::RandomAccessFile> source_;
   std::shared_ptr<arrow::Schema> schema_;
   std::shared_ptr<void> reader_;  // parquet::ParquetFileReader
   std::vector<RawColumn> cols_;

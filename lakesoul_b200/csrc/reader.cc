@@ -15,9 +15,12 @@
 #include <parquet/file_reader.h>
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <future>
 #include <set>
 #include <stdexcept>
 
@@ -159,6 +162,166 @@ bool force_host_decode() {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
+// Streaming of a bucket by primary-key range. The reference streams a bucket batch by batch
+// (sorted_stream_merger.rs:454-524); the GPU reader merges a whole scan at once, so a bucket too large for that is read
+// as a sequence of scans over ascending, disjoint ranges of the FIRST primary-key column: every version of a key falls
+// into the same range, so merging the ranges one after the other and concatenating gives the bucket's merge result, in
+// the same order (nulls first). A range is an ordinary pushed key predicate: row groups outside it are pruned by their
+// statistics (page_plan.cc PruneRowGroups), only the byte span of the kept row groups is read (LoadKept), and rows of
+// straddling row groups are dropped by the post-merge filter on the device.
+// ---------------------------------------------------------------------------------------
+namespace {
+struct SplitKey {
+  int64_t i = 0;
+  std::string s;
+  bool bytes = false;
+  bool operator<(const SplitKey& o) const { return bytes ? s < o.s : i < o.i; }
+  bool operator==(const SplitKey& o) const { return bytes ? s == o.s : i == o.i; }
+};
+
+// literal of the column's own filter-literal type (filter.cc parse_literal); nullptr = type not usable for splitting
+std::shared_ptr<arrow::Scalar> split_literal(const arrow::DataType& type, const SplitKey& k) {
+  switch (type.id()) {
+    case arrow::Type::INT8: return std::make_shared<arrow::Int8Scalar>((int8_t)k.i);
+    case arrow::Type::INT16: return std::make_shared<arrow::Int16Scalar>((int16_t)k.i);
+    case arrow::Type::INT32: return std::make_shared<arrow::Int32Scalar>((int32_t)k.i);
+    case arrow::Type::INT64: return std::make_shared<arrow::Int64Scalar>(k.i);
+    case arrow::Type::DATE32: return std::make_shared<arrow::Date32Scalar>((int32_t)k.i);
+    case arrow::Type::TIMESTAMP:
+      if (static_cast<const arrow::TimestampType&>(type).unit() != arrow::TimeUnit::MICRO) return nullptr;
+      return std::make_shared<arrow::TimestampScalar>(k.i, arrow::timestamp(arrow::TimeUnit::MICRO, "UTC"));
+    case arrow::Type::STRING: return std::make_shared<arrow::StringScalar>(k.s);
+    case arrow::Type::BINARY: return std::make_shared<arrow::BinaryScalar>(arrow::Buffer::FromString(k.s));
+    default: return nullptr;
+  }
+}
+
+std::shared_ptr<FilterExpr> cmp_expr(const std::string& col, FilterExpr::Op op, std::shared_ptr<arrow::Scalar> lit) {
+  auto e = std::make_shared<FilterExpr>();
+  e->kind = FilterExpr::kCmp;
+  e->op = op;
+  e->column = col;
+  e->literal = std::move(lit);
+  return e;
+}
+std::shared_ptr<FilterExpr> bin_expr(FilterExpr::Kind k, std::shared_ptr<FilterExpr> l, std::shared_ptr<FilterExpr> r) {
+  auto e = std::make_shared<FilterExpr>();
+  e->kind = k;
+  e->left = std::move(l);
+  e->right = std::move(r);
+  return e;
+}
+}  // namespace
+
+std::vector<std::shared_ptr<FilterExpr>> plan_stream_passes(const std::vector<std::string>& paths, const std::string& pk,
+                                                            bool pk_nullable, int64_t pass_bytes) {
+  std::vector<std::shared_ptr<FilterExpr>> none;
+  struct Ev { SplitKey key, max; int64_t bytes; };
+  std::vector<Ev> evs;
+  std::shared_ptr<arrow::DataType> type;
+  int64_t total = 0, head_bytes = 0;
+  for (const auto& path : paths) {
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0 || st.st_size < 8) continue;  // reported by the scan itself
+    auto f = RawParquetFile::OpenLazy(path);
+    auto fld = f->schema()->GetFieldByName(pk);
+    if (!fld) return none;
+    if (!type) type = fld->type();
+    else if (!type->Equals(*fld->type())) return none;  // a cast below the merge: leave it to one scan
+    pk_nullable = pk_nullable || fld->nullable();
+    const auto ranges = f->KeyRanges(pk);
+    if (ranges.size() != f->kept_row_groups().size()) return none;
+    for (const auto& r : ranges) {
+      total += r.bytes;
+      if (r.rows == 0) continue;
+      if (r.fam == RowGroupKeyRange::kNone) {
+        if (r.nulls == r.rows) {  // only null keys: they sort first, the first pass takes them
+          head_bytes += r.bytes;
+          continue;
+        }
+        return none;  // no statistics: where the rows fall is unknown
+      }
+      Ev e;
+      e.key.bytes = e.max.bytes = r.fam == RowGroupKeyRange::kBytes;
+      e.key.i = r.imin; e.key.s = r.bmin;
+      e.max.i = r.imax; e.max.s = r.bmax;
+      e.bytes = r.bytes;
+      evs.push_back(std::move(e));
+    }
+  }
+  if (!type || evs.empty() || total <= pass_bytes) return none;
+  if (!split_literal(*type, evs.front().key)) return none;
+  std::stable_sort(evs.begin(), evs.end(), [](const Ev& a, const Ev& b) { return a.key < b.key; });
+  // Sweep over the distinct row-group minima m_1 < m_2 < ...: the pass [lo, m_i) decodes every row group with
+  // min < m_i and max >= lo ("active"). It is closed at m_i when taking the row groups that start at m_i would exceed
+  // the budget AND it finishes at least half a budget of row groups (max < m_i) -- row groups that span the whole key
+  // space (small delta files) are decoded by every pass whatever the cuts, they must not force tiny passes.
+  std::vector<SplitKey> cuts;
+  std::vector<const Ev*> active;
+  int64_t acc = head_bytes;
+  for (size_t i = 0; i < evs.size();) {
+    size_t j = i;
+    int64_t g = 0;
+    while (j < evs.size() && evs[j].key == evs[i].key) g += evs[j++].bytes;
+    if (i > 0 && acc + g > pass_bytes) {
+      int64_t done = 0;
+      for (const Ev* a : active) if (a->max < evs[i].key) done += a->bytes;
+      if (done >= pass_bytes / 2) {
+        cuts.push_back(evs[i].key);
+        std::vector<const Ev*> keep;
+        acc = 0;
+        for (const Ev* a : active)
+          if (!(a->max < evs[i].key)) { keep.push_back(a); acc += a->bytes; }
+        active.swap(keep);
+      }
+    }
+    for (size_t k = i; k < j; ++k) active.push_back(&evs[k]);
+    acc += g;
+    i = j;
+  }
+  if (cuts.empty()) return none;
+  std::vector<std::shared_ptr<FilterExpr>> out;
+  for (size_t k = 0; k <= cuts.size(); ++k) {
+    std::shared_ptr<FilterExpr> e;
+    if (k > 0) e = cmp_expr(pk, FilterExpr::kGe, split_literal(*type, cuts[k - 1]));
+    if (k < cuts.size()) {
+      auto lt = cmp_expr(pk, FilterExpr::kLt, split_literal(*type, cuts[k]));
+      e = e ? bin_expr(FilterExpr::kAnd, e, lt) : lt;
+    }
+    if (k == 0 && pk_nullable) {
+      auto isn = std::make_shared<FilterExpr>();
+      isn->kind = FilterExpr::kIsNull;
+      isn->column = pk;
+      e = bin_expr(FilterExpr::kOr, e, isn);
+    }
+    out.push_back(e);
+  }
+  return out;
+}
+
+// test hook (tests/test_stream_passes.py): the pass filters for `files` (newline-separated), one per line
+extern "C" __attribute__((visibility("default"))) int64_t lsb_test_stream_passes(const char* files, const char* pk, const char* opts,
+                                                                                 int64_t pass_bytes, char* out, int64_t cap) {
+  std::string text;
+  try {
+    std::vector<std::string> paths;
+    std::string cur;
+    for (const char* p = files; *p; ++p) {
+      if (*p == '\n') { if (!cur.empty()) paths.push_back(cur); cur.clear(); }
+      else cur.push_back(*p);
+    }
+    if (!cur.empty()) paths.push_back(cur);
+    for (const auto& e : plan_stream_passes(paths, pk, opts && strstr(opts, "nullable"), pass_bytes)) text += filter_to_string(*e) + "\n";
+  } catch (const std::exception& e) {
+    snprintf(out, (size_t)cap, "%s", e.what());
+    return -1;
+  }
+  if ((int64_t)text.size() + 1 > cap) return -1;
+  memcpy(out, text.c_str(), text.size() + 1);
+  return (int64_t)text.size();
+}
+
+// ---------------------------------------------------------------------------------------
 bool IOConfig::option(const std::string& key, std::string* out) const {
   auto it = options.find(key);
   if (it != options.end()) { *out = it->second; return true; }
@@ -244,13 +407,48 @@ struct Reader::Impl {
     std::shared_ptr<arrow::DataType> type;
   };
   std::vector<OutField> out_fields;
+
+  // a bucket streamed by key range: one inner reader per pass, the next one prepared while this one is consumed
+  std::vector<std::shared_ptr<FilterExpr>> pass_filters;
+  size_t pass = 0;
+  std::unique_ptr<Reader> inner;
+  std::future<std::unique_ptr<Reader>> next_inner;
+
+  std::unique_ptr<Reader> make_pass(size_t k) const {
+    IOConfig c = cfg;
+    c.pass_filter = pass_filters[k];
+    c.lazy_files = true;
+    auto r = std::make_unique<Reader>(std::move(c));
+    r->Start();
+    return r;
+  }
+  void prefetch() {
+    if (pass + 1 >= pass_filters.size()) return;
+    static const bool off = [] { const char* v = getenv("LAKESOUL_B200_STREAM_PREFETCH"); return v && *v == '0'; }();
+    const size_t k = pass + 1;
+    next_inner = std::async(off ? std::launch::deferred : std::launch::async, [this, k] { return make_pass(k); });
+  }
+  void absorb(const ReaderStats& s) {
+    stats.rows_in += s.rows_in; stats.rows_out += s.rows_out;
+    stats.h2d_bytes += s.h2d_bytes; stats.d2h_bytes += s.d2h_bytes;
+    stats.kernel_launches += s.kernel_launches;
+    stats.device_decoded_pages += s.device_decoded_pages; stats.host_decoded_files += s.host_decoded_files;
+    stats.device_decompressed_pages += s.device_decompressed_pages;
+    stats.decode_ms += s.decode_ms; stats.upload_ms += s.upload_ms; stats.merge_ms += s.merge_ms;
+    stats.gather_ms += s.gather_ms; stats.download_ms += s.download_ms;
+    stats.path = s.path;
+  }
 };
 
 Reader::Reader(IOConfig cfg) : impl_(new Impl()) {
   if (cfg.files.empty()) fail("LakeSoulReader has the wrong number of files");  // reader.rs:108-110
   impl_->cfg = std::move(cfg);
 }
-Reader::~Reader() = default;
+Reader::~Reader() {
+  if (impl_ && impl_->next_inner.valid()) {
+    try { impl_->next_inner.get(); } catch (...) {}
+  }
+}
 const ReaderStats& Reader::stats() const { return impl_->stats; }
 const IOConfig& Reader::config() const { return impl_->cfg; }
 std::shared_ptr<arrow::Schema> Reader::schema() const { return impl_->out_schema; }
@@ -311,7 +509,7 @@ void Reader::Start() {
   trace_mark("start");
   // the scan slot (stream + device arena) is taken now: every file image is sent to the GPU as soon as
   // it is in pinned memory, overlapping the read of the next file
-  std::shared_ptr<ScanSession> session = begin_scan_session();
+  std::shared_ptr<ScanSession> session;  // taken below, once it is known that this reader scans by itself
   const bool early_upload = !force_host_decode();
   // Extension (option b200_file_groups = "n0,n1,..."): the file list is several hash buckets back to back, n_i files
   // each; every bucket is merged on its own, in ONE device scan (one framing pass, one launch set -- SURVEY.md 7.2
@@ -336,24 +534,57 @@ void Reader::Start() {
       ngroups = g;
     }
   }
-  // The whole scan group is resident at once (file images in pinned memory, decoded columns and outputs in HBM): a
-  // group far beyond what that can hold is refused up front with a clear message instead of failing in an allocator
-  // (streaming by primary-key range is not built).
-  {
+  // The whole scan group is resident at once (file images in pinned memory, decoded columns and outputs in HBM). A
+  // merged bucket whose files hold more than the pass budget is streamed instead: a sequence of scans over ascending
+  // primary-key ranges (plan_stream_passes above), each an inner reader with the range pushed as a key predicate;
+  // pass k + 1 is prepared while the caller consumes pass k. What cannot be split (no key, no statistics, file
+  // groups) stays one scan and is refused above LAKESOUL_B200_MAX_SCAN_BYTES with a clear message instead of failing
+  // in an allocator.
+  if (!cfg.lazy_files) {
     static const int64_t max_bytes = [] {
       const char* v = getenv("LAKESOUL_B200_MAX_SCAN_BYTES");
       return v ? atoll(v) : ((int64_t)24 << 30);
     }();
+    int64_t pass_bytes = (int64_t)4 << 30;  // uncompressed bytes per pass
+    {
+      std::string v;
+      if (cfg.option("b200_stream_pass_bytes", &v) && !v.empty()) pass_bytes = atoll(v.c_str());
+    }
     int64_t total = 0;
+    std::vector<std::string> paths;
     for (const auto& raw : cfg.files) {
       struct stat st0;
-      if (raw.find("://") == std::string::npos || raw.rfind("file:", 0) == 0)
-        if (stat(strip_scheme(raw).c_str(), &st0) == 0) total += (int64_t)st0.st_size;
+      if (raw.find("://") == std::string::npos || raw.rfind("file:", 0) == 0) {
+        paths.push_back(strip_scheme(raw));
+        if (stat(paths.back().c_str(), &st0) == 0) total += (int64_t)st0.st_size;
+      }
+    }
+    const bool merged = !cfg.primary_keys.empty() && !cfg.skip_merge_on_read();
+    // (file bytes are a lower bound of the uncompressed bytes: footers are read only when streaming is plausible)
+    if (pass_bytes > 0 && merged && ngroups == 1 && paths.size() == cfg.files.size() && total > pass_bytes / 8) {
+      bool nullable = true;
+      if (!cfg.inferring_schema && cfg.target_schema)
+        if (auto f = cfg.target_schema->GetFieldByName(cfg.primary_keys[0])) nullable = f->nullable();
+      I.pass_filters = plan_stream_passes(paths, cfg.primary_keys[0], nullable, pass_bytes);
+      if (I.pass_filters.size() > 1) {
+        I.pass = 0;
+        I.inner = I.make_pass(0);
+        I.out_schema = I.inner->schema();
+        I.absorb(I.inner->stats());
+        I.stats.pruned_row_groups = 0;  // (row groups outside a pass are not "pruned by the filter")
+        I.stats.stream_passes = (int32_t)I.pass_filters.size();
+        I.prefetch();
+        I.started = true;
+        return;
+      }
+      I.pass_filters.clear();
     }
     if (total > max_bytes)
       fail("the files of this reader hold " + std::to_string(total >> 20) + " MiB, more than LAKESOUL_B200_MAX_SCAN_BYTES (" +
-           std::to_string(max_bytes >> 20) + " MiB): the GPU reader keeps a whole scan group resident; compact the bucket or raise the limit");
+           std::to_string(max_bytes >> 20) + " MiB), and cannot be streamed by key range (no primary-key statistics, a single "
+           "key value, or several file groups): the GPU reader keeps a whole scan resident; compact the bucket or raise the limit");
   }
+  session = begin_scan_session();
   std::vector<FileInfo> files;
   size_t file_no = 0;
   for (const auto& raw : cfg.files) {
@@ -368,8 +599,8 @@ void Reader::Start() {
     FileInfo fi;
     fi.path = path;
     fi.group = this_group;
-    fi.raw = RawParquetFile::Open(path);
-    if (early_upload)
+    fi.raw = cfg.lazy_files ? RawParquetFile::OpenLazy(path) : RawParquetFile::Open(path);
+    if (early_upload && !cfg.lazy_files)
       fi.raw->set_device_image(session_upload(*session, fi.raw->image(), (size_t)fi.raw->image_bytes()));
     std::vector<std::shared_ptr<arrow::Field>> kept;
     for (const auto& f : fi.raw->schema()->fields())
@@ -399,6 +630,7 @@ void Reader::Start() {
   // ---- filters (config/mod.rs:702-731) -------------------------------------------------------
   std::vector<std::shared_ptr<FilterExpr>> fexprs;
   for (const auto& s : cfg.filter_strs) fexprs.push_back(parse_filter(s, *table_schema));
+  if (cfg.pass_filter) fexprs.push_back(cfg.pass_filter);
   std::shared_ptr<FilterExpr> filter = conjunction(fexprs);
   if (filter) {
     // predicates on default-valued / partition columns and on columns no file carries are constants: the reference
@@ -433,6 +665,15 @@ void Reader::Start() {
         fi.rows = fi.raw->num_rows();
       }
     }
+  }
+
+  if (cfg.lazy_files) {  // only now is it known which row groups this pass reads
+    for (auto& fi : files) {
+      fi.raw->LoadKept();
+      if (early_upload && fi.raw->image_bytes() > 0)
+        fi.raw->set_device_image(session_upload(*session, fi.raw->image(), (size_t)fi.raw->image_bytes()));
+    }
+    trace_mark("load_kept");
   }
 
   // ---- merged schema: requested + filter + pk + cdc columns, table order (file_format.rs:254-265)
@@ -491,8 +732,9 @@ void Reader::Start() {
   // ---- merge decision (merge/mod.rs:297-304) --------------------------------------------------
   bool merge_on_read;
   if (cfg.skip_merge_on_read() || cfg.primary_keys.empty()) merge_on_read = false;
-  else merge_on_read = !(cfg.files.size() == 1 && cfg.merge_operators.empty() && cfg.is_compacted());
-  // (with file groups a one-file bucket is merged like the others: a sorted, compacted file comes out unchanged)
+  else merge_on_read = cfg.lazy_files || !(cfg.files.size() == 1 && cfg.merge_operators.empty() && cfg.is_compacted());
+  // (with file groups, and in the passes of a streamed bucket, a one-file bucket is merged like the others: a sorted,
+  // compacted file comes out unchanged)
 
   if (files.empty()) {  // no valid file: empty stream with the requested schema
     I.started = true;
@@ -525,9 +767,8 @@ void Reader::Start() {
     }
     if (!host_only && getenv("LAKESOUL_B200_VERBOSE"))
       fprintf(stderr, "[lakesoul_b200] %s: host decode (%s)\n", fi.path.c_str(), why.c_str());
-    // host fallback: Arrow C++ decode from the pinned image already in memory
-    auto buf = std::make_shared<arrow::Buffer>(fi.raw->image(), fi.raw->image_bytes());
-    auto rd = parquet::arrow::OpenFile(std::make_shared<arrow::io::BufferReader>(buf), arrow::default_memory_pool());
+    // host fallback: Arrow C++ decode from the pinned image already in memory (a lazily opened file: image + pread)
+    auto rd = parquet::arrow::OpenFile(fi.raw->source(), arrow::default_memory_pool());
     if (!rd.ok()) fail(rd.status().ToString());
     std::unique_ptr<parquet::arrow::FileReader> reader = std::move(*rd);
     reader->set_use_threads(false);
@@ -624,6 +865,17 @@ std::shared_ptr<arrow::RecordBatch> Reader::Next() {
     if (I.count_rows_left <= 0) return nullptr;
     rows = std::min(bs, I.count_rows_left);
     I.count_rows_left -= rows;
+  } else if (!I.pass_filters.empty()) {  // streamed bucket: the passes one after the other
+    while (true) {
+      if (!I.inner) return nullptr;
+      if (auto b = I.inner->Next()) return b;  // (the inner reader already produced the output fields)
+      I.inner.reset();
+      if (I.pass + 1 >= I.pass_filters.size()) return nullptr;
+      I.inner = I.next_inner.get();  // rethrows what the pass threw
+      I.pass += 1;
+      I.absorb(I.inner->stats());
+      I.prefetch();
+    }
   } else {
     if (!I.scan) return nullptr;
     while (I.next_batch >= I.n_batches) {  // next bucket of the scan

@@ -16,6 +16,8 @@
 
 namespace lsb {
 
+struct FilterExpr;
+
 struct IOConfig {
   std::string prefix;
   std::vector<std::string> files;             // commit order: later file wins
@@ -39,6 +41,10 @@ struct IOConfig {
   std::map<std::string, std::string> default_column_value;  // column -> string value
   std::map<std::string, std::string> options;
 
+  // set by the reader itself for the passes of a bucket streamed by key range (never through the C-ABI)
+  std::shared_ptr<FilterExpr> pass_filter;    // key range of this pass, ANDed to the pushed filters
+  bool lazy_files = false;                    // footers first, then only the byte span of the row groups the pass keeps
+
   // config/mod.rs:157-162: option map first, then env LAKESOUL_<KEY>
   bool option(const std::string& key, std::string* out) const;
   std::string cdc_column() const;
@@ -51,6 +57,7 @@ struct ReaderStats {
   int64_t h2d_bytes = 0, d2h_bytes = 0;
   int32_t kernel_launches = 0;
   int64_t device_decoded_pages = 0, host_decoded_files = 0, pruned_row_groups = 0, device_decompressed_pages = 0;
+  int32_t stream_passes = 0;   // > 1: the bucket was read in that many passes over ascending primary-key ranges
   int64_t pruned_buckets = 0;  // 1: an equality filter on the whole key selects another hash bucket than this reader's
   double decode_ms = 0, upload_ms = 0, merge_ms = 0, gather_ms = 0, download_ms = 0;
   std::string path;  // "merge-full" | "merge-general" | "concat"
@@ -70,6 +77,12 @@ class Reader {
   struct Impl;
   std::unique_ptr<Impl> impl_;
 };
+
+// Key ranges for streaming a bucket (reader.cc): filters of the passes over ascending ranges of the first primary-key
+// column so that every pass decodes about `pass_bytes` (uncompressed) -- cut at row-group minima, from footers only.
+// Empty when the bucket cannot be split (no statistics, unsupported key type, one key value) or fits one pass.
+std::vector<std::shared_ptr<FilterExpr>> plan_stream_passes(const std::vector<std::string>& paths, const std::string& pk,
+                                                            bool pk_nullable, int64_t pass_bytes);
 
 // device selection for this process (LOCAL_RANK / LAKESOUL_B200_DEVICE aware); throws when no GPU.
 int ensure_device();
