@@ -36,6 +36,7 @@ typedef struct LsbReaderStats {
   int64_t pruned_row_groups;    /* row groups skipped by primary-key min/max statistics (pushed key filters) */
   int64_t device_decompressed_pages; /* ZSTD page payloads expanded by the GPU (the rest is decompressed on the host) */
   int64_t pruned_buckets;       /* 1: an equality filter on the whole primary key selects another hash bucket: nothing was read */
+  int64_t pruned_pages;         /* data pages skipped by the key columns' page index (pushed key filters) */
 } LsbReaderStats;
 int32_t lsb_reader_get_stats(CResult_Reader *reader, LsbReaderStats *out);
 
@@ -56,6 +57,9 @@ int64_t lsb_test_walk_page_heads(const uint8_t *image, int64_t off, int64_t len,
 /* test hook: frames row groups [rg_lo, rg_hi) of a file from the whole image (lazy = 0) or from the byte span of those row
  * groups (lazy = 1) and prints one position-independent line per page; returns the text length, -1 on error. */
 int64_t lsb_test_plan_digest(const char *path, int32_t lazy, int32_t rg_lo, int32_t rg_hi, char *out, int64_t cap);
+/* test hook: prunes row groups, then pages, of a file by a filter (parquet-mr string form) over the key columns `pks` (comma
+ * separated) and prints the live row range and the framed pages of every column */
+int64_t lsb_test_page_prune(const char *path, const char *filter, const char *pks, char *out, int64_t cap);
 /* test hook: the key-range filters of the passes a bucket with these files (newline separated) is streamed in, one per line */
 int64_t lsb_test_stream_passes(const char *files, const char *pk, const char *opts, int64_t pass_bytes, char *out, int64_t cap);
 

@@ -28,7 +28,7 @@ class LsbReaderStats(Structure):
                 ("kernel_launches", c_int32), ("stream_passes", c_int32), ("decode_ms", c_double), ("upload_ms", c_double),
                 ("merge_ms", c_double), ("gather_ms", c_double), ("download_ms", c_double),
                 ("device_decoded_pages", c_int64), ("host_decoded_files", c_int64), ("pruned_row_groups", c_int64),
-                ("device_decompressed_pages", c_int64), ("pruned_buckets", c_int64)]
+                ("device_decompressed_pages", c_int64), ("pruned_buckets", c_int64), ("pruned_pages", c_int64)]
 
 
 class LsbWriterStats(Structure):
@@ -108,6 +108,7 @@ EXT_SYMBOLS = {
     "lsb_writer_get_stats": (c_int32, [c_void_p, POINTER(LsbWriterStats)]),
     "lsb_test_walk_page_heads": (c_int64, [c_void_p, c_int64, c_int64, c_void_p, c_int64]),
     "lsb_test_plan_digest": (c_int64, [c_char_p, c_int32, c_int32, c_int32, c_void_p, c_int64]),
+    "lsb_test_page_prune": (c_int64, [c_char_p, c_char_p, c_char_p, c_void_p, c_int64]),
     "lsb_test_stream_passes": (c_int64, [c_char_p, c_char_p, c_char_p, c_int64, c_void_p, c_int64]),
     "lsb_plan_create": (c_void_p, [c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     "lsb_plan_destroy": (None, [c_void_p]),

@@ -493,6 +493,7 @@ int32_t lsb_reader_get_stats(CResult_Reader* reader, LsbReaderStats* out) {
   out->device_decoded_pages = s.device_decoded_pages; out->host_decoded_files = s.host_decoded_files;
   out->pruned_row_groups = s.pruned_row_groups;
   out->pruned_buckets = s.pruned_buckets;
+  out->pruned_pages = s.pruned_pages;
   out->device_decompressed_pages = s.device_decompressed_pages;
   return 0;
 }

@@ -315,7 +315,8 @@ struct DeviceScan::Impl : std::enable_shared_from_this<DeviceScan::Impl> {
   // input layout
   int nb = 0, F = 0, C = 0;
   std::vector<int32_t> bucket_file_begin;
-  std::vector<int64_t> file_rows, file_row_base;
+  std::vector<int64_t> file_rows, file_row_base;   // rows of every file in the column buffers (what was framed), their first row
+  std::vector<int64_t> live_rows, live_row_base;   // the rows the merge reads: all of them, or the page-pruned range
   std::vector<const FileInput*> file_in;
   int64_t span = 0;
 
@@ -399,17 +400,24 @@ void DeviceScan::Impl::layout() {
   F = bucket_file_begin[nb];
   file_rows.resize(F);
   file_row_base.resize(F);
+  live_rows.resize(F);
+  live_row_base.resize(F);
   file_in.resize(F);
   int64_t pos = 0;
   for (int b = 0, f = 0; b < nb; ++b) {
     for (auto& fi : buckets[b].files) {
       file_in[f] = &fi;
-      file_rows[f] = fi.raw ? fi.raw->num_rows() : fi.table->num_rows();
+      file_rows[f] = fi.raw ? fi.raw->layout_rows() : fi.table->num_rows();
       // 64-row alignment keeps validity bitmaps byte-copyable and 16-byte alignment for
       // every fixed width; the spare row after each file holds the closing string offset.
       file_row_base[f] = pos;
+      // page pruning by a pushed key predicate (RawParquetFile::PrunePages): only the pages that overlap the rows that
+      // can match were framed; the merge reads that row range of the file, the boundary pages' other rows are decoded
+      // but never referenced
+      live_rows[f] = fi.raw ? fi.raw->live_rows() : file_rows[f];
+      live_row_base[f] = pos + (fi.raw ? fi.raw->live_offset() : 0);
       pos = (pos + file_rows[f] + 1 + 63) & ~63ll;
-      ctr.rows_in += file_rows[f];
+      ctr.rows_in += live_rows[f];
       if (!fi.raw) ctr.host_decoded_files += 1;
       ++f;
     }
@@ -1007,7 +1015,7 @@ void DeviceScan::Impl::merge_and_gather() {
   }
 
   const double t0 = now_ms();
-  plan = plan_create(nb, bucket_file_begin.data(), file_rows.data(), file_row_base.data(), span,
+  plan = plan_create(nb, bucket_file_begin.data(), live_rows.data(), live_row_base.data(), span,
                      do_merge ? key_bits : 64, spec.batch_size, stream);
   if (do_merge && encoded_keys) {
     // the encoder walks string offsets of the key columns: a malformed page must surface as its own error first

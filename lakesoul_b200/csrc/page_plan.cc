@@ -8,6 +8,7 @@
 #include <parquet/column_reader.h>
 #include <parquet/file_reader.h>
 #include <parquet/metadata.h>
+#include <parquet/page_index.h>
 #include <parquet/statistics.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -357,6 +358,7 @@ std::shared_ptr<RawParquetFile> RawParquetFile::Open(const std::string& path) {
   auto buf = std::make_shared<arrow::Buffer>(f->image_.get(), f->image_bytes_);
   f->source_ = std::make_shared<arrow::io::BufferReader>(buf);
   parse_footer(f->source_, &f->reader_, &f->rows_, &f->schema_, &f->kept_rg_);
+  f->live_hi_ = f->layout_rows_ = f->rows_;
   return f;
 }
 
@@ -372,6 +374,7 @@ std::shared_ptr<RawParquetFile> RawParquetFile::OpenLazy(const std::string& path
   f->loaded_ = false;
   f->source_ = std::make_shared<WindowFile>(fd, (int64_t)st.st_size);  // owns fd
   parse_footer(f->source_, &f->reader_, &f->rows_, &f->schema_, &f->kept_rg_);
+  f->live_hi_ = f->layout_rows_ = f->rows_;
   return f;
 }
 
@@ -436,31 +439,32 @@ struct Bound {          // min / max of one column chunk, comparable with a lite
   double rmin = 0, rmax = 0;
   std::string bmin, bmax;
   int64_t nulls = -1;   // null count of the chunk, -1 unknown
+  bool all_null = false;  // a page of nulls only (column index null_pages)
 };
 
-Bound chunk_bound(const parquet::ColumnChunkMetaData& ccm, const parquet::ColumnDescriptor& cd, const arrow::DataType& type) {
-  Bound b;
-  if (!ccm.is_stats_set()) return b;
-  auto st = ccm.statistics();
-  if (!st) return b;
-  if (st->HasNullCount()) b.nulls = st->null_count();
-  else if (cd.max_definition_level() == 0) b.nulls = 0;
-  if (!st->HasMinMax()) return b;
+// min / max as the statistics or the column index hold them, before the column's logical type is applied
+struct RawMinMax {
+  int64_t imin = 0, imax = 0;
+  double rmin = 0, rmax = 0;
+  std::string bmin, bmax;
+};
+
+// applies the logical type: which family the values compare in, unsigned reinterpretation, timestamp units
+void finish_bound(Bound* bp, parquet::Type::type phys, const arrow::DataType& type, const RawMinMax& m) {
+  Bound& b = *bp;
   using AT = arrow::Type;
-  switch (cd.physical_type()) {
+  switch (phys) {
     case parquet::Type::INT32: {
-      if (!arrow::is_integer(type.id()) && type.id() != AT::DATE32 && type.id() != AT::TIME32) return b;
-      auto ts = std::static_pointer_cast<parquet::Int32Statistics>(st);
+      if (!arrow::is_integer(type.id()) && type.id() != AT::DATE32 && type.id() != AT::TIME32) return;
       const bool uns = arrow::is_unsigned_integer(type.id());
-      b.imin = uns ? (int64_t)(uint32_t)ts->min() : ts->min();
-      b.imax = uns ? (int64_t)(uint32_t)ts->max() : ts->max();
+      b.imin = uns ? (int64_t)(uint32_t)(int32_t)m.imin : m.imin;
+      b.imax = uns ? (int64_t)(uint32_t)(int32_t)m.imax : m.imax;
       b.fam = Bound::kInt;
     } break;
     case parquet::Type::INT64: {
-      if (type.id() == AT::UINT64) return b;  // would need unsigned 64-bit compares: not worth a special case
-      if (!arrow::is_integer(type.id()) && type.id() != AT::TIMESTAMP && type.id() != AT::TIME64) return b;
-      auto ts = std::static_pointer_cast<parquet::Int64Statistics>(st);
-      b.imin = ts->min(); b.imax = ts->max(); b.fam = Bound::kInt;
+      if (type.id() == AT::UINT64) return;  // would need unsigned 64-bit compares: not worth a special case
+      if (!arrow::is_integer(type.id()) && type.id() != AT::TIMESTAMP && type.id() != AT::TIME64) return;
+      b.imin = m.imin; b.imax = m.imax; b.fam = Bound::kInt;
       if (type.id() == AT::TIMESTAMP) {
         // filter literals are microseconds (filter.cc parse_literal); the statistics are in the column's own
         // unit. Bring the bounds to microseconds, widening (never narrowing) the interval; no bound on overflow.
@@ -476,29 +480,96 @@ Bound chunk_bound(const parquet::ColumnChunkMetaData& ccm, const parquet::Column
         if (unit == arrow::TimeUnit::SECOND) mul(1000000);
         else if (unit == arrow::TimeUnit::MILLI) mul(1000);
         else if (unit == arrow::TimeUnit::NANO) {
+          const int64_t hi = b.imax;
           b.imin = floor_div(b.imin, 1000);
-          b.imax = floor_div(b.imax, 1000) + (b.imax % 1000 != 0 ? 1 : 0);
+          b.imax = floor_div(hi, 1000) + (hi % 1000 != 0 ? 1 : 0);
         }
       }
     } break;
-    case parquet::Type::FLOAT: {
-      auto ts = std::static_pointer_cast<parquet::FloatStatistics>(st);
-      b.rmin = ts->min(); b.rmax = ts->max(); b.fam = Bound::kReal;
-    } break;
-    case parquet::Type::DOUBLE: {
-      auto ts = std::static_pointer_cast<parquet::DoubleStatistics>(st);
-      b.rmin = ts->min(); b.rmax = ts->max(); b.fam = Bound::kReal;
-    } break;
-    case parquet::Type::BYTE_ARRAY: {
-      if (type.id() != AT::STRING && type.id() != AT::BINARY) return b;
-      auto ts = std::static_pointer_cast<parquet::ByteArrayStatistics>(st);
-      b.bmin.assign(reinterpret_cast<const char*>(ts->min().ptr), ts->min().len);
-      b.bmax.assign(reinterpret_cast<const char*>(ts->max().ptr), ts->max().len);
-      b.fam = Bound::kBytes;
-    } break;
+    case parquet::Type::FLOAT:
+    case parquet::Type::DOUBLE:
+      b.rmin = m.rmin; b.rmax = m.rmax; b.fam = Bound::kReal;
+      break;
+    case parquet::Type::BYTE_ARRAY:
+      if (type.id() != AT::STRING && type.id() != AT::BINARY) return;
+      b.bmin = m.bmin; b.bmax = m.bmax; b.fam = Bound::kBytes;
+      break;
     default: break;
   }
   if (b.fam == Bound::kReal && (b.rmin != b.rmin || b.rmax != b.rmax)) b.fam = Bound::kNone;  // NaN bounds
+}
+
+Bound chunk_bound(const parquet::ColumnChunkMetaData& ccm, const parquet::ColumnDescriptor& cd, const arrow::DataType& type) {
+  Bound b;
+  if (!ccm.is_stats_set()) return b;
+  auto st = ccm.statistics();
+  if (!st) return b;
+  if (st->HasNullCount()) b.nulls = st->null_count();
+  else if (cd.max_definition_level() == 0) b.nulls = 0;
+  if (!st->HasMinMax()) return b;
+  RawMinMax m;
+  switch (cd.physical_type()) {
+    case parquet::Type::INT32: {
+      auto ts = std::static_pointer_cast<parquet::Int32Statistics>(st);
+      m.imin = ts->min(); m.imax = ts->max();
+    } break;
+    case parquet::Type::INT64: {
+      auto ts = std::static_pointer_cast<parquet::Int64Statistics>(st);
+      m.imin = ts->min(); m.imax = ts->max();
+    } break;
+    case parquet::Type::FLOAT: {
+      auto ts = std::static_pointer_cast<parquet::FloatStatistics>(st);
+      m.rmin = ts->min(); m.rmax = ts->max();
+    } break;
+    case parquet::Type::DOUBLE: {
+      auto ts = std::static_pointer_cast<parquet::DoubleStatistics>(st);
+      m.rmin = ts->min(); m.rmax = ts->max();
+    } break;
+    case parquet::Type::BYTE_ARRAY: {
+      auto ts = std::static_pointer_cast<parquet::ByteArrayStatistics>(st);
+      m.bmin.assign(reinterpret_cast<const char*>(ts->min().ptr), ts->min().len);
+      m.bmax.assign(reinterpret_cast<const char*>(ts->max().ptr), ts->max().len);
+    } break;
+    default: return b;
+  }
+  finish_bound(&b, cd.physical_type(), type, m);
+  return b;
+}
+
+// the same for page `i` of a column index (min / max of every page of a column chunk)
+Bound page_bound(const parquet::ColumnIndex& ci, size_t i, const parquet::ColumnDescriptor& cd, const arrow::DataType& type) {
+  Bound b;
+  if (ci.has_null_counts() && i < ci.null_counts().size()) b.nulls = ci.null_counts()[i];
+  else if (cd.max_definition_level() == 0) b.nulls = 0;
+  if (i < ci.null_pages().size() && ci.null_pages()[i]) { b.all_null = true; return b; }
+  RawMinMax m;
+  switch (cd.physical_type()) {
+    case parquet::Type::INT32: {
+      const auto& t = static_cast<const parquet::Int32ColumnIndex&>(ci);
+      m.imin = t.min_values()[i]; m.imax = t.max_values()[i];
+    } break;
+    case parquet::Type::INT64: {
+      const auto& t = static_cast<const parquet::Int64ColumnIndex&>(ci);
+      m.imin = t.min_values()[i]; m.imax = t.max_values()[i];
+    } break;
+    case parquet::Type::FLOAT: {
+      const auto& t = static_cast<const parquet::FloatColumnIndex&>(ci);
+      m.rmin = t.min_values()[i]; m.rmax = t.max_values()[i];
+    } break;
+    case parquet::Type::DOUBLE: {
+      const auto& t = static_cast<const parquet::DoubleColumnIndex&>(ci);
+      m.rmin = t.min_values()[i]; m.rmax = t.max_values()[i];
+    } break;
+    case parquet::Type::BYTE_ARRAY: {
+      const auto& t = static_cast<const parquet::ByteArrayColumnIndex&>(ci);
+      const auto& lo = t.min_values()[i];
+      const auto& hi = t.max_values()[i];
+      m.bmin.assign(reinterpret_cast<const char*>(lo.ptr), lo.len);
+      m.bmax.assign(reinterpret_cast<const char*>(hi.ptr), hi.len);
+    } break;
+    default: return b;
+  }
+  finish_bound(&b, cd.physical_type(), type, m);
   return b;
 }
 
@@ -566,6 +637,7 @@ Possible possible(const FilterExpr& e, const BoundFn& bound_of) {
     case FilterExpr::kCmp: {
       if (!e.literal) return unknown;
       const Bound b = bound_of(e.column);
+      if (b.all_null) return {false, false};  // NULL for every row: neither TRUE nor FALSE
       int cmin = 0, cmax = 0;
       if (b.fam == Bound::kNone || !compare_literal(b, *e.literal, &cmin, &cmax)) return unknown;
       // values of the chunk lie in [min, max]; cmin/cmax = sign(min - lit), sign(max - lit)
@@ -581,10 +653,12 @@ Possible possible(const FilterExpr& e, const BoundFn& bound_of) {
     }
     case FilterExpr::kIsNull: {  // a chunk proven free of nulls cannot satisfy it
       const Bound b = bound_of(e.column);
+      if (b.all_null) return {true, false};
       return b.nulls == 0 ? Possible{false, true} : unknown;
     }
     case FilterExpr::kIsNotNull: {
       const Bound b = bound_of(e.column);
+      if (b.all_null) return {false, true};
       return b.nulls == 0 ? Possible{true, false} : unknown;
     }
     default: return unknown;
@@ -616,7 +690,85 @@ int RawParquetFile::PruneRowGroups(const FilterExpr& filter, const std::set<std:
   const int dropped = (int)(kept_rg_.size() - kept.size());
   kept_rg_ = std::move(kept);
   rows_ = rows;
+  live_lo_ = 0;
+  live_hi_ = layout_rows_ = rows_;
   return dropped;
+}
+
+int64_t RawParquetFile::PrunePages(const FilterExpr& filter, const std::set<std::string>& pk_columns) {
+  auto* rd = static_cast<parquet::ParquetFileReader*>(reader_.get());
+  auto md = rd->metadata();
+  const auto* sd = md->schema();
+  if (sd->num_columns() != schema_->num_fields() || kept_rg_.empty()) return 0;
+  std::set<std::string> fcols;
+  filter_columns(filter, &fcols);
+  std::vector<int> key_cis;
+  for (const auto& n : fcols)
+    if (pk_columns.count(n) && schema_->GetFieldIndex(n) >= 0) key_cis.push_back(schema_->GetFieldIndex(n));
+  if (key_cis.empty()) return 0;
+  std::shared_ptr<parquet::PageIndexReader> pir;
+  try {
+    pir = rd->GetPageIndexReader();
+  } catch (const std::exception&) {
+    return 0;
+  }
+  if (!pir) return 0;
+  int64_t lo = INT64_MAX, hi = -1;  // hull of the rows that can match, in kept-row coordinates
+  int64_t rg_first = 0;
+  bool any_index = false;
+  for (int rg : kept_rg_) {
+    const int64_t rg_rows = md->RowGroup(rg)->num_rows();
+    int64_t a = 0, b = rg_rows;  // this row group: intersection over the key columns of the hulls of their possible pages
+    std::shared_ptr<parquet::RowGroupPageIndexReader> rgi;
+    try {
+      rgi = pir->RowGroup(rg);
+    } catch (const std::exception&) {
+      rgi = nullptr;
+    }
+    for (int ci : key_cis) {
+      if (!rgi) break;
+      std::shared_ptr<parquet::ColumnIndex> cidx;
+      std::shared_ptr<parquet::OffsetIndex> oidx;
+      try {
+        cidx = rgi->GetColumnIndex(ci);
+        oidx = rgi->GetOffsetIndex(ci);
+      } catch (const std::exception&) {
+        continue;
+      }
+      if (!cidx || !oidx) continue;
+      const auto& locs = oidx->page_locations();
+      const size_t np = locs.size();
+      if (np == 0 || cidx->null_pages().size() != np) continue;
+      any_index = true;
+      const std::string& cname = schema_->field(ci)->name();
+      int64_t ca = rg_rows, cb = 0;
+      for (size_t i = 0; i < np; ++i) {
+        BoundFn bound_of = [&](const std::string& name) -> Bound {
+          if (name != cname) return Bound{};
+          return page_bound(*cidx, i, *sd->Column(ci), *schema_->field(ci)->type());
+        };
+        if (!possible(filter, bound_of).t) continue;
+        const int64_t start = locs[i].first_row_index;
+        const int64_t end = i + 1 < np ? locs[i + 1].first_row_index : rg_rows;
+        ca = std::min(ca, start);
+        cb = std::max(cb, end);
+      }
+      a = std::max(a, ca);
+      b = std::min(b, cb);
+      if (a >= b) break;
+    }
+    if (a < b) {
+      lo = std::min(lo, rg_first + a);
+      hi = std::max(hi, rg_first + b);
+    }
+    rg_first += rg_rows;
+  }
+  if (!any_index) return 0;
+  if (hi < 0) lo = hi = 0;  // no page can hold a match
+  page_pruned_ = true;
+  live_lo_ = lo;
+  live_hi_ = hi;
+  return rows_ - (hi - lo);
 }
 
 void RawParquetFile::KeepRowGroups(int lo, int hi) {
@@ -628,6 +780,8 @@ void RawParquetFile::KeepRowGroups(int lo, int hi) {
     if (rg >= lo && rg < hi) { kept.push_back(rg); rows += md->RowGroup(rg)->num_rows(); }
   kept_rg_ = std::move(kept);
   rows_ = rows;
+  live_lo_ = 0;
+  live_hi_ = layout_rows_ = rows_;
 }
 
 std::vector<RowGroupKeyRange> RawParquetFile::KeyRanges(const std::string& column) const {
@@ -661,6 +815,8 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
   const auto* sd = md->schema();
   cols_.clear();
   cols_.resize(want.size());
+  pruned_pages_ = 0;
+  int64_t emit_lo = INT64_MAX, emit_hi = -1;  // rows covered by the framed pages (kept-row coordinates)
   // flat schemas only: leaf index == field index
   if (sd->num_columns() != schema_->num_fields()) { *why = "nested schema"; return false; }
   // which compressed column chunks the GPU expands. SNAPPY: all of them; ZSTD: by the configured share / size policy
@@ -788,6 +944,11 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
     // pages
     int64_t first_row = 0;
     for (int rg : kept_rg_) {
+      if (page_pruned_) {  // a row group outside the rows that can match: nothing of it is framed
+        if (!rg_md[(size_t)rg]) rg_md[(size_t)rg] = md->RowGroup(rg);
+        const int64_t n = rg_md[(size_t)rg]->num_rows();
+        if (first_row + n <= live_lo_ || first_row >= live_hi_) { first_row += n; continue; }
+      }
       auto* ccm = chunk_md(rg, ci);
       for (auto e : ccm->encodings())
         if (map_encoding(e) < 0) { *why = "encoding " + parquet::EncodingToString(e) + " in column " + rc.name; return false; }
@@ -950,13 +1111,18 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
           if (!(pg.encoding == ENC_PLAIN || is_dict || rle_bool)) { *why = "value encoding " + parquet::EncodingToString(enc) + " in column " + rc.name; return false; }
           if (is_dict && dict_idx < 0) { *why = "dictionary page missing"; return false; }
           if (pc.conv == CONV_BOOL && is_dict) { *why = "dictionary coded boolean"; return false; }
-          place(&pg.src_off, &pg.aux);
-          pg.size = (int32_t)size;
           if (raw_zstd && v2 && row_in_rg == 0) {
             // v2 pages keep their levels outside the compressed section: let libparquet decompress this chunk
             if (!restart_on_host()) return false;
             continue;
           }
+          if (page_pruned_ && (first_row + row_in_rg + pg.num_values <= live_lo_ || first_row + row_in_rg >= live_hi_)) {
+            row_in_rg += pg.num_values;  // no row of this page can match the pushed key predicate
+            pruned_pages_ += 1;
+            continue;
+          }
+          place(&pg.src_off, &pg.aux);
+          pg.size = (int32_t)size;
           if (raw_zstd) {
             if (v2 || pg.aux || page.uncompressed <= 0 || page.uncompressed > (int64_t)1 << 30) {
               *why = "ZSTD page shape in column " + rc.name;
@@ -968,6 +1134,8 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
           }
           pg.row_group = rg;
           pg.first_row = first_row + row_in_rg;
+          emit_lo = std::min(emit_lo, pg.first_row);
+          emit_hi = std::max(emit_hi, pg.first_row + pg.num_values);
           row_in_rg += pg.num_values;
           rc.pages.push_back(pg);
           rc.page_dict.push_back(is_dict ? dict_idx : -1);
@@ -976,6 +1144,16 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
       if (row_in_rg != rg_md[(size_t)rg]->num_rows()) { *why = "page row count mismatch in column " + rc.name; return false; }
       first_row += rg_md[(size_t)rg]->num_rows();
     }
+  }
+  // the file's rows in the scan = what was framed; pages count from there
+  if (page_pruned_) {
+    origin_ = emit_lo <= emit_hi ? emit_lo : live_lo_;
+    layout_rows_ = emit_lo <= emit_hi ? emit_hi - emit_lo : 0;
+    for (auto& c : cols_)
+      for (auto& pg : c.pages) pg.first_row -= origin_;
+  } else {
+    origin_ = 0;
+    layout_rows_ = rows_;
   }
   return true;
 }
@@ -1019,6 +1197,43 @@ extern "C" __attribute__((visibility("default"))) int64_t lsb_test_plan_digest(c
     return -1;
   }
   if ((int64_t)text.size() + 1 > cap) { snprintf(out, (size_t)cap, "digest needs %zu bytes", text.size() + 1); return -1; }
+  memcpy(out, text.c_str(), text.size() + 1);
+  return (int64_t)text.size();
+}
+
+// test hook (tests/test_page_pruning.py): row groups, then pages, pruned by `filter` (parquet-mr string form) over the key
+// columns `pks` (comma separated); prints the live range and the framed pages of every column.
+extern "C" __attribute__((visibility("default"))) int64_t lsb_test_page_prune(const char* path, const char* filter, const char* pks, char* out,
+                                                                              int64_t cap) {
+  std::string text;
+  try {
+    auto f = RawParquetFile::Open(path);
+    std::set<std::string> pk;
+    std::string cur;
+    for (const char* p = pks; ; ++p) {
+      if (*p == ',' || *p == 0) { if (!cur.empty()) pk.insert(cur); cur.clear(); if (*p == 0) break; }
+      else cur.push_back(*p);
+    }
+    auto fe = parse_filter(filter, *f->schema());
+    const int dropped = f->PruneRowGroups(*fe, pk);
+    const int64_t outside = f->PrunePages(*fe, pk);
+    std::vector<std::shared_ptr<arrow::Field>> want = f->schema()->fields();
+    std::string why;
+    if (!f->Plan(want, &why)) throw std::runtime_error("not framed: " + why);
+    text += "dropped_rg " + std::to_string(dropped) + " first_kept_rg " + std::to_string(f->kept_row_groups().empty() ? -1 : f->kept_row_groups()[0]) +
+            " kept_rows " + std::to_string(f->num_rows()) + " outside " + std::to_string(outside) + " live_begin " +
+            std::to_string(f->live_begin()) + " live_rows " + std::to_string(f->live_rows()) + " live_offset " + std::to_string(f->live_offset()) +
+            " layout_rows " + std::to_string(f->layout_rows()) + " pruned_pages " + std::to_string(f->pruned_pages()) + "\n";
+    for (const auto& c : f->columns()) {
+      text += "C " + c.name;
+      for (const auto& g : c.pages) text += " " + std::to_string(g.first_row) + ":" + std::to_string(g.num_values);
+      text += "\n";
+    }
+  } catch (const std::exception& e) {
+    snprintf(out, (size_t)cap, "%s", e.what());
+    return -1;
+  }
+  if ((int64_t)text.size() + 1 > cap) { snprintf(out, (size_t)cap, "needs %zu bytes", text.size() + 1); return -1; }
   memcpy(out, text.c_str(), text.size() + 1);
   return (int64_t)text.size();
 }

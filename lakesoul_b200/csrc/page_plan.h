@@ -83,6 +83,21 @@ class RawParquetFile {
   // by a key predicate is pruned in every file alike and the merge result is unchanged. Call before Plan();
   // num_rows() then counts the kept row groups. Returns the number of row groups dropped.
   int PruneRowGroups(const FilterExpr& filter, const std::set<std::string>& pk_columns);
+  // Page-level refinement (reference session.rs:685-717 enables the page index for exactly this): the min / max of the
+  // key columns' PAGES (ColumnIndex + OffsetIndex, written by parquet-rs by default) narrow the rows in which `filter`
+  // can be TRUE to one contiguous range of the kept rows -- contiguous because a file is sorted by primary key; for
+  // predicates that are not a range the range is the hull. Plan() then frames only the pages that overlap it, the merge
+  // takes rows [live_offset(), live_offset() + live_rows()) of the file's (smaller) row space. Call after
+  // PruneRowGroups(), before Plan(). Returns the number of kept rows outside the range (0 without a page index).
+  int64_t PrunePages(const FilterExpr& filter, const std::set<std::string>& pk_columns);
+  // After Plan(): the rows of this file in the scan's row space = pages framed (layout_rows), of which the merge reads
+  // [live_offset, live_offset + live_rows). Without page pruning: layout_rows = live_rows = num_rows, offset 0.
+  int64_t layout_rows() const { return layout_rows_; }
+  int64_t live_offset() const { return live_lo_ - origin_; }
+  int64_t live_rows() const { return live_hi_ - live_lo_; }
+  // the live range in kept-row coordinates (host-decoded files are sliced by it)
+  int64_t live_begin() const { return live_lo_; }
+  int64_t pruned_pages() const { return pruned_pages_; }
   const std::vector<int>& kept_row_groups() const { return kept_rg_; }  // indices, ascending (all by default)
   void KeepRowGroups(int lo, int hi);  // keeps the kept row groups with lo <= index < hi (before LoadKept / Plan)
 
@@ -109,6 +124,8 @@ class RawParquetFile {
   std::shared_ptr<uint8_t> image_, aux_;
   int64_t image_bytes_ = 0, aux_cap_ = 0, aux_used_ = 0, rows_ = 0;
   int64_t base_ = 0, file_bytes_ = 0;
+  int64_t live_lo_ = 0, live_hi_ = 0, origin_ = 0, layout_rows_ = 0, pruned_pages_ = 0;
+  bool page_pruned_ = false;
   bool lazy_ = false, loaded_ = true;
   std::shared_ptr<arrow::io::RandomAccessFile> source_;
   std::shared_ptr<arrow::Schema> schema_;

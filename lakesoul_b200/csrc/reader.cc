@@ -434,6 +434,7 @@ struct Reader::Impl {
     stats.kernel_launches += s.kernel_launches;
     stats.device_decoded_pages += s.device_decoded_pages; stats.host_decoded_files += s.host_decoded_files;
     stats.device_decompressed_pages += s.device_decompressed_pages;
+    stats.pruned_pages += s.pruned_pages;
     stats.decode_ms += s.decode_ms; stats.upload_ms += s.upload_ms; stats.merge_ms += s.merge_ms;
     stats.gather_ms += s.gather_ms; stats.download_ms += s.download_ms;
     stats.path = s.path;
@@ -660,8 +661,10 @@ void Reader::Start() {
     bool touches_pk = false;
     for (const auto& c : fcols) touches_pk = touches_pk || pk_set.count(c) > 0;
     if (touches_pk) {
+      static const bool page_pruning = [] { const char* v = getenv("LAKESOUL_B200_PAGE_PRUNING"); return !(v && *v == '0'); }();
       for (auto& fi : files) {
         I.stats.pruned_row_groups += fi.raw->PruneRowGroups(*filter, pk_set);
+        if (page_pruning) fi.raw->PrunePages(*filter, pk_set);  // session.rs:685-717: the reference prunes by page index too
         fi.rows = fi.raw->num_rows();
       }
     }
@@ -762,6 +765,7 @@ void Reader::Start() {
     if (!host_only && fi.raw->Plan(phys_fields, &why)) {
       FileInput in;
       in.raw = fi.raw;
+      I.stats.pruned_pages += fi.raw->pruned_pages();
       groups[(size_t)fi.group].files.push_back(std::move(in));
       continue;
     }
@@ -788,6 +792,7 @@ void Reader::Start() {
     auto tr = reader->ReadRowGroups(fi.raw->kept_row_groups(), leaf);
     if (!tr.ok()) fail(tr.status().ToString());
     std::shared_ptr<arrow::Table> table = *tr;
+    if (fi.raw->live_rows() != table->num_rows()) table = table->Slice(fi.raw->live_begin(), fi.raw->live_rows());  // page-pruned
     // a2: reorder to target order + cast to the target type (helpers/transform.rs:107-354)
     std::vector<std::shared_ptr<arrow::ChunkedArray>> cols;
     std::vector<std::shared_ptr<arrow::Field>> flds;

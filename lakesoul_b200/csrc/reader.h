@@ -58,6 +58,7 @@ struct ReaderStats {
   int32_t kernel_launches = 0;
   int64_t device_decoded_pages = 0, host_decoded_files = 0, pruned_row_groups = 0, device_decompressed_pages = 0;
   int32_t stream_passes = 0;   // > 1: the bucket was read in that many passes over ascending primary-key ranges
+  int64_t pruned_pages = 0;    // data pages outside the rows in which a pushed key predicate can hold (column index)
   int64_t pruned_buckets = 0;  // 1: an equality filter on the whole key selects another hash bucket than this reader's
   double decode_ms = 0, upload_ms = 0, merge_ms = 0, gather_ms = 0, download_ms = 0;
   std::string path;  // "merge-full" | "merge-general" | "concat"
