@@ -59,7 +59,7 @@ int64_t lsb_test_walk_page_heads(const uint8_t *image, int64_t off, int64_t len,
 int64_t lsb_test_plan_digest(const char *path, int32_t lazy, int32_t rg_lo, int32_t rg_hi, char *out, int64_t cap);
 /* test hook: prunes row groups, then pages, of a file by a filter (parquet-mr string form) over the key columns `pks` (comma
  * separated) and prints the live row range and the framed pages of every column */
-int64_t lsb_test_page_prune(const char *path, const char *filter, const char *pks, char *out, int64_t cap);
+int64_t lsb_test_page_prune(const char *path, const char *filter, const char *pks, int32_t lazy, char *out, int64_t cap);
 /* test hook: the key-range filters of the passes a bucket with these files (newline separated) is streamed in, one per line */
 int64_t lsb_test_stream_passes(const char *files, const char *pk, const char *opts, int64_t pass_bytes, char *out, int64_t cap);
 

@@ -108,7 +108,7 @@ EXT_SYMBOLS = {
     "lsb_writer_get_stats": (c_int32, [c_void_p, POINTER(LsbWriterStats)]),
     "lsb_test_walk_page_heads": (c_int64, [c_void_p, c_int64, c_int64, c_void_p, c_int64]),
     "lsb_test_plan_digest": (c_int64, [c_char_p, c_int32, c_int32, c_int32, c_void_p, c_int64]),
-    "lsb_test_page_prune": (c_int64, [c_char_p, c_char_p, c_char_p, c_void_p, c_int64]),
+    "lsb_test_page_prune": (c_int64, [c_char_p, c_char_p, c_char_p, c_int32, c_void_p, c_int64]),
     "lsb_test_stream_passes": (c_int64, [c_char_p, c_char_p, c_char_p, c_int64, c_void_p, c_int64]),
     "lsb_plan_create": (c_void_p, [c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     "lsb_plan_destroy": (None, [c_void_p]),

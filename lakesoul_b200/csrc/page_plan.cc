@@ -238,7 +238,17 @@ class WindowFile : public arrow::io::RandomAccessFile {
  public:
   WindowFile(int fd, int64_t size) : fd_(fd), size_(size) {}
   ~WindowFile() override { if (fd_ >= 0) ::close(fd_); }
-  void set_window(const uint8_t* p, int64_t base, int64_t len) { win_ = p; base_ = base; len_ = len; }
+  void set_segments(const uint8_t* image, std::vector<RawParquetFile::Segment> segs) { win_ = image; segs_ = std::move(segs); }
+  // image position of [position, position + nbytes) when one loaded segment holds all of it, else nullptr
+  const uint8_t* loaded(int64_t position, int64_t nbytes) const {
+    if (!win_ || segs_.empty()) return nullptr;
+    auto it = std::upper_bound(segs_.begin(), segs_.end(), position,
+                               [](int64_t p, const RawParquetFile::Segment& s) { return p < s.file_off; });
+    if (it == segs_.begin()) return nullptr;
+    --it;
+    if (position + nbytes > it->file_off + it->len) return nullptr;
+    return win_ + it->img_off + (position - it->file_off);
+  }
   arrow::Status Close() override {
     if (fd_ >= 0) ::close(fd_);
     fd_ = -1;
@@ -266,8 +276,8 @@ class WindowFile : public arrow::io::RandomAccessFile {
     if (position < 0 || nbytes < 0) return arrow::Status::IOError("bad read");
     nbytes = std::max<int64_t>(0, std::min(nbytes, size_ - position));
     if (nbytes == 0) return 0;
-    if (win_ && position >= base_ && position + nbytes <= base_ + len_) {
-      memcpy(out, win_ + (position - base_), (size_t)nbytes);
+    if (const uint8_t* src = loaded(position, nbytes)) {
+      memcpy(out, src, (size_t)nbytes);
       return nbytes;
     }
     if (fd_ < 0) return arrow::Status::IOError("file is closed");
@@ -282,8 +292,8 @@ class WindowFile : public arrow::io::RandomAccessFile {
   arrow::Result<std::shared_ptr<arrow::Buffer>> ReadAt(int64_t position, int64_t nbytes) override {
     if (position < 0 || nbytes < 0) return arrow::Status::IOError("bad read");
     nbytes = std::max<int64_t>(0, std::min(nbytes, size_ - position));
-    if (win_ && nbytes > 0 && position >= base_ && position + nbytes <= base_ + len_)
-      return std::make_shared<arrow::Buffer>(win_ + (position - base_), nbytes);  // the owner outlives every reader
+    if (nbytes > 0)
+      if (const uint8_t* src = loaded(position, nbytes)) return std::make_shared<arrow::Buffer>(src, nbytes);  // the owner outlives every reader
     ARROW_ASSIGN_OR_RAISE(auto buf, arrow::AllocateResizableBuffer(nbytes));
     ARROW_ASSIGN_OR_RAISE(int64_t n, ReadAt(position, nbytes, buf->mutable_data()));
     if (n != nbytes) ARROW_RETURN_NOT_OK(buf->Resize(n));
@@ -294,7 +304,7 @@ class WindowFile : public arrow::io::RandomAccessFile {
   int fd_;
   int64_t size_, pos_ = 0;
   const uint8_t* win_ = nullptr;
-  int64_t base_ = 0, len_ = 0;
+  std::vector<RawParquetFile::Segment> segs_;
 };
 
 // footer -> row count, Arrow schema, row-group list
@@ -355,6 +365,7 @@ std::shared_ptr<RawParquetFile> RawParquetFile::Open(const std::string& path) {
     got += n;
   }
   ::close(fd);
+  f->segs_.push_back(Segment{0, f->image_bytes_, 0});
   auto buf = std::make_shared<arrow::Buffer>(f->image_.get(), f->image_bytes_);
   f->source_ = std::make_shared<arrow::io::BufferReader>(buf);
   parse_footer(f->source_, &f->reader_, &f->rows_, &f->schema_, &f->kept_rg_);
@@ -378,33 +389,118 @@ std::shared_ptr<RawParquetFile> RawParquetFile::OpenLazy(const std::string& path
   return f;
 }
 
-void RawParquetFile::LoadKept() {
+int64_t RawParquetFile::image_offset_of(int64_t file_off, int64_t len) const {
+  auto it = std::upper_bound(segs_.begin(), segs_.end(), file_off, [](int64_t p, const Segment& s) { return p < s.file_off; });
+  if (it == segs_.begin()) return -1;
+  --it;
+  if (file_off + len > it->file_off + it->len) return -1;
+  return it->img_off + (file_off - it->file_off);
+}
+
+void RawParquetFile::LoadKept(const std::vector<std::string>* columns) {
   if (!lazy_ || loaded_) return;
   auto* rd = static_cast<parquet::ParquetFileReader*>(reader_.get());
   auto md = rd->metadata();
-  int64_t lo = INT64_MAX, hi = 0;
+  const bool flat = md->schema()->num_columns() == schema_->num_fields();
+  std::vector<char> wanted((size_t)md->schema()->num_columns(), 1);
+  if (columns && flat) {
+    std::fill(wanted.begin(), wanted.end(), 0);
+    for (const auto& n : *columns) {
+      const int ci = schema_->GetFieldIndex(n);
+      if (ci >= 0) wanted[(size_t)ci] = 1;
+    }
+  }
+  std::shared_ptr<parquet::PageIndexReader> pir;
+  if (page_pruned_ && flat) {
+    try {
+      pir = rd->GetPageIndexReader();
+    } catch (const std::exception&) {
+      pir = nullptr;
+    }
+  }
+  std::vector<Segment> segs;
+  auto add = [&](int64_t off, int64_t len) {
+    if (len > 0 && off >= 0 && off + len <= file_bytes_) segs.push_back(Segment{off, len, 0});
+  };
+  int64_t first_row = 0;
   for (int rg : kept_rg_) {
     auto rgm = md->RowGroup(rg);
-    for (int ci = 0; ci < rgm->num_columns(); ++ci) {
+    const int64_t rg_rows = rgm->num_rows();
+    const bool live_rg = !page_pruned_ || (first_row < live_hi_ && first_row + rg_rows > live_lo_);
+    std::shared_ptr<parquet::RowGroupPageIndexReader> rgi;
+    if (pir && live_rg) {
+      try {
+        rgi = pir->RowGroup(rg);
+      } catch (const std::exception&) {
+        rgi = nullptr;
+      }
+    }
+    for (int ci = 0; ci < rgm->num_columns() && live_rg; ++ci) {
+      if (!wanted[(size_t)ci]) continue;
       auto ccm = rgm->ColumnChunk(ci);
       int64_t first = ccm->data_page_offset();
       if (ccm->has_dictionary_page() && ccm->dictionary_page_offset() > 0) first = std::min(first, ccm->dictionary_page_offset());
       if (first <= 0) continue;
-      lo = std::min(lo, first);
-      hi = std::max(hi, first + ccm->total_compressed_size());
+      const int64_t bytes = ccm->total_compressed_size();
+      std::shared_ptr<parquet::OffsetIndex> oi;
+      if (rgi) {
+        try {
+          oi = rgi->GetOffsetIndex(ci);
+        } catch (const std::exception&) {
+          oi = nullptr;
+        }
+      }
+      const int64_t lo_row = live_lo_ - first_row, hi_row = live_hi_ - first_row;  // inside this row group
+      if (!oi || oi->page_locations().empty() || oi->page_locations()[0].offset < first ||
+          oi->page_locations()[0].first_row_index != 0) {
+        add(first, bytes);  // no (usable) offset index: the whole chunk
+        continue;
+      }
+      const auto& locs = oi->page_locations();
+      const size_t np = locs.size();
+      size_t a = np, b = 0;
+      for (size_t i = 0; i < np; ++i) {
+        const int64_t start = locs[i].first_row_index;
+        const int64_t end = i + 1 < np ? locs[i + 1].first_row_index : rg_rows;
+        if (end > lo_row && start < hi_row) { a = std::min(a, i); b = i; }
+      }
+      if (a == np) continue;  // (cannot happen for a live row group)
+      PageSpan sp;
+      sp.dict_off = first;
+      sp.dict_len = locs[0].offset - first;
+      sp.data_off = locs[a].offset;
+      sp.data_len = locs[b].offset + locs[b].compressed_page_size - locs[a].offset;
+      sp.first_row = locs[a].first_row_index;
+      sp.end_row = b + 1 < np ? locs[b + 1].first_row_index : rg_rows;
+      sp.skipped_pages = (int32_t)(np - (b - a + 1));
+      if (sp.data_off + sp.data_len > first + bytes || sp.data_len <= 0) {  // an index that disagrees with the footer
+        add(first, bytes);
+        continue;
+      }
+      spans_[{rg, ci}] = sp;
+      add(sp.dict_off, sp.dict_len);
+      add(sp.data_off, sp.data_len);
     }
+    first_row += rg_rows;
   }
-  if (lo >= hi) { lo = 0; hi = 0; }
-  hi = std::min(hi, file_bytes_);
-  base_ = lo;
-  image_bytes_ = hi - lo;
+  // sorted, merged, laid out back to back
+  std::sort(segs.begin(), segs.end(), [](const Segment& x, const Segment& y) { return x.file_off < y.file_off; });
+  for (const auto& sg : segs) {
+    if (!segs_.empty() && sg.file_off <= segs_.back().file_off + segs_.back().len)
+      segs_.back().len = std::max(segs_.back().len, sg.file_off + sg.len - segs_.back().file_off);
+    else
+      segs_.push_back(sg);
+  }
+  int64_t total = 0;
+  for (auto& sg : segs_) { sg.img_off = total; total += sg.len; }
+  image_bytes_ = total;
   image_ = pinned_alloc((size_t)image_bytes_ + 64);
   auto* wf = static_cast<WindowFile*>(source_.get());
-  if (image_bytes_ > 0) {
-    auto r = wf->ReadAt(lo, image_bytes_, image_.get());
-    if (!r.ok() || *r != image_bytes_) fail("short read on " + path_);
-    wf->set_window(image_.get(), base_, image_bytes_);
+  for (const auto& sg : segs_) {
+    auto r = wf->ReadAt(sg.file_off, sg.len, image_.get() + sg.img_off);
+    if (!r.ok() || *r != sg.len) fail("short read on " + path_);
   }
+  if (image_bytes_ > 0) wf->set_segments(image_.get(), segs_);
   loaded_ = true;
 }
 
@@ -809,7 +905,10 @@ std::vector<RowGroupKeyRange> RawParquetFile::KeyRanges(const std::string& colum
 bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want, std::string* why) {
   if (lazy_ && !loaded_) LoadKept();
   // a chunk [first, first + bytes) of the file lies inside the image?
-  auto in_window = [&](int64_t first, int64_t bytes) { return first > 0 && first >= base_ && first - base_ + bytes <= image_bytes_; };
+  // (what LoadKept() read of it: all of it, or -- page-pruned with an offset index -- its dictionary and live pages)
+  auto in_window = [&](int rg, int ci, int64_t first, int64_t bytes) {
+    return first > 0 && (spans_.count({rg, ci}) > 0 || image_offset_of(first, bytes) >= 0);
+  };
   auto* rd = static_cast<parquet::ParquetFileReader*>(reader_.get());
   auto md = rd->metadata();
   const auto* sd = md->schema();
@@ -850,7 +949,7 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
       for (int rg : kept_rg_) {
         auto* ccm = chunk_md(rg, ci);
         const int64_t first = ccm->has_dictionary_page() ? ccm->dictionary_page_offset() : ccm->data_page_offset();
-        if (ccm->compression() != parquet::Compression::SNAPPY || !in_window(first, ccm->total_compressed_size())) continue;
+        if (ccm->compression() != parquet::Compression::SNAPPY || !in_window(rg, ci, first, ccm->total_compressed_size())) continue;
         device_chunks.insert({rg, ci});
         chunk_codec_v[device_chunks.at(rg, ci)] = kCodecSnappy;
       }
@@ -865,7 +964,7 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
       for (int rg : kept_rg_) {
         auto* ccm = chunk_md(rg, ci);
         const int64_t first = ccm->has_dictionary_page() ? ccm->dictionary_page_offset() : ccm->data_page_offset();
-        if (ccm->compression() != parquet::Compression::ZSTD || !in_window(first, ccm->total_compressed_size())) continue;
+        if (ccm->compression() != parquet::Compression::ZSTD || !in_window(rg, ci, first, ccm->total_compressed_size())) continue;
         chunk_codec_v[device_chunks.at(rg, ci)] = kCodecZstd;
         cand.push_back({ccm->total_uncompressed_size(), {rg, ci}});
         total += ccm->total_uncompressed_size();
@@ -967,11 +1066,24 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
       const uint8_t codec = raw_zstd ? chunk_codec_v[device_chunks.at(rg, ci)] : (uint8_t)0;
       const int64_t chunk_first = ccm->has_dictionary_page() ? ccm->dictionary_page_offset() : ccm->data_page_offset();
       const int64_t chunk_bytes = ccm->total_compressed_size();
-      const bool in_image = in_window(chunk_first, chunk_bytes);
+      const bool in_image = in_window(rg, ci, chunk_first, chunk_bytes);
+      const PageSpan* span = nullptr;
+      if (auto it = spans_.find({rg, ci}); it != spans_.end()) span = &it->second;
       // own header walk (read_page_head) when the payloads are not touched on the host
       bool walk = in_image && (raw_zstd || ccm->compression() == parquet::Compression::UNCOMPRESSED);
-      const uint8_t* wp = image_.get() + (chunk_first - base_);
-      const uint8_t* const wend = wp + chunk_bytes;
+      // the walk covers the chunk, or the two loaded pieces of it: dictionary page(s), then the live data pages
+      const uint8_t* wp = nullptr;
+      const uint8_t* wend = nullptr;
+      int walk_phase = 0;  // spans only: 0 = dictionary piece, 1 = data piece
+      int64_t row_in_rg = 0;
+      if (walk && !span) {
+        wp = image_.get() + image_offset_of(chunk_first, chunk_bytes);
+        wend = wp + chunk_bytes;
+      } else if (walk) {
+        const int64_t o = span->dict_len > 0 ? image_offset_of(span->dict_off, span->dict_len) : 0;
+        wp = image_.get() + o;
+        wend = wp + span->dict_len;
+      }
       std::unique_ptr<parquet::PageReader> pr;
       auto open_libparquet = [&]() -> bool {
         try {
@@ -999,6 +1111,12 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
       auto next_page = [&](PageView* v) -> int {
         if (walk) {
           while (true) {
+            if (wp >= wend && span && walk_phase == 0) {  // on to the live data pages
+              walk_phase = 1;
+              wp = image_.get() + image_offset_of(span->data_off, span->data_len);
+              wend = wp + span->data_len;
+              row_in_rg = span->first_row;
+            }
             if (wp >= wend) return 0;
             PageHead h;
             if (!read_page_head(wp, wend, &h) || wp + h.header_len + h.compressed > wend) { *why = "malformed page header in column " + rc.name; return -1; }
@@ -1054,7 +1172,7 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
         return open_libparquet();
       };
       int dict_idx = -1;
-      int64_t row_in_rg = 0;
+      int chunk_pages = 0;  // data pages of this chunk framed so far
       while (true) {
         PageView page;
         const int got = next_page(&page);
@@ -1111,9 +1229,11 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
           if (!(pg.encoding == ENC_PLAIN || is_dict || rle_bool)) { *why = "value encoding " + parquet::EncodingToString(enc) + " in column " + rc.name; return false; }
           if (is_dict && dict_idx < 0) { *why = "dictionary page missing"; return false; }
           if (pc.conv == CONV_BOOL && is_dict) { *why = "dictionary coded boolean"; return false; }
-          if (raw_zstd && v2 && row_in_rg == 0) {
+          if (raw_zstd && v2 && chunk_pages == 0) {
             // v2 pages keep their levels outside the compressed section: let libparquet decompress this chunk
+            // (from its first page: nothing of it was framed yet)
             if (!restart_on_host()) return false;
+            row_in_rg = 0;
             continue;
           }
           if (page_pruned_ && (first_row + row_in_rg + pg.num_values <= live_lo_ || first_row + row_in_rg >= live_hi_)) {
@@ -1137,11 +1257,13 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
           emit_lo = std::min(emit_lo, pg.first_row);
           emit_hi = std::max(emit_hi, pg.first_row + pg.num_values);
           row_in_rg += pg.num_values;
+          chunk_pages += 1;
           rc.pages.push_back(pg);
           rc.page_dict.push_back(is_dict ? dict_idx : -1);
         }
       }
-      if (row_in_rg != rg_md[(size_t)rg]->num_rows()) { *why = "page row count mismatch in column " + rc.name; return false; }
+      if (walk && span) pruned_pages_ += span->skipped_pages;  // pages that were never read
+      if (row_in_rg != (walk && span ? span->end_row : rg_md[(size_t)rg]->num_rows())) { *why = "page row count mismatch in column " + rc.name; return false; }
       first_row += rg_md[(size_t)rg]->num_rows();
     }
   }
@@ -1202,12 +1324,13 @@ extern "C" __attribute__((visibility("default"))) int64_t lsb_test_plan_digest(c
 }
 
 // test hook (tests/test_page_pruning.py): row groups, then pages, pruned by `filter` (parquet-mr string form) over the key
-// columns `pks` (comma separated); prints the live range and the framed pages of every column.
-extern "C" __attribute__((visibility("default"))) int64_t lsb_test_page_prune(const char* path, const char* filter, const char* pks, char* out,
-                                                                              int64_t cap) {
+// columns `pks` (comma separated); prints the live range and the framed pages of every column (with a hash of the
+// payload bytes the device would read). lazy = 1: footer first, then only the needed byte segments of the file.
+extern "C" __attribute__((visibility("default"))) int64_t lsb_test_page_prune(const char* path, const char* filter, const char* pks, int32_t lazy,
+                                                                              char* out, int64_t cap) {
   std::string text;
   try {
-    auto f = RawParquetFile::Open(path);
+    auto f = lazy ? RawParquetFile::OpenLazy(path) : RawParquetFile::Open(path);
     std::set<std::string> pk;
     std::string cur;
     for (const char* p = pks; ; ++p) {
@@ -1217,16 +1340,25 @@ extern "C" __attribute__((visibility("default"))) int64_t lsb_test_page_prune(co
     auto fe = parse_filter(filter, *f->schema());
     const int dropped = f->PruneRowGroups(*fe, pk);
     const int64_t outside = f->PrunePages(*fe, pk);
+    f->LoadKept();
     std::vector<std::shared_ptr<arrow::Field>> want = f->schema()->fields();
     std::string why;
     if (!f->Plan(want, &why)) throw std::runtime_error("not framed: " + why);
+    auto hash = [&](bool aux, int64_t off, int64_t n) {
+      const uint8_t* p = (aux ? f->aux() : f->image()) + off;
+      uint64_t h = 1469598103934665603ull;
+      for (int64_t i = 0; i < n; ++i) h = (h ^ p[i]) * 1099511628211ull;
+      return h;
+    };
     text += "dropped_rg " + std::to_string(dropped) + " first_kept_rg " + std::to_string(f->kept_row_groups().empty() ? -1 : f->kept_row_groups()[0]) +
             " kept_rows " + std::to_string(f->num_rows()) + " outside " + std::to_string(outside) + " live_begin " +
             std::to_string(f->live_begin()) + " live_rows " + std::to_string(f->live_rows()) + " live_offset " + std::to_string(f->live_offset()) +
-            " layout_rows " + std::to_string(f->layout_rows()) + " pruned_pages " + std::to_string(f->pruned_pages()) + "\n";
+            " layout_rows " + std::to_string(f->layout_rows()) + " pruned_pages " + std::to_string(f->pruned_pages()) + " image_bytes " +
+            std::to_string(f->image_bytes()) + " file_bytes " + std::to_string(f->file_bytes()) + "\n";
     for (const auto& c : f->columns()) {
       text += "C " + c.name;
-      for (const auto& g : c.pages) text += " " + std::to_string(g.first_row) + ":" + std::to_string(g.num_values);
+      for (const auto& g : c.pages)
+        text += " " + std::to_string(g.first_row) + ":" + std::to_string(g.num_values) + ":" + std::to_string(hash(g.aux, g.src_off, g.codec ? g.comp_size : g.size));
       text += "\n";
     }
   } catch (const std::exception& e) {

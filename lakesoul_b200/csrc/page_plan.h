@@ -8,6 +8,7 @@
 #include <arrow/api.h>
 #include <arrow/io/interfaces.h>
 
+#include <map>
 #include <memory>
 #include <set>
 #include <string>
@@ -67,7 +68,10 @@ class RawParquetFile {
   // (files are sorted by primary key: the row groups a key range keeps are neighbours). Used when a bucket is
   // streamed by key range (reader.cc) so that pinned memory holds one pass, not the bucket.
   static std::shared_ptr<RawParquetFile> OpenLazy(const std::string& path);
-  void LoadKept();                                  // no-op for files opened with Open()
+  // no-op for files opened with Open(). After PrunePages() found a live row range and the file has an offset index, only
+  // the pages that overlap it (plus dictionary pages) of the columns in `columns` (nullptr = all) are read; the image is
+  // then a concatenation of byte segments of the file.
+  void LoadKept(const std::vector<std::string>* columns = nullptr);
   int64_t file_bytes() const { return file_bytes_; }
   // the file as an Arrow source (host-decode fallback): the image when it is the whole file, else image + pread
   std::shared_ptr<arrow::io::RandomAccessFile> source() const;
@@ -107,10 +111,13 @@ class RawParquetFile {
   bool Plan(const std::vector<std::shared_ptr<arrow::Field>>& want, std::string* why);
 
   const std::vector<RawColumn>& columns() const { return cols_; }
-  // bytes [image_base(), image_base() + image_bytes()) of the file; page records hold offsets into image()
+  // the bytes of the file in memory -- all of it, or the segments LoadKept() read, back to back; page records hold
+  // offsets into image()
   const uint8_t* image() const { return image_.get(); }
   int64_t image_bytes() const { return image_bytes_; }
-  int64_t image_base() const { return base_; }
+  struct Segment { int64_t file_off = 0, len = 0, img_off = 0; };
+  // where `len` bytes at `file_off` of the file sit inside image(), or -1 when they are not (all) loaded
+  int64_t image_offset_of(int64_t file_off, int64_t len) const;
   const uint8_t* aux() const { return aux_.get(); }
   int64_t aux_bytes() const { return aux_used_; }
   int64_t host_decompressed_bytes() const { return aux_used_; }
@@ -123,7 +130,14 @@ class RawParquetFile {
   std::string path_;
   std::shared_ptr<uint8_t> image_, aux_;
   int64_t image_bytes_ = 0, aux_cap_ = 0, aux_used_ = 0, rows_ = 0;
-  int64_t base_ = 0, file_bytes_ = 0;
+  int64_t file_bytes_ = 0;
+  std::vector<Segment> segs_;  // ascending file offsets, disjoint
+  struct PageSpan {            // (row group, column) of a lazily loaded, page-pruned file: what LoadKept() read of the chunk
+    int64_t dict_off = 0, dict_len = 0, data_off = 0, data_len = 0;
+    int64_t first_row = 0, end_row = 0;  // rows of the row group the data pages cover
+    int32_t skipped_pages = 0;
+  };
+  std::map<std::pair<int, int>, PageSpan> spans_;
   int64_t live_lo_ = 0, live_hi_ = 0, origin_ = 0, layout_rows_ = 0, pruned_pages_ = 0;
   bool page_pruned_ = false;
   bool lazy_ = false, loaded_ = true;

@@ -670,15 +670,6 @@ void Reader::Start() {
     }
   }
 
-  if (cfg.lazy_files) {  // only now is it known which row groups this pass reads
-    for (auto& fi : files) {
-      fi.raw->LoadKept();
-      if (early_upload && fi.raw->image_bytes() > 0)
-        fi.raw->set_device_image(session_upload(*session, fi.raw->image(), (size_t)fi.raw->image_bytes()));
-    }
-    trace_mark("load_kept");
-  }
-
   // ---- merged schema: requested + filter + pk + cdc columns, table order (file_format.rs:254-265)
   const std::string cdc = cfg.cdc_column();
   auto is_pk = [&](const std::string& n) {
@@ -752,6 +743,19 @@ void Reader::Start() {
     I.stats.path = "count";
     I.started = true;
     return;
+  }
+
+  if (cfg.lazy_files) {
+    // only now is it known which row groups, pages and columns this pass reads: the byte segments of the kept row
+    // groups -- with a page index, of the live pages -- of the physical columns
+    std::vector<std::string> names;
+    for (const auto& pf : phys_fields) names.push_back(pf->name());
+    for (auto& fi : files) {
+      fi.raw->LoadKept(&names);
+      if (early_upload && fi.raw->image_bytes() > 0)
+        fi.raw->set_device_image(session_upload(*session, fi.raw->image(), (size_t)fi.raw->image_bytes()));
+    }
+    trace_mark("load_kept");
   }
 
   // ---- frame every file for the device decoders; host Arrow decode only where they do not apply

@@ -116,3 +116,8 @@ def test_streamed_bucket_decodes_each_page_once(tmp_path):
     assert_tables_equal(got, mo.read_bucket(paths, schema, ["k"]), "streamed with page index")
     assert st["stream_passes"] >= 3 and st["pruned_pages"] > 0
     assert st["rows_in"] < total_rows * 1.5, (st, total_rows)
+    # ... and read once: with the offset index a pass reads the byte segments of its pages only (every pass would read
+    # every delta file whole otherwise: about 3 x the files here)
+    import os
+    file_bytes = sum(os.path.getsize(p) for p in paths)
+    assert st["h2d_bytes"] < file_bytes * 2.0, (st["h2d_bytes"], file_bytes)

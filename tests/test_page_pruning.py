@@ -18,10 +18,10 @@ from lakesoul_b200 import load_library  # noqa: E402
 N = 30000
 
 
-def _prune(path, flt, pks):
+def _prune_once(path, flt, pks, lazy):
     lib = load_library()
     buf = ctypes.create_string_buffer(1 << 22)
-    n = lib.lsb_test_page_prune(path.encode(), flt.encode(), pks.encode(), buf, len(buf))
+    n = lib.lsb_test_page_prune(path.encode(), flt.encode(), pks.encode(), lazy, buf, len(buf))
     assert n >= 0, buf.value.decode()
     lines = buf.value.decode().splitlines()
     head = lines[0].split()
@@ -31,6 +31,18 @@ def _prune(path, flt, pks):
         parts = ln.split()
         cols[parts[1]] = [tuple(int(x) for x in p.split(":")) for p in parts[2:]]
     return info, cols
+
+
+def _prune(path, flt, pks):
+    """eager framing, checked against the lazy one: same live range, same pages, same payload bytes, fewer bytes read"""
+    info, cols = _prune_once(path, flt, pks, 0)
+    linfo, lcols = _prune_once(path, flt, pks, 1)
+    assert lcols == cols, (flt, "lazy framing differs")
+    for k in ("dropped_rg", "kept_rows", "live_begin", "live_rows", "live_offset", "layout_rows", "pruned_pages"):
+        assert info[k] == linfo[k], (flt, k, info, linfo)
+    assert info["image_bytes"] == info["file_bytes"] and linfo["image_bytes"] <= info["file_bytes"]
+    info["lazy_image_bytes"] = linfo["image_bytes"]
+    return info, {name: [(a, n) for a, n, _ in pages] for name, pages in cols.items()}
 
 
 def _file(tmp_path, name="f.parquet", page_index=True, **kw):
@@ -83,6 +95,7 @@ def test_key_range_keeps_only_the_overlapping_pages(tmp_path):
     k = t["k"].to_numpy()
     info = _check(t, path, "and(gteq(k, 30300), lt(k, 33000))", "k,k2", (k >= 30300) & (k < 33000))
     assert info["dropped_rg"] == 2 and info["pruned_pages"] > 20 and info["live_rows"] < 3000
+    assert info["lazy_image_bytes"] < info["file_bytes"] * 0.08  # the pages of ~1000 of 30000 rows (+ the boolean chunk)
     # (the boolean column has one small page per row group: it alone keeps the layout at the row group's size)
     assert info["layout_rows"] == 10000
     # across a row-group boundary
@@ -134,3 +147,22 @@ def test_null_key_pages(tmp_path):
     assert info["live_begin"] == 4000 and info["live_rows"] == 6000, info
     info, cols = _prune(path, "eq(k, null)", "k")
     assert info["live_begin"] == 0 and info["live_rows"] == 4000, info
+
+
+@pytest.mark.parametrize("layout", ["plain", "snappy_dict", "zstd_dict", "v2"])
+def test_lazy_segments_for_every_page_layout(tmp_path, layout):
+    """dictionary pages travel with the live data pages (two byte segments per chunk); chunks libparquet has to read
+    (v2 pages, host-decompressed ones) get what was not loaded by pread"""
+    kw = dict(plain=dict(compression="NONE"), snappy_dict=dict(compression="SNAPPY", use_dictionary=True),
+              zstd_dict=dict(compression="ZSTD", use_dictionary=["v", "s"]), v2=dict(data_page_version="2.0"))[layout]
+    rng = np.random.default_rng(4)
+    t = pa.table({"k": pa.array(np.arange(N, dtype=np.int64)), "v": pa.array(rng.integers(0, 50, N).astype(np.int64)),
+                  "s": pa.array(["tag%02d" % (i % 37) if i % 5 else None for i in range(N)], pa.string())})
+    path = str(tmp_path / "f.parquet")
+    args = dict(row_group_size=10000, data_page_size=4 << 10, write_page_index=True, compression="ZSTD", use_dictionary=False)
+    args.update(kw)
+    pq.write_table(t, path, **args)
+    k = t["k"].to_numpy()
+    for lo, hi in [(12000, 13500), (9500, 10500), (0, 800), (29000, 10**9)]:
+        info = _check(t, path, f"and(gteq(k, {lo}), lt(k, {hi}))", "k", (k >= lo) & (k < hi))
+        assert info["lazy_image_bytes"] < info["file_bytes"] * 0.5
