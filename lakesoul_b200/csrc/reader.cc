@@ -586,6 +586,16 @@ void Reader::Start() {
            "key value, or several file groups): the GPU reader keeps a whole scan resident; compact the bucket or raise the limit");
   }
   session = begin_scan_session();
+  // Lazy IO -- footers first, then only the byte segments of the row groups / pages / columns that are read: always for
+  // the passes of a streamed bucket, and for readers whose pushed filters name a primary-key column (a key lookup or a
+  // key range reads a few pages of every file instead of the files). Everything else reads whole files and sends each
+  // to the GPU while the next one is read.
+  bool lazy_io = cfg.lazy_files;
+  if (!lazy_io && !cfg.primary_keys.empty() && getenv("LAKESOUL_B200_NO_PRUNING") == nullptr) {
+    static const bool on = [] { const char* v = getenv("LAKESOUL_B200_LAZY_FILTERED"); return !(v && *v == '0'); }();
+    for (const auto& fs : cfg.filter_strs)
+      for (const auto& pk : cfg.primary_keys) lazy_io = lazy_io || (on && fs.find(pk) != std::string::npos);
+  }
   std::vector<FileInfo> files;
   size_t file_no = 0;
   for (const auto& raw : cfg.files) {
@@ -600,8 +610,8 @@ void Reader::Start() {
     FileInfo fi;
     fi.path = path;
     fi.group = this_group;
-    fi.raw = cfg.lazy_files ? RawParquetFile::OpenLazy(path) : RawParquetFile::Open(path);
-    if (early_upload && !cfg.lazy_files)
+    fi.raw = lazy_io ? RawParquetFile::OpenLazy(path) : RawParquetFile::Open(path);
+    if (early_upload && !lazy_io)
       fi.raw->set_device_image(session_upload(*session, fi.raw->image(), (size_t)fi.raw->image_bytes()));
     std::vector<std::shared_ptr<arrow::Field>> kept;
     for (const auto& f : fi.raw->schema()->fields())
@@ -745,7 +755,7 @@ void Reader::Start() {
     return;
   }
 
-  if (cfg.lazy_files) {
+  if (lazy_io) {
     // only now is it known which row groups, pages and columns this pass reads: the byte segments of the kept row
     // groups -- with a page index, of the live pages -- of the physical columns
     std::vector<std::string> names;
