@@ -1,9 +1,12 @@
 // SPDX-License-Identifier: Apache-2.0
 //
-// page_plan.h -- host-side framing of Parquet files for the device decoders: the file is read once
-// into pinned memory, footer + page headers are parsed (libparquet's thrift reader), compressed pages
-// are decompressed on the host (SNAPPY / ZSTD / ... through Arrow's codecs), and every data page is
-// described by a POD record that points into the raw image. Values are never touched on the host.
+// page_plan.h -- host-side framing of Parquet files for the device decoders. A file is read once into pinned memory --
+// whole, or (lazily opened files: key-filtered readers, passes of a streamed bucket) footer first and then only the byte
+// segments of the row groups / pages / columns that are needed --, the footer is parsed by libparquet, page headers by a
+// purpose-built thrift-compact reader, row groups and pages are pruned by the key columns' statistics, and every data
+// page is described by a POD record that points into the raw image. Page payloads stay compressed (ZSTD, SNAPPY: expanded
+// on the GPU) or are used in place (uncompressed); only chunks the device cannot expand go through Arrow's codecs on
+// the host. Values are never touched on the host.
 #pragma once
 #include <arrow/api.h>
 #include <arrow/io/interfaces.h>
