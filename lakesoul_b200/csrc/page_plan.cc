@@ -1270,7 +1270,10 @@ bool RawParquetFile::Plan(const std::vector<std::shared_ptr<arrow::Field>>& want
   // the file's rows in the scan = what was framed; pages count from there
   if (page_pruned_) {
     origin_ = emit_lo <= emit_hi ? emit_lo : live_lo_;
-    layout_rows_ = emit_lo <= emit_hi ? emit_hi - emit_lo : 0;
+    // the rows the merge reads start on a 64-row boundary of the scan's row space, like an unpruned file's do (files are
+    // laid out on 64-row boundaries, device_scan.cc): up to 63 unused rows in front of the first framed page
+    if (const int64_t mis = (live_lo_ - origin_) % 64) origin_ -= 64 - mis;
+    layout_rows_ = emit_lo <= emit_hi ? emit_hi - origin_ : 0;
     for (auto& c : cols_)
       for (auto& pg : c.pages) pg.first_row -= origin_;
   } else {

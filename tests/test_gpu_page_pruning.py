@@ -107,6 +107,15 @@ def test_with_other_predicates_cdc_and_merge_operators(tmp_path):
     assert st["pruned_pages"] == 0
 
 
+def test_odd_page_boundaries(tmp_path):
+    """pages of 77 rows (parquet-rs pages end wherever the size limit says): live ranges and page starts on odd rows"""
+    schema, paths = _bucket(tmp_path, INT_KEY, write_batch_size=11, max_rows_per_page=77)
+    for flt in ["and(gteq(k, 17011), lt(k, 19513))", "eq(k, 12345)", "and(gt(k, 15990), lteq(k, 16013))", "lt(k, 131)"]:
+        got, st = _read(paths, schema, ["k"], [flt])
+        assert st["pruned_pages"] > 0 and got.num_rows > 0
+    _read(paths, schema, ["k"], ["and(gteq(k, 3001), lt(k, 9007))"], merge_ops={"v": "SumAll", "s": "JoinedAllByComma"})
+
+
 def test_streamed_bucket_decodes_each_page_once(tmp_path):
     """with a page index the passes of a streamed bucket decode the delta files' pages of their key range only: the rows
     decoded over all passes stay close to the bucket's rows (without it every pass decodes every straddling row group)"""

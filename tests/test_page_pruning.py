@@ -85,7 +85,7 @@ def _check(t, path, flt, pks, mask, slack_pages=2):
         assert pages[-1][0] + pages[-1][1] >= info["live_offset"] + info["live_rows"], name
         assert pages[-1][0] + pages[-1][1] <= info["layout_rows"], name
     if info["live_rows"]:
-        assert min(p[0][0] for p in cols.values()) == 0
+        assert 0 <= min(p[0][0] for p in cols.values()) < 64 and info["live_offset"] % 64 == 0  # merge range on a 64-row boundary
         assert max(p[-1][0] + p[-1][1] for p in cols.values()) == info["layout_rows"]
     return info
 
@@ -97,7 +97,7 @@ def test_key_range_keeps_only_the_overlapping_pages(tmp_path):
     assert info["dropped_rg"] == 2 and info["pruned_pages"] > 20 and info["live_rows"] < 3000
     assert info["lazy_image_bytes"] < info["file_bytes"] * 0.08  # the pages of ~1000 of 30000 rows (+ the boolean chunk)
     # (the boolean column has one small page per row group: it alone keeps the layout at the row group's size)
-    assert info["layout_rows"] == 10000
+    assert 10000 <= info["layout_rows"] < 10064
     # across a row-group boundary
     info = _check(t, path, "and(gteq(k, 29000), lteq(k, 31000))", "k,k2", (k >= 29000) & (k <= 31000))
     assert info["dropped_rg"] == 1 and info["live_rows"] < 3000
