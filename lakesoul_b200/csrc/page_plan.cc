@@ -1358,6 +1358,9 @@ extern "C" __attribute__((visibility("default"))) int64_t lsb_test_page_prune(co
             std::to_string(f->live_begin()) + " live_rows " + std::to_string(f->live_rows()) + " live_offset " + std::to_string(f->live_offset()) +
             " layout_rows " + std::to_string(f->layout_rows()) + " pruned_pages " + std::to_string(f->pruned_pages()) + " image_bytes " +
             std::to_string(f->image_bytes()) + " file_bytes " + std::to_string(f->file_bytes()) + "\n";
+    text += "K";
+    for (int rg : f->kept_row_groups()) text += " " + std::to_string(rg);
+    text += "\n";
     for (const auto& c : f->columns()) {
       text += "C " + c.name;
       for (const auto& g : c.pages)

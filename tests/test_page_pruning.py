@@ -29,6 +29,9 @@ def _prune_once(path, flt, pks, lazy):
     cols = {}
     for ln in lines[1:]:
         parts = ln.split()
+        if parts[0] == "K":
+            info["kept_rgs"] = [int(x) for x in parts[1:]]
+            continue
         cols[parts[1]] = [tuple(int(x) for x in p.split(":")) for p in parts[2:]]
     return info, cols
 
@@ -38,7 +41,7 @@ def _prune(path, flt, pks):
     info, cols = _prune_once(path, flt, pks, 0)
     linfo, lcols = _prune_once(path, flt, pks, 1)
     assert lcols == cols, (flt, "lazy framing differs")
-    for k in ("dropped_rg", "kept_rows", "live_begin", "live_rows", "live_offset", "layout_rows", "pruned_pages"):
+    for k in ("dropped_rg", "kept_rows", "live_begin", "live_rows", "live_offset", "layout_rows", "pruned_pages", "kept_rgs"):
         assert info[k] == linfo[k], (flt, k, info, linfo)
     assert info["image_bytes"] == info["file_bytes"] and linfo["image_bytes"] <= info["file_bytes"]
     info["lazy_image_bytes"] = linfo["image_bytes"]

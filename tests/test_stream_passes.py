@@ -96,3 +96,34 @@ def test_unsplittable_buckets_stay_one_scan(tmp_path):
     pq.write_table(pa.table({"k": pa.array(np.arange(9000, dtype=np.int64))}), p, row_group_size=1000, write_statistics=False)
     assert _passes([p], "k", 1000) == []
     assert _passes([p], "missing", 1000) == []
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_buckets_give_ascending_disjoint_passes(tmp_path, seed):
+    """random file counts / sizes / overlaps and budgets: the cuts ascend strictly, every cut is a row-group minimum, no
+    pass is closed before it finished half a budget of row groups (except the last), one scan when nothing can be cut"""
+    rng = np.random.default_rng(500 + seed)
+    nfiles = int(rng.integers(1, 9))
+    keys = []
+    for i in range(nfiles):
+        span = int(rng.integers(2000, 90000))
+        off = int(rng.integers(0, 50000))
+        keys.append(off + np.sort(rng.choice(span, int(rng.integers(1000, min(span, 20000))), replace=False)).astype(np.int64))
+    files = _bucket(tmp_path, keys, rg=int(rng.integers(700, 5000)))
+    mds = [pq.ParquetFile(f).metadata for f in files]
+    rgs = [(md.row_group(g).column(0).statistics.min, md.row_group(g).column(0).statistics.max, md.row_group(g).total_byte_size)
+           for md in mds for g in range(md.num_row_groups)]
+    total = sum(b for _, _, b in rgs)
+    budget = int(total / rng.uniform(1.5, 12))
+    lines = _passes(files, "k", budget)
+    if not lines:
+        return
+    b = _bounds(lines)
+    cuts = [hi for _, hi in b[:-1]]
+    assert cuts == sorted(set(cuts))
+    mins = {mn for mn, _, _ in rgs}
+    assert all(c in mins for c in cuts) and min(mins) < cuts[0]
+    los = [None] + cuts
+    for lo, hi in zip(los, cuts):  # every closed pass finishes at least half a budget of row groups
+        done = sum(by for mn, mx, by in rgs if mx < hi and (lo is None or mx >= lo))
+        assert done >= budget // 2, (lo, hi, done, budget)
