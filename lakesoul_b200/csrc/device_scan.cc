@@ -57,7 +57,12 @@ class PinnedPool {
     }
     if (!p) {
       // host-logic tests on machines without a GPU (framing of files, tests/test_lazy_files.py) ask for pageable memory
-      static const bool test_host_alloc = getenv("LAKESOUL_B200_TEST_HOST_ALLOC") != nullptr;
+      // -- honoured only when there is no CUDA device at all: with a GPU every buffer is pinned
+      static const bool test_host_alloc = [] {
+        if (getenv("LAKESOUL_B200_TEST_HOST_ALLOC") == nullptr) return false;
+        int n = 0;
+        return cudaGetDeviceCount(&n) != cudaSuccess || n == 0;
+      }();
       if (test_host_alloc) {
         p = static_cast<uint8_t*>(aligned_alloc(4096, cls));
         if (!p) fail("out of memory");

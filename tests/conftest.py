@@ -10,6 +10,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
+# Host-logic tests of the file framing (test_lazy_files, test_page_pruning*, test_stream_passes) open files through the
+# library on machines without a GPU: there -- and only there -- the library may hand out pageable instead of pinned
+# memory. On a GPU box nothing is set and every test runs on the production allocator (the library ignores the switch
+# when a CUDA device exists).
+if not os.path.exists("/dev/nvidia0") and not os.path.exists("/dev/nvidiactl"):
+    os.environ.setdefault("LAKESOUL_B200_TEST_HOST_ALLOC", "1")
+
 _TYPES = {"int32": pa.int32(), "int64": pa.int64(), "float64": pa.float64(), "utf8": pa.string()}
 
 

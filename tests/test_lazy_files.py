@@ -10,7 +10,6 @@ import pyarrow as pa
 import pyarrow.parquet as pq
 import pytest
 
-os.environ.setdefault("LAKESOUL_B200_TEST_HOST_ALLOC", "1")  # framing only: no GPU, pageable memory
 from lakesoul_b200 import load_library  # noqa: E402
 
 

@@ -12,7 +12,6 @@ import pyarrow.compute as pc
 import pyarrow.parquet as pq
 import pytest
 
-os.environ.setdefault("LAKESOUL_B200_TEST_HOST_ALLOC", "1")
 from lakesoul_b200 import load_library  # noqa: E402
 
 N = 30000

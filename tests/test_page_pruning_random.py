@@ -10,7 +10,6 @@ import pyarrow as pa
 import pyarrow.parquet as pq
 import pytest
 
-os.environ.setdefault("LAKESOUL_B200_TEST_HOST_ALLOC", "1")
 import mor_oracle as mo  # noqa: E402
 from test_page_pruning import _prune  # noqa: E402
 
