@@ -84,3 +84,39 @@ def test_truncated_and_garbage_headers_are_errors():
     assert lib.lsb_test_walk_page_heads(junk.ctypes.data, 0, len(junk), out.ctypes.data, 16) == -1
     rnd = np.random.default_rng(1).integers(0, 256, 4096).astype(np.uint8)
     assert lib.lsb_test_walk_page_heads(rnd.ctypes.data, 0, len(rnd), out.ctypes.data, 16) < 0
+
+
+def test_malformed_headers_are_rejected_not_followed(tmp_path):
+    """truncated and bit-flipped page headers: the walker answers -1 / -2 (or a consistent walk), never reads outside the
+    byte range it was given (the buffer ends exactly there: an over-read would fault under the guard page below)"""
+    import mmap
+    lib = load_library()
+    t = pa.table({"a": pa.array(np.arange(5000, dtype=np.int64)), "s": pa.array(["x" * (i % 50) for i in range(5000)])})
+    path = str(tmp_path / "f.parquet")
+    pq.write_table(t, path, data_page_size=2 << 10, compression="ZSTD", use_dictionary=False, write_statistics=True)
+    md = pq.ParquetFile(path).metadata
+    cc = md.row_group(0).column(1)
+    raw = np.fromfile(path, dtype=np.uint8)[cc.data_page_offset:cc.data_page_offset + cc.total_compressed_size].copy()
+    page = mmap.PAGESIZE
+    rng = np.random.default_rng(9)
+    out = np.zeros((4096, 8), dtype=np.int32)
+    for trial in range(300):
+        n = int(rng.integers(1, len(raw) + 1)) if trial % 2 else len(raw)
+        buf = raw[:n].copy()
+        for _ in range(int(rng.integers(0, 4))):
+            buf[int(rng.integers(0, min(n, 64)))] ^= np.uint8(1 << int(rng.integers(0, 8)))
+        # place the bytes so that they END at a page boundary followed by an inaccessible page
+        size = (n + page - 1) // page * page + page
+        m = mmap.mmap(-1, size)
+        start = size - page - n
+        m[start:start + n] = buf.tobytes()
+        addr = ctypes.addressof(ctypes.c_char.from_buffer(m))
+        libc = ctypes.CDLL(None, use_errno=True)
+        assert libc.mprotect(ctypes.c_void_p(addr + size - page), ctypes.c_size_t(page), 0) == 0
+        r = lib.lsb_test_walk_page_heads(ctypes.c_void_p(addr), start, n, out.ctypes.data, 4096)
+        assert r >= -2
+        if trial % 2 == 0 and (buf == raw).all():
+            assert r > 0
+        libc.mprotect(ctypes.c_void_p(addr + size - page), ctypes.c_size_t(page), 3)
+        del addr
+        m.close()
